@@ -1,0 +1,246 @@
+/*
+ * mobi_b200 — C ABI of the B200-native (sm_100a) kernels behind MObI's denoising hot path.
+ *
+ * The reference (alexbuburuzan/MObI) has no FFI of its own on this path: every operator is a stock
+ * torch.nn module created through `instantiate_from_config` (ldm/util.py:76-91).  This header is the
+ * boundary a maintainer binds instead: the Python drop-in classes in `mobi_b200/` (same class names,
+ * constructor kwargs and state-dict keys as the reference) call these entry points through ctypes with
+ * raw device pointers.  Each entry cites the reference code it replaces.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch); nothing is allocated or freed here;
+ *   - every call is asynchronous on `stream` (a cudaStream_t passed as void*), never synchronises, and is
+ *     CUDA-graph capturable;
+ *   - return value 0 = ok, nonzero = error; `mobi_last_error()` returns a thread-local message;
+ *   - activations are channels-last: images are [N, H, W, C], token matrices are [rows, C];
+ *   - "bf16" is __nv_bfloat16, "f32" is float.  dtype codes: 0 = bf16, 1 = f32.
+ */
+#ifndef MOBI_B200_H
+#define MOBI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MOBI_DTYPE_BF16 0
+#define MOBI_DTYPE_F32 1
+
+/* Epilogue layouts of mobi_gemm (what is done with each fp32 accumulator tile). */
+#define MOBI_EPI_PLAIN 0   /* out[m, n]                                     (row stride ldo)            */
+#define MOBI_EPI_GEGLU 1   /* columns come in 16-groups [8 value | 8 gate]; out[m, n/2] = v * gelu(g)  */
+#define MOBI_EPI_HEADS 2   /* out[((m / tokens) * heads + n / d) , m % tokens, n % d]   (q, k)          */
+#define MOBI_EPI_HEADS_T 3 /* out[((m / tokens) * heads + n / d) , n % d, m % tokens]   (v transposed)  */
+#define MOBI_EPI_QKV 4     /* n / (heads*d) selects q (HEADS -> out), k (HEADS -> out2), v (HEADS_T -> out3) */
+
+const char* mobi_last_error(void);
+int mobi_version(void);
+
+/*
+ * C[M,N] = A[M,K] . B[N,K]^T on tcgen05 tensor cores (bf16 in, fp32 accumulate in TMEM, TMA-staged tiles),
+ * followed by a fused epilogue:  v = acc + bias[n] + row_bias[m / rows_per_group, n] + residual[m, n].
+ *
+ * Replaces torch.nn.Linear / 1x1 nn.Conv2d everywhere on the path: CrossAttention.to_q/to_k/to_v/to_out
+ * (ldm/modules/attention.py:162-169), GEGLU.proj + FeedForward.net[2] (attention.py:38-62), the adapter
+ * connectors (attention.py:218-223), SpatialTransformer.proj_in/proj_out (attention.py:285-300), ResBlock
+ * skip_connection (openaimodel.py:241), emb_layers / time_embed (openaimodel.py:204-210, 627-631), and the
+ * VAE nin_shortcut / AttnBlock q,k,v,proj_out (model.py:115-119, 156-175).
+ *
+ * With `conv = 1` the A operand is an NHWC image and the K loop walks the KHxKW filter taps with shifted,
+ * zero-filled 4-D TMA boxes (implicit GEMM): replaces nn.Conv2d 3x3 / (1,5), stride 1, "same" zero padding
+ * (openaimodel.py:192, 216, 115; model.py:45, 96, 106, 384-401, 559-578).  B is then [N, KH*KW*C] with K
+ * ordered (kh, kw, c).
+ */
+typedef struct {
+    const void* A;         /* bf16 [M, K] row-major (lda), or NHWC image when conv=1 */
+    const void* B;         /* bf16 [N, K] row-major (ldb) */
+    void* out;             /* see epilogue */
+    void* out2;            /* MOBI_EPI_QKV: k */
+    void* out3;            /* MOBI_EPI_QKV: v (transposed) */
+    const float* bias;     /* f32 [N] or NULL */
+    const float* row_bias; /* f32 [ceil(M / rows_per_group), N] or NULL */
+    const void* residual;  /* [M, N] (ldo) of res_dtype or NULL; may alias out */
+    int64_t M, N, K;
+    int64_t lda, ldb, ldo; /* row strides in elements */
+    int64_t rows_per_group;
+    int64_t ld_row_bias;   /* row stride of row_bias in elements (0 = N) */
+    int32_t out_dtype, res_dtype;
+    int32_t epilogue;
+    int32_t act;           /* 0 = none, 1 = SiLU applied after bias (PLAIN only; time_embed, openaimodel.py:627-631) */
+    int32_t heads, head_dim, tokens;
+    /* implicit conv */
+    int32_t conv;
+    int32_t n_img, H, W, C, KH, KW, pad_h, pad_w;
+    int32_t tile_n; /* 0 = choose */
+} mobi_gemm_args;
+
+int mobi_gemm(const mobi_gemm_args* args, void* stream);
+
+/*
+ * Flash-style fused attention: O = softmax(Q K^T) V per (batch*head), scores never leave the SM.
+ * q, k: bf16 [BH, Tq|Tk, d]; vt: bf16 [BH, d, Tk] (transposed V); out: bf16 [B, Tq, heads*d] token-major.
+ * The softmax scale (d^-0.5, attention.py:159,181; C^-0.5 in the VAE AttnBlock, model.py:191) times log2(e)
+ * must already be folded into q.  Replaces CrossAttention.forward lines 179-193 and AttnBlock.forward
+ * lines 184-198.  Cross-modal attention (attention.py:246-261) is the same call
+ * with q built from one modality's rows and k/vt from the partner rows.
+ */
+typedef struct {
+    const void* q;
+    const void* k;
+    const void* vt;
+    void* out;
+    int32_t batch, heads, head_dim, tq, tk;
+    int64_t ld_out; /* row stride of out in elements (>= heads*head_dim) */
+} mobi_attn_args;
+
+int mobi_attention(const mobi_attn_args* args, void* stream);
+
+/*
+ * GroupNorm (+ optional SiLU) over an NHWC f32 or bf16 image, fp32 statistics (GroupNorm32,
+ * ldm/modules/diffusionmodules/util.py:214-216; eps 1e-5 in ResBlocks, 1e-6 in SpatialTransformer.norm
+ * and the VAE, attention.py:77-78, model.py:38-39), fused with the following SiLU (openaimodel.py:190,
+ * 213; model.py:33-35).  The input may be the channel concatenation of two tensors (x1 | x2), which is how
+ * UNetModel.forward feeds skip connections (openaimodel.py:892).  Output bf16 NHWC [N, HW, C1+C2].
+ * `partials` is caller-provided scratch of mobi_groupnorm_scratch_bytes() bytes.
+ */
+typedef struct {
+    const void* x1;
+    const void* x2; /* NULL when there is no concatenation */
+    const float* gamma;
+    const float* beta;
+    void* out;        /* bf16 [N, HW, C] */
+    void* out_concat; /* optional: the raw concatenation in in_dtype, [N, HW, C] (NULL to skip) */
+    float* partials;
+    int32_t n_img, hw, c1, c2, groups;
+    int32_t in_dtype;
+    int32_t silu;
+    float eps;
+} mobi_groupnorm_args;
+
+int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);
+int mobi_groupnorm(const mobi_groupnorm_args* args, void* stream);
+
+/*
+ * LayerNorm over the last dim of an f32 token matrix -> bf16 (nn.LayerNorm, eps 1e-5, attention.py:213-223).
+ * Row gather: output row i reads input row  (i / seg) * seg_stride + seg_offset + i % seg , which selects the
+ * camera (even) or lidar (odd) batch rows of the interleaved batch (attention.py:246-247) without a copy.
+ * gamma == NULL means "cast only" (the un-normalised partner tokens used as cross-modal context).
+ * add_vec: optional f32 [rows / add_rows_per_vec, C] added to the input row before normalising, and written
+ * back to x (x += vec) — the broadcast form of the single-key attn2 (attention.py:235).
+ */
+typedef struct {
+    void* x; /* f32 [*, C] (read; written when add_vec != NULL) */
+    const float* gamma;
+    const float* beta;
+    void* out; /* bf16 [rows, C] */
+    const float* add_vec;
+    int64_t rows;
+    int32_t C;
+    int64_t seg, seg_stride, seg_offset;
+    int64_t add_rows_per_vec;
+    float eps;
+} mobi_layernorm_args;
+
+int mobi_layernorm(const mobi_layernorm_args* args, void* stream);
+
+/* timestep_embedding (ldm/modules/diffusionmodules/util.py:151-171): out bf16 [n, dim] = [cos | sin]. */
+int mobi_timestep_embedding(const int64_t* t, void* out_bf16, int32_t n, int32_t dim, float max_period,
+                            void* stream);
+
+/* y = silu(x) elementwise, f32 or bf16 in -> bf16 out (emb_layers[0], openaimodel.py:204). */
+int mobi_silu(const void* x, int32_t in_dtype, void* out_bf16, int64_t n, void* stream);
+
+/* Layout changes at the module boundary: NCHW f32 <-> NHWC (f32 or bf16). */
+int mobi_nchw_to_nhwc(const float* x, void* out, int32_t out_dtype, int32_t n, int32_t c, int32_t hw,
+                      void* stream);
+int mobi_nhwc_to_nchw(const void* x, int32_t in_dtype, float* out, int32_t n, int32_t c, int32_t hw,
+                      void* stream);
+
+/* Nearest-neighbour x2 upsampling of an NHWC image (F.interpolate(scale_factor=2, mode="nearest"),
+ * openaimodel.py:116, model.py:53).  in/out dtype f32 or bf16 (converted on the fly). */
+int mobi_upsample_nearest2x(const void* x, int32_t in_dtype, void* out, int32_t out_dtype, int32_t n, int32_t h,
+                            int32_t w, int32_t c, void* stream);
+
+/* Explicit im2col (bf16 NHWC -> bf16 [N*Ho*Wo, Kpad]) for the few convolutions the implicit path does not
+ * take: stride 2 (Downsample, openaimodel.py:151-153; VAE Downsample with pad (0,1,0,1), model.py:72-76)
+ * and tiny channel counts (first conv 9->320, openaimodel.py:666).  K order (kh, kw, c), zero padded to kpad. */
+typedef struct {
+    const void* x; /* NHWC in_dtype */
+    void* out;     /* bf16 [n*ho*wo, kpad] */
+    int32_t in_dtype;
+    int32_t n, h, w, c, kh, kw, stride, pad_top, pad_left, ho, wo, kpad;
+} mobi_im2col_args;
+int mobi_im2col(const mobi_im2col_args* args, void* stream);
+
+/*
+ * Folded 2-key cross attention (cond_adapter_attn + connector, attention.py:237-243): per token
+ *   s[h, j] = xn . U[b, h*2+j, :]      (U already holds W_q^T k * scale)
+ *   p = softmax_j(s) ;  x += sum_{h,j} p[h,j] * Z[b, h*2+j, :] + zb
+ * xn: bf16 [B*T, C] (LayerNorm output), U: f32 [B, 2*heads, C], Z: f32 [B, 2*heads, C], zb: f32 [C],
+ * x: f32 [B*T, C] updated in place.
+ */
+typedef struct {
+    const void* xn;
+    const float* U;
+    const float* Z;
+    const float* zb;
+    float* x;
+    int32_t batch, tokens, C, heads, keys;
+} mobi_ctx_attn_args;
+int mobi_ctx_attention(const mobi_ctx_attn_args* args, void* stream);
+
+/*
+ * One sampler update (DDIMSampler.p_sample_ddim, ldm/models/diffusion/ddim.py:184-212 and
+ * PLMSSampler.p_sample_plms, plms.py:200-237), fused:
+ *   e      = e_uncond + scale * (e_cond - e_uncond)                       (CFG, ddim.py:184)
+ *   e'     = c0*e + c1*old1 + c2*old2 + c3*old3                           (PLMS multistep, plms.py:221-235; DDIM: c0=1)
+ *   pred   = (x - sqrt(1-a_t) * e') / sqrt(a_t)                           (ddim.py:201-204)
+ *   x_prev = sqrt(a_prev) * pred + sqrt(1 - a_prev - sigma^2) * e' + sigma * noise * temperature  (ddim.py:208-212)
+ * and the next UNet input  [x_prev | inpaint_image | inpaint_mask]  (ddim.py:172) is assembled for both CFG
+ * halves.  All NCHW f32.  eps holds [uncond ; cond] rows when cfg != 0.
+ */
+typedef struct {
+    const float* eps;   /* [(cfg?2:1)*B, 4, H, W] */
+    const float* x;     /* [B, 4, H, W] */
+    const float* noise; /* [B, 4, H, W] or NULL */
+    const float* old1;
+    const float* old2;
+    const float* old3; /* previous combined eps (PLMS) or NULL */
+    float* e_out;      /* optional: CFG-combined eps e (before multistep) [B,4,H,W] */
+    float* x_prev;     /* [B, 4, H, W] */
+    float* pred_x0;    /* [B, 4, H, W] */
+    int64_t n;         /* B*4*H*W */
+    int32_t cfg;
+    float scale, c0, c1, c2, c3;
+    float sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_temp;
+} mobi_sampler_args;
+int mobi_sampler_update(const mobi_sampler_args* args, void* stream);
+
+/* x_in[(cfg?2:1)*B, 9, H, W] = cat([x, inpaint_image, inpaint_mask], 1) repeated for the CFG halves
+ * (ddim.py:172,180).  Optional known-latent blend first: x = x0_noised*mask + (1-mask)*x (ddim.py:145-148),
+ * where x0_noised = sqrt_ac * x0 + sqrt_1mac * noise (q_sample, ddpm.py:284-287). */
+typedef struct {
+    float* x;               /* [B,4,H,W]; updated in place when blend_mask != NULL */
+    const float* inpaint_image; /* [B,4,H,W] */
+    const float* inpaint_mask;  /* [B,1,H,W] */
+    const float* blend_mask;    /* [B,1,H,W] or [B,4,H,W]? -> broadcast over channel when blend_c == 1 */
+    const float* blend_x0;
+    const float* blend_noise;
+    float* x_in; /* [(cfg?2:1)*B, 9, H, W] */
+    int32_t B, hw, cfg, blend_c, rest_c;
+    float sqrt_ac, sqrt_1mac;
+} mobi_assemble_args;
+int mobi_assemble_input(const mobi_assemble_args* args, void* stream);
+
+/* out[i] = a[i] + b[i] (f32), used for residual joins that have no GEMM to fuse into. */
+int mobi_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);
+/* out = x * s (f32 -> f32), e.g. z / scale_factor before decode (ddpm.py:846-849). */
+int mobi_scale_f32(const float* x, float s, float* out, int64_t n, void* stream);
+/* f32 -> bf16 cast */
+int mobi_cast_bf16(const float* x, void* out, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MOBI_B200_H */

@@ -1,0 +1,157 @@
+"""ctypes binding of libmobi_b200.so (the C ABI declared in include/mobi_b200.h).
+
+There is deliberately no fallback: if the CUDA library is missing or fails to load, every op raises.
+"""
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libmobi_b200.so")
+
+DT_BF16, DT_F32 = 0, 1
+EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV = 0, 1, 2, 3, 4
+
+_vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
+
+
+class GemmArgs(C.Structure):
+    _fields_ = [
+        ("A", _vp), ("B", _vp), ("out", _vp), ("out2", _vp), ("out3", _vp),
+        ("bias", _vp), ("row_bias", _vp), ("residual", _vp),
+        ("M", _i64), ("N", _i64), ("K", _i64),
+        ("lda", _i64), ("ldb", _i64), ("ldo", _i64),
+        ("rows_per_group", _i64), ("ld_row_bias", _i64),
+        ("out_dtype", _i32), ("res_dtype", _i32), ("epilogue", _i32), ("act", _i32),
+        ("heads", _i32), ("head_dim", _i32), ("tokens", _i32),
+        ("conv", _i32), ("n_img", _i32), ("H", _i32), ("W", _i32), ("C", _i32),
+        ("KH", _i32), ("KW", _i32), ("pad_h", _i32), ("pad_w", _i32), ("tile_n", _i32),
+    ]
+
+
+class AttnArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("k", _vp), ("vt", _vp), ("out", _vp),
+        ("batch", _i32), ("heads", _i32), ("head_dim", _i32), ("tq", _i32), ("tk", _i32),
+        ("ld_out", _i64),
+    ]
+
+
+class GroupNormArgs(C.Structure):
+    _fields_ = [
+        ("x1", _vp), ("x2", _vp), ("gamma", _vp), ("beta", _vp), ("out", _vp), ("out_concat", _vp),
+        ("partials", _vp),
+        ("n_img", _i32), ("hw", _i32), ("c1", _i32), ("c2", _i32), ("groups", _i32),
+        ("in_dtype", _i32), ("silu", _i32), ("eps", _f32),
+    ]
+
+
+class LayerNormArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("gamma", _vp), ("beta", _vp), ("out", _vp), ("add_vec", _vp),
+        ("rows", _i64), ("C", _i32),
+        ("seg", _i64), ("seg_stride", _i64), ("seg_offset", _i64), ("add_rows_per_vec", _i64),
+        ("eps", _f32),
+    ]
+
+
+class Im2colArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("out", _vp), ("in_dtype", _i32),
+        ("n", _i32), ("h", _i32), ("w", _i32), ("c", _i32), ("kh", _i32), ("kw", _i32),
+        ("stride", _i32), ("pad_top", _i32), ("pad_left", _i32), ("ho", _i32), ("wo", _i32), ("kpad", _i32),
+    ]
+
+
+class CtxAttnArgs(C.Structure):
+    _fields_ = [
+        ("xn", _vp), ("U", _vp), ("Z", _vp), ("zb", _vp), ("x", _vp),
+        ("batch", _i32), ("tokens", _i32), ("C", _i32), ("heads", _i32), ("keys", _i32),
+    ]
+
+
+class SamplerArgs(C.Structure):
+    _fields_ = [
+        ("eps", _vp), ("x", _vp), ("noise", _vp), ("old1", _vp), ("old2", _vp), ("old3", _vp),
+        ("e_out", _vp), ("x_prev", _vp), ("pred_x0", _vp),
+        ("n", _i64), ("cfg", _i32),
+        ("scale", _f32), ("c0", _f32), ("c1", _f32), ("c2", _f32), ("c3", _f32),
+        ("sqrt_one_minus_at", _f32), ("sqrt_at", _f32), ("sqrt_a_prev", _f32), ("dir_coef", _f32),
+        ("sigma_temp", _f32),
+    ]
+
+
+class AssembleArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("inpaint_image", _vp), ("inpaint_mask", _vp),
+        ("blend_mask", _vp), ("blend_x0", _vp), ("blend_noise", _vp), ("x_in", _vp),
+        ("B", _i32), ("hw", _i32), ("cfg", _i32), ("blend_c", _i32), ("rest_c", _i32),
+        ("sqrt_ac", _f32), ("sqrt_1mac", _f32),
+    ]
+
+
+# name -> (restype, argtypes); also the list of symbols include/mobi_b200.h declares
+SIGNATURES = {
+    "mobi_last_error": (C.c_char_p, []),
+    "mobi_version": (C.c_int, []),
+    "mobi_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "mobi_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
+    "mobi_groupnorm_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "mobi_groupnorm": (C.c_int, [C.POINTER(GroupNormArgs), _vp]),
+    "mobi_layernorm": (C.c_int, [C.POINTER(LayerNormArgs), _vp]),
+    "mobi_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
+    "mobi_silu": (C.c_int, [_vp, _i32, _vp, _i64, _vp]),
+    "mobi_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "mobi_nhwc_to_nchw": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),
+    "mobi_upsample_nearest2x": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "mobi_im2col": (C.c_int, [C.POINTER(Im2colArgs), _vp]),
+    "mobi_ctx_attention": (C.c_int, [C.POINTER(CtxAttnArgs), _vp]),
+    "mobi_sampler_update": (C.c_int, [C.POINTER(SamplerArgs), _vp]),
+    "mobi_assemble_input": (C.c_int, [C.POINTER(AssembleArgs), _vp]),
+    "mobi_add_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
+    "mobi_scale_f32": (C.c_int, [_vp, _f32, _vp, _i64, _vp]),
+    "mobi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
+}
+
+_lib = None
+
+
+def load():
+    """Loads the library (building is a separate, explicit step: `python -m mobi_b200.build`)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            "mobi_b200: %s is missing. Build it with `python -m mobi_b200.build` (needs nvcc); "
+            "there is no CPU or PyTorch fallback for this path." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError here means the .so is stale
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(status, what):
+    if status != 0:
+        msg = load().mobi_last_error().decode("utf-8", "replace")
+        raise RuntimeError("mobi_b200.%s failed (status %d): %s" % (what, status, msg))
+
+
+def ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def dt(t):
+    if t.dtype == torch.bfloat16:
+        return DT_BF16
+    if t.dtype == torch.float32:
+        return DT_F32
+    raise TypeError("mobi_b200: unsupported dtype %s" % t.dtype)

@@ -1,0 +1,72 @@
+#include "common.cuh"
+
+#include <cudaTypedefs.h>
+#include <stdarg.h>
+#include <string.h>
+
+#include "../../include/mobi_b200.h"
+
+namespace mobi {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+static PFN_cuTensorMapEncodeTiled_v12000 get_encode() {
+    static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+    if (fn) return fn;
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres);
+    if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || p == nullptr) return nullptr;
+    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+    return fn;
+}
+
+int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
+                         const uint64_t* strides_bytes, const uint32_t* box) {
+    auto enc = get_encode();
+    MOBI_CHECK(enc != nullptr, "cuTensorMapEncodeTiled driver entry point not available");
+    MOBI_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "tensor map base %p is not 16-byte aligned", base);
+    cuuint64_t gdim[5];
+    cuuint64_t gstr[5];
+    cuuint32_t bdim[5];
+    cuuint32_t estr[5];
+    for (int i = 0; i < rank; ++i) {
+        gdim[i] = dims[i];
+        bdim[i] = box[i];
+        estr[i] = 1;
+        MOBI_CHECK(box[i] >= 1 && box[i] <= 256, "tensor map box dim %d = %u out of range", i, box[i]);
+    }
+    for (int i = 0; i + 1 < rank; ++i) {
+        gstr[i] = strides_bytes[i];
+        MOBI_CHECK((strides_bytes[i] & 15) == 0, "tensor map stride %d = %llu bytes is not a multiple of 16", i,
+                   (unsigned long long)strides_bytes[i]);
+    }
+    CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr,
+                     bdim, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    MOBI_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed with CUresult %d (rank %d dims %llu %llu box %u %u)",
+               (int)r, rank, (unsigned long long)dims[0], (unsigned long long)(rank > 1 ? dims[1] : 0), box[0],
+               rank > 1 ? box[1] : 0);
+    return 0;
+}
+
+int sm_count() {
+    static int n = 0;
+    if (n) return n;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
+    return n;
+}
+
+}  // namespace mobi
+
+extern "C" const char* mobi_last_error(void) { return mobi::g_err; }
+extern "C" int mobi_version(void) { return 100; }

@@ -1,0 +1,702 @@
+// HBM-bound kernels of the denoising path: GroupNorm(+SiLU), LayerNorm, timestep embedding, layout
+// changes, nearest upsampling, im2col for the strided convolutions, the folded 2-key context attention
+// and the fused sampler update.  All are coalesced along the channel (innermost) dimension, vectorised to
+// 16-byte accesses where alignment allows, and use warp-shuffle reductions; none stages through shared
+// memory unless data is reused.
+#include "../../include/mobi_b200.h"
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace mobi {
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)); }
+
+// ------------------------------------------------------------------------------------------------
+// GroupNorm: pass 1 = deterministic per-slab partial sums, pass 2 = finalize + normalise (+SiLU).
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_THREADS = 256;
+constexpr int GN_WARPS = GN_THREADS / 32;
+
+template <bool IN_F32>
+__device__ __forceinline__ float2 gn_load2(const void* x1, const void* x2, int c1, int c2, long long pix, int c) {
+    // c is even; c1 is even, so a pair never straddles the concatenation boundary
+    const void* src = (c < c1) ? x1 : x2;
+    const int cc = (c < c1) ? c : c - c1;
+    const int cw = (c < c1) ? c1 : c2;
+    if (IN_F32) {
+        return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(src) + pix * cw + cc);
+    } else {
+        const __nv_bfloat162 v =
+            *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(src) + pix * cw + cc);
+        return __bfloat1622float2(v);
+    }
+}
+
+// grid (slabs, n_img). partials layout [n_img][slabs][groups][2] (sum, sumsq)
+template <bool IN_F32>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const void* x1, const void* x2, float* partials, int hw, int c1, int c2, int groups,
+                int pix_per_slab) {
+    extern __shared__ float gn_smem[];  // [GN_WARPS][C/2][2]
+    const int C = c1 + c2;
+    const int half = C / 2;
+    const int cpg = C / groups;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n = blockIdx.y;
+    const int p0 = blockIdx.x * pix_per_slab;
+    const int p1 = min(hw, p0 + pix_per_slab);
+    const long long img_off = (long long)n * hw;
+
+    // each lane owns channel pairs v = lane + 32*k; accumulate over this warp's pixels
+    for (int vbase = 0; vbase < half; vbase += 32 * 4) {
+        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
+        for (int p = p0 + warp; p < p1; p += GN_WARPS) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const int v = vbase + lane + 32 * k;
+                if (v < half) {
+                    const float2 f = gn_load2<IN_F32>(x1, x2, c1, c2, img_off + p, 2 * v);
+                    s[k] += f.x + f.y;
+                    q[k] += f.x * f.x + f.y * f.y;
+                }
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const int v = vbase + lane + 32 * k;
+            if (v < half) {
+                gn_smem[(warp * half + v) * 2 + 0] = s[k];
+                gn_smem[(warp * half + v) * 2 + 1] = q[k];
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < groups) {
+        const int g = threadIdx.x;
+        float s = 0.f, q = 0.f;
+        const int v0 = g * cpg / 2, v1 = (g + 1) * cpg / 2;
+        for (int w = 0; w < GN_WARPS; ++w)
+            for (int v = v0; v < v1; ++v) {
+                s += gn_smem[(w * half + v) * 2 + 0];
+                q += gn_smem[(w * half + v) * 2 + 1];
+            }
+        float* out = partials + (((long long)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+        out[0] = s;
+        out[1] = q;
+    }
+}
+
+// grid (slabs2, n_img): each CTA finalises the statistics of its image (cheap) and normalises a slab.
+template <bool IN_F32>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_concat,
+                const float* __restrict__ partials, int n_stat_slabs, int hw, int c1, int c2, int groups, float eps,
+                int silu, int pix_per_slab) {
+    extern __shared__ float gn_smem[];  // scale[C], shift[C]
+    __shared__ float s_mean[64], s_rstd[64];
+    const int C = c1 + c2;
+    const int cpg = C / groups;
+    const int n = blockIdx.y;
+    if (threadIdx.x < groups) {
+        const int g = threadIdx.x;
+        double s = 0.0, q = 0.0;
+        const float* pp = partials + ((long long)n * n_stat_slabs * groups + g) * 2;
+        for (int i = 0; i < n_stat_slabs; ++i) {
+            s += (double)pp[(long long)i * groups * 2 + 0];
+            q += (double)pp[(long long)i * groups * 2 + 1];
+        }
+        const double cnt = (double)hw * cpg;
+        const double mean = s / cnt;
+        double var = q / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[g] = (float)mean;
+        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    float* s_scale = gn_smem;
+    float* s_shift = gn_smem + C;
+    for (int c = threadIdx.x; c < C; c += GN_THREADS) {
+        const int g = c / cpg;
+        const float a = gamma[c] * s_rstd[g];
+        s_scale[c] = a;
+        s_shift[c] = beta[c] - s_mean[g] * a;
+    }
+    __syncthreads();
+    const int half = C / 2;
+    const int p0 = blockIdx.x * pix_per_slab;
+    const int p1 = min(hw, p0 + pix_per_slab);
+    const long long img_off = (long long)n * hw;
+    const long long total = (long long)(p1 - p0) * half;
+    for (long long i = threadIdx.x; i < total; i += GN_THREADS) {
+        const int p = p0 + (int)(i / half);
+        const int v = (int)(i % half);
+        const int c = 2 * v;
+        const float2 f = gn_load2<IN_F32>(x1, x2, c1, c2, img_off + p, c);
+        float y0 = f.x * s_scale[c] + s_shift[c];
+        float y1 = f.y * s_scale[c + 1] + s_shift[c + 1];
+        if (silu) {
+            y0 = silu_f(y0);
+            y1 = silu_f(y1);
+        }
+        const long long o = (img_off + p) * C + c;
+        *reinterpret_cast<__nv_bfloat162*>(out + o) = __floats2bfloat162_rn(y0, y1);
+        if (out_concat) *reinterpret_cast<__nv_bfloat162*>(out_concat + o) = __floats2bfloat162_rn(f.x, f.y);
+    }
+}
+
+static int gn_slabs(int hw, int C) {
+    // ~64 KB of fp32 input per slab, at least GN_WARPS pixels
+    long long pix = (64 * 1024) / ((long long)C * 4);
+    if (pix < GN_WARPS) pix = GN_WARPS;
+    int slabs = (int)((hw + pix - 1) / pix);
+    if (slabs > 256) slabs = 256;
+    if (slabs < 1) slabs = 1;
+    return slabs;
+}
+
+// ------------------------------------------------------------------------------------------------
+// LayerNorm (one warp per token row), optional broadcast add and row gather.
+// ------------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 12;  // float4 vectors per lane: C <= 12*128 = 1536
+
+__global__ void __launch_bounds__(256)
+layernorm_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
+                 __nv_bfloat16* __restrict__ out, const float* __restrict__ add_vec, long long rows, int C,
+                 long long seg, long long seg_stride, long long seg_offset, long long add_rows_per_vec, float eps) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const long long in_row = (row / seg) * seg_stride + seg_offset + (row % seg);
+    float4* xr = reinterpret_cast<float4*>(x + in_row * C);
+    const int nv = C >> 2;
+    float4 v[LN_MAXV];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            v[k] = xr[i];
+            if (add_vec) {
+                const float4 a = reinterpret_cast<const float4*>(add_vec + (in_row / add_rows_per_vec) * C)[i];
+                v[k].x += a.x;
+                v[k].y += a.y;
+                v[k].z += a.z;
+                v[k].w += a.w;
+                xr[i] = v[k];
+            }
+            sum += v[k].x + v[k].y + v[k].z + v[k].w;
+        }
+    }
+    uint2* orow = reinterpret_cast<uint2*>(out + row * C);
+    if (gamma == nullptr) {  // cast only
+#pragma unroll
+        for (int k = 0; k < LN_MAXV; ++k) {
+            const int i = lane + 32 * k;
+            if (i < nv) orow[i] = make_uint2(pack_bf16x2(v[k].x, v[k].y), pack_bf16x2(v[k].z, v[k].w));
+        }
+        return;
+    }
+    const float mean = warp_sum(sum) / (float)C;
+    float sq = 0.f;
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
+            sq += a * a + b * b + c * c + d * d;
+        }
+    }
+    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
+#pragma unroll
+    for (int k = 0; k < LN_MAXV; ++k) {
+        const int i = lane + 32 * k;
+        if (i < nv) {
+            const float4 g = reinterpret_cast<const float4*>(gamma)[i];
+            const float4 b = reinterpret_cast<const float4*>(beta)[i];
+            const float y0 = (v[k].x - mean) * rstd * g.x + b.x;
+            const float y1 = (v[k].y - mean) * rstd * g.y + b.y;
+            const float y2 = (v[k].z - mean) * rstd * g.z + b.z;
+            const float y3 = (v[k].w - mean) * rstd * g.w + b.w;
+            orow[i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+__global__ void timestep_embedding_kernel(const int64_t* __restrict__ t, __nv_bfloat16* __restrict__ out, int n,
+                                          int dim, float log_max_period) {
+    const int half = dim / 2;
+    const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+    if (idx >= n * half) return;
+    const int r = idx / half, i = idx % half;
+    const float freq = expf(-log_max_period * (float)i / (float)half);
+    const float arg = (float)t[r] * freq;
+    out[(long long)r * dim + i] = __float2bfloat16(cosf(arg));
+    out[(long long)r * dim + half + i] = __float2bfloat16(sinf(arg));
+    if ((dim & 1) && i == 0) out[(long long)r * dim + dim - 1] = __float2bfloat16(0.f);
+}
+
+template <bool IN_F32>
+__global__ void silu_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float v = IN_F32 ? reinterpret_cast<const float*>(x)[i]
+                           : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
+    out[i] = __float2bfloat16(silu_f(v));
+}
+
+// NCHW f32 -> NHWC: tile transpose through shared memory, coalesced on both sides.
+template <bool OUT_F32>
+__global__ void nchw_to_nhwc_kernel(const float* __restrict__ x, void* __restrict__ out, int c, int hw) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int cc = c0 + j, p = p0 + threadIdx.x;
+        tile[j][threadIdx.x] = (cc < c && p < hw) ? x[((long long)n * c + cc) * hw + p] : 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int p = p0 + j, cc = c0 + threadIdx.x;
+        if (p < hw && cc < c) {
+            const long long o = ((long long)n * hw + p) * c + cc;
+            if (OUT_F32)
+                reinterpret_cast<float*>(out)[o] = tile[threadIdx.x][j];
+            else
+                reinterpret_cast<__nv_bfloat16*>(out)[o] = __float2bfloat16(tile[threadIdx.x][j]);
+        }
+    }
+}
+
+template <bool IN_F32>
+__global__ void nhwc_to_nchw_kernel(const void* __restrict__ x, float* __restrict__ out, int c, int hw) {
+    __shared__ float tile[32][33];
+    const int n = blockIdx.z;
+    const int p0 = blockIdx.x * 32, c0 = blockIdx.y * 32;
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int p = p0 + j, cc = c0 + threadIdx.x;
+        float v = 0.f;
+        if (p < hw && cc < c) {
+            const long long i = ((long long)n * hw + p) * c + cc;
+            v = IN_F32 ? reinterpret_cast<const float*>(x)[i]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[i]);
+        }
+        tile[j][threadIdx.x] = v;
+    }
+    __syncthreads();
+    for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+        const int cc = c0 + j, p = p0 + threadIdx.x;
+        if (cc < c && p < hw) out[((long long)n * c + cc) * hw + p] = tile[threadIdx.x][j];
+    }
+}
+
+// nearest x2: each thread produces 2 channels of one output pixel
+template <bool IN_F32, bool OUT_F32>
+__global__ void upsample2x_kernel(const void* __restrict__ x, void* __restrict__ out, int n, int h, int w, int c) {
+    const long long half = c / 2;
+    const long long total = (long long)n * (2 * h) * (2 * w) * half;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int v = (int)(i % half);
+    long long p = i / half;
+    const int ox = (int)(p % (2 * w));
+    p /= (2 * w);
+    const int oy = (int)(p % (2 * h));
+    const int b = (int)(p / (2 * h));
+    const long long src = (((long long)b * h + (oy >> 1)) * w + (ox >> 1)) * c + 2 * v;
+    const long long dst = (((long long)b * 2 * h + oy) * (2 * w) + ox) * c + 2 * v;
+    float2 f;
+    if (IN_F32)
+        f = *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + src);
+    else
+        f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(x) + src));
+    if (OUT_F32)
+        *reinterpret_cast<float2*>(reinterpret_cast<float*>(out) + dst) = f;
+    else
+        *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out) + dst) = __floats2bfloat162_rn(f.x, f.y);
+}
+
+// im2col: one thread per output element of the [M, kpad] matrix (K order kh, kw, c)
+template <bool IN_F32>
+__global__ void im2col_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, mobi_im2col_args a) {
+    const long long total = (long long)a.n * a.ho * a.wo * a.kpad;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int k = (int)(i % a.kpad);
+    long long m = i / a.kpad;
+    const int ox = (int)(m % a.wo);
+    m /= a.wo;
+    const int oy = (int)(m % a.ho);
+    const int b = (int)(m / a.ho);
+    float v = 0.f;
+    if (k < a.kh * a.kw * a.c) {
+        const int c = k % a.c;
+        const int tap = k / a.c;
+        const int kx = tap % a.kw, ky = tap / a.kw;
+        const int iy = oy * a.stride + ky - a.pad_top;
+        const int ix = ox * a.stride + kx - a.pad_left;
+        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+            const long long s = (((long long)b * a.h + iy) * a.w + ix) * a.c + c;
+            v = IN_F32 ? reinterpret_cast<const float*>(x)[s]
+                       : __bfloat162float(reinterpret_cast<const __nv_bfloat16*>(x)[s]);
+        }
+    }
+    out[i] = __float2bfloat16(v);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Folded 2-key context attention: one warp per token.
+// ------------------------------------------------------------------------------------------------
+constexpr int CTX_MAX_HK = 16;
+
+__global__ void __launch_bounds__(256)
+ctx_attention_kernel(const __nv_bfloat16* __restrict__ xn, const float* __restrict__ U, const float* __restrict__ Z,
+                     const float* __restrict__ zb, float* __restrict__ x, int tokens, int C, int heads, int keys,
+                     long long rows) {
+    const int lane = threadIdx.x & 31;
+    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int b = (int)(row / tokens);
+    const int hk = heads * keys;
+    const float* Ub = U + (long long)b * hk * C;
+    const float* Zb = Z + (long long)b * hk * C;
+    const __nv_bfloat16* xr = xn + row * C;
+    float s[CTX_MAX_HK];
+#pragma unroll
+    for (int j = 0; j < CTX_MAX_HK; ++j) s[j] = 0.f;
+    for (int c = lane * 2; c < C; c += 64) {
+        const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(xr + c));
+#pragma unroll
+        for (int j = 0; j < CTX_MAX_HK; ++j) {
+            if (j < hk) {
+                const float2 u = __ldg(reinterpret_cast<const float2*>(Ub + (long long)j * C + c));
+                s[j] += f.x * u.x + f.y * u.y;
+            }
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CTX_MAX_HK; ++j) s[j] = warp_sum(s[j]);
+    // softmax over the `keys` scores of each head (layout j = key * heads + head)
+    float pr[CTX_MAX_HK];
+#pragma unroll
+    for (int h = 0; h < CTX_MAX_HK; ++h) {
+        if (h < heads) {
+            float mx = -INFINITY;
+            for (int k = 0; k < keys; ++k) mx = fmaxf(mx, s[k * heads + h]);
+            float den = 0.f;
+            for (int k = 0; k < keys; ++k) {
+                const float e = __expf(s[k * heads + h] - mx);
+                pr[k * heads + h] = e;
+                den += e;
+            }
+            const float inv = 1.0f / den;
+            for (int k = 0; k < keys; ++k) pr[k * heads + h] *= inv;
+        }
+    }
+    float* xo = x + row * C;
+    for (int c = lane * 2; c < C; c += 64) {
+        float2 acc = *reinterpret_cast<const float2*>(zb + c);
+#pragma unroll
+        for (int j = 0; j < CTX_MAX_HK; ++j) {
+            if (j < hk) {
+                const float2 z = __ldg(reinterpret_cast<const float2*>(Zb + (long long)j * C + c));
+                acc.x += pr[j] * z.x;
+                acc.y += pr[j] * z.y;
+            }
+        }
+        float2 cur = *reinterpret_cast<float2*>(xo + c);
+        cur.x += acc.x;
+        cur.y += acc.y;
+        *reinterpret_cast<float2*>(xo + c) = cur;
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Sampler kernels (NCHW f32, tiny tensors: launch-bound, so everything is one kernel)
+// ------------------------------------------------------------------------------------------------
+__global__ void sampler_update_kernel(mobi_sampler_args a) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= a.n) return;
+    float e;
+    if (a.cfg) {
+        const float eu = a.eps[i];
+        const float ec = a.eps[a.n + i];
+        e = eu + a.scale * (ec - eu);
+    } else {
+        e = a.eps[i];
+    }
+    if (a.e_out) a.e_out[i] = e;
+    float ep = a.c0 * e;
+    if (a.old1) ep += a.c1 * a.old1[i];
+    if (a.old2) ep += a.c2 * a.old2[i];
+    if (a.old3) ep += a.c3 * a.old3[i];
+    const float xv = a.x[i];
+    const float pred = (xv - a.sqrt_one_minus_at * ep) / a.sqrt_at;
+    float xp = a.sqrt_a_prev * pred + a.dir_coef * ep;
+    if (a.noise) xp += a.sigma_temp * a.noise[i];
+    a.pred_x0[i] = pred;
+    a.x_prev[i] = xp;
+}
+
+__global__ void assemble_input_kernel(mobi_assemble_args a) {
+    // one thread per (b, pixel)
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long total = (long long)a.B * a.hw;
+    if (i >= total) return;
+    const int b = (int)(i / a.hw);
+    const int p = (int)(i % a.hw);
+    const int ctot = 4 + a.rest_c;
+    float xv[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+        const long long xi = ((long long)b * 4 + c) * a.hw + p;
+        float v = a.x[xi];
+        if (a.blend_mask) {
+            const float m = a.blend_mask[((long long)b * a.blend_c + (a.blend_c == 1 ? 0 : c)) * a.hw + p];
+            const float xo = a.sqrt_ac * a.blend_x0[xi] + a.sqrt_1mac * a.blend_noise[xi];
+            v = xo * m + (1.0f - m) * v;
+            a.x[xi] = v;
+        }
+        xv[c] = v;
+    }
+    const int reps = a.cfg ? 2 : 1;
+    for (int r = 0; r < reps; ++r) {
+        float* dst = a.x_in + ((long long)(r * a.B + b) * ctot) * a.hw + p;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) dst[(long long)c * a.hw] = xv[c];
+        if (a.rest_c == 5) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) dst[(long long)(4 + c) * a.hw] = a.inpaint_image[((long long)b * 4 + c) * a.hw + p];
+            dst[(long long)8 * a.hw] = a.inpaint_mask[(long long)b * a.hw + p];
+        } else {
+            // generic `rest` tensor [B, rest_c, H, W] passed through inpaint_image
+            for (int c = 0; c < a.rest_c; ++c)
+                dst[(long long)(4 + c) * a.hw] = a.inpaint_image[((long long)b * a.rest_c + c) * a.hw + p];
+        }
+    }
+}
+
+__global__ void add_f32_kernel(const float* a, const float* b, float* o, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] + b[i];
+}
+__global__ void scale_f32_kernel(const float* a, float s, float* o, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = a[i] * s;
+}
+__global__ void cast_bf16_kernel(const float* a, __nv_bfloat16* o, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) o[i] = __float2bfloat16(a[i]);
+}
+
+static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
+
+}  // namespace mobi
+
+using namespace mobi;
+
+extern "C" int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups) {
+    return (int64_t)n_img * gn_slabs(hw, c) * groups * 2 * sizeof(float);
+}
+
+extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(a && a->x1 && a->gamma && a->beta && a->out && a->partials, "mobi_groupnorm: null argument");
+    const int C = a->c1 + a->c2;
+    MOBI_CHECK(a->groups > 0 && a->groups <= 64 && C % a->groups == 0, "mobi_groupnorm: C=%d groups=%d", C, a->groups);
+    MOBI_CHECK((C / a->groups) % 2 == 0 && a->c1 % 2 == 0 && a->c2 % 2 == 0,
+               "mobi_groupnorm: channels per group and concat halves must be even (C=%d c1=%d)", C, a->c1);
+    MOBI_CHECK(a->c2 == 0 || a->x2 != nullptr, "mobi_groupnorm: c2 > 0 needs x2");
+    const int slabs = gn_slabs(a->hw, C);
+    const int pix_per_slab = (a->hw + slabs - 1) / slabs;
+    const size_t smem1 = (size_t)GN_WARPS * (C / 2) * 2 * sizeof(float);
+    const size_t smem2 = (size_t)2 * C * sizeof(float);
+    const bool f32 = a->in_dtype == MOBI_DTYPE_F32;
+    static bool configured = false;
+    if (!configured) {
+        MOBI_CUDA(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        MOBI_CUDA(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
+        configured = true;
+    }
+    MOBI_CHECK(smem1 <= 160 * 1024, "mobi_groupnorm: C=%d too large", C);
+    dim3 grid1(slabs, a->n_img);
+    if (f32)
+        gn_stats_kernel<true><<<grid1, GN_THREADS, smem1, stream>>>(a->x1, a->x2, a->partials, a->hw, a->c1, a->c2,
+                                                                    a->groups, pix_per_slab);
+    else
+        gn_stats_kernel<false><<<grid1, GN_THREADS, smem1, stream>>>(a->x1, a->x2, a->partials, a->hw, a->c1, a->c2,
+                                                                     a->groups, pix_per_slab);
+    MOBI_CUDA(cudaGetLastError());
+    // apply: finer slabs so small images still fill the machine
+    long long pix2 = (32 * 1024) / ((long long)C * 4);
+    if (pix2 < 1) pix2 = 1;
+    int slabs2 = (int)((a->hw + pix2 - 1) / pix2);
+    const int pix_per_slab2 = (a->hw + slabs2 - 1) / slabs2;
+    dim3 grid2(slabs2, a->n_img);
+    if (f32)
+        gn_apply_kernel<true><<<grid2, GN_THREADS, smem2, stream>>>(
+            a->x1, a->x2, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out),
+            reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, a->hw, a->c1, a->c2, a->groups, a->eps,
+            a->silu, pix_per_slab2);
+    else
+        gn_apply_kernel<false><<<grid2, GN_THREADS, smem2, stream>>>(
+            a->x1, a->x2, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out),
+            reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, a->hw, a->c1, a->c2, a->groups, a->eps,
+            a->silu, pix_per_slab2);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_layernorm(const mobi_layernorm_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(a && a->x && a->out, "mobi_layernorm: null argument");
+    MOBI_CHECK(a->C % 4 == 0 && a->C <= LN_MAXV * 128, "mobi_layernorm: C=%d must be a multiple of 4 and <= %d", a->C,
+               LN_MAXV * 128);
+    MOBI_CHECK(a->gamma == nullptr || a->beta != nullptr, "mobi_layernorm: gamma without beta");
+    if (a->rows == 0) return 0;
+    const long long seg = a->seg > 0 ? a->seg : a->rows;
+    const long long seg_stride = a->seg > 0 ? a->seg_stride : a->rows;
+    const long long rpv = a->add_rows_per_vec > 0 ? a->add_rows_per_vec : 1;
+    const int warps = 8;
+    layernorm_kernel<<<blocks_for(a->rows, warps), warps * 32, 0, stream>>>(
+        reinterpret_cast<float*>(a->x), a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out), a->add_vec,
+        a->rows, a->C, seg, seg_stride, a->seg_offset, rpv, a->eps);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_timestep_embedding(const int64_t* t, void* out, int32_t n, int32_t dim, float max_period,
+                                       void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(t && out && n > 0 && dim >= 2, "mobi_timestep_embedding: bad argument");
+    const long long total = (long long)n * (dim / 2);
+    timestep_embedding_kernel<<<blocks_for(total, 128), 128, 0, stream>>>(t, reinterpret_cast<__nv_bfloat16*>(out), n,
+                                                                          dim, logf(max_period));
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_silu(const void* x, int32_t in_dtype, void* out, int64_t n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(x && out, "mobi_silu: null argument");
+    if (n == 0) return 0;
+    if (in_dtype == MOBI_DTYPE_F32)
+        silu_kernel<true><<<blocks_for(n, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+    else
+        silu_kernel<false><<<blocks_for(n, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_nchw_to_nhwc(const float* x, void* out, int32_t out_dtype, int32_t n, int32_t c, int32_t hw,
+                                 void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(x && out && n > 0 && c > 0 && hw > 0, "mobi_nchw_to_nhwc: bad argument");
+    dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+    if (out_dtype == MOBI_DTYPE_F32)
+        nchw_to_nhwc_kernel<true><<<grid, block, 0, stream>>>(x, out, c, hw);
+    else
+        nchw_to_nhwc_kernel<false><<<grid, block, 0, stream>>>(x, out, c, hw);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_nhwc_to_nchw(const void* x, int32_t in_dtype, float* out, int32_t n, int32_t c, int32_t hw,
+                                 void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(x && out && n > 0 && c > 0 && hw > 0, "mobi_nhwc_to_nchw: bad argument");
+    dim3 grid((hw + 31) / 32, (c + 31) / 32, n), block(32, 8);
+    if (in_dtype == MOBI_DTYPE_F32)
+        nhwc_to_nchw_kernel<true><<<grid, block, 0, stream>>>(x, out, c, hw);
+    else
+        nhwc_to_nchw_kernel<false><<<grid, block, 0, stream>>>(x, out, c, hw);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_upsample_nearest2x(const void* x, int32_t in_dtype, void* out, int32_t out_dtype, int32_t n,
+                                       int32_t h, int32_t w, int32_t c, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(x && out && c % 2 == 0, "mobi_upsample_nearest2x: bad argument (C must be even)");
+    const long long total = (long long)n * 4 * h * w * (c / 2);
+    const unsigned blocks = blocks_for(total, 256);
+    const bool i32 = in_dtype == MOBI_DTYPE_F32, o32 = out_dtype == MOBI_DTYPE_F32;
+    if (i32 && o32)
+        upsample2x_kernel<true, true><<<blocks, 256, 0, stream>>>(x, out, n, h, w, c);
+    else if (i32 && !o32)
+        upsample2x_kernel<true, false><<<blocks, 256, 0, stream>>>(x, out, n, h, w, c);
+    else if (!i32 && o32)
+        upsample2x_kernel<false, true><<<blocks, 256, 0, stream>>>(x, out, n, h, w, c);
+    else
+        upsample2x_kernel<false, false><<<blocks, 256, 0, stream>>>(x, out, n, h, w, c);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_im2col(const mobi_im2col_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(a && a->x && a->out, "mobi_im2col: null argument");
+    MOBI_CHECK(a->kpad >= a->kh * a->kw * a->c && a->kpad % 8 == 0, "mobi_im2col: kpad=%d too small or not %%8", a->kpad);
+    const long long total = (long long)a->n * a->ho * a->wo * a->kpad;
+    if (a->in_dtype == MOBI_DTYPE_F32)
+        im2col_kernel<true><<<blocks_for(total, 256), 256, 0, stream>>>(a->x, reinterpret_cast<__nv_bfloat16*>(a->out), *a);
+    else
+        im2col_kernel<false><<<blocks_for(total, 256), 256, 0, stream>>>(a->x, reinterpret_cast<__nv_bfloat16*>(a->out), *a);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_ctx_attention(const mobi_ctx_attn_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(a && a->xn && a->U && a->Z && a->zb && a->x, "mobi_ctx_attention: null argument");
+    MOBI_CHECK(a->heads * a->keys <= CTX_MAX_HK && a->C % 2 == 0, "mobi_ctx_attention: heads*keys=%d > %d",
+               a->heads * a->keys, CTX_MAX_HK);
+    const long long rows = (long long)a->batch * a->tokens;
+    const int warps = 8;
+    ctx_attention_kernel<<<blocks_for(rows, warps), warps * 32, 0, stream>>>(
+        reinterpret_cast<const __nv_bfloat16*>(a->xn), a->U, a->Z, a->zb, a->x, a->tokens, a->C, a->heads, a->keys, rows);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_sampler_update(const mobi_sampler_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(a && a->eps && a->x && a->x_prev && a->pred_x0 && a->n > 0, "mobi_sampler_update: bad argument");
+    sampler_update_kernel<<<blocks_for(a->n, 256), 256, 0, stream>>>(*a);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_assemble_input(const mobi_assemble_args* a, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(a && a->x && a->x_in && a->inpaint_image, "mobi_assemble_input: null argument");
+    MOBI_CHECK(a->rest_c != 5 || a->inpaint_mask, "mobi_assemble_input: inpaint_mask missing");
+    MOBI_CHECK(!a->blend_mask || (a->blend_x0 && a->blend_noise), "mobi_assemble_input: blend needs x0 and noise");
+    const long long total = (long long)a->B * a->hw;
+    assemble_input_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(*a);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    add_f32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(a, b, out, n);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int mobi_scale_f32(const float* x, float s, float* out, int64_t n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    scale_f32_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(x, s, out, n);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+extern "C" int mobi_cast_bf16(const float* x, void* out, int64_t n, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    if (n == 0) return 0;
+    cast_bf16_kernel<<<blocks_for(n, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), n);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}

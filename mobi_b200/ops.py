@@ -1,0 +1,293 @@
+"""Tensor-level wrappers over the C ABI: they check devices/dtypes/contiguity, allocate outputs with
+torch.empty (the library never allocates) and launch on PyTorch's current stream.
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib as L
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is None:
+            continue
+        if not t.is_cuda:
+            raise RuntimeError("mobi_b200 ops need CUDA tensors (no CPU fallback)")
+        if not t.is_contiguous():
+            raise RuntimeError("mobi_b200 ops need contiguous tensors, got strides %s" % (t.stride(),))
+
+
+def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
+         out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
+         tile_n=0, M=None, lda=None, ldo=None):
+    """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
+
+    Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.
+    """
+    _cuda(a, w, bias, row_bias, residual, out, out2, out3)
+    assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "gemm operands must be bf16"
+    K = w.shape[1]
+    N = w.shape[0]
+    if M is None:
+        M = a.numel() // a.shape[-1]
+    lda = a.shape[-1] if lda is None else lda
+    assert a.shape[-1] == K or lda is not None
+    if epilogue == L.EPI_PLAIN:
+        if out is None:
+            out = torch.empty((M, N), device=a.device, dtype=out_dtype)
+        ldo_v = N if ldo is None else ldo
+    elif epilogue == L.EPI_GEGLU:
+        if out is None:
+            out = torch.empty((M, N // 2), device=a.device, dtype=torch.bfloat16)
+        ldo_v = N // 2 if ldo is None else ldo
+    else:
+        assert out is not None, "head layouts need preallocated outputs"
+        ldo_v = 0
+    args = L.GemmArgs()
+    args.A, args.B, args.out = a.data_ptr(), w.data_ptr(), out.data_ptr()
+    args.out2, args.out3 = L.ptr(out2), L.ptr(out3)
+    if bias is not None:
+        assert bias.dtype == torch.float32 and bias.numel() >= N
+    if row_bias is not None:
+        assert row_bias.dtype == torch.float32
+    args.bias, args.row_bias, args.residual = L.ptr(bias), L.ptr(row_bias), L.ptr(residual)
+    args.M, args.N, args.K = M, N, K
+    args.lda, args.ldb, args.ldo = lda, w.stride(0), ldo_v
+    args.rows_per_group, args.ld_row_bias = rows_per_group, ld_row_bias
+    args.out_dtype = L.dt(out)
+    args.res_dtype = L.dt(residual) if residual is not None else L.DT_F32
+    args.epilogue, args.act = epilogue, act
+    args.heads, args.head_dim, args.tokens = heads, head_dim, tokens
+    args.conv = 0
+    args.tile_n = tile_n
+    L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
+    return out
+
+
+def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_row_bias=0, residual=None, out=None,
+                  out_dtype=torch.float32, tile_n=0):
+    """Stride-1 'same' convolution of an NHWC bf16 image by implicit GEMM.
+
+    x: [N, H, W, C] bf16; w: [Cout, kh*kw*C] bf16 with K ordered (kh, kw, c). Returns [N, H, W, Cout].
+    row_bias: f32 [N, Cout]-like (one row per image): the timestep-embedding add (openaimodel.py:264-272).
+    """
+    _cuda(x, w, bias, row_bias, residual, out)
+    n, h, wd, c = x.shape
+    cout = w.shape[0]
+    assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
+    assert w.shape[1] == kh * kw * c, (w.shape, kh, kw, c)
+    if out is None:
+        out = torch.empty((n, h, wd, cout), device=x.device, dtype=out_dtype)
+    args = L.GemmArgs()
+    args.A, args.B, args.out = x.data_ptr(), w.data_ptr(), out.data_ptr()
+    args.bias, args.row_bias, args.residual = L.ptr(bias), L.ptr(row_bias), L.ptr(residual)
+    args.M, args.N, args.K = n * h * wd, cout, kh * kw * c
+    args.lda, args.ldb, args.ldo = c, w.stride(0), cout
+    args.rows_per_group, args.ld_row_bias = h * wd, ld_row_bias
+    args.out_dtype = L.dt(out)
+    args.res_dtype = L.dt(residual) if residual is not None else L.DT_F32
+    args.epilogue, args.act = L.EPI_PLAIN, 0
+    args.conv, args.n_img, args.H, args.W, args.C = 1, n, h, wd, c
+    args.KH, args.KW, args.pad_h, args.pad_w = kh, kw, pad_h, pad_w
+    args.tile_n = tile_n
+    L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm(conv)")
+    return out
+
+
+def conv_implicit_ok(h, w, c):
+    """Shapes the implicit path tiles (see mobi_gemm): everything else goes through im2col."""
+    if c % 8 != 0 or c < 64:
+        return False
+    if w >= 128:
+        return w % 128 == 0
+    if 128 % w != 0:
+        return False
+    bh = min(128 // w, h)
+    return h % bh == 0 and 128 % (w * bh) == 0
+
+
+def im2col(x, kh, kw, stride, pad_top, pad_left, ho, wo):
+    _cuda(x)
+    n, h, w, c = x.shape
+    k = kh * kw * c
+    kpad = (k + 7) // 8 * 8
+    out = torch.empty((n * ho * wo, kpad), device=x.device, dtype=torch.bfloat16)
+    a = L.Im2colArgs()
+    a.x, a.out, a.in_dtype = x.data_ptr(), out.data_ptr(), L.dt(x)
+    a.n, a.h, a.w, a.c, a.kh, a.kw = n, h, w, c, kh, kw
+    a.stride, a.pad_top, a.pad_left, a.ho, a.wo, a.kpad = stride, pad_top, pad_left, ho, wo, kpad
+    L.check(L.load().mobi_im2col(C.byref(a), L.stream()), "im2col")
+    return out
+
+
+def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None):
+    """q,k: bf16 [batch*heads, T, d]; vt: bf16 [batch*heads, d, Tk]; returns bf16 [batch, tq, heads*d]."""
+    _cuda(q, k, vt, out)
+    assert q.dtype == k.dtype == vt.dtype == torch.bfloat16
+    if out is None:
+        out = torch.empty((batch, tq, heads * head_dim), device=q.device, dtype=torch.bfloat16)
+    a = L.AttnArgs()
+    a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
+    a.batch, a.heads, a.head_dim, a.tq, a.tk = batch, heads, head_dim, tq, tk
+    a.ld_out = heads * head_dim
+    L.check(L.load().mobi_attention(C.byref(a), L.stream()), "attention")
+    return out
+
+
+def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_concat=False):
+    """x1 (and optionally x2, concatenated on channels): NHWC [N, H, W, C] f32|bf16 -> bf16 NHWC."""
+    _cuda(x1, x2, gamma, beta)
+    n = x1.shape[0]
+    hw = x1.numel() // (n * x1.shape[-1])
+    c1 = x1.shape[-1]
+    c2 = x2.shape[-1] if x2 is not None else 0
+    if x2 is not None:
+        assert x2.dtype == x1.dtype and x2.shape[:-1] == x1.shape[:-1]
+    c = c1 + c2
+    out = torch.empty(x1.shape[:-1] + (c,), device=x1.device, dtype=torch.bfloat16)
+    cat = torch.empty_like(out) if want_concat else None
+    lib = L.load()
+    nbytes = lib.mobi_groupnorm_scratch_bytes(n, hw, c, groups)
+    partials = torch.empty((nbytes // 4,), device=x1.device, dtype=torch.float32)
+    a = L.GroupNormArgs()
+    a.x1, a.x2, a.gamma, a.beta = x1.data_ptr(), L.ptr(x2), gamma.data_ptr(), beta.data_ptr()
+    a.out, a.out_concat, a.partials = out.data_ptr(), L.ptr(cat), partials.data_ptr()
+    a.n_img, a.hw, a.c1, a.c2, a.groups = n, hw, c1, c2, groups
+    a.in_dtype, a.silu, a.eps = L.dt(x1), int(silu), eps
+    L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")
+    return (out, cat) if want_concat else out
+
+
+def layernorm(x, gamma, beta, *, rows=None, seg=0, seg_stride=0, seg_offset=0, add_vec=None, add_rows_per_vec=0,
+              eps=1e-5):
+    """x: f32 [*, C] -> bf16 [rows, C]. gamma=None casts only. See mobi_layernorm for the row gather."""
+    _cuda(x, gamma, beta, add_vec)
+    assert x.dtype == torch.float32
+    c = x.shape[-1]
+    if rows is None:
+        rows = x.numel() // c
+    out = torch.empty((rows, c), device=x.device, dtype=torch.bfloat16)
+    a = L.LayerNormArgs()
+    a.x, a.gamma, a.beta, a.out, a.add_vec = x.data_ptr(), L.ptr(gamma), L.ptr(beta), out.data_ptr(), L.ptr(add_vec)
+    a.rows, a.C = rows, c
+    a.seg, a.seg_stride, a.seg_offset, a.add_rows_per_vec = seg, seg_stride, seg_offset, add_rows_per_vec
+    a.eps = eps
+    L.check(L.load().mobi_layernorm(C.byref(a), L.stream()), "layernorm")
+    return out
+
+
+def timestep_embedding(t, dim, max_period=10000.0):
+    _cuda(t)
+    assert t.dtype == torch.int64
+    out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.bfloat16)
+    L.check(L.load().mobi_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, max_period, L.stream()),
+            "timestep_embedding")
+    return out
+
+
+def silu(x):
+    _cuda(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().mobi_silu(x.data_ptr(), L.dt(x), out.data_ptr(), x.numel(), L.stream()), "silu")
+    return out
+
+
+def nchw_to_nhwc(x, out_dtype=torch.float32):
+    _cuda(x)
+    assert x.dtype == torch.float32
+    n, c, h, w = x.shape
+    out = torch.empty((n, h, w, c), device=x.device, dtype=out_dtype)
+    L.check(L.load().mobi_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), L.dt(out), n, c, h * w, L.stream()),
+            "nchw_to_nhwc")
+    return out
+
+
+def nhwc_to_nchw(x):
+    _cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    L.check(L.load().mobi_nhwc_to_nchw(x.data_ptr(), L.dt(x), out.data_ptr(), n, c, h * w, L.stream()),
+            "nhwc_to_nchw")
+    return out
+
+
+def upsample_nearest2x(x, out_dtype=None):
+    _cuda(x)
+    n, h, w, c = x.shape
+    out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
+    L.check(L.load().mobi_upsample_nearest2x(x.data_ptr(), L.dt(x), out.data_ptr(), L.dt(out), n, h, w, c,
+                                             L.stream()), "upsample_nearest2x")
+    return out
+
+
+def ctx_attention(xn, U, Z, zb, x, batch, tokens, heads, keys):
+    _cuda(xn, U, Z, zb, x)
+    assert xn.dtype == torch.bfloat16 and x.dtype == torch.float32
+    assert U.dtype == Z.dtype == zb.dtype == torch.float32
+    a = L.CtxAttnArgs()
+    a.xn, a.U, a.Z, a.zb, a.x = xn.data_ptr(), U.data_ptr(), Z.data_ptr(), zb.data_ptr(), x.data_ptr()
+    a.batch, a.tokens, a.C, a.heads, a.keys = batch, tokens, x.shape[-1], heads, keys
+    L.check(L.load().mobi_ctx_attention(C.byref(a), L.stream()), "ctx_attention")
+    return x
+
+
+def add_f32(a, b, out=None):
+    _cuda(a, b, out)
+    if out is None:
+        out = torch.empty_like(a)
+    L.check(L.load().mobi_add_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), L.stream()), "add_f32")
+    return out
+
+
+def scale_f32(x, s, out=None):
+    _cuda(x, out)
+    if out is None:
+        out = torch.empty_like(x)
+    L.check(L.load().mobi_scale_f32(x.data_ptr(), float(s), out.data_ptr(), x.numel(), L.stream()), "scale_f32")
+    return out
+
+
+def cast_bf16(x):
+    _cuda(x)
+    out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    L.check(L.load().mobi_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), L.stream()), "cast_bf16")
+    return out
+
+
+def sampler_update(eps, x, *, cfg, scale, coefs, sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_temp=0.0,
+                   noise=None, old=(), e_out=None, x_prev=None, pred_x0=None):
+    _cuda(eps, x, noise, e_out, x_prev, pred_x0, *old)
+    if x_prev is None:
+        x_prev = torch.empty_like(x)
+    if pred_x0 is None:
+        pred_x0 = torch.empty_like(x)
+    a = L.SamplerArgs()
+    a.eps, a.x, a.noise = eps.data_ptr(), x.data_ptr(), L.ptr(noise)
+    olds = list(old) + [None] * (3 - len(old))
+    a.old1, a.old2, a.old3 = L.ptr(olds[0]), L.ptr(olds[1]), L.ptr(olds[2])
+    a.e_out, a.x_prev, a.pred_x0 = L.ptr(e_out), x_prev.data_ptr(), pred_x0.data_ptr()
+    a.n, a.cfg, a.scale = x.numel(), int(cfg), scale
+    cs = list(coefs) + [0.0] * (4 - len(coefs))
+    a.c0, a.c1, a.c2, a.c3 = cs
+    a.sqrt_one_minus_at, a.sqrt_at, a.sqrt_a_prev, a.dir_coef, a.sigma_temp = (
+        sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_temp)
+    L.check(L.load().mobi_sampler_update(C.byref(a), L.stream()), "sampler_update")
+    return x_prev, pred_x0
+
+
+def assemble_input(x, rest_image, rest_mask, x_in, *, cfg, blend=None):
+    """x_in = cat([x, rest...], 1) (twice under CFG). blend = (mask, x0, noise, sqrt_ac, sqrt_1mac) or None."""
+    _cuda(x, rest_image, rest_mask, x_in)
+    b, _, h, w = x.shape
+    a = L.AssembleArgs()
+    a.x, a.inpaint_image, a.inpaint_mask, a.x_in = x.data_ptr(), rest_image.data_ptr(), L.ptr(rest_mask), x_in.data_ptr()
+    a.B, a.hw, a.cfg = b, h * w, int(cfg)
+    a.rest_c = 5 if rest_mask is not None else rest_image.shape[1]
+    if blend is not None:
+        mask, x0, noise, sa, s1 = blend
+        _cuda(mask, x0, noise)
+        a.blend_mask, a.blend_x0, a.blend_noise = mask.data_ptr(), x0.data_ptr(), noise.data_ptr()
+        a.blend_c, a.sqrt_ac, a.sqrt_1mac = mask.shape[1], sa, s1
+    L.check(L.load().mobi_assemble_input(C.byref(a), L.stream()), "assemble_input")
+    return x_in

@@ -1,0 +1,326 @@
+"""Kernel-level parity: every CUDA kernel, called through the C ABI, against plain PyTorch fp32 math on the
+same seeded inputs.  Tolerances: bf16 operands with fp32 accumulation -> relative-to-max error <= 1e-2
+(typically ~3e-3); fp32 elementwise kernels <= 1e-5."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _ops():
+    from mobi_b200 import ops
+    return ops
+
+
+def _L():
+    from mobi_b200 import _lib
+    return _lib
+
+
+def relerr(a, b):
+    a = a.float()
+    b = b.float()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-12)).item()
+
+
+def describe(a, b):
+    """Where does a mismatch live? (row/col pattern helps to find layout bugs)"""
+    d = (a.float() - b.float()).abs()
+    d2 = d.reshape(-1, d.shape[-1])
+    rows = d2.max(dim=1).values
+    cols = d2.max(dim=0).values
+    br = torch.nonzero(rows > 0.05 * d.max()).flatten()[:16].tolist()
+    bc = torch.nonzero(cols > 0.05 * d.max()).flatten()[:16].tolist()
+    return "max %.4g ref-max %.4g bad rows %s bad cols %s" % (d.max().item(), b.float().abs().max().item(), br, bc)
+
+
+def rnd(*shape, seed=0, dtype=torch.bfloat16, scale=1.0):
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    return (torch.randn(*shape, generator=g) * scale).to("cuda").to(dtype)
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [
+    (128, 64, 64, 64), (128, 128, 64, 128), (256, 256, 128, 256), (128, 160, 64, 160),
+    (512, 320, 320, 0), (1000, 320, 320, 64), (4096, 640, 640, 0), (300, 1280, 1280, 256),
+    (4, 1280, 320, 0), (260, 4, 2880, 64), (128, 128, 88, 128), (1024, 2560, 320, 0),
+])
+def test_gemm_plain(M, N, K, tile_n):
+    ops = _ops()
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    ref = a.float() @ w.float().t() + bias
+    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, tile_n=tile_n)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) < 2e-3, describe(out, ref)
+    out16 = ops.gemm(a, w, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n)
+    assert relerr(out16, ref) < 1e-2, describe(out16, ref)
+
+
+def test_gemm_residual_rowbias_act():
+    ops = _ops()
+    M, N, K = 2 * 384, 320, 640
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    rb = rnd(2, 3 * N, seed=4, dtype=torch.float32)  # wider row stride than N: slice [N:2N]
+    res = rnd(M, N, seed=5, dtype=torch.float32)
+    ref = a.float() @ w.float().t() + bias + rb[:, N:2 * N].repeat_interleave(384, 0) + res
+    out = ops.gemm(a, w, bias=bias, row_bias=rb[:, N:2 * N], rows_per_group=384, ld_row_bias=3 * N, residual=res,
+                   out_dtype=torch.float32)
+    assert relerr(out, ref) < 2e-3, describe(out, ref)
+    # in-place residual (out aliases residual), bf16 residual
+    res16 = res.to(torch.bfloat16)
+    ref2 = a.float() @ w.float().t() + res16.float()
+    out2 = ops.gemm(a, w, residual=res16, out=res16.clone(), out_dtype=torch.bfloat16)
+    assert relerr(out2, ref2) < 1e-2, describe(out2, ref2)
+    x = res.clone()
+    ops.gemm(a, w, residual=x, out=x)
+    assert relerr(x, a.float() @ w.float().t() + res) < 2e-3
+    # SiLU activation
+    ref3 = torch.nn.functional.silu(a.float() @ w.float().t() + bias)
+    out3 = ops.gemm(a, w, bias=bias, act=1, out_dtype=torch.float32)
+    assert relerr(out3, ref3) < 2e-3, describe(out3, ref3)
+
+
+def test_gemm_geglu():
+    ops = _ops()
+    L = _L()
+    M, C = 512, 320
+    a = rnd(M, C, seed=1)
+    w = rnd(8 * C, C, seed=2, scale=C ** -0.5)      # reference layout: [value rows | gate rows]
+    b = rnd(8 * C, seed=3, dtype=torch.float32)
+    h = a.float() @ w.float().t() + b
+    val, gate = h.chunk(2, dim=-1)
+    ref = val * torch.nn.functional.gelu(gate)
+    from mobi_b200.packing import interleave_geglu
+    wp, bp = interleave_geglu(w, b)
+    out = ops.gemm(a, wp, bias=bp, epilogue=L.EPI_GEGLU)
+    assert out.shape == (M, 4 * C)
+    assert relerr(out, ref) < 1e-2, describe(out, ref)
+
+
+@pytest.mark.parametrize("B,T,H,D", [(2, 256, 8, 40), (1, 128, 2, 16), (2, 64, 8, 160), (1, 1024, 8, 80)])
+def test_gemm_head_layouts(B, T, H, D):
+    ops = _ops()
+    L = _L()
+    C = H * D
+    a = rnd(B * T, C, seed=1)
+    w = rnd(3 * C, C, seed=2, scale=C ** -0.5)
+    ref = (a.float() @ w.float().t()).reshape(B, T, 3, H, D)
+    q = torch.empty(B * H, T, D, device="cuda", dtype=torch.bfloat16)
+    k = torch.empty_like(q)
+    vt = torch.empty(B * H, D, T, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(a, w, epilogue=L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=vt)
+    rq = ref[:, :, 0].permute(0, 2, 1, 3).reshape(B * H, T, D)
+    rk = ref[:, :, 1].permute(0, 2, 1, 3).reshape(B * H, T, D)
+    rv = ref[:, :, 2].permute(0, 2, 3, 1).reshape(B * H, D, T)
+    assert relerr(q, rq) < 1e-2, describe(q, rq)
+    assert relerr(k, rk) < 1e-2, describe(k, rk)
+    assert relerr(vt, rv) < 1e-2, describe(vt, rv)
+    q2 = torch.empty_like(q)
+    ops.gemm(a, w[:C], epilogue=L.EPI_HEADS, heads=H, head_dim=D, tokens=T, out=q2)
+    assert relerr(q2, rq) < 1e-2
+    v2 = torch.empty_like(vt)
+    ops.gemm(a, w[2 * C:], epilogue=L.EPI_HEADS_T, heads=H, head_dim=D, tokens=T, out=v2)
+    assert relerr(v2, rv) < 1e-2
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout,kh,kw", [
+    (2, 64, 64, 320, 320, 3, 3), (4, 32, 32, 640, 640, 3, 3), (4, 16, 16, 1280, 1280, 3, 3),
+    (4, 8, 8, 2560, 1280, 3, 3), (3, 8, 8, 1280, 1280, 3, 3), (8, 4, 4, 1280, 1280, 3, 3),
+    (2, 64, 64, 320, 4, 3, 3), (1, 128, 128, 128, 128, 3, 3), (1, 256, 256, 128, 128, 1, 5),
+    (2, 32, 32, 960, 640, 3, 3), (1, 64, 64, 64, 64, 3, 3),
+])
+def test_conv_implicit(N, H, W, C, Cout, kh, kw):
+    ops = _ops()
+    x = rnd(N, C, H, W, seed=1, dtype=torch.float32)
+    w = rnd(Cout, C, kh, kw, seed=2, dtype=torch.float32, scale=(C * kh * kw) ** -0.5)
+    b = rnd(Cout, seed=3, dtype=torch.float32)
+    emb = rnd(N, Cout, seed=4, dtype=torch.float32)
+    res = rnd(N, H, W, Cout, seed=5, dtype=torch.float32)
+    xb = x.to(torch.bfloat16)
+    wb = w.to(torch.bfloat16)
+    ref = torch.nn.functional.conv2d(xb.float(), wb.float(), b, padding=(kh // 2, kw // 2))
+    ref = ref + emb[:, :, None, None]
+    ref = ref.permute(0, 2, 3, 1) + res
+    x_nhwc = xb.permute(0, 2, 3, 1).contiguous()
+    wp = wb.permute(0, 2, 3, 1).reshape(Cout, kh * kw * C).contiguous()
+    assert ops.conv_implicit_ok(H, W, C)
+    out = ops.conv_implicit(x_nhwc, wp, kh, kw, kh // 2, kw // 2, bias=b, row_bias=emb, residual=res)
+    assert relerr(out, ref) < 2e-3, describe(out.reshape(-1, Cout), ref.reshape(-1, Cout))
+
+
+@pytest.mark.parametrize("N,H,W,C,Cout,k,stride,pads", [
+    (2, 64, 64, 320, 320, 3, 2, (1, 1)), (2, 32, 32, 9, 320, 3, 1, (1, 1)), (1, 64, 64, 128, 128, 3, 2, (0, 0)),
+])
+def test_conv_im2col(N, H, W, C, Cout, k, stride, pads):
+    ops = _ops()
+    x = rnd(N, C, H, W, seed=1, dtype=torch.float32).to(torch.bfloat16)
+    w = rnd(Cout, C, k, k, seed=2, dtype=torch.float32, scale=(C * k * k) ** -0.5).to(torch.bfloat16)
+    b = rnd(Cout, seed=3, dtype=torch.float32)
+    if pads == (0, 0):  # VAE downsample: pad right/bottom by one, then valid conv (model.py:72-76)
+        xp = torch.nn.functional.pad(x.float(), (0, 1, 0, 1))
+        ref = torch.nn.functional.conv2d(xp, w.float(), b, stride=stride)
+    else:
+        ref = torch.nn.functional.conv2d(x.float(), w.float(), b, stride=stride, padding=pads)
+    ho, wo = ref.shape[2], ref.shape[3]
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous()
+    cols = ops.im2col(x_nhwc, k, k, stride, pads[0], pads[1], ho, wo)
+    from mobi_b200.packing import pack_conv_weight
+    wp = pack_conv_weight(w.float(), kpad=cols.shape[1])
+    out = ops.gemm(cols, wp, bias=b, out_dtype=torch.float32).reshape(N, ho, wo, Cout)
+    assert relerr(out, ref.permute(0, 2, 3, 1)) < 2e-3, describe(out, ref.permute(0, 2, 3, 1))
+
+
+@pytest.mark.parametrize("B,H,D,Tq,Tk", [
+    (1, 1, 64, 128, 128), (2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 80, 256, 256),
+    (2, 8, 160, 256, 256), (2, 8, 160, 64, 64), (1, 2, 16, 64, 64), (1, 2, 32, 16, 16),
+    (1, 8, 40, 4096, 4096), (1, 4, 80, 384, 200),
+])
+def test_attention(B, H, D, Tq, Tk):
+    ops = _ops()
+    q = rnd(B * H, Tq, D, seed=1, dtype=torch.float32)
+    k = rnd(B * H, Tk, D, seed=2, dtype=torch.float32)
+    v = rnd(B * H, Tk, D, seed=3, dtype=torch.float32)
+    # make the softmax peaky in places so the running-max / rescale path is exercised
+    k[:, Tk // 2:] *= 3.0
+    scale = D ** -0.5
+    qs = (q * (scale * math.log2(math.e))).to(torch.bfloat16)
+    kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
+    s = torch.einsum("bid,bjd->bij", qs.float(), kb.float()) * math.log(2.0)
+    ref = torch.einsum("bij,bjd->bid", s.softmax(-1), vb.float())
+    ref = ref.reshape(B, H, Tq, D).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
+    vt = vb.transpose(1, 2).contiguous()
+    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk)
+    torch.cuda.synchronize()
+    assert relerr(out, ref) < 1e-2, describe(out, ref)
+
+
+@pytest.mark.parametrize("N,HW,C1,C2,dtype,eps", [
+    (2, 4096, 320, 0, torch.float32, 1e-5), (2, 1024, 1280, 640, torch.float32, 1e-5),
+    (3, 64, 1280, 1280, torch.float32, 1e-5), (1, 65536, 128, 0, torch.bfloat16, 1e-6),
+    (2, 256, 32, 0, torch.float32, 1e-6), (2, 4096, 640, 320, torch.float32, 1e-5),
+])
+def test_groupnorm(N, HW, C1, C2, dtype, eps):
+    ops = _ops()
+    side = int(HW ** 0.5)
+    x1 = (rnd(N, side, side, C1, seed=1, dtype=torch.float32) * 2 + 0.5).to(dtype)
+    x2 = (rnd(N, side, side, C2, seed=2, dtype=torch.float32) - 1.0).to(dtype) if C2 else None
+    C = C1 + C2
+    g = rnd(C, seed=3, dtype=torch.float32)
+    b = rnd(C, seed=4, dtype=torch.float32)
+    xc = torch.cat([x1, x2], -1) if C2 else x1
+    ref = torch.nn.functional.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, b, eps)
+    ref = torch.nn.functional.silu(ref).permute(0, 2, 3, 1)
+    out, cat = ops.groupnorm(x1, g, b, eps, x2=x2, silu=True, want_concat=True)
+    assert relerr(out, ref) < 8e-3, describe(out, ref)
+    assert torch.equal(cat, xc.to(torch.bfloat16))
+    out2 = ops.groupnorm(x1, g, b, eps, x2=x2, silu=False)
+    ref2 = torch.nn.functional.group_norm(xc.float().permute(0, 3, 1, 2), 32, g, b, eps).permute(0, 2, 3, 1)
+    assert relerr(out2, ref2) < 8e-3, describe(out2, ref2)
+
+
+def test_layernorm_variants():
+    ops = _ops()
+    R, T, C = 4, 256, 320
+    x = rnd(R, T, C, seed=1, dtype=torch.float32) * 1.5 + 0.3
+    g = rnd(C, seed=2, dtype=torch.float32)
+    b = rnd(C, seed=3, dtype=torch.float32)
+    ref = torch.nn.functional.layer_norm(x, (C,), g, b, 1e-5)
+    out = ops.layernorm(x, g, b)
+    assert relerr(out, ref.reshape(-1, C)) < 8e-3
+    # camera rows (even) / lidar rows (odd) gathered from the interleaved batch (attention.py:246-247)
+    cam = ops.layernorm(x, g, b, rows=R // 2 * T, seg=T, seg_stride=2 * T, seg_offset=0)
+    lid = ops.layernorm(x, None, None, rows=R // 2 * T, seg=T, seg_stride=2 * T, seg_offset=T)
+    assert relerr(cam, ref[0::2].reshape(-1, C)) < 8e-3
+    assert torch.equal(lid, x[1::2].reshape(-1, C).to(torch.bfloat16))
+    # broadcast add + write back (attn2 with one key, attention.py:235)
+    vec = rnd(R, C, seed=4, dtype=torch.float32)
+    x2 = x.clone()
+    out2 = ops.layernorm(x2, g, b, add_vec=vec, add_rows_per_vec=T)
+    xr = x + vec[:, None, :]
+    assert torch.allclose(x2, xr, atol=1e-6)
+    assert relerr(out2, torch.nn.functional.layer_norm(xr, (C,), g, b, 1e-5).reshape(-1, C)) < 8e-3
+    for C2 in (640, 1280, 32):
+        xx = rnd(64, C2, seed=5, dtype=torch.float32)
+        gg = rnd(C2, seed=6, dtype=torch.float32)
+        bb = rnd(C2, seed=7, dtype=torch.float32)
+        assert relerr(ops.layernorm(xx, gg, bb), torch.nn.functional.layer_norm(xx, (C2,), gg, bb, 1e-5)) < 8e-3
+
+
+def test_small_kernels():
+    ops = _ops()
+    t = torch.tensor([981, 1, 500, 21], device="cuda", dtype=torch.int64)
+    half = 160
+    freqs = torch.exp(-math.log(10000) * torch.arange(half, dtype=torch.float32) / half).cuda()
+    args = t[:, None].float() * freqs[None]
+    ref = torch.cat([torch.cos(args), torch.sin(args)], -1)
+    out = ops.timestep_embedding(t, 320)
+    assert (out.float() - ref).abs().max() < 1e-2
+    x = rnd(3, 9, 32, 32, seed=1, dtype=torch.float32)
+    nhwc = ops.nchw_to_nhwc(x)
+    assert torch.equal(nhwc, x.permute(0, 2, 3, 1).contiguous())
+    assert torch.equal(ops.nhwc_to_nchw(nhwc), x)
+    assert torch.equal(ops.nchw_to_nhwc(x, torch.bfloat16), x.permute(0, 2, 3, 1).to(torch.bfloat16))
+    y = rnd(2, 8, 8, 64, seed=2, dtype=torch.float32)
+    up = ops.upsample_nearest2x(y, torch.bfloat16)
+    ref = torch.nn.functional.interpolate(y.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(up, ref.to(torch.bfloat16))
+    assert relerr(ops.silu(y), torch.nn.functional.silu(y)) < 8e-3
+    assert torch.equal(ops.add_f32(y, y), y + y)
+    assert torch.equal(ops.cast_bf16(y), y.to(torch.bfloat16))
+    assert torch.allclose(ops.scale_f32(y, 1 / 0.18215), y * (1 / 0.18215), rtol=1e-6)
+
+
+def test_ctx_attention():
+    ops = _ops()
+    B, T, C, H, Kk = 4, 256, 320, 8, 2
+    xn = rnd(B * T, C, seed=1)
+    U = rnd(B, Kk * H, C, seed=2, dtype=torch.float32, scale=C ** -0.5)
+    Z = rnd(B, Kk * H, C, seed=3, dtype=torch.float32)
+    zb = rnd(C, seed=4, dtype=torch.float32)
+    x = rnd(B * T, C, seed=5, dtype=torch.float32)
+    s = torch.einsum("btc,bjc->btj", xn.float().reshape(B, T, C), U).reshape(B, T, Kk, H)
+    p = s.softmax(dim=2).reshape(B, T, Kk * H)
+    ref = x.reshape(B, T, C) + torch.einsum("btj,bjc->btc", p, Z) + zb
+    out = ops.ctx_attention(xn, U, Z, zb, x.clone(), B, T, H, Kk)
+    assert relerr(out, ref.reshape(-1, C)) < 1e-4, describe(out, ref.reshape(-1, C))
+
+
+def test_sampler_kernels():
+    ops = _ops()
+    B, H = 4, 32
+    x = rnd(B, 4, H, H, seed=1, dtype=torch.float32)
+    eps = rnd(2 * B, 4, H, H, seed=2, dtype=torch.float32)
+    old = [rnd(B, 4, H, H, seed=3 + i, dtype=torch.float32) for i in range(3)]
+    noise = rnd(B, 4, H, H, seed=9, dtype=torch.float32)
+    a_t, a_prev, sigma, s = 0.3, 0.4, 0.1, 5.0
+    e = eps[:B] + s * (eps[B:] - eps[:B])
+    ep = (55 * e - 59 * old[0] + 37 * old[1] - 9 * old[2]) / 24
+    pred = (x - math.sqrt(1 - a_t) * ep) / math.sqrt(a_t)
+    xp = math.sqrt(a_prev) * pred + math.sqrt(1 - a_prev - sigma ** 2) * ep + sigma * noise
+    e_out = torch.empty_like(x)
+    x_prev, pred_x0 = ops.sampler_update(
+        eps, x, cfg=True, scale=s, coefs=(55 / 24, -59 / 24, 37 / 24, -9 / 24), sqrt_one_minus_at=math.sqrt(1 - a_t),
+        sqrt_at=math.sqrt(a_t), sqrt_a_prev=math.sqrt(a_prev), dir_coef=math.sqrt(1 - a_prev - sigma ** 2),
+        sigma_temp=sigma, noise=noise, old=old, e_out=e_out)
+    assert torch.allclose(e_out, e, atol=1e-5)
+    assert torch.allclose(pred_x0, pred, atol=1e-4, rtol=1e-5)
+    assert torch.allclose(x_prev, xp, atol=1e-4, rtol=1e-5)
+    img = rnd(B, 4, H, H, seed=20, dtype=torch.float32)
+    mask = (rnd(B, 1, H, H, seed=21, dtype=torch.float32) > 0).float()
+    x_in = torch.empty(2 * B, 9, H, H, device="cuda")
+    ops.assemble_input(x, img, mask, x_in, cfg=True)
+    ref = torch.cat([x, img, mask], 1)
+    assert torch.equal(x_in, torch.cat([ref, ref]))
+    bm = (rnd(B, 1, H, H, seed=22, dtype=torch.float32) > 0).float()
+    x0 = rnd(B, 4, H, H, seed=23, dtype=torch.float32)
+    nz = rnd(B, 4, H, H, seed=24, dtype=torch.float32)
+    xb = x.clone()
+    ops.assemble_input(xb, img, mask, x_in, cfg=False, blend=(bm, x0, nz, 0.8, 0.6))
+    xr = (0.8 * x0 + 0.6 * nz) * bm + (1 - bm) * x
+    assert torch.allclose(xb, xr, atol=1e-6)
+    assert torch.allclose(x_in[:B], torch.cat([xr, img, mask], 1), atol=1e-6)
