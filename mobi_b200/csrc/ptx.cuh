@@ -54,14 +54,15 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded spin: a protocol bug must trap (reported as a launch failure), never hang the GPU box.
-#ifndef MOBI_SPIN_LIMIT
-#define MOBI_SPIN_LIMIT (1u << 26)
+// Bounded wait: a protocol bug must trap (reported as a launch failure), never hang the GPU box.
+#ifndef MOBI_WAIT_LIMIT_CYCLES
+#define MOBI_WAIT_LIMIT_CYCLES 6000000000ll  /* ~3-4 s at B200 clocks */
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    uint32_t spins = 0;
+    if (mbar_try_wait(bar, parity)) return;
+    const long long start = clock64();
     while (!mbar_try_wait(bar, parity)) {
-        if (++spins > MOBI_SPIN_LIMIT) {
+        if (clock64() - start > MOBI_WAIT_LIMIT_CYCLES) {
             asm volatile("trap;");
         }
     }

@@ -25,7 +25,11 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.
     """
-    _cuda(a, w, bias, row_bias, residual, out, out2, out3)
+    _cuda(a, w, bias, residual, out, out2, out3)
+    if row_bias is not None:  # may be a column slice of a wider matrix (ld_row_bias = its row stride)
+        assert row_bias.is_cuda and row_bias.stride(-1) == 1
+        if ld_row_bias == 0 and row_bias.dim() == 2:
+            ld_row_bias = row_bias.stride(0)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "gemm operands must be bf16"
     K = w.shape[1]
     N = w.shape[0]
@@ -72,7 +76,11 @@ def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_ro
     x: [N, H, W, C] bf16; w: [Cout, kh*kw*C] bf16 with K ordered (kh, kw, c). Returns [N, H, W, Cout].
     row_bias: f32 [N, Cout]-like (one row per image): the timestep-embedding add (openaimodel.py:264-272).
     """
-    _cuda(x, w, bias, row_bias, residual, out)
+    _cuda(x, w, bias, residual, out)
+    if row_bias is not None:
+        assert row_bias.is_cuda and row_bias.stride(-1) == 1
+        if ld_row_bias == 0 and row_bias.dim() == 2:
+            ld_row_bias = row_bias.stride(0)
     n, h, wd, c = x.shape
     cout = w.shape[0]
     assert x.dtype == torch.bfloat16 and w.dtype == torch.bfloat16
