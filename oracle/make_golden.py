@@ -1,0 +1,167 @@
+"""TEST INFRASTRUCTURE ONLY — generates tests/golden/*.npz by running the UNMODIFIED reference
+(/root/reference, imported through oracle/ref_shims.py) on deterministic synthetic weights and inputs.
+
+Run here (the build container) with:  python -m oracle.make_golden
+The GPU box has no /root/reference; tests there read only the committed fixtures.
+
+What is pinned (all with the tiny topology-complete configs from oracle/*_oracle.py so fixtures stay small):
+  unet_tiny.npz        UNetModel.forward(x, t, context) through LatentDiffusion.apply_model
+  ddim_tiny.npz        DDIMSampler.sample, 4 steps of S=10, CFG 3.0, test_model_kwargs path (+ mask/x0 blend run)
+  plms_tiny.npz        PLMSSampler.sample, 4 steps of S=10, CFG 3.0
+  vae_tiny.npz         AutoencoderKL.decode / encode moments for the camera and the lidar-adapter autoencoder
+  schedule.npz         register_schedule + DDIM parameters for S=50 on the real (1000-step) schedule
+  shapes_512.json      state_dict key -> shape of the real mobi_nusc_512 UNet (1,118 tensors) and both VAEs
+"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, ROOT)
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+
+from oracle import ref_shims, sampler_oracle, unet_oracle, vae_oracle  # noqa: E402
+
+
+def build_reference_ldm(unet_cfg, cam_dd=None, lid_dd=None):
+    from ldm.models.diffusion.ddpm import LatentDiffusion
+
+    def ae(dd):
+        return None if dd is None else dict(target="ldm.models.autoencoder.AutoencoderKL",
+                                            params=dict(embed_dim=4, ddconfig=dd,
+                                                        lossconfig=dict(target="torch.nn.Identity")))
+
+    model = LatentDiffusion(
+        cond_stage_config="__is_unconditional__", first_stage_config=ae(cam_dd), lidar_stage_config=ae(lid_dd),
+        unet_config=dict(target="ldm.modules.diffusionmodules.openaimodel.UNetModel", params=unet_cfg),
+        linear_start=0.00085, linear_end=0.0120, num_timesteps_cond=1, log_every_t=200, timesteps=1000,
+        first_stage_key="inpaint", cond_stage_key=["ref_image", "ref_bbox"], image_size=unet_cfg["image_size"],
+        channels=4, cond_stage_trainable=False, conditioning_key="crossattn", monitor=None, u_cond_percent=0.2,
+        scale_factor=0.18215, lidar_scale_factor=0.18215, use_ema=False, use_camera=True, use_lidar=True)
+    # "__is_unconditional__" resets conditioning_key to None in __init__ (ddpm.py:469-470); restore crossattn,
+    # the value every shipped config uses (configs/mobi_nusc_512.yaml:42)
+    model.model.conditioning_key = "crossattn"
+    return model.eval()
+
+
+def load_synth(module, shapes_fn_result, seed):
+    ref_sd = module.state_dict()
+    mine = shapes_fn_result
+    assert set(ref_sd.keys()) == set(mine.keys()), (
+        sorted(set(ref_sd) - set(mine))[:5], sorted(set(mine) - set(ref_sd))[:5])
+    for k, v in ref_sd.items():
+        assert tuple(v.shape) == tuple(mine[k]), (k, tuple(v.shape), mine[k])
+    sd = unet_oracle.synth_state_dict(mine, seed=seed)
+    module.load_state_dict(sd, strict=True)
+    return sd
+
+
+def main():
+    ref_shims.install()
+    torch.set_grad_enabled(False)
+    os.makedirs(GOLDEN, exist_ok=True)
+    from ldm.models.diffusion.ddim import DDIMSampler
+    from ldm.models.diffusion.plms import PLMSSampler
+
+    # ---- tiny joint model
+    ucfg = unet_oracle.tiny_unet_config()
+    cam_dd, lid_dd = vae_oracle.tiny_ddconfig(False), vae_oracle.tiny_ddconfig(True)
+    ldm = build_reference_ldm(ucfg, cam_dd, lid_dd)
+    load_synth(ldm.model.diffusion_model, unet_oracle.state_dict_shapes(ucfg), seed=0)
+    load_synth(ldm.first_stage_model, vae_oracle.state_dict_shapes(cam_dd), seed=10)
+    load_synth(ldm.lidar_stage_model, vae_oracle.state_dict_shapes(lid_dd), seed=20)
+
+    inp = unet_oracle.synth_inputs(2, 16, context_dim=ucfg["context_dim"], seed=1)
+    x9 = torch.cat([inp["x_T"], inp["inpaint_image"], inp["inpaint_mask"]], 1)
+    t = torch.tensor([981, 981, 21, 21], dtype=torch.long)
+    eps = ldm.apply_model(x9, t, inp["cond"])
+    np.savez(os.path.join(GOLDEN, "unet_tiny.npz"), x=x9.numpy(), t=t.numpy(), context=inp["cond"].numpy(),
+             eps=eps.numpy())
+    print("unet_tiny eps std %.4f absmax %.4f" % (eps.std(), eps.abs().max()))
+
+    # ---- samplers (S=10 schedule, first 4 steps via timesteps subset is awkward: run full S=4 instead)
+    S, scale = 4, 3.0
+    samples, inter = DDIMSampler(ldm).sample(
+        S=S, conditioning=inp["cond"], batch_size=4, shape=[4, 16, 16], verbose=False,
+        unconditional_guidance_scale=scale, unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
+        log_every_t=1,
+        test_model_kwargs=dict(inpaint_image=inp["inpaint_image"], inpaint_mask=inp["inpaint_mask"]))
+    out = dict(samples=samples.numpy(), pred_x0_last=inter["pred_x0"][-1].numpy(),
+               x_inter=np.stack([a.numpy() for a in inter["x_inter"]]))
+    # known-latent blend path (ddim.py:145-148): q_sample draws randn_like -> seed torch and record the draws
+    rng = np.random.default_rng(7)
+    bmask = torch.from_numpy((rng.random((4, 1, 16, 16)) > 0.5).astype(np.float32))
+    bx0 = torch.from_numpy(rng.standard_normal((4, 4, 16, 16), dtype=np.float32))
+    torch.manual_seed(123)
+    noises = [torch.randn(4, 4, 16, 16) for _ in range(2 * S)]
+    it = iter(noises)
+    orig_q = ldm.q_sample
+    ldm.q_sample = lambda x_start, tt, noise=None: orig_q(x_start, tt, noise=next(it))
+    # eta=0 still draws noise_like every step (ddim.py:209) but multiplies it by sigma=0
+    samples_b, _ = DDIMSampler(ldm).sample(
+        S=S, conditioning=inp["cond"], batch_size=4, shape=[4, 16, 16], verbose=False,
+        unconditional_guidance_scale=scale, unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
+        mask=bmask, x0=bx0,
+        test_model_kwargs=dict(inpaint_image=inp["inpaint_image"], inpaint_mask=inp["inpaint_mask"]))
+    ldm.q_sample = orig_q
+    out.update(blend_mask=bmask.numpy(), blend_x0=bx0.numpy(), blend_noise=np.stack([n.numpy() for n in noises[:S]]),
+               samples_blend=samples_b.numpy())
+    np.savez(os.path.join(GOLDEN, "ddim_tiny.npz"), S=S, scale=scale, **{k: v.numpy() for k, v in inp.items()}, **out)
+    print("ddim_tiny samples std %.4f" % samples.std())
+
+    samples_p, _ = PLMSSampler(ldm).sample(
+        S=S, conditioning=inp["cond"], batch_size=4, shape=[4, 16, 16], verbose=False,
+        unconditional_guidance_scale=scale, unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
+        inpaint_image=inp["inpaint_image"], inpaint_mask=inp["inpaint_mask"])
+    np.savez(os.path.join(GOLDEN, "plms_tiny.npz"), S=S, scale=scale, samples=samples_p.numpy())
+    print("plms_tiny samples std %.4f" % samples_p.std())
+
+    # ---- VAEs: decode_sample + decode_first_stage for both modalities, encode moments
+    h_cam, h_lid = ldm.decode_sample(samples, samples[1::2].clone())
+    img = ldm.decode_first_stage(h_cam)
+    rng_img = ldm.decode_first_stage(h_lid, module_name="lidar_stage_model")
+    gx = np.random.default_rng(3)
+    cam_in = torch.from_numpy(gx.standard_normal((1, 3, 64, 64), dtype=np.float32))
+    lid_in = torch.from_numpy(gx.standard_normal((1, 2, 64, 64), dtype=np.float32))
+    cam_m = ldm.first_stage_model.encode(cam_in).parameters
+    lid_m = ldm.lidar_stage_model.encode(lid_in).parameters
+    np.savez(os.path.join(GOLDEN, "vae_tiny.npz"), z=samples.numpy(), image=img.numpy(), range=rng_img.numpy(),
+             cam_in=cam_in.numpy(), lid_in=lid_in.numpy(), cam_moments=cam_m.numpy(), lid_moments=lid_m.numpy())
+    print("vae_tiny image std %.4f range std %.4f" % (img.std(), rng_img.std()))
+
+    # ---- schedule buffers on the real schedule, S=50
+    smp = DDIMSampler(ldm)
+    smp.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+    np.savez(os.path.join(GOLDEN, "schedule.npz"), betas=ldm.betas.numpy(), alphas_cumprod=ldm.alphas_cumprod.numpy(),
+             alphas_cumprod_prev=ldm.alphas_cumprod_prev.numpy(),
+             sqrt_alphas_cumprod=ldm.sqrt_alphas_cumprod.numpy(),
+             sqrt_one_minus_alphas_cumprod=ldm.sqrt_one_minus_alphas_cumprod.numpy(),
+             ddim_timesteps=np.asarray(smp.ddim_timesteps), ddim_alphas=np.asarray(smp.ddim_alphas),
+             ddim_alphas_prev=np.asarray(smp.ddim_alphas_prev), ddim_sigmas=np.asarray(smp.ddim_sigmas),
+             ddim_sqrt_one_minus_alphas=np.asarray(smp.ddim_sqrt_one_minus_alphas))
+
+    # ---- full-size key/shape inventory (meta device: no memory)
+    from ldm.models.autoencoder import AutoencoderKL
+    from ldm.modules.diffusionmodules.openaimodel import UNetModel
+    shapes = {}
+    with torch.device("meta"):
+        full = UNetModel(**unet_oracle.default_unet_config())
+        pbe = UNetModel(**unet_oracle.default_unet_config(use_lidar=False))
+        cam = AutoencoderKL(ddconfig=vae_oracle.default_ddconfig(False), lossconfig=dict(target="torch.nn.Identity"),
+                            embed_dim=4)
+        lid = AutoencoderKL(ddconfig=vae_oracle.default_ddconfig(True), lossconfig=dict(target="torch.nn.Identity"),
+                            embed_dim=4)
+    for name, m in (("unet_512", full), ("unet_pbe", pbe), ("vae_camera", cam), ("vae_lidar", lid)):
+        shapes[name] = {k: list(v.shape) for k, v in m.state_dict().items()}
+    with open(os.path.join(GOLDEN, "shapes_512.json"), "w") as fh:
+        json.dump(shapes, fh, indent=0, sort_keys=True)
+    print("unet_512 tensors:", len(shapes["unet_512"]), "params:",
+          sum(int(np.prod(s)) for s in shapes["unet_512"].values()))
+
+
+if __name__ == "__main__":
+    main()
