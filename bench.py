@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py — MObI joint camera+lidar inpainting throughput on B200 (contract: see the task brief).
+
+One "step" = one full 50-step DDIM sampling run with classifier-free guidance of a batch of joint samples at the
+mobi_nusc_512 shape (latent 64x64; 2 UNet rows per joint sample, 4 with CFG).  Work is sharded over GPUs by
+sample (no collective on the data path): every rank samples `--samples-per-gpu` joint samples, so the 8-GPU run
+is config[2] of BASELINE.json (batch 64 over 8 B200) and scaling is weak.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--samples-per-gpu 8] [--latent 64] [--ddim-steps 50]
+  python bench.py --impl reference ...     # the reference algorithm (oracle port) on the host CPU cores
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+# SURVEY.md §8(d) / BASELINE.md §2: algorithmic FLOPs of the REFERENCE forward per joint sample (2 rows), no CFG
+UNET_FLOPS_PER_JOINT = {64: 2043895808000, 32: 419359047680}
+CFG_SCALE = 5.0
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="native", choices=["native", "reference"])
+    ap.add_argument("--samples-per-gpu", type=int, default=8)
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--ddim-steps", type=int, default=50)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    return ap.parse_args()
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clocks and throttle reasons with nvidia-smi while the timed region runs."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+        self.proc = None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workload_name(args):
+    return ("mobi_nusc_512" if args.latent == 64 else "mobi_nusc_256") + \
+        " %d-step DDIM + CFG %.1f joint camera+lidar inpainting, %d joint samples/GPU" % (
+            args.ddim_steps, CFG_SCALE, args.samples_per_gpu)
+
+
+# ---------------------------------------------------------------------------------------------- reference arm
+def cpu_reference_step(latent, threads, n_joint=1, repeats=1):
+    """The reference algorithm (oracle port: oracle/unet_oracle.py + sampler_oracle.py) on the host CPU, fp32, all
+    cores: ONE DDIM step with CFG of `n_joint` joint samples (4 rows each).  Returns seconds per step."""
+    import torch
+    from oracle import sampler_oracle as so
+    from oracle import unet_oracle as uo
+    torch.set_num_threads(threads)
+    cfg = uo.default_unet_config(image_size=latent)
+    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
+    inp = uo.synth_inputs(n_joint, latent, seed=1)
+    sched = so.register_schedule()
+    apply_model = lambda x, t, c: uo.unet_forward(sd, cfg, x, t, c)
+    times = []
+    with torch.no_grad():
+        for _ in range(repeats):
+            t0 = time.perf_counter()
+            so.ddim_sample(apply_model, sched, 50, inp["x_T"], inp["cond"], inp["uc"], CFG_SCALE, inp["inpaint_image"],
+                           inp["inpaint_mask"], steps_to_run=1)
+            times.append(time.perf_counter() - t0)
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    threads = os.cpu_count() or 1
+    # bounded sample: each bench "step" is ONE DDIM step (one CFG UNet evaluation) of ONE joint sample at the
+    # workload's latent size; samples/s = 1 / (ddim_steps * seconds per DDIM step)
+    times = cpu_reference_step(args.latent, threads, 1, repeats=args.warmup + args.steps)[args.warmup:]
+    sec = sum(times) / len(times)
+    value = 1.0 / (args.ddim_steps * sec)
+    sample = "1 DDIM step (CFG UNet call, 4 rows) of 1 joint sample at latent %d, fp32, x%d => /%d steps" % (
+        args.latent, args.ddim_steps, args.ddim_steps)
+    line = {"impl": "reference", "metric": "inpainted joint samples/sec (50-step DDIM + CFG)", "value": value,
+            "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": sec * 1e3 * args.ddim_steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": workload_name(args), "inputs": "larger than L2 (4.2 GB fp32 weights)"},
+            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- native arm
+def run_native(args):
+    import torch
+    import torch.distributed as dist
+    from mobi_b200 import ops, synth
+    from mobi_b200.ddim import DDIMSampler
+
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py: no CUDA device; the native arm has no CPU fallback")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.samples_per_gpu
+    latent = args.latent
+    ldm = synth.build_synthetic_ldm(latent=latent, device=dev, seed=0)
+    sampler = DDIMSampler(ldm, use_cuda_graph=not args.no_graph)
+    # per-rank inputs: sample index = rank * n + i  (results do not depend on the sharding)
+    host = synth.synthetic_inputs(n, latent, seed=1 + rank, pin=True)
+    devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
+    host_out = torch.empty((2 * n, 4, latent, latent), dtype=torch.float32).pin_memory()
+
+    def sample_from(inp):
+        return sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=2 * n, shape=[4, latent, latent],
+                              verbose=False, unconditional_guidance_scale=CFG_SCALE,
+                              unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
+                              test_model_kwargs=dict(inpaint_image=inp["inpaint_image"],
+                                                     inpaint_mask=inp["inpaint_mask"]))[0]
+
+    def step_device():
+        return sample_from(devin)
+
+    def step_e2e():
+        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
+        out = sample_from(inp)
+        host_out.copy_(out, non_blocking=True)                                  # D2H of the result
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, k):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(k):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(args.warmup):
+        step_device()
+    clocks = ClockSampler(local)
+    clocks.start()
+    launches0, evals0 = ops.Stats.launches, sampler.launches
+    ms = timed(step_device, args.steps)
+    gpu_launches = ops.Stats.launches - launches0
+    unet_evals = sampler.launches - evals0
+    clock_info = clocks.finish()
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    total_samples = n * world * args.steps
+    value = total_samples / (ms / 1e3)
+    e2e_value = total_samples / (ms_e2e / 1e3)
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    d2h = host_out.numel() * host_out.element_size()
+
+    # ---- roofline of the dominant kernel class (tcgen05 GEMM / implicit conv), timed live with CUDA events on
+    # the launching stream over one eager UNet evaluation of the same batch
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
+    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    roofline = None
+    if rank == 0:
+        x_in = torch.randn(4 * n, 9, latent, latent, device=dev)
+        t_in = torch.full((4 * n,), 481, device=dev, dtype=torch.long)
+        c_in = torch.cat([devin["uc"], devin["cond"]]).contiguous()
+        unet = ldm.model.diffusion_model
+        unet(x_in, t_in, context=c_in)
+        torch.cuda.synchronize()
+        ops.Stats.begin_profile()
+        unet(x_in, t_in, context=c_in)
+        prof = ops.Stats.end_profile()
+        tc_ms = sum(prof[k]["ms"] for k in ("gemm", "conv") if k in prof)
+        tc_fl = sum(prof[k]["flops"] for k in ("gemm", "conv") if k in prof)
+        tc_n = sum(prof[k]["launches"] for k in ("gemm", "conv") if k in prof)
+        all_ms = sum(v["ms"] for v in prof.values())
+        achieved = tc_fl / (tc_ms / 1e3) / 1e12
+        step_flops = UNET_FLOPS_PER_JOINT.get(latent, 0) * 2 * n   # x2: CFG doubles the rows
+        ms_unet = ms / args.steps / max(1, unet_evals // args.steps)
+        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
+                    "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "peak_source": peak_src, "traffic": None,
+                    "launches_per_unet_call": tc_n, "flops_per_launch_avg": tc_fl / max(1, tc_n),
+                    "ms_per_launch_avg": tc_ms / max(1, tc_n),
+                    "share_of_unet_time": tc_ms / all_ms if all_ms else None,
+                    "by_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items())},
+                    "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12)
+                    if "attention" in prof else None,
+                    "unet_step_ms": ms_unet,
+                    "unet_step_algorithmic_tflops": step_flops / (ms_unet / 1e3) / 1e12 if step_flops else None,
+                    "unet_step_frac_of_peak": step_flops / (ms_unet / 1e3) / 1e12 / peak_tf if step_flops else None}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        threads = os.cpu_count() or 1
+        t = cpu_reference_step(latent, threads, 1, repeats=1)[0]
+        cpu_baseline = {"value": 1.0 / (args.ddim_steps * t), "unit": "samples/s", "cores": threads, "kind": "port",
+                        "sample": "1 DDIM step (CFG UNet call, 4 rows) of 1 joint sample at latent %d, fp32 oracle "
+                                  "port, %.1f s, extrapolated x%d steps" % (latent, t, args.ddim_steps)}
+    line = {"metric": "inpainted joint samples/sec (50-step DDIM + CFG)", "value": value, "unit": "samples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16 operands, fp32 accumulate/norms/residuals", "data": "synthetic",
+            "config": {"workload": workload_name(args), "latent": latent, "rows_per_unet_call": 4 * n,
+                       "ddim_steps": args.ddim_steps, "cfg_scale": CFG_SCALE, "sharding": "samples/%d GPUs, no collective" % world,
+                       "l2": "inputs larger than L2 (2.1 GB bf16 weights streamed per UNet call)",
+                       "cuda_graph": not args.no_graph},
+            "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": gpu_launches, "unet_evals": unet_evals, "clocks": clock_info,
+            "roofline": roofline, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_native(args)
+
+
+if __name__ == "__main__":
+    main()

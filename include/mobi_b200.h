@@ -33,6 +33,7 @@ extern "C" {
 #define MOBI_EPI_HEADS 2   /* out[((m / tokens) * heads + n / d) , m % tokens, n % d]   (q, k)          */
 #define MOBI_EPI_HEADS_T 3 /* out[((m / tokens) * heads + n / d) , n % d, m % tokens]   (v transposed)  */
 #define MOBI_EPI_QKV 4     /* n / (heads*d) selects q (HEADS -> out), k (HEADS -> out2), v (HEADS_T -> out3) */
+#define MOBI_EPI_KV 5      /* n / (heads*d) selects k (HEADS -> out), v (HEADS_T -> out2)                     */
 
 const char* mobi_last_error(void);
 int mobi_version(void);
@@ -69,6 +70,10 @@ typedef struct {
     int32_t epilogue;
     int32_t act;           /* 0 = none, 1 = SiLU applied after bias (PLAIN only; time_embed, openaimodel.py:627-631) */
     int32_t heads, head_dim, tokens;
+    /* PLAIN only: output (and residual) row of GEMM row m is (m / out_seg) * out_seg_stride + out_seg_offset +
+     * m % out_seg; out_seg = 0 means identity.  Writes the camera-only / lidar-only token rows of the
+     * interleaved batch in place (attention.py:246-263). */
+    int64_t out_seg, out_seg_stride, out_seg_offset;
     /* implicit conv */
     int32_t conv;
     int32_t n_img, H, W, C, KH, KW, pad_h, pad_w;
@@ -110,7 +115,7 @@ typedef struct {
     const float* gamma;
     const float* beta;
     void* out;        /* bf16 [N, HW, C] */
-    void* out_concat; /* optional: the raw concatenation in in_dtype, [N, HW, C] (NULL to skip) */
+    void* out_concat; /* optional: the raw (un-normalised) concatenation as bf16 [N, HW, C] (NULL to skip) */
     float* partials;
     int32_t n_img, hw, c1, c2, groups;
     int32_t in_dtype;
@@ -224,7 +229,7 @@ typedef struct {
     float* x;               /* [B,4,H,W]; updated in place when blend_mask != NULL */
     const float* inpaint_image; /* [B,4,H,W] */
     const float* inpaint_mask;  /* [B,1,H,W] */
-    const float* blend_mask;    /* [B,1,H,W] or [B,4,H,W]? -> broadcast over channel when blend_c == 1 */
+    const float* blend_mask;    /* [B, blend_c, H, W], blend_c = 1 (broadcast over channels) or 4; NULL = no blend */
     const float* blend_x0;
     const float* blend_noise;
     float* x_in; /* [(cfg?2:1)*B, 9, H, W] */

@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmobi_b200.so")
 
 DT_BF16, DT_F32 = 0, 1
-EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV = 0, 1, 2, 3, 4
+EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV, EPI_KV = 0, 1, 2, 3, 4, 5
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -25,6 +25,7 @@ class GemmArgs(C.Structure):
         ("rows_per_group", _i64), ("ld_row_bias", _i64),
         ("out_dtype", _i32), ("res_dtype", _i32), ("epilogue", _i32), ("act", _i32),
         ("heads", _i32), ("head_dim", _i32), ("tokens", _i32),
+        ("out_seg", _i64), ("out_seg_stride", _i64), ("out_seg_offset", _i64),
         ("conv", _i32), ("n_img", _i32), ("H", _i32), ("W", _i32), ("C", _i32),
         ("KH", _i32), ("KW", _i32), ("pad_h", _i32), ("pad_w", _i32), ("tile_n", _i32),
     ]

@@ -37,6 +37,7 @@ struct GemmParams {
     int mode;
     int act;
     int heads, head_dim, tokens;
+    long long out_seg, out_seg_stride, out_seg_offset;
 };
 
 constexpr int BM = 128;
@@ -56,7 +57,7 @@ __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + e
 // Stores 8 consecutive output columns [n0, n0+8) of row m.  v already has bias etc. applied.
 __device__ __forceinline__ void store8(const GemmParams& p, long long m, int n0, const float (&v)[8]) {
     if (p.mode == MOBI_EPI_PLAIN) {
-        const long long off = m * p.ldo + n0;
+        const long long off = m * p.ldo + n0;  // m is already the (remapped) output row
         const bool full = (n0 + 8 <= p.N);
         if (p.out_f32) {
             float* o = reinterpret_cast<float*>(p.out) + off;
@@ -90,10 +91,11 @@ __device__ __forceinline__ void store8(const GemmParams& p, long long m, int n0,
     const int inner = p.heads * p.head_dim;
     int which = 0, n = n0;
     int mode = p.mode;
-    if (mode == MOBI_EPI_QKV) {
+    if (mode == MOBI_EPI_QKV || mode == MOBI_EPI_KV) {
         which = n0 / inner;
         n = n0 - which * inner;
-        mode = (which == 2) ? MOBI_EPI_HEADS_T : MOBI_EPI_HEADS;
+        const int last = (mode == MOBI_EPI_QKV) ? 2 : 1;
+        mode = (which == last) ? MOBI_EPI_HEADS_T : MOBI_EPI_HEADS;
     }
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
     const int h = n / p.head_dim;
@@ -214,6 +216,10 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(accum_bar, 0);
         tc_fence_after();
         const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
+        // output row: identity, or gathered segments (camera-only / lidar-only rows of the interleaved batch)
+        const long long mo = (p.out_seg > 0 && p.mode <= MOBI_EPI_GEGLU)
+                                 ? (m / p.out_seg) * p.out_seg_stride + p.out_seg_offset + (m % p.out_seg)
+                                 : m;
 #pragma unroll 1
         for (int c = 0; c < BN; c += 16) {
             uint32_t r[16];
@@ -247,11 +253,11 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 GemmParams q = p;
                 q.mode = MOBI_EPI_PLAIN;
                 q.N = p.N / 2;
-                store8(q, m, n0 / 2, o);
+                store8(q, mo, n0 / 2, o);
                 continue;
             }
             if (p.residual) {
-                const long long off = m * p.ldo + n0;
+                const long long off = mo * p.ldo + n0;
                 if (p.res_f32) {
                     const float* rs = reinterpret_cast<const float*>(p.residual) + off;
 #pragma unroll
@@ -270,8 +276,8 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 lo[j] = v[j];
                 hi[j] = v[8 + j];
             }
-            store8(p, m, n0, lo);
-            store8(p, m, n0 + 8, hi);
+            store8(p, mo, n0, lo);
+            store8(p, mo, n0 + 8, hi);
         }
     }
     tc_fence_before();
@@ -327,7 +333,10 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     p.heads = a->heads;
     p.head_dim = a->head_dim;
     p.tokens = a->tokens;
-    MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_QKV, "mobi_gemm: bad epilogue %d", p.mode);
+    p.out_seg = a->out_seg;
+    p.out_seg_stride = a->out_seg_stride;
+    p.out_seg_offset = a->out_seg_offset;
+    MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_KV, "mobi_gemm: bad epilogue %d", p.mode);
     if (p.mode == MOBI_EPI_GEGLU) {
         MOBI_CHECK(a->N % 16 == 0, "mobi_gemm: GEGLU needs N %% 16 == 0 (N=%lld)", (long long)a->N);
         MOBI_CHECK(a->residual == nullptr, "mobi_gemm: GEGLU epilogue takes no residual");
@@ -336,11 +345,12 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         MOBI_CHECK(p.heads > 0 && p.head_dim > 0 && p.tokens > 0 && p.head_dim % 8 == 0,
                    "mobi_gemm: head layouts need heads, head_dim %% 8 == 0, tokens");
         const long long inner = (long long)p.heads * p.head_dim;
-        MOBI_CHECK(a->N == (p.mode == MOBI_EPI_QKV ? 3 * inner : inner), "mobi_gemm: N=%lld does not match heads*d",
-                   (long long)a->N);
+        const long long parts = p.mode == MOBI_EPI_QKV ? 3 : (p.mode == MOBI_EPI_KV ? 2 : 1);
+        MOBI_CHECK(a->N == parts * inner, "mobi_gemm: N=%lld does not match heads*d", (long long)a->N);
         MOBI_CHECK(a->M % p.tokens == 0, "mobi_gemm: M must be a multiple of tokens");
         MOBI_CHECK(a->out_dtype == MOBI_DTYPE_BF16 && a->residual == nullptr, "mobi_gemm: head layouts are bf16");
         if (p.mode == MOBI_EPI_QKV) MOBI_CHECK(a->out2 && a->out3, "mobi_gemm: QKV needs out2/out3");
+        if (p.mode == MOBI_EPI_KV) MOBI_CHECK(a->out2 != nullptr, "mobi_gemm: KV needs out2");
     }
 
     CUtensorMap tmA, tmB;

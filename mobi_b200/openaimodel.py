@@ -1,0 +1,375 @@
+"""B200-native drop-in for ldm/modules/diffusionmodules/openaimodel.py: UNetModel, ResBlock, Upsample,
+Downsample, TimestepEmbedSequential with the reference's constructor arguments and state-dict keys
+(so `unet_config.target: mobi_b200.openaimodel.UNetModel` works in the reference YAMLs and reference
+checkpoints load with load_state_dict).  forward() takes/returns NCHW fp32 like the reference; inside, the
+feature maps are fp32 NHWC, GEMM/conv operands bf16, and all math runs in the C-ABI CUDA library.
+"""
+import torch
+import torch.nn as nn
+
+from . import ops
+from .attention import SpatialTransformer, _bf16, _f32, zero_module
+from .packing import pack_conv_weight
+
+
+class GroupNorm32(nn.GroupNorm):
+    """ldm/modules/diffusionmodules/util.py:214-216 (parameter container; eps 1e-5, fp32 statistics)."""
+
+
+def normalization(channels):
+    return GroupNorm32(32, channels)
+
+
+class TimestepBlock(nn.Module):
+    pass
+
+
+class Conv3x3(nn.Module):
+    """Runs an nn.Conv2d (3x3 or (1,5), stride 1 'same', or stride 2) that lives in `conv` on NHWC input."""
+
+    @staticmethod
+    def pack(conv):
+        o, i, kh, kw = conv.weight.shape
+        k = kh * kw * i
+        kpad = (k + 7) // 8 * 8
+        return dict(w=pack_conv_weight(conv.weight.detach().float(), kpad), b=_f32(conv.bias), kh=kh, kw=kw, cin=i,
+                    cout=o, stride=conv.stride[0], pad=(conv.padding[0], conv.padding[1]))
+
+    @staticmethod
+    def run(p, x, *, row_bias=None, residual=None, out_dtype=torch.float32, pad_override=None):
+        """x: NHWC (bf16 for the implicit path; f32 or bf16 for the im2col path)."""
+        n, h, w, c = x.shape
+        kh, kw, stride = p["kh"], p["kw"], p["stride"]
+        ph, pw = p["pad"]
+        if stride == 1 and pad_override is None and x.dtype == torch.bfloat16 and ops.conv_implicit_ok(h, w, c) \
+                and p["w"].shape[1] == kh * kw * c:
+            return ops.conv_implicit(x, p["w"], kh, kw, ph, pw, bias=p["b"], row_bias=row_bias, residual=residual,
+                                     out_dtype=out_dtype)
+        if pad_override is not None:  # VAE Downsample: pad (0,1,0,1) then a valid stride-2 conv (model.py:72-76)
+            pt, pl, pb, pr = pad_override
+        else:
+            pt = pb = ph
+            pl = pr = pw
+        ho = (h + pt + pb - kh) // stride + 1
+        wo = (w + pl + pr - kw) // stride + 1
+        cols = ops.im2col(x, kh, kw, stride, pt, pl, ho, wo)
+        out = ops.gemm(cols, p["w"], bias=p["b"], row_bias=row_bias, rows_per_group=ho * wo,
+                       residual=None if residual is None else residual.reshape(n * ho * wo, p["cout"]),
+                       out_dtype=out_dtype)
+        return out.reshape(n, ho, wo, p["cout"])
+
+
+class Upsample(nn.Module):
+    """openaimodel.py:91-119 (dims=2)."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        assert dims == 2
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        if use_conv:
+            self.conv = nn.Conv2d(self.channels, self.out_channels, 3, padding=padding)
+        self._p = None
+
+    def pack(self):
+        self._p = Conv3x3.pack(self.conv) if self.use_conv else {}
+
+    def run(self, h):
+        assert h.shape[-1] == self.channels
+        if not self.use_conv:
+            return ops.upsample_nearest2x(h)
+        up = ops.upsample_nearest2x(h, torch.bfloat16)
+        return Conv3x3.run(self._p, up)
+
+    def forward(self, x):
+        if self._p is None:
+            self.pack()
+        return ops.nhwc_to_nchw(self.run(ops.nchw_to_nhwc(x.detach().float().contiguous())))
+
+
+class Downsample(nn.Module):
+    """openaimodel.py:134-160 (dims=2, use_conv=True: conv3x3 stride 2 pad 1)."""
+
+    def __init__(self, channels, use_conv, dims=2, out_channels=None, padding=1):
+        super().__init__()
+        assert dims == 2
+        if not use_conv:
+            raise NotImplementedError("mobi_b200.Downsample: avg-pool variant is not on the hot path")
+        self.channels = channels
+        self.out_channels = out_channels or channels
+        self.use_conv = use_conv
+        self.dims = dims
+        self.op = nn.Conv2d(self.channels, self.out_channels, 3, stride=2, padding=padding)
+        self._p = None
+
+    def pack(self):
+        self._p = Conv3x3.pack(self.op)
+
+    def run(self, h):
+        assert h.shape[-1] == self.channels
+        return Conv3x3.run(self._p, h)
+
+    def forward(self, x):
+        if self._p is None:
+            self.pack()
+        return ops.nhwc_to_nchw(self.run(ops.nchw_to_nhwc(x.detach().float().contiguous())))
+
+
+class ResBlock(TimestepBlock):
+    """openaimodel.py:163-275 with use_scale_shift_norm=False, up=down=False, use_conv=False (every config)."""
+
+    def __init__(self, channels, emb_channels, dropout, out_channels=None, use_conv=False,
+                 use_scale_shift_norm=False, dims=2, use_checkpoint=False, up=False, down=False):
+        super().__init__()
+        if use_scale_shift_norm or up or down or use_conv or dims != 2:
+            raise NotImplementedError("mobi_b200.ResBlock: only the configuration used by MObI's configs is built")
+        self.channels = channels
+        self.emb_channels = emb_channels
+        self.dropout = dropout
+        self.out_channels = out_channels or channels
+        self.in_layers = nn.Sequential(normalization(channels), nn.SiLU(),
+                                       nn.Conv2d(channels, self.out_channels, 3, padding=1))
+        self.emb_layers = nn.Sequential(nn.SiLU(), nn.Linear(emb_channels, self.out_channels))
+        self.out_layers = nn.Sequential(normalization(self.out_channels), nn.SiLU(), nn.Dropout(p=dropout),
+                                        zero_module(nn.Conv2d(self.out_channels, self.out_channels, 3, padding=1)))
+        if self.out_channels == channels:
+            self.skip_connection = nn.Identity()
+        else:
+            self.skip_connection = nn.Conv2d(channels, self.out_channels, 1)
+        self._p = None
+
+    def pack(self):
+        p = dict(gn1=(_f32(self.in_layers[0].weight), _f32(self.in_layers[0].bias)),
+                 gn2=(_f32(self.out_layers[0].weight), _f32(self.out_layers[0].bias)),
+                 conv1=Conv3x3.pack(self.in_layers[2]), conv2=Conv3x3.pack(self.out_layers[3]))
+        if not isinstance(self.skip_connection, nn.Identity):
+            p["w_skip"] = _bf16(self.skip_connection.weight.reshape(self.out_channels, self.channels))
+            p["b_skip"] = _f32(self.skip_connection.bias)
+        self._p = p
+
+    def run(self, h, emb_out, skip=None):
+        """h: f32 NHWC [R,H,W,C1]; skip: optional second input concatenated on channels (openaimodel.py:892);
+        emb_out: f32 [R, out_channels] view = emb_layers(emb) (computed for all blocks at once by the UNet)."""
+        p = self._p
+        R, Hh, Ww, _ = h.shape
+        need_raw = "w_skip" in p
+        g = ops.groupnorm(h, p["gn1"][0], p["gn1"][1], 1e-5, x2=skip, silu=True, want_concat=need_raw)
+        hn, raw = g if need_raw else (g, None)
+        h1 = Conv3x3.run(p["conv1"], hn, row_bias=emb_out)                       # conv + bias + emb (255-272)
+        hn2 = ops.groupnorm(h1, p["gn2"][0], p["gn2"][1], 1e-5, silu=True)
+        if need_raw:
+            res = ops.gemm(raw.reshape(R * Hh * Ww, -1), p["w_skip"], bias=p["b_skip"], out_dtype=torch.float32)
+            res = res.reshape(R, Hh, Ww, self.out_channels)
+        else:
+            assert skip is None
+            res = h
+        return Conv3x3.run(p["conv2"], hn2, residual=res)                        # skip_connection(x) + h (275)
+
+    def forward(self, x, emb):
+        """Reference signature: x NCHW, emb [N, emb_channels] -> NCHW."""
+        if self._p is None:
+            self.pack()
+        e = ops.silu(emb.detach().float().contiguous())
+        emb_out = ops.gemm(e, _bf16(self.emb_layers[1].weight), bias=_f32(self.emb_layers[1].bias),
+                           out_dtype=torch.float32)
+        return ops.nhwc_to_nchw(self.run(ops.nchw_to_nhwc(x.detach().float().contiguous()), emb_out))
+
+
+class TimestepEmbedSequential(nn.Sequential, TimestepBlock):
+    """openaimodel.py:74-88."""
+
+    def forward(self, x, emb, context=None):
+        for layer in self:
+            if isinstance(layer, TimestepBlock):
+                x = layer(x, emb)
+            elif isinstance(layer, SpatialTransformer):
+                x = layer(x, context)
+            else:
+                x = layer(x)
+        return x
+
+
+class UNetModel(nn.Module):
+    """openaimodel.py:528-898, for use_spatial_transformer=True (every MObI / PbE config)."""
+
+    def __init__(self, image_size, in_channels, model_channels, out_channels, num_res_blocks, attention_resolutions,
+                 dropout=0, channel_mult=(1, 2, 4, 8), conv_resample=True, dims=2, num_classes=None,
+                 use_checkpoint=False, use_fp16=False, num_heads=-1, num_head_channels=-1, num_heads_upsample=-1,
+                 use_scale_shift_norm=False, resblock_updown=False, use_new_attention_order=False,
+                 use_spatial_transformer=False, transformer_depth=1, context_dim=None, n_embed=None, legacy=True,
+                 add_conv_in_front_of_unet=False, bbox_cond=False, use_camera=True, use_lidar=False):
+        super().__init__()
+        if not use_spatial_transformer or context_dim is None:
+            raise NotImplementedError("mobi_b200.UNetModel needs use_spatial_transformer=True and a context_dim")
+        if num_classes is not None or n_embed is not None or add_conv_in_front_of_unet or resblock_updown \
+                or use_scale_shift_norm or dims != 2 or not conv_resample:
+            raise NotImplementedError("mobi_b200.UNetModel: option outside MObI's shipped configs")
+        if isinstance(context_dim, (list, tuple)) or type(context_dim).__name__ == "ListConfig":
+            context_dim = list(context_dim)
+        if num_heads_upsample == -1:
+            num_heads_upsample = num_heads
+        if num_heads == -1:
+            assert num_head_channels != -1, "Either num_heads or num_head_channels has to be set"
+        self.image_size = image_size
+        self.in_channels = in_channels
+        self.model_channels = model_channels
+        self.out_channels = out_channels
+        self.num_res_blocks = num_res_blocks
+        self.attention_resolutions = list(attention_resolutions)
+        self.dropout = dropout
+        self.channel_mult = list(channel_mult)
+        self.conv_resample = conv_resample
+        self.num_classes = num_classes
+        self.use_checkpoint = use_checkpoint
+        self.dtype = torch.float32
+        self.num_heads = num_heads
+        self.num_head_channels = num_head_channels
+        self.num_heads_upsample = num_heads_upsample
+        self.predict_codebook_ids = False
+        self.add_conv_in_front_of_unet = False
+        self.use_camera = use_camera
+        self.use_lidar = use_lidar
+        self.multimodal = bool(use_camera and use_lidar)
+
+        time_embed_dim = model_channels * 4
+        self.time_embed = nn.Sequential(nn.Linear(model_channels, time_embed_dim), nn.SiLU(),
+                                        nn.Linear(time_embed_dim, time_embed_dim))
+
+        def heads_for(ch):
+            if num_head_channels == -1:
+                return num_heads, ch // num_heads
+            return ch // num_head_channels, num_head_channels
+
+        def st(ch):
+            nh, dh = heads_for(ch)
+            return SpatialTransformer(ch, nh, dh, depth=transformer_depth, context_dim=context_dim,
+                                      bbox_cond=bbox_cond, multimodal=self.multimodal)
+
+        self.input_blocks = nn.ModuleList(
+            [TimestepEmbedSequential(nn.Conv2d(in_channels, model_channels, 3, padding=1))])
+        input_block_chans = [model_channels]
+        ch = model_channels
+        ds = 1
+        for level, mult in enumerate(channel_mult):
+            for _ in range(num_res_blocks):
+                layers = [ResBlock(ch, time_embed_dim, dropout, out_channels=mult * model_channels)]
+                ch = mult * model_channels
+                if ds in attention_resolutions:
+                    layers.append(st(ch))
+                self.input_blocks.append(TimestepEmbedSequential(*layers))
+                input_block_chans.append(ch)
+            if level != len(channel_mult) - 1:
+                self.input_blocks.append(TimestepEmbedSequential(Downsample(ch, conv_resample, out_channels=ch)))
+                input_block_chans.append(ch)
+                ds *= 2
+        self.middle_block = TimestepEmbedSequential(ResBlock(ch, time_embed_dim, dropout), st(ch),
+                                                    ResBlock(ch, time_embed_dim, dropout))
+        self.output_blocks = nn.ModuleList([])
+        for level, mult in list(enumerate(channel_mult))[::-1]:
+            for i in range(num_res_blocks + 1):
+                ich = input_block_chans.pop()
+                layers = [ResBlock(ch + ich, time_embed_dim, dropout, out_channels=model_channels * mult)]
+                ch = model_channels * mult
+                if ds in attention_resolutions:
+                    layers.append(st(ch))
+                if level and i == num_res_blocks:
+                    layers.append(Upsample(ch, conv_resample, out_channels=ch))
+                    ds //= 2
+                self.output_blocks.append(TimestepEmbedSequential(*layers))
+        self.out = nn.Sequential(normalization(ch), nn.SiLU(),
+                                 zero_module(nn.Conv2d(model_channels, out_channels, 3, padding=1)))
+        self._p = None
+        self._ctx_key = None
+        self._ctx_tabs = None
+        self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
+
+    # ------------------------------------------------------------------ packing
+    def invalidate(self):
+        """Drop packed weights (call after changing parameters in place)."""
+        self._p = None
+        self._ctx_key = None
+        self._ctx_tabs = None
+
+    def _resblocks(self):
+        return [m for m in self.modules() if isinstance(m, ResBlock)]
+
+    def _transformers(self):
+        return [m for m in self.modules() if isinstance(m, SpatialTransformer)]
+
+    @torch.no_grad()
+    def pack(self):
+        for m in self.modules():
+            if m is not self and hasattr(m, "pack") and isinstance(m, (ResBlock, SpatialTransformer, Upsample, Downsample)):
+                m.pack()
+        rbs = self._resblocks()
+        # all 22 emb_layers Linears as ONE GEMM over silu(emb) (openaimodel.py:204-210, 264)
+        w_emb = torch.cat([rb.emb_layers[1].weight.detach().float() for rb in rbs], 0)
+        b_emb = torch.cat([rb.emb_layers[1].bias.detach().float() for rb in rbs], 0)
+        offs, o = [], 0
+        for rb in rbs:
+            offs.append(o)
+            o += rb.out_channels
+        self._p = dict(
+            w_t0=_bf16(self.time_embed[0].weight), b_t0=_f32(self.time_embed[0].bias),
+            w_t2=_bf16(self.time_embed[2].weight), b_t2=_f32(self.time_embed[2].bias),
+            w_emb=_bf16(w_emb), b_emb=_f32(b_emb), emb_offs={id(rb): off for rb, off in zip(rbs, offs)},
+            conv_in=Conv3x3.pack(self.input_blocks[0][0]),
+            gn_out=(_f32(self.out[0].weight), _f32(self.out[0].bias)), conv_out=Conv3x3.pack(self.out[2]))
+
+    @torch.no_grad()
+    def prepare_context(self, context):
+        """Context-only work (attn2 vectors, adapter tables): once per sampling run, not per step."""
+        if self._p is None:
+            self.pack()
+        ctx = context.detach().float().contiguous()
+        self._ctx_tabs = {id(t): t.context_tables(ctx) for t in self._transformers()}
+        self._ctx_key = (context.data_ptr(), context._version, tuple(context.shape))
+        return self._ctx_tabs
+
+    # ------------------------------------------------------------------ execution
+    def _run_block(self, seq, h, skip, emb_all):
+        for layer in seq:
+            if isinstance(layer, ResBlock):
+                off = self._p["emb_offs"][id(layer)]
+                h = layer.run(h, emb_all[:, off:off + layer.out_channels], skip=skip)
+                skip = None
+            elif isinstance(layer, SpatialTransformer):
+                h = layer.run(h, self._ctx_tabs[id(layer)])
+            elif isinstance(layer, (Upsample, Downsample)):
+                h = layer.run(h)
+            else:
+                raise RuntimeError("unexpected layer %s" % type(layer))
+        return h
+
+    @torch.no_grad()
+    def forward(self, x, timesteps=None, context=None, y=None, **kwargs):
+        """openaimodel.py:861-898.  x [R, in_ch, h, w] f32 NCHW, timesteps [R] int64, context [R, n, ctx]."""
+        assert y is None, "class-conditional UNet is not part of MObI"
+        if not x.is_cuda:
+            raise RuntimeError("mobi_b200.UNetModel runs on CUDA only (no CPU fallback)")
+        if self._p is None:
+            self.pack()
+        key = (context.data_ptr(), context._version, tuple(context.shape))
+        if self._ctx_key != key:
+            self.prepare_context(context)
+        p = self._p
+        t_emb = ops.timestep_embedding(timesteps.to(torch.int64).contiguous(), self.model_channels)
+        e1 = ops.gemm(t_emb, p["w_t0"], bias=p["b_t0"], act=1)                       # Linear + SiLU
+        e2 = ops.gemm(e1, p["w_t2"], bias=p["b_t2"], act=1)                          # Linear, then emb_layers' SiLU
+        emb_all = ops.gemm(e2, p["w_emb"], bias=p["b_emb"], out_dtype=torch.float32)  # [R, sum(out_channels)]
+
+        h = ops.nchw_to_nhwc(x.detach().float().contiguous())
+        hs = []
+        h = Conv3x3.run(p["conv_in"], h)
+        hs.append(h)
+        for seq in list(self.input_blocks)[1:]:
+            h = self._run_block(seq, h, None, emb_all)
+            hs.append(h)
+        h = self._run_block(self.middle_block, h, None, emb_all)
+        for seq in self.output_blocks:
+            h = self._run_block(seq, h, hs.pop(), emb_all)                           # cat([h, hs.pop()], 1)
+        hn = ops.groupnorm(h, p["gn_out"][0], p["gn_out"][1], 1e-5, silu=True)
+        eps = Conv3x3.run(p["conv_out"], hn)
+        return ops.nhwc_to_nchw(eps)

@@ -8,6 +8,49 @@ import torch
 from . import _lib as L
 
 
+class Stats:
+    """Launch accounting (every C-ABI call = the number of CUDA kernels it launches) and optional per-op CUDA-event
+    timing on the launching stream (bench.py's roofline leg)."""
+    launches = 0
+    records = None  # list of (kind, flops, bytes, ev_start, ev_end) when profiling
+
+    @classmethod
+    def begin_profile(cls):
+        cls.records = []
+
+    @classmethod
+    def end_profile(cls):
+        torch.cuda.synchronize()
+        out = {}
+        for kind, flops, nbytes, e0, e1 in cls.records:
+            d = out.setdefault(kind, dict(launches=0, flops=0.0, bytes=0.0, ms=0.0))
+            d["launches"] += 1
+            d["flops"] += flops
+            d["bytes"] += nbytes
+            d["ms"] += e0.elapsed_time(e1)
+        cls.records = None
+        return out
+
+
+class _timed:
+    def __init__(self, kind, flops=0.0, nbytes=0.0, kernels=1):
+        self.kind, self.flops, self.nbytes, self.kernels = kind, flops, nbytes, kernels
+
+    def __enter__(self):
+        Stats.launches += self.kernels
+        if Stats.records is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *exc):
+        if Stats.records is not None and exc[0] is None:
+            e1 = torch.cuda.Event(enable_timing=True)
+            e1.record()
+            Stats.records.append((self.kind, self.flops, self.nbytes, self.e0, e1))
+        return False
+
+
 def _cuda(*ts):
     for t in ts:
         if t is None:
@@ -18,35 +61,53 @@ def _cuda(*ts):
             raise RuntimeError("mobi_b200 ops need contiguous tensors, got strides %s" % (t.stride(),))
 
 
+def _rows_view(t, what):
+    """Checks that `t` is a CUDA matrix view (unit inner stride, uniform row stride) and returns its row stride."""
+    if not t.is_cuda:
+        raise RuntimeError("mobi_b200 ops need CUDA tensors (no CPU fallback)")
+    if t.stride(-1) != 1:
+        raise RuntimeError("mobi_b200.gemm: %s must have a unit inner stride, got %s" % (what, t.stride(),))
+    if t.dim() == 1:
+        return t.shape[0]
+    ld = t.stride(-2)
+    for d in range(t.dim() - 2):  # leading dims must collapse onto the row dim
+        if t.shape[d] != 1 and t.stride(d) != t.stride(d + 1) * t.shape[d + 1]:
+            raise RuntimeError("mobi_b200.gemm: %s rows are not uniformly strided: %s" % (what, t.stride(),))
+    return ld
+
+
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
-         tile_n=0, M=None, lda=None, ldo=None):
+         tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
-    Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.
+    Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
+    may be column slices of wider matrices (row strides are taken from the views or given explicitly).
     """
-    _cuda(a, w, bias, residual, out, out2, out3)
+    _cuda(bias, out2, out3)
     if row_bias is not None:  # may be a column slice of a wider matrix (ld_row_bias = its row stride)
         assert row_bias.is_cuda and row_bias.stride(-1) == 1
         if ld_row_bias == 0 and row_bias.dim() == 2:
             ld_row_bias = row_bias.stride(0)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "gemm operands must be bf16"
-    K = w.shape[1]
+    lda_v = _rows_view(a, "a")
+    ldb_v = _rows_view(w, "w")
+    lda = lda_v if lda is None else lda
+    ldb = ldb_v if ldb is None else ldb
+    K = w.shape[1] if K is None else K
     N = w.shape[0]
     if M is None:
         M = a.numel() // a.shape[-1]
-    lda = a.shape[-1] if lda is None else lda
-    assert a.shape[-1] == K or lda is not None
-    if epilogue == L.EPI_PLAIN:
+    if epilogue in (L.EPI_PLAIN, L.EPI_GEGLU):
+        n_out = N if epilogue == L.EPI_PLAIN else N // 2
         if out is None:
-            out = torch.empty((M, N), device=a.device, dtype=out_dtype)
-        ldo_v = N if ldo is None else ldo
-    elif epilogue == L.EPI_GEGLU:
-        if out is None:
-            out = torch.empty((M, N // 2), device=a.device, dtype=torch.bfloat16)
-        ldo_v = N // 2 if ldo is None else ldo
+            out = torch.empty((M, n_out), device=a.device, dtype=out_dtype if epilogue == L.EPI_PLAIN else torch.bfloat16)
+        ldo_v = _rows_view(out, "out") if ldo is None else ldo
+        if residual is not None and residual is not out:
+            assert _rows_view(residual, "residual") == ldo_v, "residual must share the output row stride"
     else:
         assert out is not None, "head layouts need preallocated outputs"
+        _cuda(out)
         ldo_v = 0
     args = L.GemmArgs()
     args.A, args.B, args.out = a.data_ptr(), w.data_ptr(), out.data_ptr()
@@ -57,15 +118,17 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
         assert row_bias.dtype == torch.float32
     args.bias, args.row_bias, args.residual = L.ptr(bias), L.ptr(row_bias), L.ptr(residual)
     args.M, args.N, args.K = M, N, K
-    args.lda, args.ldb, args.ldo = lda, w.stride(0), ldo_v
+    args.lda, args.ldb, args.ldo = lda, ldb, ldo_v
     args.rows_per_group, args.ld_row_bias = rows_per_group, ld_row_bias
     args.out_dtype = L.dt(out)
     args.res_dtype = L.dt(residual) if residual is not None else L.DT_F32
     args.epilogue, args.act = epilogue, act
     args.heads, args.head_dim, args.tokens = heads, head_dim, tokens
+    args.out_seg, args.out_seg_stride, args.out_seg_offset = out_seg, out_seg_stride, out_seg_offset
     args.conv = 0
     args.tile_n = tile_n
-    L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
+    with _timed("gemm", 2.0 * M * N * K):
+        L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
     return out
 
 
@@ -99,7 +162,8 @@ def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_ro
     args.conv, args.n_img, args.H, args.W, args.C = 1, n, h, wd, c
     args.KH, args.KW, args.pad_h, args.pad_w = kh, kw, pad_h, pad_w
     args.tile_n = tile_n
-    L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm(conv)")
+    with _timed("conv", 2.0 * n * h * wd * cout * kh * kw * c):
+        L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm(conv)")
     return out
 
 
@@ -125,7 +189,8 @@ def im2col(x, kh, kw, stride, pad_top, pad_left, ho, wo):
     a.x, a.out, a.in_dtype = x.data_ptr(), out.data_ptr(), L.dt(x)
     a.n, a.h, a.w, a.c, a.kh, a.kw = n, h, w, c, kh, kw
     a.stride, a.pad_top, a.pad_left, a.ho, a.wo, a.kpad = stride, pad_top, pad_left, ho, wo, kpad
-    L.check(L.load().mobi_im2col(C.byref(a), L.stream()), "im2col")
+    with _timed("im2col", 0.0, out.numel() * 2.0 + x.numel() * x.element_size()):
+        L.check(L.load().mobi_im2col(C.byref(a), L.stream()), "im2col")
     return out
 
 
@@ -139,7 +204,8 @@ def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None):
     a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
     a.batch, a.heads, a.head_dim, a.tq, a.tk = batch, heads, head_dim, tq, tk
     a.ld_out = heads * head_dim
-    L.check(L.load().mobi_attention(C.byref(a), L.stream()), "attention")
+    with _timed("attention", 4.0 * batch * heads * tq * tk * head_dim):
+        L.check(L.load().mobi_attention(C.byref(a), L.stream()), "attention")
     return out
 
 
@@ -163,7 +229,9 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_conca
     a.out, a.out_concat, a.partials = out.data_ptr(), L.ptr(cat), partials.data_ptr()
     a.n_img, a.hw, a.c1, a.c2, a.groups = n, hw, c1, c2, groups
     a.in_dtype, a.silu, a.eps = L.dt(x1), int(silu), eps
-    L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")
+    with _timed("groupnorm", 0.0, x1.numel() * x1.element_size() * 2 + (x2.numel() * x2.element_size() * 2 if x2 is not None else 0)
+                + out.numel() * 2 * (2 if want_concat else 1), kernels=2):
+        L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")
     return (out, cat) if want_concat else out
 
 
@@ -181,7 +249,8 @@ def layernorm(x, gamma, beta, *, rows=None, seg=0, seg_stride=0, seg_offset=0, a
     a.rows, a.C = rows, c
     a.seg, a.seg_stride, a.seg_offset, a.add_rows_per_vec = seg, seg_stride, seg_offset, add_rows_per_vec
     a.eps = eps
-    L.check(L.load().mobi_layernorm(C.byref(a), L.stream()), "layernorm")
+    with _timed("layernorm", 0.0, rows * c * (4 + 2 + (8 if add_vec is not None else 0))):
+        L.check(L.load().mobi_layernorm(C.byref(a), L.stream()), "layernorm")
     return out
 
 
@@ -189,6 +258,7 @@ def timestep_embedding(t, dim, max_period=10000.0):
     _cuda(t)
     assert t.dtype == torch.int64
     out = torch.empty((t.shape[0], dim), device=t.device, dtype=torch.bfloat16)
+    Stats.launches += 1
     L.check(L.load().mobi_timestep_embedding(t.data_ptr(), out.data_ptr(), t.shape[0], dim, max_period, L.stream()),
             "timestep_embedding")
     return out
@@ -197,6 +267,7 @@ def timestep_embedding(t, dim, max_period=10000.0):
 def silu(x):
     _cuda(x)
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    Stats.launches += 1
     L.check(L.load().mobi_silu(x.data_ptr(), L.dt(x), out.data_ptr(), x.numel(), L.stream()), "silu")
     return out
 
@@ -206,6 +277,7 @@ def nchw_to_nhwc(x, out_dtype=torch.float32):
     assert x.dtype == torch.float32
     n, c, h, w = x.shape
     out = torch.empty((n, h, w, c), device=x.device, dtype=out_dtype)
+    Stats.launches += 1
     L.check(L.load().mobi_nchw_to_nhwc(x.data_ptr(), out.data_ptr(), L.dt(out), n, c, h * w, L.stream()),
             "nchw_to_nhwc")
     return out
@@ -215,6 +287,7 @@ def nhwc_to_nchw(x):
     _cuda(x)
     n, h, w, c = x.shape
     out = torch.empty((n, c, h, w), device=x.device, dtype=torch.float32)
+    Stats.launches += 1
     L.check(L.load().mobi_nhwc_to_nchw(x.data_ptr(), L.dt(x), out.data_ptr(), n, c, h * w, L.stream()),
             "nhwc_to_nchw")
     return out
@@ -224,6 +297,7 @@ def upsample_nearest2x(x, out_dtype=None):
     _cuda(x)
     n, h, w, c = x.shape
     out = torch.empty((n, 2 * h, 2 * w, c), device=x.device, dtype=out_dtype or x.dtype)
+    Stats.launches += 1
     L.check(L.load().mobi_upsample_nearest2x(x.data_ptr(), L.dt(x), out.data_ptr(), L.dt(out), n, h, w, c,
                                              L.stream()), "upsample_nearest2x")
     return out
@@ -236,7 +310,8 @@ def ctx_attention(xn, U, Z, zb, x, batch, tokens, heads, keys):
     a = L.CtxAttnArgs()
     a.xn, a.U, a.Z, a.zb, a.x = xn.data_ptr(), U.data_ptr(), Z.data_ptr(), zb.data_ptr(), x.data_ptr()
     a.batch, a.tokens, a.C, a.heads, a.keys = batch, tokens, x.shape[-1], heads, keys
-    L.check(L.load().mobi_ctx_attention(C.byref(a), L.stream()), "ctx_attention")
+    with _timed("ctx_attention", 0.0, xn.numel() * 2.0 + x.numel() * 8.0):
+        L.check(L.load().mobi_ctx_attention(C.byref(a), L.stream()), "ctx_attention")
     return x
 
 
@@ -244,6 +319,7 @@ def add_f32(a, b, out=None):
     _cuda(a, b, out)
     if out is None:
         out = torch.empty_like(a)
+    Stats.launches += 1
     L.check(L.load().mobi_add_f32(a.data_ptr(), b.data_ptr(), out.data_ptr(), a.numel(), L.stream()), "add_f32")
     return out
 
@@ -252,6 +328,7 @@ def scale_f32(x, s, out=None):
     _cuda(x, out)
     if out is None:
         out = torch.empty_like(x)
+    Stats.launches += 1
     L.check(L.load().mobi_scale_f32(x.data_ptr(), float(s), out.data_ptr(), x.numel(), L.stream()), "scale_f32")
     return out
 
@@ -259,6 +336,7 @@ def scale_f32(x, s, out=None):
 def cast_bf16(x):
     _cuda(x)
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)
+    Stats.launches += 1
     L.check(L.load().mobi_cast_bf16(x.data_ptr(), out.data_ptr(), x.numel(), L.stream()), "cast_bf16")
     return out
 
@@ -280,6 +358,7 @@ def sampler_update(eps, x, *, cfg, scale, coefs, sqrt_one_minus_at, sqrt_at, sqr
     a.c0, a.c1, a.c2, a.c3 = cs
     a.sqrt_one_minus_at, a.sqrt_at, a.sqrt_a_prev, a.dir_coef, a.sigma_temp = (
         sqrt_one_minus_at, sqrt_at, sqrt_a_prev, dir_coef, sigma_temp)
+    Stats.launches += 1
     L.check(L.load().mobi_sampler_update(C.byref(a), L.stream()), "sampler_update")
     return x_prev, pred_x0
 
@@ -297,5 +376,6 @@ def assemble_input(x, rest_image, rest_mask, x_in, *, cfg, blend=None):
         _cuda(mask, x0, noise)
         a.blend_mask, a.blend_x0, a.blend_noise = mask.data_ptr(), x0.data_ptr(), noise.data_ptr()
         a.blend_c, a.sqrt_ac, a.sqrt_1mac = mask.shape[1], sa, s1
+    Stats.launches += 1
     L.check(L.load().mobi_assemble_input(C.byref(a), L.stream()), "assemble_input")
     return x_in

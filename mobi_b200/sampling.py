@@ -1,0 +1,162 @@
+"""Shared machinery of the DDIM / PLMS drop-in samplers: schedule buffers, the fused CUDA step
+(input assembly + CFG combine + x0 / x_prev update in two tiny kernels) and an optional CUDA graph of the
+UNet call, so the 50-step loop issues no Python-side tensor math at all.
+"""
+import numpy as np
+import torch
+
+from . import ops
+
+
+def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=True):
+    """ldm/modules/diffusionmodules/util.py:46-60."""
+    if ddim_discr_method == "uniform":
+        c = num_ddpm_timesteps // num_ddim_timesteps
+        ddim_timesteps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
+    elif ddim_discr_method == "quad":
+        ddim_timesteps = ((np.linspace(0, np.sqrt(num_ddpm_timesteps * .8), num_ddim_timesteps)) ** 2).astype(int)
+    else:
+        raise NotImplementedError(f'There is no ddim discretization method called "{ddim_discr_method}"')
+    steps_out = ddim_timesteps + 1
+    if verbose:
+        print(f"Selected timesteps for ddim sampler: {steps_out}")
+    return steps_out
+
+
+def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
+    """util.py:63-74.  alphacums: float32 numpy array; returns float32 (alphas) / float64 (alphas_prev, sigmas)
+    arrays exactly like the reference's mixed torch/numpy arithmetic."""
+    alphacums = np.asarray(alphacums, dtype=np.float32)
+    alphas = alphacums[ddim_timesteps]
+    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
+    if verbose:
+        print(f"Selected alphas for ddim sampler: a_t: {alphas}; a_(t-1): {alphas_prev}")
+        print(f"For the chosen value of eta, which is {eta}, "
+              f"this results in the following sigma_t schedule for ddim sampler {sigmas}")
+    return sigmas, alphas, alphas_prev
+
+
+class StepCoefficients:
+    """The four per-step scalars of ddim.py:195-212, evaluated in float32 like the reference's 0-d tensors."""
+
+    def __init__(self, alphas, alphas_prev, sqrt_one_minus_alphas, sigmas, index):
+        f = np.float32
+        a_t, a_prev, sigma_t = f(alphas[index]), f(alphas_prev[index]), f(sigmas[index])
+        self.sqrt_one_minus_at = float(f(sqrt_one_minus_alphas[index]))
+        self.sqrt_at = float(np.sqrt(a_t))
+        self.sqrt_a_prev = float(np.sqrt(a_prev))
+        self.dir_coef = float(np.sqrt(f(1.0) - a_prev - sigma_t * sigma_t))
+        self.sigma = float(sigma_t)
+
+
+class SamplerBase(object):
+    def __init__(self, model, schedule="linear", use_cuda_graph=None, **kwargs):
+        super().__init__()
+        self.model = model
+        self.ddpm_num_timesteps = model.num_timesteps
+        self.schedule = schedule
+        self.use_cuda_graph = use_cuda_graph
+        self._graph = None
+        self.launches = 0  # UNet evaluations issued (for bench accounting)
+
+    def register_buffer(self, name, attr):
+        """The reference forces .to("cuda") here (ddim.py:19-23); the drop-in follows the model's device."""
+        if type(attr) == torch.Tensor and attr.device != self.model.device:
+            attr = attr.to(self.model.device)
+        setattr(self, name, attr)
+
+    def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
+        """ddim.py:25-54 / plms.py:24-55."""
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
+                                                  num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
+        alphas_cumprod = self.model.alphas_cumprod
+        assert alphas_cumprod.shape[0] == self.ddpm_num_timesteps, "alphas have to be defined for each timestep"
+        to_torch = lambda x: x.clone().detach().to(torch.float32).to(self.model.device)
+        ac = alphas_cumprod.detach().cpu()
+        self.register_buffer("betas", to_torch(self.model.betas))
+        self.register_buffer("alphas_cumprod", to_torch(alphas_cumprod))
+        self.register_buffer("alphas_cumprod_prev", to_torch(self.model.alphas_cumprod_prev))
+        self.register_buffer("sqrt_alphas_cumprod", to_torch(np.sqrt(ac)))
+        self.register_buffer("sqrt_one_minus_alphas_cumprod", to_torch(np.sqrt(1. - ac)))
+        self.register_buffer("log_one_minus_alphas_cumprod", to_torch(np.log(1. - ac)))
+        self.register_buffer("sqrt_recip_alphas_cumprod", to_torch(np.sqrt(1. / ac)))
+        self.register_buffer("sqrt_recipm1_alphas_cumprod", to_torch(np.sqrt(1. / ac - 1)))
+        ddim_sigmas, ddim_alphas, ddim_alphas_prev = make_ddim_sampling_parameters(
+            alphacums=ac.numpy(), ddim_timesteps=self.ddim_timesteps, eta=ddim_eta, verbose=verbose)
+        # host-side copies (numpy): the step kernels take scalars, nothing is indexed on the device
+        self.ddim_sigmas = ddim_sigmas
+        self.ddim_alphas = ddim_alphas
+        self.ddim_alphas_prev = ddim_alphas_prev
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(np.float32(1.) - ddim_alphas)
+        self._sqrt_ac_host = np.sqrt(ac.numpy())
+        self._sqrt_1mac_host = np.sqrt(np.float32(1.) - ac.numpy())
+        acp = self.model.alphas_cumprod_prev.detach().cpu()
+        self.register_buffer("ddim_sigmas_for_original_num_steps", ddim_eta * torch.sqrt(
+            (1 - acp) / (1 - ac) * (1 - ac / acp)).to(self.model.device))
+
+    # ------------------------------------------------------------------ model evaluation
+    def _native_unet(self):
+        from .openaimodel import UNetModel
+        inner = getattr(getattr(self.model, "model", None), "diffusion_model", None)
+        return inner if isinstance(inner, UNetModel) else None
+
+    def _setup_eval(self, b, shape_rest, cond, uc, scale):
+        """Static buffers for one sampling run (and, for the native UNet, a CUDA graph of apply_model)."""
+        dev = self.model.device
+        self._cfg = not (uc is None or scale == 1.)
+        rows = 2 * b if self._cfg else b
+        self._x_in = torch.empty((rows,) + tuple(shape_rest), device=dev, dtype=torch.float32)
+        self._t_in = torch.empty((rows,), device=dev, dtype=torch.long)
+        if isinstance(cond, dict) or isinstance(cond, list):
+            raise NotImplementedError("mobi_b200 samplers take the conditioning as one [B, n, ctx] tensor")
+        self._c_in = torch.cat([uc, cond]).contiguous() if self._cfg else cond.contiguous()
+        self._graph = None
+        self._eps = None
+        unet = self._native_unet()
+        want_graph = self.use_cuda_graph if self.use_cuda_graph is not None else (unet is not None)
+        if unet is not None:
+            unet.prepare_context(self._c_in.float())
+        if want_graph and unet is not None and dev.type == "cuda":
+            self._t_in.fill_(1)
+            self._x_in.zero_()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                for _ in range(2):  # warm-up: lazy packing, cudaFuncSetAttribute, allocator pools
+                    self.model.apply_model(self._x_in, self._t_in, self._c_in)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = ops.Stats.launches
+            with torch.cuda.graph(g):
+                self._eps = self.model.apply_model(self._x_in, self._t_in, self._c_in)
+            self._graph_kernels = ops.Stats.launches - before  # kernels replayed per UNet evaluation
+            self._graph = g
+
+    def _eval_model(self, step):
+        """eps for the current self._x_in at timestep `step` ([uncond ; cond] rows under CFG)."""
+        self._t_in.fill_(int(step))
+        self.launches += 1
+        if self._graph is not None:
+            self._graph.replay()
+            ops.Stats.launches += self._graph_kernels
+            return self._eps
+        return self.model.apply_model(self._x_in, self._t_in, self._c_in).float().contiguous()
+
+    @staticmethod
+    def _rest_from_kwargs(kwargs):
+        if "test_model_kwargs" in kwargs:
+            kw = kwargs["test_model_kwargs"]
+            return kw["inpaint_image"].float().contiguous(), kw["inpaint_mask"].float().contiguous()
+        if "rest" in kwargs:
+            return kwargs["rest"].float().contiguous(), None
+        if "inpaint_image" in kwargs:
+            return kwargs["inpaint_image"].float().contiguous(), kwargs["inpaint_mask"].float().contiguous()
+        raise Exception("kwargs must contain either 'test_model_kwargs' or 'rest' key")
+
+    @staticmethod
+    def _check_unsupported(quantize_denoised, score_corrector, noise_dropout):
+        if quantize_denoised or score_corrector is not None or noise_dropout > 0.:
+            raise NotImplementedError(
+                "mobi_b200 samplers: quantize_denoised / score_corrector / noise_dropout are not used by MObI")

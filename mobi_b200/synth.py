@@ -1,0 +1,70 @@
+"""Synthetic weights and inputs for benchmarking (there is no network for checkpoints or nuScenes).
+
+Random init of the reference architecture is not usable as-is: `zero_module` (openaimodel.py:229-231, 836;
+attention.py:218-223, 296-300) makes a fresh UNet output exactly 0.  Every matrix/filter is therefore drawn
+N(0, 1/fan_in), biases N(0, 0.1^2), norm scales 1 + N(0, 0.1^2), on the device, from a seeded generator.
+"""
+import torch
+
+
+@torch.no_grad()
+def init_synthetic_(module, seed=0):
+    dev = next(module.parameters()).device
+    g = torch.Generator(device=dev).manual_seed(seed)
+    for name, p in module.named_parameters():
+        if p.dim() >= 2:
+            fan_in = p[0].numel()
+            p.copy_(torch.randn(p.shape, generator=g, device=dev) * fan_in ** -0.5)
+        elif name.endswith(".weight"):
+            p.copy_(1.0 + 0.1 * torch.randn(p.shape, generator=g, device=dev))
+        else:
+            p.copy_(0.1 * torch.randn(p.shape, generator=g, device=dev))
+    if hasattr(module, "invalidate"):
+        module.invalidate()
+    for m in module.modules():
+        if hasattr(m, "invalidate"):
+            m.invalidate()
+    return module
+
+
+def mobi_unet_config(latent=64, use_lidar=True):
+    """configs/mobi_nusc_512.yaml:62-81 (latent 64) / mobi_nusc_256.yaml (latent 32) / pbe.yaml (use_lidar False)."""
+    return dict(image_size=latent, in_channels=9, out_channels=4, model_channels=320, attention_resolutions=[4, 2, 1],
+                num_res_blocks=2, channel_mult=[1, 2, 4, 4], num_heads=8, use_spatial_transformer=True,
+                transformer_depth=1, context_dim=768, use_checkpoint=False, legacy=False,
+                add_conv_in_front_of_unet=False, bbox_cond=True, use_camera=True, use_lidar=use_lidar)
+
+
+def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_cfg=None):
+    from .ddpm import LatentDiffusion
+    cfg = unet_cfg or mobi_unet_config(latent, use_lidar)
+    with torch.device("meta"):
+        ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg),
+                              linear_start=0.00085, linear_end=0.0120, timesteps=1000, first_stage_key="inpaint",
+                              image_size=cfg["image_size"], channels=4, conditioning_key="crossattn",
+                              scale_factor=0.18215, lidar_scale_factor=0.18215, use_camera=True, use_lidar=use_lidar)
+    ldm = ldm.to_empty(device=device)
+    ldm.register_schedule(linear_start=0.00085, linear_end=0.0120, timesteps=1000)  # buffers were meta: rebuild
+    ldm = ldm.to(device)
+    init_synthetic_(ldm.model.diffusion_model, seed)
+    return ldm.eval()
+
+
+def synthetic_inputs(n_joint, latent, context_dim=768, seed=1, device="cpu", rows_per_sample=2, n_ctx=2, pin=False):
+    """x_T, inpaint_image ~ N(0,1); mask = 1 outside a centred ~20 % box; cond, uc ~ N(0,1)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    r = rows_per_sample * n_joint
+    x_T = torch.randn(r, 4, latent, latent, generator=g)
+    inpaint_image = torch.randn(r, 4, latent, latent, generator=g)
+    mask = torch.ones(r, 1, latent, latent)
+    side = max(1, int(round(latent * (0.2 ** 0.5))))
+    lo = (latent - side) // 2
+    mask[:, :, lo:lo + side, lo:lo + side] = 0.0
+    cond = torch.randn(r, n_ctx, context_dim, generator=g)
+    uc = torch.randn(1, n_ctx, context_dim, generator=g).repeat(r, 1, 1)
+    out = dict(x_T=x_T, inpaint_image=inpaint_image, inpaint_mask=mask, cond=cond, uc=uc)
+    if pin and torch.cuda.is_available():
+        out = {k: v.pin_memory() for k, v in out.items()}
+    if device != "cpu":
+        out = {k: v.to(device) for k, v in out.items()}
+    return out
