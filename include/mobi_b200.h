@@ -97,6 +97,7 @@ typedef struct {
     void* out;
     int32_t batch, heads, head_dim, tq, tk;
     int64_t ld_out; /* row stride of out in elements (>= heads*head_dim) */
+    int32_t kernel; /* 0 = choose (two-tile kernel for head_dim <= 128), 1 = force the one-tile kernel */
 } mobi_attn_args;
 
 int mobi_attention(const mobi_attn_args* args, void* stream);
@@ -148,6 +149,51 @@ typedef struct {
 } mobi_layernorm_args;
 
 int mobi_layernorm(const mobi_layernorm_args* args, void* stream);
+
+/*
+ * One pass over ALL token rows of the interleaved batch x f32 [batch, tokens, C]: with pair = 1, even batch rows
+ * (camera) take slot 0 and odd batch rows (lidar) slot 1 (attention.py:246-247); each slot has its own action
+ * (mode 0 = skip, 1 = LayerNorm with its own gamma/beta, 2 = plain cast) and its own COMPACT bf16 output
+ * [batch/2, tokens, C].  With pair = 0 every row takes slot 0 and the output is [batch, tokens, C].
+ * Produces, in one launch, the normalised queries of one modality and the un-normalised context tokens of the other
+ * (attention.py:249-261).
+ */
+typedef struct {
+    const float* gamma[2];
+    const float* beta[2];
+    void* out[2];
+    int32_t mode[2];
+    int32_t pair;
+} mobi_ln_dual_spec;
+int mobi_ln_dual(const float* x, const mobi_ln_dual_spec* spec, int32_t batch, int32_t tokens, int32_t C, float eps,
+                 void* stream);
+
+/*
+ * The bbox / reference-image adapter (cond_adapter_norm -> cond_adapter_attn -> cond_adapter_connector,
+ * attention.py:237-243) in folded form, fused with the pending attn2 vector add (attention.py:235) before it and
+ * the LayerNorm(s) after it.  Per token row of batch row b:
+ *     x += add_vec[b]                                  (optional)
+ *     d = (x - mean) * rstd                            (cond_adapter_norm statistics, eps)
+ *     s_j = <d, Ug[b, j]> + sb[b, j]     j = key*8 + head, 2 keys x 8 head slots (unused heads zero)
+ *     p = softmax over the 2 keys of each head ;  x += sum_j p_j Z[b, j] + zb ;  x written back
+ *     then `next` is applied to the updated row exactly like mobi_ln_dual.
+ * Ug = gamma * (W_q^T k * scale), sb = <beta, W_q^T k * scale>, Z = (W_connector W_out) v: all f32, built once per
+ * sampling run from the context.
+ */
+typedef struct {
+    float* x;             /* f32 [batch, tokens, C], updated in place */
+    const float* add_vec; /* f32 [batch, C] or NULL */
+    const float* gamma;
+    const float* beta;
+    const float* Ug; /* f32 [batch, 16, C] */
+    const float* sb; /* f32 [batch, 16] */
+    const float* Z;  /* f32 [batch, 16, C] */
+    const float* zb; /* f32 [C] */
+    int32_t batch, tokens, C;
+    float eps;
+    mobi_ln_dual_spec next;
+} mobi_ln_adapter_args;
+int mobi_ln_adapter(const mobi_ln_adapter_args* args, void* stream);
 
 /* timestep_embedding (ldm/modules/diffusionmodules/util.py:151-171): out bf16 [n, dim] = [cos | sin]. */
 int mobi_timestep_embedding(const int64_t* t, void* out_bf16, int32_t n, int32_t dim, float max_period,

@@ -35,7 +35,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", _vp), ("k", _vp), ("vt", _vp), ("out", _vp),
         ("batch", _i32), ("heads", _i32), ("head_dim", _i32), ("tq", _i32), ("tk", _i32),
-        ("ld_out", _i64),
+        ("ld_out", _i64), ("kernel", _i32),
     ]
 
 
@@ -54,6 +54,17 @@ class LayerNormArgs(C.Structure):
         ("rows", _i64), ("C", _i32),
         ("seg", _i64), ("seg_stride", _i64), ("seg_offset", _i64), ("add_rows_per_vec", _i64),
         ("eps", _f32),
+    ]
+
+
+class LnDualSpec(C.Structure):
+    _fields_ = [("gamma", _vp * 2), ("beta", _vp * 2), ("out", _vp * 2), ("mode", _i32 * 2), ("pair", _i32)]
+
+
+class LnAdapterArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("add_vec", _vp), ("gamma", _vp), ("beta", _vp), ("Ug", _vp), ("sb", _vp), ("Z", _vp), ("zb", _vp),
+        ("batch", _i32), ("tokens", _i32), ("C", _i32), ("eps", _f32), ("next", LnDualSpec),
     ]
 
 
@@ -101,6 +112,8 @@ SIGNATURES = {
     "mobi_groupnorm_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "mobi_groupnorm": (C.c_int, [C.POINTER(GroupNormArgs), _vp]),
     "mobi_layernorm": (C.c_int, [C.POINTER(LayerNormArgs), _vp]),
+    "mobi_ln_dual": (C.c_int, [_vp, C.POINTER(LnDualSpec), _i32, _i32, _i32, _f32, _vp]),
+    "mobi_ln_adapter": (C.c_int, [C.POINTER(LnAdapterArgs), _vp]),
     "mobi_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
     "mobi_silu": (C.c_int, [_vp, _i32, _vp, _i64, _vp]),
     "mobi_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),

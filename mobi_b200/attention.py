@@ -172,7 +172,24 @@ class BasicTransformerBlock(nn.Module):
                          lda=2 * C, ldb=C, ldo=H * C)
                 ops.gemm(kv[:, C + h * D:], p["c_wf"][:, h * D:], out=Z[:, :, h], out_dtype=torch.float32, M=R * nk,
                          K=D, lda=2 * C, ldb=C, ldo=H * C)
-            tab["U"], tab["Z"], tab["nk"] = U, Z, nk
+            if nk == 1:
+                # one key: softmax == 1, the adapter adds a constant vector per batch row -> merge with attn2's
+                tab["vec2"] = (tab["vec2"] + Z.sum(dim=(1, 2)) + p["c_bf"]).contiguous()
+                tab["adapter"] = "folded"
+            elif nk == 2 and H <= 8:
+                # tables of mobi_ln_adapter: slot j = key*8 + head, LayerNorm affine folded in (once per run)
+                g, b = p["cond_adapter_norm"]
+                Ug = torch.zeros((R, 2, 8, C), device=context.device, dtype=torch.float32)
+                Zp = torch.zeros_like(Ug)
+                sb = torch.zeros((R, 2, 8), device=context.device, dtype=torch.float32)
+                Ug[:, :, :H] = U * g
+                Zp[:, :, :H] = Z
+                sb[:, :, :H] = (U * b).sum(-1)
+                tab["Ug"], tab["Zp"], tab["sb"] = Ug.reshape(R, 16, C), Zp.reshape(R, 16, C), sb.reshape(R, 16)
+                tab["adapter"] = "fused"
+            else:
+                tab["U"], tab["Z"], tab["nk"] = U, Z, nk
+                tab["adapter"] = "generic"
         return tab
 
     # ------------------------------------------------------------------ execution
@@ -190,27 +207,46 @@ class BasicTransformerBlock(nn.Module):
         ops.gemm(xn, p["w_qkv"], epilogue=L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=vt)
         o = ops.attention(q, k, vt, R, H, D, T, T)
         ops.gemm(o.reshape(R * T, C), p["w_o"], bias=p["b_o"], residual=x, out=x)
-        # 2. attn2 == broadcast add of tab["vec2"][row] (attention.py:235), fused into the next LayerNorm pass
+        # 2. attn2 == broadcast add of tab["vec2"][row] (attention.py:235), fused into the next normalisation pass
         pending = tab["vec2"]
-        # 3. bbox/ref adapter with two keys (attention.py:237-243)
-        if self.bbox_cond:
-            xn = ops.layernorm(x, *p["cond_adapter_norm"], add_vec=pending, add_rows_per_vec=T)
+        cam = (ops.LN_NORM,) + p["cross_modal_norm_camera"] if self.multimodal else None
+        lid = (ops.LN_NORM,) + p["cross_modal_norm_lidar"] if self.multimodal else None
+        cast = (ops.LN_CAST, None, None)
+        n3 = (ops.LN_NORM,) + p["norm3"]
+        qn = ctx = xn = None
+        # 3. bbox/ref adapter with two keys (attention.py:237-243), fused with the LayerNorm(s) that follow it
+        mode = tab.get("adapter") if self.bbox_cond else None
+        if mode == "fused":
+            g, b = p["cond_adapter_norm"]
+            outs = ops.ln_adapter(x, R, T, g, b, tab["Ug"], tab["sb"], tab["Zp"], p["c_bf"],
+                                  [cam, cast] if self.multimodal else [n3], pair=self.multimodal, add_vec=pending)
             pending = None
-            ops.ctx_attention(xn, tab["U"], tab["Z"], p["c_bf"], x, R, T, H, tab["nk"])
+            if self.multimodal:
+                qn, ctx = outs
+            else:
+                xn = outs[0]
+        elif mode == "generic":
+            xa = ops.layernorm(x, *p["cond_adapter_norm"], add_vec=pending, add_rows_per_vec=T)
+            pending = None
+            ops.ctx_attention(xa, tab["U"], tab["Z"], p["c_bf"], x, R, T, H, tab["nk"])
         # 4. cross-modal attention (attention.py:245-263): camera rows are even, lidar rows odd
         if self.multimodal:
             Rh = R // 2
-            seg = dict(rows=Rh * T, seg=T, seg_stride=2 * T)
-            qn = ops.layernorm(x, *p["cross_modal_norm_camera"], seg_offset=0, add_vec=pending, add_rows_per_vec=T,
-                               **seg)
-            ctx = ops.layernorm(x, None, None, seg_offset=T, add_vec=pending, add_rows_per_vec=T, **seg)
-            pending = None
+            if qn is None:
+                if pending is not None:
+                    seg = dict(rows=Rh * T, seg=T, seg_stride=2 * T, add_vec=pending, add_rows_per_vec=T)
+                    qn = ops.layernorm(x, *p["cross_modal_norm_camera"], seg_offset=0, **seg)
+                    ctx = ops.layernorm(x, None, None, seg_offset=T, **seg)
+                    pending = None
+                else:
+                    qn, ctx = ops.ln_dual(x, R, T, [cam, cast])
             self._cross(p, "camera", qn, ctx, x, Rh, T, 0)
-            qn = ops.layernorm(x, *p["cross_modal_norm_lidar"], seg_offset=T, **seg)
-            ctx = ops.layernorm(x, None, None, seg_offset=0, **seg)  # the UPDATED camera tokens (attention.py:259)
+            # lidar queries attend to the UPDATED camera tokens (attention.py:259)
+            ctx, qn = ops.ln_dual(x, R, T, [cast, lid])
             self._cross(p, "lidar", qn, ctx, x, Rh, T, T)
         # 5. GEGLU feed-forward (attention.py:265)
-        xn = ops.layernorm(x, *p["norm3"], add_vec=pending, add_rows_per_vec=T)
+        if xn is None:
+            xn = ops.layernorm(x, *p["norm3"], add_vec=pending, add_rows_per_vec=T)
         hmid = ops.gemm(xn, p["w_ff1"], bias=p["b_ff1"], epilogue=L.EPI_GEGLU)
         if out_bf16:
             return ops.gemm(hmid, p["w_ff2"], bias=p["b_ff2"], residual=x, out_dtype=torch.bfloat16)

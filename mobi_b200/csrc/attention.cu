@@ -10,6 +10,7 @@
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2-5 = softmax /
 // correction / epilogue.
 #include "../../include/mobi_b200.h"
+#include "attention_common.cuh"
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -18,17 +19,6 @@ namespace mobi {
 constexpr int ATT_BM = 128;   // query rows per CTA
 constexpr int ATT_BKV = 128;  // keys per block
 constexpr int ATT_TILE = 128 * 128;  // bytes of a 128-row x 64-col bf16 chunk
-
-struct AttnParams {
-    int heads, head_dim, tq, tk;
-    int nch;        // 64-wide chunks of the head dim
-    int dk16;       // k-steps of QK^T  (ceil(d/16))
-    int dn;         // N of the PV MMA  (d rounded up to 16)
-    int kv_stages;  // 1 or 2
-    int p_bufs;     // 1 or 2
-    long long ld_out;
-    __nv_bfloat16* out;
-};
 
 __host__ __device__ inline int att_v_tile_bytes(int dn) { return dn * 128; }
 
@@ -279,6 +269,8 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     p.ld_out = a->ld_out;
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     const long long BH = (long long)a->batch * a->heads;
+    MOBI_CHECK(BH <= 65535, "mobi_attention: batch*heads=%lld exceeds grid.y", BH);
+    if (d <= 128 && a->kernel != 1) return attention2_dispatch(a, p, stream);
     // shared memory plan: prefer double-buffered K/V and P; fall back to single buffers for wide heads
     auto smem_need = [&](int kvs, int pbs) {
         return (long long)p.nch * ATT_TILE * (1 + kvs) + (long long)kvs * 2 * att_v_tile_bytes(p.dn) +

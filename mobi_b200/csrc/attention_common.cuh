@@ -1,0 +1,24 @@
+// Shared between the two fused-attention kernels (attention.cu: any head_dim <= 192, one query tile per CTA;
+// attention2.cu: head_dim <= 128, two query tiles and two softmax warpgroups per CTA).
+#pragma once
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "../../include/mobi_b200.h"
+
+namespace mobi {
+
+struct AttnParams {
+    int heads, head_dim, tq, tk;
+    int nch;        // 64-wide chunks of the head dim
+    int dk16;       // k-steps of QK^T  (ceil(d/16))
+    int dn;         // N of the PV MMA  (d rounded up to 16)
+    int kv_stages;  // 1 or 2            (attention.cu only)
+    int p_bufs;     // 1 or 2            (attention.cu only)
+    long long ld_out;
+    __nv_bfloat16* out;
+};
+
+int attention2_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);
+
+}  // namespace mobi

@@ -127,10 +127,11 @@ gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
     const int p0 = blockIdx.x * pix_per_slab;
     const int p1 = min(hw, p0 + pix_per_slab);
     const long long img_off = (long long)n * hw;
-    const long long total = (long long)(p1 - p0) * half;
-    for (long long i = threadIdx.x; i < total; i += GN_THREADS) {
-        const int p = p0 + (int)(i / half);
-        const int v = (int)(i % half);
+    // thread -> (pixel, channel pair) without per-element division: the pair index advances by GN_THREADS mod half
+    const int step_p = GN_THREADS / half, step_v = GN_THREADS % half;
+    int p = p0 + (int)threadIdx.x / half;
+    int v = (int)threadIdx.x % half;
+    while (p < p1) {
         const int c = 2 * v;
         const float2 f = gn_load2<IN_F32>(x1, x2, c1, c2, img_off + p, c);
         float y0 = f.x * s_scale[c] + s_shift[c];
@@ -142,6 +143,12 @@ gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
         const long long o = (img_off + p) * C + c;
         *reinterpret_cast<__nv_bfloat162*>(out + o) = __floats2bfloat162_rn(y0, y1);
         if (out_concat) *reinterpret_cast<__nv_bfloat162*>(out_concat + o) = __floats2bfloat162_rn(f.x, f.y);
+        p += step_p;
+        v += step_v;
+        if (v >= half) {
+            v -= half;
+            ++p;
+        }
     }
 }
 
@@ -153,74 +160,6 @@ static int gn_slabs(int hw, int C) {
     if (slabs > 256) slabs = 256;
     if (slabs < 1) slabs = 1;
     return slabs;
-}
-
-// ------------------------------------------------------------------------------------------------
-// LayerNorm (one warp per token row), optional broadcast add and row gather.
-// ------------------------------------------------------------------------------------------------
-constexpr int LN_MAXV = 12;  // float4 vectors per lane: C <= 12*128 = 1536
-
-__global__ void __launch_bounds__(256)
-layernorm_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
-                 __nv_bfloat16* __restrict__ out, const float* __restrict__ add_vec, long long rows, int C,
-                 long long seg, long long seg_stride, long long seg_offset, long long add_rows_per_vec, float eps) {
-    const int lane = threadIdx.x & 31;
-    const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const long long in_row = (row / seg) * seg_stride + seg_offset + (row % seg);
-    float4* xr = reinterpret_cast<float4*>(x + in_row * C);
-    const int nv = C >> 2;
-    float4 v[LN_MAXV];
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
-        const int i = lane + 32 * k;
-        if (i < nv) {
-            v[k] = xr[i];
-            if (add_vec) {
-                const float4 a = reinterpret_cast<const float4*>(add_vec + (in_row / add_rows_per_vec) * C)[i];
-                v[k].x += a.x;
-                v[k].y += a.y;
-                v[k].z += a.z;
-                v[k].w += a.w;
-                xr[i] = v[k];
-            }
-            sum += v[k].x + v[k].y + v[k].z + v[k].w;
-        }
-    }
-    uint2* orow = reinterpret_cast<uint2*>(out + row * C);
-    if (gamma == nullptr) {  // cast only
-#pragma unroll
-        for (int k = 0; k < LN_MAXV; ++k) {
-            const int i = lane + 32 * k;
-            if (i < nv) orow[i] = make_uint2(pack_bf16x2(v[k].x, v[k].y), pack_bf16x2(v[k].z, v[k].w));
-        }
-        return;
-    }
-    const float mean = warp_sum(sum) / (float)C;
-    float sq = 0.f;
-#pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
-        const int i = lane + 32 * k;
-        if (i < nv) {
-            const float a = v[k].x - mean, b = v[k].y - mean, c = v[k].z - mean, d = v[k].w - mean;
-            sq += a * a + b * b + c * c + d * d;
-        }
-    }
-    const float rstd = rsqrtf(warp_sum(sq) / (float)C + eps);
-#pragma unroll
-    for (int k = 0; k < LN_MAXV; ++k) {
-        const int i = lane + 32 * k;
-        if (i < nv) {
-            const float4 g = reinterpret_cast<const float4*>(gamma)[i];
-            const float4 b = reinterpret_cast<const float4*>(beta)[i];
-            const float y0 = (v[k].x - mean) * rstd * g.x + b.x;
-            const float y1 = (v[k].y - mean) * rstd * g.y + b.y;
-            const float y2 = (v[k].z - mean) * rstd * g.z + b.z;
-            const float y3 = (v[k].w - mean) * rstd * g.w + b.w;
-            orow[i] = make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
-        }
-    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -544,24 +483,6 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
             a->x1, a->x2, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out),
             reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, a->hw, a->c1, a->c2, a->groups, a->eps,
             a->silu, pix_per_slab2);
-    MOBI_CUDA(cudaGetLastError());
-    return 0;
-}
-
-extern "C" int mobi_layernorm(const mobi_layernorm_args* a, void* stream_) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
-    MOBI_CHECK(a && a->x && a->out, "mobi_layernorm: null argument");
-    MOBI_CHECK(a->C % 4 == 0 && a->C <= LN_MAXV * 128, "mobi_layernorm: C=%d must be a multiple of 4 and <= %d", a->C,
-               LN_MAXV * 128);
-    MOBI_CHECK(a->gamma == nullptr || a->beta != nullptr, "mobi_layernorm: gamma without beta");
-    if (a->rows == 0) return 0;
-    const long long seg = a->seg > 0 ? a->seg : a->rows;
-    const long long seg_stride = a->seg > 0 ? a->seg_stride : a->rows;
-    const long long rpv = a->add_rows_per_vec > 0 ? a->add_rows_per_vec : 1;
-    const int warps = 8;
-    layernorm_kernel<<<blocks_for(a->rows, warps), warps * 32, 0, stream>>>(
-        reinterpret_cast<float*>(a->x), a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out), a->add_vec,
-        a->rows, a->C, seg, seg_stride, a->seg_offset, rpv, a->eps);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

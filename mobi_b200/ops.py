@@ -194,7 +194,7 @@ def im2col(x, kh, kw, stride, pad_top, pad_left, ho, wo):
     return out
 
 
-def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None):
+def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0):
     """q,k: bf16 [batch*heads, T, d]; vt: bf16 [batch*heads, d, Tk]; returns bf16 [batch, tq, heads*d]."""
     _cuda(q, k, vt, out)
     assert q.dtype == k.dtype == vt.dtype == torch.bfloat16
@@ -204,6 +204,7 @@ def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None):
     a.q, a.k, a.vt, a.out = q.data_ptr(), k.data_ptr(), vt.data_ptr(), out.data_ptr()
     a.batch, a.heads, a.head_dim, a.tq, a.tk = batch, heads, head_dim, tq, tk
     a.ld_out = heads * head_dim
+    a.kernel = kernel
     with _timed("attention", 4.0 * batch * heads * tq * tk * head_dim):
         L.check(L.load().mobi_attention(C.byref(a), L.stream()), "attention")
     return out
@@ -252,6 +253,55 @@ def layernorm(x, gamma, beta, *, rows=None, seg=0, seg_stride=0, seg_offset=0, a
     with _timed("layernorm", 0.0, rows * c * (4 + 2 + (8 if add_vec is not None else 0))):
         L.check(L.load().mobi_layernorm(C.byref(a), L.stream()), "layernorm")
     return out
+
+
+LN_SKIP, LN_NORM, LN_CAST = 0, 1, 2
+
+
+def _dual_spec(spec, slots, pair, batch, tokens, c, device):
+    """slots: [(mode, gamma, beta)] for slot 0 (even batch rows, or all rows when pair=False) and slot 1."""
+    outs = []
+    spec.pair = int(pair)
+    for i in range(2):
+        mode, gamma, beta = slots[i] if i < len(slots) else (LN_SKIP, None, None)
+        out = None
+        if mode != LN_SKIP:
+            _cuda(gamma, beta)
+            out = torch.empty(((batch // 2 if pair else batch) * tokens, c), device=device, dtype=torch.bfloat16)
+        spec.mode[i] = mode
+        spec.gamma[i], spec.beta[i], spec.out[i] = L.ptr(gamma), L.ptr(beta), L.ptr(out)
+        outs.append(out)
+    return outs
+
+
+def ln_dual(x, batch, tokens, slots, *, pair=True, eps=1e-5):
+    """One pass over x f32 [batch*tokens, C]; see mobi_ln_dual.  Returns the per-slot bf16 outputs (None if skipped)."""
+    _cuda(x)
+    assert x.dtype == torch.float32
+    c = x.shape[-1]
+    spec = L.LnDualSpec()
+    outs = _dual_spec(spec, slots, pair, batch, tokens, c, x.device)
+    n_out = sum(o.numel() for o in outs if o is not None)
+    with _timed("layernorm", 0.0, n_out * 6.0):
+        L.check(L.load().mobi_ln_dual(x.data_ptr(), C.byref(spec), batch, tokens, c, eps, L.stream()), "ln_dual")
+    return outs
+
+
+def ln_adapter(x, batch, tokens, gamma, beta, Ug, sb, Z, zb, slots, *, pair, add_vec=None, eps=1e-5):
+    """Fused attn2-vector add + folded bbox/reference adapter + following LayerNorm(s); see mobi_ln_adapter."""
+    _cuda(x, gamma, beta, Ug, sb, Z, zb, add_vec)
+    assert x.dtype == torch.float32 and Ug.dtype == Z.dtype == sb.dtype == zb.dtype == torch.float32
+    c = x.shape[-1]
+    assert Ug.shape == (batch, 16, c) and Z.shape == (batch, 16, c) and sb.shape == (batch, 16)
+    a = L.LnAdapterArgs()
+    a.x, a.add_vec, a.gamma, a.beta = x.data_ptr(), L.ptr(add_vec), gamma.data_ptr(), beta.data_ptr()
+    a.Ug, a.sb, a.Z, a.zb = Ug.data_ptr(), sb.data_ptr(), Z.data_ptr(), zb.data_ptr()
+    a.batch, a.tokens, a.C, a.eps = batch, tokens, c, eps
+    outs = _dual_spec(a.next, slots, pair, batch, tokens, c, x.device)
+    n_out = sum(o.numel() for o in outs if o is not None)
+    with _timed("ln_adapter", 0.0, x.numel() * 8.0 + n_out * 2.0):
+        L.check(L.load().mobi_ln_adapter(C.byref(a), L.stream()), "ln_adapter")
+    return outs
 
 
 def timestep_embedding(t, dim, max_period=10000.0):

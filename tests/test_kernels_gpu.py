@@ -178,9 +178,11 @@ def test_conv_im2col(N, H, W, C, Cout, k, stride, pads):
 @pytest.mark.parametrize("B,H,D,Tq,Tk", [
     (1, 1, 64, 128, 128), (2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 80, 256, 256),
     (2, 8, 160, 256, 256), (2, 8, 160, 64, 64), (1, 2, 16, 64, 64), (1, 2, 32, 16, 16),
-    (1, 8, 40, 4096, 4096), (1, 4, 80, 384, 200),
+    (1, 8, 40, 4096, 4096), (1, 4, 80, 384, 200), (2, 3, 40, 300, 136), (1, 2, 128, 512, 320), (1, 2, 64, 256, 1024),
 ])
-def test_attention(B, H, D, Tq, Tk):
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_attention(B, H, D, Tq, Tk, kernel):
+    """kernel 0 = automatic (two-tile kernel for head_dim <= 128), 1 = the one-tile kernel."""
     ops = _ops()
     q = rnd(B * H, Tq, D, seed=1, dtype=torch.float32)
     k = rnd(B * H, Tk, D, seed=2, dtype=torch.float32)
@@ -194,7 +196,7 @@ def test_attention(B, H, D, Tq, Tk):
     ref = torch.einsum("bij,bjd->bid", s.softmax(-1), vb.float())
     ref = ref.reshape(B, H, Tq, D).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
     vt = vb.transpose(1, 2).contiguous()
-    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk)
+    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk, kernel=kernel)
     torch.cuda.synchronize()
     assert relerr(out, ref) < 1e-2, describe(out, ref)
 
@@ -249,6 +251,62 @@ def test_layernorm_variants():
         gg = rnd(C2, seed=6, dtype=torch.float32)
         bb = rnd(C2, seed=7, dtype=torch.float32)
         assert relerr(ops.layernorm(xx, gg, bb), torch.nn.functional.layer_norm(xx, (C2,), gg, bb, 1e-5)) < 8e-3
+
+
+def test_layernorm_dual():
+    """mobi_ln_dual: camera rows normalised + lidar rows cast (and the reverse) in one pass (attention.py:246-261)."""
+    ops = _ops()
+    for R, T, C in ((4, 256, 320), (2, 64, 1280), (6, 16, 640), (2, 128, 64)):
+        x = rnd(R, T, C, seed=1, dtype=torch.float32) * 1.5 + 0.3
+        g = rnd(C, seed=2, dtype=torch.float32)
+        b = rnd(C, seed=3, dtype=torch.float32)
+        ref = torch.nn.functional.layer_norm(x, (C,), g, b, 1e-5)
+        qn, ctx = ops.ln_dual(x.reshape(R * T, C), R, T, [(ops.LN_NORM, g, b), (ops.LN_CAST, None, None)])
+        assert relerr(qn, ref[0::2].reshape(-1, C)) < 8e-3
+        assert torch.equal(ctx, x[1::2].reshape(-1, C).to(torch.bfloat16))
+        ctx, qn = ops.ln_dual(x.reshape(R * T, C), R, T, [(ops.LN_CAST, None, None), (ops.LN_NORM, g, b)])
+        assert relerr(qn, ref[1::2].reshape(-1, C)) < 8e-3
+        assert torch.equal(ctx, x[0::2].reshape(-1, C).to(torch.bfloat16))
+        full, none = ops.ln_dual(x.reshape(R * T, C), R, T, [(ops.LN_NORM, g, b)], pair=False)
+        assert none is None and relerr(full, ref.reshape(-1, C)) < 8e-3
+
+
+@pytest.mark.parametrize("R,T,C,H,multimodal", [(4, 256, 320, 8, True), (2, 64, 1280, 8, True), (4, 30, 640, 8, False),
+                                                (2, 16, 64, 4, True), (2, 4096, 320, 8, True)])
+def test_ln_adapter(R, T, C, H, multimodal):
+    """mobi_ln_adapter vs the unfused math of attention.py:235-247 in fp32: attn2 vector add, cond_adapter_norm,
+    2-key cross attention in folded (U, Z) form, connector, then the following LayerNorm / cast."""
+    ops = _ops()
+    x = rnd(R, T, C, seed=1, dtype=torch.float32) * 1.3 + 0.2
+    vec = rnd(R, C, seed=2, dtype=torch.float32)
+    g, b = 1 + 0.1 * rnd(C, seed=3, dtype=torch.float32), 0.1 * rnd(C, seed=4, dtype=torch.float32)
+    g2, b2 = 1 + 0.1 * rnd(C, seed=5, dtype=torch.float32), 0.1 * rnd(C, seed=6, dtype=torch.float32)
+    U = rnd(R, 2, H, C, seed=7, dtype=torch.float32, scale=2.0 * C ** -0.5)
+    Z = rnd(R, 2, H, C, seed=8, dtype=torch.float32)
+    zb = rnd(C, seed=9, dtype=torch.float32)
+    # reference
+    x1 = x + vec[:, None]
+    xn = torch.nn.functional.layer_norm(x1, (C,), g, b, 1e-5)
+    s = torch.einsum("btc,bkhc->btkh", xn, U)
+    pr = s.softmax(dim=2)
+    x2 = x1 + torch.einsum("btkh,bkhc->btc", pr, Z) + zb
+    # tables as BasicTransformerBlock.context_tables builds them
+    Ug = torch.zeros(R, 2, 8, C, device="cuda")
+    Zp = torch.zeros_like(Ug)
+    sb = torch.zeros(R, 2, 8, device="cuda")
+    Ug[:, :, :H], Zp[:, :, :H], sb[:, :, :H] = U * g, Z, (U * b).sum(-1)
+    xx = x.clone().reshape(R * T, C)
+    slots = [(ops.LN_NORM, g2, b2), (ops.LN_CAST, None, None)] if multimodal else [(ops.LN_NORM, g2, b2)]
+    outs = ops.ln_adapter(xx, R, T, g, b, Ug.reshape(R, 16, C), sb.reshape(R, 16), Zp.reshape(R, 16, C), zb, slots,
+                          pair=multimodal, add_vec=vec)
+    torch.cuda.synchronize()
+    assert relerr(xx, x2.reshape(-1, C)) < 1e-5, describe(xx, x2.reshape(-1, C))
+    ln2 = torch.nn.functional.layer_norm(x2, (C,), g2, b2, 1e-5)
+    if multimodal:
+        assert relerr(outs[0], ln2[0::2].reshape(-1, C)) < 8e-3
+        assert relerr(outs[1], x2[1::2].reshape(-1, C)) < 8e-3
+    else:
+        assert relerr(outs[0], ln2.reshape(-1, C)) < 8e-3
 
 
 def test_small_kernels():
