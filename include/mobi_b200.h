@@ -78,6 +78,7 @@ typedef struct {
     int32_t conv;
     int32_t n_img, H, W, C, KH, KW, pad_h, pad_w;
     int32_t tile_n; /* 0 = choose */
+    int32_t kernel; /* 0 = choose (persistent kernel when its epilogue supports the problem), 1 = one-tile kernel */
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);
@@ -97,7 +98,8 @@ typedef struct {
     void* out;
     int32_t batch, heads, head_dim, tq, tk;
     int64_t ld_out; /* row stride of out in elements (>= heads*head_dim) */
-    int32_t kernel; /* 0 = choose (two-tile kernel for head_dim <= 128), 1 = force the one-tile kernel */
+    int32_t kernel; /* 0 = choose (two-tile kernel for head_dim <= 128), 1 = force the one-tile kernel,
+                       2 = two-tile kernel with 128-key blocks and one CTA per SM (head_dim <= 64) */
 } mobi_attn_args;
 
 int mobi_attention(const mobi_attn_args* args, void* stream);

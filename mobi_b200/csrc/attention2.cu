@@ -34,11 +34,15 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
-template <int BKV>
-__global__ void __launch_bounds__(384, 1)
+// MINB = 2: two CTAs per SM (BKV = 64, head_dim <= 64): four softmax warps per SM sub-partition instead of two.
+template <int BKV, int MINB>
+__global__ void __launch_bounds__(384, MINB)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
     constexpr int KCH = BKV / 64;            // 64-key chunks per block (P / V tiles)
+    constexpr int O_STRIDE = MINB == 2 ? 64 : 128;             // TMEM columns reserved per O accumulator
+    constexpr int TMEM_COLS = MINB == 2 ? 256 : 512;           // S: 2 x BKV columns, O: 2 x O_STRIDE columns
+    constexpr int O_BASE = 2 * BKV;
     constexpr int K_CHUNK = BKV * 128;       // bytes of a BKV-row x 64-col bf16 chunk of K
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -84,7 +88,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             fence_barrier_init();
         }
     } else if (warp == 9) {
-        tmem_alloc(tmem_slot, 512);
+        tmem_alloc(tmem_slot, TMEM_COLS);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -93,7 +97,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= 8) {
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");  // donate registers to the softmax warpgroups
         if (warp == 8) {
             if (elect_one()) {
                 // ---------------- TMA producer
@@ -118,7 +122,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 const uint32_t idesc_o = make_idesc_bf16(128, p.dn);
                 auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K(j)^T
                     const int s = j & 1;
-                    const uint32_t d_tmem = tmem_base + t * 128;
+                    const uint32_t d_tmem = tmem_base + t * BKV;
                     for (int k = 0; k < p.dk16; ++k) {
                         const uint64_t a =
                             make_kmajor_sw128_desc(smem_u32(sQ + t * q_tile_bytes + (k >> 2) * A2_CHUNK)) + 2 * (k & 3);
@@ -147,7 +151,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     for (int t = 0; t < ntiles; ++t) {
                         mbar_wait(&p_full[t], ph);
                         tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + 256 + t * 128;
+                        const uint32_t d_tmem = tmem_base + O_BASE + t * O_STRIDE;
                         for (int k = 0; k < BKV / 16; ++k) {
                             const uint64_t a =
                                 make_kmajor_sw128_desc(smem_u32(sP + (t * KCH + (k >> 2)) * A2_CHUNK)) + 2 * (k & 3);
@@ -162,15 +166,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
         }
     } else {
-        asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
+        if constexpr (MINB == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 96;");
+        else asm volatile("setmaxnreg.inc.sync.aligned.u32 208;");
         // ---------------- softmax / correction / epilogue of tile t: thread <-> query row
         const int t = warp >> 2;
         if (t < ntiles) {
             const int lg = warp & 3;
             const int row = lg * 32 + lane;
             const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
-            const uint32_t tS = tmem_base + t * 128 + lane_addr;
-            const uint32_t tO = tmem_base + 256 + t * 128 + lane_addr;
+            const uint32_t tS = tmem_base + t * BKV + lane_addr;
+            const uint32_t tO = tmem_base + O_BASE + t * O_STRIDE + lane_addr;
             uint8_t* prow = sP + t * KCH * A2_CHUNK + (row >> 3) * 1024 + (row & 7) * 128;
             float m_used = -INFINITY;
             float l = 0.f;
@@ -267,11 +272,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     __syncthreads();
     if (warp == 9) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 512);
+        tmem_dealloc(tmem_base, TMEM_COLS);
     }
 }
 
-template <int BKV>
+template <int BKV, int MINB>
 static int launch_attention2(const mobi_attn_args* a, AttnParams p, cudaStream_t stream) {
     const int d = a->head_dim;
     const long long BH = (long long)a->batch * a->heads;
@@ -300,18 +305,19 @@ static int launch_attention2(const mobi_attn_args* a, AttnParams p, cudaStream_t
     }
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(attention2_kernel<BKV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+        MOBI_CUDA(cudaFuncSetAttribute(attention2_kernel<BKV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         configured = true;
     }
     dim3 grid((a->tq + 255) / 256, (unsigned)BH, 1);
-    attention2_kernel<BKV><<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, p);
+    attention2_kernel<BKV, MINB><<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, p);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
 
 int attention2_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream) {
-    if (a->head_dim <= 64) return launch_attention2<128>(a, p, stream);
-    return launch_attention2<64>(a, p, stream);
+    if (a->head_dim <= 64 && a->kernel != 2) return launch_attention2<64, 2>(a, p, stream);
+    if (a->head_dim <= 64) return launch_attention2<128, 1>(a, p, stream);
+    return launch_attention2<64, 1>(a, p, stream);
 }
 
 }  // namespace mobi

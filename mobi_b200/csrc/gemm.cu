@@ -13,36 +13,10 @@
 // out-of-bounds halo is zero-filled by the TMA unit, so no im2col buffer exists.
 #include "../../include/mobi_b200.h"
 #include "common.cuh"
+#include "gemm_common.cuh"
 #include "ptx.cuh"
 
 namespace mobi {
-
-struct GemmParams {
-    int M, N;
-    int num_k_blocks;
-    // conv
-    int conv;
-    int C, H, W, KW, pad_h, pad_w, cblocks;
-    // epilogue
-    void* out;
-    void* out2;
-    void* out3;
-    const float* bias;
-    const float* row_bias;
-    const void* residual;
-    long long ldo;
-    long long ld_row_bias;
-    int rows_per_group;
-    int out_f32, res_f32;
-    int mode;
-    int act;
-    int heads, head_dim, tokens;
-    long long out_seg, out_seg_stride, out_seg_offset;
-};
-
-constexpr int BM = 128;
-constexpr int BK = 64;
-constexpr int A_TILE_BYTES = BM * BK * 2;
 
 template <int BN>
 struct GemmCfg {
@@ -426,6 +400,7 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         uint32_t box[2] = {BK, (uint32_t)bn_tile};
         if (make_tensor_map_bf16(&tmB, a->B, 2, dims, strides, box)) return 1;
     }
+    if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);
     switch (bn_tile) {
         case 64: return launch_gemm<64>(tmA, tmB, p, stream);
         case 128: return launch_gemm<128>(tmA, tmB, p, stream);

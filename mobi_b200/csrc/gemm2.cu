@@ -1,0 +1,430 @@
+// Persistent tcgen05 GEMM / implicit-GEMM convolution for sm_100a.
+//
+//   C[M,N] = A[M,K] . B[N,K]^T     bf16 operands, fp32 accumulation in TMEM
+//
+// One CTA per SM walks output tiles (128 x BN, n-tile fastest so that the CTAs running at the same time share the
+// same A rows through L2).  Warp roles (320 threads):
+//   warp 0      TMA producer: 128x64 A tiles / BNx64 B tiles (128B swizzle) through a STAGES-deep ring that keeps
+//               running across tile boundaries (the loads of tile i+1 start while tile i is still in the MMA);
+//   warp 1      MMA issuer: tcgen05.mma M=128 N=BN K=16, accumulating into one of TWO TMEM accumulator stages, so
+//               the epilogue of tile i overlaps the main loop of tile i+1; owns the TMEM allocation;
+//   warps 2-9   epilogue: two warps per 32-lane TMEM group, each takes half of the tile's columns in 32-column
+//               chunks: tcgen05.ld (thread = row) -> XOR-swizzled shared-memory transpose -> thread = 4 consecutive
+//               columns, 8 lanes per row.  All global traffic of the epilogue (bias, per-image row bias, residual
+//               in fp32/bf16, output in fp32/bf16/head-split layouts) is then 16-byte vectors, 128 contiguous bytes
+//               per row, and the residual of a chunk is prefetched before its accumulator is read.
+// With `conv` set the A tile of filter tap (kh,kw) is a shifted 4-D TMA box over the NHWC image (zero-filled halo).
+#include "../../include/mobi_b200.h"
+#include "common.cuh"
+#include "gemm_common.cuh"
+#include "ptx.cuh"
+
+namespace mobi {
+
+constexpr int G2_THREADS = 320;
+constexpr int G2_STAGING_BYTES = 8 * 4096;  // 8 epilogue warps x (32 rows x 128 B)
+
+template <int BN>
+struct Gemm2Cfg {
+    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
+    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
+    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+    static constexpr int BUDGET = 227 * 1024 - 1024 - G2_STAGING_BYTES - 512;
+    static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
+    static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 512 + 1024;
+    static constexpr int CHUNKS = BN / 32;  // 32-column epilogue chunks (BN is a multiple of 32)
+};
+
+// erf by Abramowitz-Stegun 7.1.26 (|error| <= 1.5e-7, far below bf16 output resolution): 2 MUFU + ~10 FMA
+__device__ __forceinline__ float erf_fast(float x) {
+    const float ax = fabsf(x);
+    const float t = __fdividef(1.0f, fmaf(0.3275911f, ax, 1.0f));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    const float y = 1.0f - poly * t * __expf(-ax * ax);
+    return copysignf(y, x);
+}
+__device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
+
+struct EpiRow {          // per-lane view of the 8 rows this lane serves in the transposed domain
+    long long off[8];    // element offset of the row in the output (layout dependent)
+    int rb[8];           // row-bias row offset (elements)
+    unsigned ok;         // bit i: row i exists (m < M)
+};
+
+template <int BN>
+__device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc_tmem, float* stg, int m_tile,
+                                               int n_tile, int lg, int half, int lane) {
+    using Cfg = Gemm2Cfg<BN>;
+    const int u = lane & 7;        // 4-column unit inside a 32-column chunk
+    const int rsub = lane >> 3;    // row inside a group of 4
+    const int m_base = m_tile * BM + lg * 32;
+    const int inner = p.heads * p.head_dim;
+    const bool head_mode = p.mode >= MOBI_EPI_HEADS;
+    const int nparts_last = p.mode == MOBI_EPI_QKV ? 2 : (p.mode == MOBI_EPI_KV ? 1 : (p.mode == MOBI_EPI_HEADS_T ? 0 : -1));
+
+    EpiRow er;
+    er.ok = 0;
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+        const int m = m_base + it * 4 + rsub;
+        if (m < p.M) er.ok |= 1u << it;
+        if (head_mode) {
+            const int b = m / p.tokens, t = m - b * p.tokens;
+            er.off[it] = ((long long)b * p.heads * p.tokens + t) * p.head_dim;  // + (h*tokens*d + dd) per column
+        } else {
+            long long mo = m;
+            if (p.out_seg > 0) {
+                const int sg = m / (int)p.out_seg;
+                mo = (long long)sg * p.out_seg_stride + p.out_seg_offset + (m - sg * (int)p.out_seg);
+            }
+            er.off[it] = mo * p.ldo;
+        }
+        er.rb[it] = p.row_bias ? (m / p.rows_per_group) * (int)p.ld_row_bias : 0;
+    }
+    // row-domain identity (thread = TMEM lane = row), needed for the transposed-V layout
+    const int m_own = m_base + lane;
+    long long vt_row = 0;
+    if (head_mode && m_own < p.M) {
+        const int b = m_own / p.tokens, t = m_own - b * p.tokens;
+        vt_row = (long long)b * inner * p.tokens + t;
+    }
+    const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+    uint8_t* srow = reinterpret_cast<uint8_t*>(stg) + lane * 128;  // row-domain staging row of this thread
+
+    const int c_begin = half * ((Cfg::CHUNKS + 1) / 2);
+    const int c_end = half == 0 ? (Cfg::CHUNKS + 1) / 2 : Cfg::CHUNKS;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= p.N) break;
+        const int n = n0 + 4 * u;             // first of this lane's 4 columns (transposed domain)
+        const bool col_ok = n < p.N;          // N % 4 == 0: the unit is entirely inside or outside
+        // ---- prefetch the residual of this chunk (transposed domain)
+        float4 res[8];
+        if (p.residual != nullptr && p.mode == MOBI_EPI_PLAIN) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (col_ok && ((er.ok >> it) & 1)) {
+                    if (p.res_f32) {
+                        res[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) + er.off[it] + n);
+                    } else {
+                        const uint2 rw = *reinterpret_cast<const uint2*>(
+                            reinterpret_cast<const __nv_bfloat16*>(p.residual) + er.off[it] + n);
+                        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw.x));
+                        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rw.y));
+                        res[it] = make_float4(lo.x, lo.y, hi.x, hi.y);
+                    }
+                }
+            }
+        }
+        // ---- accumulator chunk -> registers (thread = row)
+        uint32_t r[32];
+        tmem_ld32(acc_tmem + lane_addr + c * 32, r);
+        tmem_ld_wait();
+        int out_units = 8;  // 16-byte units per staged row
+        if (p.mode == MOBI_EPI_GEGLU) {
+            // [8 value | 8 gate] groups: activation in the row domain, 16 outputs per chunk
+            out_units = 4;
+#pragma unroll
+            for (int g = 0; g < 2; ++g) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float val = __uint_as_float(r[16 * g + j]);
+                    float gate = __uint_as_float(r[16 * g + 8 + j]);
+                    if (p.bias) {
+                        val += __ldg(p.bias + n0 + 16 * g + j);
+                        gate += __ldg(p.bias + n0 + 16 * g + 8 + j);
+                    }
+                    o[j] = val * gelu_fast(gate);
+                }
+#pragma unroll
+                for (int q = 0; q < 2; ++q) {
+                    const int unit = 2 * g + q;
+                    *reinterpret_cast<float4*>(srow + ((unit ^ (lane & 7)) << 4)) =
+                        make_float4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+                }
+            }
+        } else {
+            if (nparts_last >= 0 && m_own < p.M) {
+                // transposed-V columns go straight from the row domain: 32 consecutive tokens per store
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    const int ng = n0 + 8 * g;
+                    if (ng < p.N && ng / inner == nparts_last) {
+                        __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(
+                            nparts_last == 2 ? p.out3 : (nparts_last == 1 ? p.out2 : p.out));
+                        __nv_bfloat16* o = base + vt_row + (long long)(ng - nparts_last * inner) * p.tokens;
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            float val = __uint_as_float(r[8 * g + j]);
+                            if (p.bias) val += __ldg(p.bias + ng + j);
+                            o[(long long)j * p.tokens] = __float2bfloat16(val);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int unit = 0; unit < 8; ++unit)
+                *reinterpret_cast<uint4*>(srow + ((unit ^ (lane & 7)) << 4)) =
+                    make_uint4(r[4 * unit], r[4 * unit + 1], r[4 * unit + 2], r[4 * unit + 3]);
+        }
+        __syncwarp();
+        // ---- transposed domain
+        if (out_units == 8) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            // head-split column part
+            long long coloff = 0;
+            __nv_bfloat16* hbase = nullptr;
+            bool is_vt = false;
+            if (head_mode && col_ok) {
+                const int which = n / inner;
+                const int nn = n - which * inner;
+                is_vt = (which == nparts_last);
+                const int h = nn / p.head_dim, dd = nn - h * p.head_dim;
+                coloff = (long long)h * p.tokens * p.head_dim + dd;
+                hbase = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rsub;
+                float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + rr * 128 +
+                                                            ((u ^ (rr & 7)) << 4));
+                if (!col_ok || !((er.ok >> it) & 1)) continue;
+                if (head_mode) {
+                    if (is_vt) continue;
+                    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                    uint2 pk;
+                    pk.x = pack_bf16x2(v.x, v.y);
+                    pk.y = pack_bf16x2(v.z, v.w);
+                    *reinterpret_cast<uint2*>(hbase + er.off[it] + coloff) = pk;
+                    continue;
+                }
+                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+                if (p.row_bias) {
+                    const float4 rb = __ldg(reinterpret_cast<const float4*>(p.row_bias + er.rb[it] + n));
+                    v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
+                }
+                if (p.act == 1) {
+                    v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+                }
+                if (p.residual) {
+                    v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w;
+                }
+                if (p.out_f32) {
+                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + er.off[it] + n) = v;
+                } else {
+                    uint2 pk;
+                    pk.x = pack_bf16x2(v.x, v.y);
+                    pk.y = pack_bf16x2(v.z, v.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + er.off[it] + n) = pk;
+                }
+            }
+        } else {
+            // GEGLU: 16 bf16 outputs per row: lane -> (row = it*8 + lane/4, unit = lane%4)
+            const int u4 = lane & 3, r8 = lane >> 2;
+            const int no = n0 / 2 + 4 * u4;
+#pragma unroll
+            for (int it = 0; it < 4; ++it) {
+                const int rr = it * 8 + r8;
+                const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + rr * 128 +
+                                                                  ((u4 ^ (rr & 7)) << 4));
+                const int m = m_base + rr;
+                if (m < p.M && no < p.N / 2) {
+                    uint2 pk;
+                    pk.x = pack_bf16x2(v.x, v.y);
+                    pk.y = pack_bf16x2(v.z, v.w);
+                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + (long long)m * p.ldo + no) = pk;
+                }
+            }
+        }
+        __syncwarp();
+    }
+}
+
+template <int BN>
+__global__ void __launch_bounds__(G2_THREADS, 1)
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
+             const int m_tiles, const int n_tiles) {
+    using Cfg = Gemm2Cfg<BN>;
+    constexpr int STAGES = Cfg::STAGES;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* sA = smem;
+    uint8_t* sB = smem + STAGES * A_TILE_BYTES;
+    float* staging = reinterpret_cast<float*>(sB + STAGES * Cfg::B_TILE_BYTES);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + G2_STAGING_BYTES);
+    uint64_t* empty_bar = full_bar + STAGES;
+    uint64_t* tfull_bar = empty_bar + STAGES;   // 2
+    uint64_t* tempty_bar = tfull_bar + 2;       // 2
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    const int lane = threadIdx.x & 31;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            tma_prefetch_desc(&tmA);
+            tma_prefetch_desc(&tmB);
+            for (int s = 0; s < STAGES; ++s) {
+                mbar_init(&full_bar[s], 1);
+                mbar_init(&empty_bar[s], 1);
+            }
+            for (int s = 0; s < 2; ++s) {
+                mbar_init(&tfull_bar[s], 1);
+                mbar_init(&tempty_bar[s], 8);  // one elected arrive per epilogue warp
+            }
+            fence_barrier_init();
+        }
+    } else if (warp == 1) {
+        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+    const int nkb = p.num_k_blocks;
+    const int total = m_tiles * n_tiles;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            // ---------------- TMA producer
+            uint32_t it = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+                const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+                int x0 = 0, y0 = 0, n0 = 0;
+                if (p.conv) {
+                    const long long pix = (long long)m_tile * BM;
+                    x0 = (int)(pix % p.W);
+                    y0 = (int)((pix / p.W) % p.H);
+                    n0 = (int)(pix / ((long long)p.W * p.H));
+                }
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&empty_bar[s], ph ^ 1);
+                    mbar_arrive_expect_tx(&full_bar[s], A_TILE_BYTES + Cfg::B_TILE_BYTES);
+                    if (p.conv) {
+                        const int tap = kb / p.cblocks;
+                        const int cb = kb - tap * p.cblocks;
+                        const int kh = tap / p.KW;
+                        const int kw = tap - kh * p.KW;
+                        tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w,
+                                    y0 + kh - p.pad_h, n0);
+                        tma_load_2d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], tap * p.C + cb * BK, n_tile * BN);
+                    } else {
+                        tma_load_2d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], kb * BK, m_tile * BM);
+                        tma_load_2d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], kb * BK, n_tile * BN);
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (elect_one()) {
+            // ---------------- MMA issuer
+            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+            uint32_t it = 0, lt = 0;
+            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+                const uint32_t as = lt & 1;
+                mbar_wait(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+                for (int kb = 0; kb < nkb; ++kb, ++it) {
+                    const int s = it % STAGES;
+                    const uint32_t ph = (it / STAGES) & 1;
+                    mbar_wait(&full_bar[s], ph);
+                    tc_fence_after();
+                    const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + s * A_TILE_BYTES));
+                    const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k)
+                        umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    umma_commit(&empty_bar[s]);
+                }
+                umma_commit(&tfull_bar[as]);
+            }
+        }
+    } else {
+        // ---------------- epilogue warps 2..9: TMEM lane group = warp % 4, column half = (warp - 2) / 4
+        const int lg = warp & 3;
+        const int half = (warp - 2) >> 2;
+        float* stg = staging + (warp - 2) * 1024;
+        uint32_t lt = 0;
+        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+            const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+            const uint32_t as = lt & 1;
+            mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
+            tc_fence_after();
+            gemm2_epilogue<BN>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane);
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+    }
+}
+
+template <int BN>
+static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN>;
+    static bool configured = false;
+    if (!configured) {
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
+    const long long total = (long long)m_tiles * n_tiles;
+    const int grid = (int)(total < sm_count() ? total : sm_count());
+    gemm2_kernel<BN><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+bool gemm2_supported(const GemmParams& p) {
+    if (p.N % 4 != 0) return false;
+    if (p.mode == MOBI_EPI_PLAIN) {
+        if (p.ldo % 4 != 0) return false;
+        const uintptr_t align = p.out_f32 ? 15 : 7;
+        if (reinterpret_cast<uintptr_t>(p.out) & align) return false;
+        if (p.residual) {
+            if (reinterpret_cast<uintptr_t>(p.residual) & (p.res_f32 ? 15 : 7)) return false;
+        }
+        if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
+        if (p.row_bias && ((reinterpret_cast<uintptr_t>(p.row_bias) & 15) || p.ld_row_bias % 4 != 0)) return false;
+        if (p.out_seg >= (1ll << 31)) return false;
+    } else if (p.mode == MOBI_EPI_GEGLU) {
+        if (p.N % 32 != 0 || p.ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(p.out) & 7)) return false;
+    } else {
+        if (p.head_dim % 8 != 0) return false;
+        if ((reinterpret_cast<uintptr_t>(p.out) & 7) || (p.out2 && (reinterpret_cast<uintptr_t>(p.out2) & 7)) ||
+            (p.out3 && (reinterpret_cast<uintptr_t>(p.out3) & 7)))
+            return false;
+    }
+    return true;
+}
+
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn_tile, cudaStream_t stream) {
+    switch (bn_tile) {
+        case 64: return launch_gemm2_t<64>(tmA, tmB, p, stream);
+        case 128: return launch_gemm2_t<128>(tmA, tmB, p, stream);
+        case 160: return launch_gemm2_t<160>(tmA, tmB, p, stream);
+        case 256: return launch_gemm2_t<256>(tmA, tmB, p, stream);
+        default: MOBI_CHECK(false, "mobi_gemm: unsupported tile_n %d", bn_tile);
+    }
+    return 0;
+}
+
+}  // namespace mobi

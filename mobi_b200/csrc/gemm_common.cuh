@@ -1,0 +1,40 @@
+// Parameter block shared by the two tcgen05 GEMM kernels (gemm.cu: one tile per CTA, fully general; gemm2.cu:
+// persistent, double-buffered TMEM accumulators, coalesced epilogue).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+namespace mobi {
+
+struct GemmParams {
+    int M, N;
+    int num_k_blocks;
+    // conv
+    int conv;
+    int C, H, W, KW, pad_h, pad_w, cblocks;
+    // epilogue
+    void* out;
+    void* out2;
+    void* out3;
+    const float* bias;
+    const float* row_bias;
+    const void* residual;
+    long long ldo;
+    long long ld_row_bias;
+    int rows_per_group;
+    int out_f32, res_f32;
+    int mode;
+    int act;
+    int heads, head_dim, tokens;
+    long long out_seg, out_seg_stride, out_seg_offset;
+};
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int A_TILE_BYTES = BM * BK * 2;
+
+// true when the persistent kernel's vectorised epilogue can take this problem
+bool gemm2_supported(const GemmParams& p);
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn_tile, cudaStream_t stream);
+
+}  // namespace mobi

@@ -78,7 +78,8 @@ def _rows_view(t, what):
 
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
-         tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0):
+         tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
+         kernel=0):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
@@ -127,13 +128,14 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.out_seg, args.out_seg_stride, args.out_seg_offset = out_seg, out_seg_stride, out_seg_offset
     args.conv = 0
     args.tile_n = tile_n
+    args.kernel = kernel
     with _timed("gemm", 2.0 * M * N * K):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
     return out
 
 
 def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_row_bias=0, residual=None, out=None,
-                  out_dtype=torch.float32, tile_n=0):
+                  out_dtype=torch.float32, tile_n=0, kernel=0):
     """Stride-1 'same' convolution of an NHWC bf16 image by implicit GEMM.
 
     x: [N, H, W, C] bf16; w: [Cout, kh*kw*C] bf16 with K ordered (kh, kw, c). Returns [N, H, W, Cout].
@@ -162,6 +164,7 @@ def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_ro
     args.conv, args.n_img, args.H, args.W, args.C = 1, n, h, wd, c
     args.KH, args.KW, args.pad_h, args.pad_w = kh, kw, pad_h, pad_w
     args.tile_n = tile_n
+    args.kernel = kernel
     with _timed("conv", 2.0 * n * h * wd * cout * kh * kw * c):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm(conv)")
     return out

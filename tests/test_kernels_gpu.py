@@ -46,16 +46,18 @@ def rnd(*shape, seed=0, dtype=torch.bfloat16, scale=1.0):
     (512, 320, 320, 0), (1000, 320, 320, 64), (4096, 640, 640, 0), (300, 1280, 1280, 256),
     (4, 1280, 320, 0), (260, 4, 2880, 64), (128, 128, 88, 128), (1024, 2560, 320, 0),
 ])
-def test_gemm_plain(M, N, K, tile_n):
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_gemm_plain(M, N, K, tile_n, kernel):
+    """kernel 0 = automatic (persistent kernel when its vector epilogue applies), 1 = one-tile kernel."""
     ops = _ops()
     a = rnd(M, K, seed=1)
     w = rnd(N, K, seed=2, scale=K ** -0.5)
     bias = rnd(N, seed=3, dtype=torch.float32)
     ref = a.float() @ w.float().t() + bias
-    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, tile_n=tile_n)
+    out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, tile_n=tile_n, kernel=kernel)
     torch.cuda.synchronize()
     assert relerr(out, ref) < 2e-3, describe(out, ref)
-    out16 = ops.gemm(a, w, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n)
+    out16 = ops.gemm(a, w, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n, kernel=kernel)
     assert relerr(out16, ref) < 1e-2, describe(out16, ref)
 
 
@@ -134,7 +136,8 @@ def test_gemm_head_layouts(B, T, H, D):
     (2, 64, 64, 320, 4, 3, 3), (1, 128, 128, 128, 128, 3, 3), (1, 256, 256, 128, 128, 1, 5),
     (2, 32, 32, 960, 640, 3, 3), (1, 64, 64, 64, 64, 3, 3),
 ])
-def test_conv_implicit(N, H, W, C, Cout, kh, kw):
+@pytest.mark.parametrize("kernel", [0, 1])
+def test_conv_implicit(N, H, W, C, Cout, kh, kw, kernel):
     ops = _ops()
     x = rnd(N, C, H, W, seed=1, dtype=torch.float32)
     w = rnd(Cout, C, kh, kw, seed=2, dtype=torch.float32, scale=(C * kh * kw) ** -0.5)
@@ -149,7 +152,7 @@ def test_conv_implicit(N, H, W, C, Cout, kh, kw):
     x_nhwc = xb.permute(0, 2, 3, 1).contiguous()
     wp = wb.permute(0, 2, 3, 1).reshape(Cout, kh * kw * C).contiguous()
     assert ops.conv_implicit_ok(H, W, C)
-    out = ops.conv_implicit(x_nhwc, wp, kh, kw, kh // 2, kw // 2, bias=b, row_bias=emb, residual=res)
+    out = ops.conv_implicit(x_nhwc, wp, kh, kw, kh // 2, kw // 2, bias=b, row_bias=emb, residual=res, kernel=kernel)
     assert relerr(out, ref) < 2e-3, describe(out.reshape(-1, Cout), ref.reshape(-1, Cout))
 
 

@@ -18,6 +18,7 @@ from mobi_b200 import _lib as L  # noqa: E402
 from mobi_b200 import ops  # noqa: E402
 
 R = int(os.environ.get("KB_ROWS", "32"))
+GK = int(os.environ.get("KB_GEMM_KERNEL", "0"))  # 1 = force the one-tile GEMM kernel
 OUT = os.path.join(ROOT, "gpurun_out", "kbench.jsonl")
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 
@@ -77,22 +78,22 @@ def bench_gemm():
             q = torch.empty(R * H, T, D, device="cuda", dtype=torch.bfloat16)
             k = torch.empty_like(q)
             vt = torch.empty(R * H, D, T, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: ops.gemm(a, w, epilogue=L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=vt)
+            fn = lambda: ops.gemm(a, w, epilogue=L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=vt, kernel=GK)
             nb = M * K * 2 + M * N * 2
         elif kind == "res":
             x = rnd(M, N, dtype=torch.float32)
-            fn = lambda: ops.gemm(a, w, bias=bias, residual=x, out=x)
+            fn = lambda: ops.gemm(a, w, bias=bias, residual=x, out=x, kernel=GK)
             nb = M * K * 2 + M * N * 8
         elif kind == "geglu":
             from mobi_b200.packing import interleave_geglu
             w2, b2 = interleave_geglu(w.float(), bias)
             w2 = w2.to(torch.bfloat16)
             o = torch.empty(M, N // 2, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU, out=o)
+            fn = lambda: ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU, out=o, kernel=GK)
             nb = M * K * 2 + M * N
         else:
             o = torch.empty(M, N, device="cuda", dtype=torch.float32)
-            fn = lambda: ops.gemm(a, w, bias=bias, out=o)
+            fn = lambda: ops.gemm(a, w, bias=bias, out=o, kernel=GK)
             nb = M * K * 2 + M * N * 4
         report("gemm %s M=%d N=%d K=%d" % (name, M, N, K), timeit(fn), fl, nb)
 
@@ -105,7 +106,7 @@ def bench_conv():
         res = rnd(R, S, S, Co, dtype=torch.float32)
         out = torch.empty(R, S, S, Co, device="cuda", dtype=torch.float32)
         fl = 2.0 * R * S * S * Co * 9 * C
-        ms = timeit(lambda: ops.conv_implicit(x, w, 3, 3, 1, 1, bias=bias, residual=res, out=out))
+        ms = timeit(lambda: ops.conv_implicit(x, w, 3, 3, 1, 1, bias=bias, residual=res, out=out, kernel=GK))
         report("conv3x3 %d->%d @%d" % (C, Co, S), ms, fl, x.numel() * 2 + out.numel() * 8)
 
 
