@@ -117,13 +117,14 @@ typedef struct {
     const void* x2; /* NULL when there is no concatenation */
     const float* gamma;
     const float* beta;
-    void* out;        /* bf16 [N, HW, C] */
+    void* out;        /* [N, HW, C] of out_dtype */
     void* out_concat; /* optional: the raw (un-normalised) concatenation as bf16 [N, HW, C] (NULL to skip) */
     float* partials;
     int32_t n_img, hw, c1, c2, groups;
     int32_t in_dtype;
     int32_t silu;
     float eps;
+    int32_t out_dtype; /* dtype of `out`: MOBI_DTYPE_BF16 (default, a GEMM/conv operand) or MOBI_DTYPE_F32 */
 } mobi_groupnorm_args;
 
 int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);
@@ -285,6 +286,12 @@ typedef struct {
     float sqrt_ac, sqrt_1mac;
 } mobi_assemble_args;
 int mobi_assemble_input(const mobi_assemble_args* args, void* stream);
+
+/* Row softmax p = 2^(s - rowmax) / rowsum of GEMM-produced scores (f32 [rows, cols], row stride ld_s) -> bf16
+ * (row stride ld_p).  The VAE AttnBlock (model.py:184-195) has ONE head of d = 512: its QK^T and PV products run as
+ * two mobi_gemm calls per image around this kernel; the C^-0.5 * log2(e) scale is folded into the q projection. */
+int mobi_softmax_rows(const float* s, void* p_bf16, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p,
+                      void* stream);
 
 /* out[i] = a[i] + b[i] (f32), used for residual joins that have no GEMM to fuse into. */
 int mobi_add_f32(const float* a, const float* b, float* out, int64_t n, void* stream);

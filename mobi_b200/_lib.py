@@ -44,7 +44,7 @@ class GroupNormArgs(C.Structure):
         ("x1", _vp), ("x2", _vp), ("gamma", _vp), ("beta", _vp), ("out", _vp), ("out_concat", _vp),
         ("partials", _vp),
         ("n_img", _i32), ("hw", _i32), ("c1", _i32), ("c2", _i32), ("groups", _i32),
-        ("in_dtype", _i32), ("silu", _i32), ("eps", _f32),
+        ("in_dtype", _i32), ("silu", _i32), ("eps", _f32), ("out_dtype", _i32),
     ]
 
 
@@ -121,6 +121,7 @@ SIGNATURES = {
     "mobi_upsample_nearest2x": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "mobi_im2col": (C.c_int, [C.POINTER(Im2colArgs), _vp]),
     "mobi_ctx_attention": (C.c_int, [C.POINTER(CtxAttnArgs), _vp]),
+    "mobi_softmax_rows": (C.c_int, [_vp, _vp, _i64, _i32, _i64, _i64, _vp]),
     "mobi_sampler_update": (C.c_int, [C.POINTER(SamplerArgs), _vp]),
     "mobi_assemble_input": (C.c_int, [C.POINTER(AssembleArgs), _vp]),
     "mobi_add_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),

@@ -132,36 +132,65 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     umma_commit(&s_full[t]);
                 };
-                mbar_wait(q_full, 0);
-                mbar_wait(&kv_full[0], 0);
-                tc_fence_after();
-                for (int t = 0; t < ntiles; ++t) issue_S(t, 0);
-                for (int j = 0; j < nblk; ++j) {
+                auto issue_PV = [&](int t, int j) {  // O_t += P_t(j) V(j)
                     const int s = j & 1;
-                    const uint32_t ph = j & 1;
-                    if (j + 1 < nblk) {
-                        // the next score tiles, as soon as the softmax threads have pulled S(j) into registers
-                        mbar_wait(&kv_full[(j + 1) & 1], ((j + 1) >> 1) & 1);
-                        for (int t = 0; t < ntiles; ++t) {
-                            mbar_wait(&s_free[t], ph);
-                            tc_fence_after();
-                            issue_S(t, j + 1);
-                        }
+                    const uint32_t d_tmem = tmem_base + O_BASE + t * O_STRIDE;
+                    for (int k = 0; k < BKV / 16; ++k) {
+                        const uint64_t a =
+                            make_kmajor_sw128_desc(smem_u32(sP + (t * KCH + (k >> 2)) * A2_CHUNK)) + 2 * (k & 3);
+                        const uint64_t b =
+                            make_kmajor_sw128_desc(smem_u32(sV + s * v_bytes + (k >> 2) * v_chunk)) + 2 * (k & 3);
+                        umma_bf16_ss(d_tmem, a, b, idesc_o, (j | k) != 0 ? 1u : 0u);
                     }
+                    umma_commit(&pv_done[t]);
+                };
+                // Event loop: the two tiles advance independently (no head-of-line blocking between them).
+                //   S_t(j+1) is issued as soon as softmax t has pulled S_t(j) into registers (s_free) and K(j+1) landed;
+                //   PV_t(j)  is issued as soon as P_t(j) is in shared memory (p_full);
+                //   a K/V stage is released once both tiles have issued their PV on it.
+                // Tile 1 starts only after tile 0 has read its first score tile: the half-block phase offset keeps one
+                // warpgroup in its exponential phase while the other one waits for TMEM loads.
+                int js[2] = {0, 0};  // next score block to issue per tile
+                int jp[2] = {0, 0};  // next PV block to issue per tile
+                int released = 0;    // K/V blocks handed back to the producer
+                mbar_wait(q_full, 0);
+                const long long t_start = clock64();
+                for (;;) {
+                    bool done = true, progress = false;
                     for (int t = 0; t < ntiles; ++t) {
-                        mbar_wait(&p_full[t], ph);
-                        tc_fence_after();
-                        const uint32_t d_tmem = tmem_base + O_BASE + t * O_STRIDE;
-                        for (int k = 0; k < BKV / 16; ++k) {
-                            const uint64_t a =
-                                make_kmajor_sw128_desc(smem_u32(sP + (t * KCH + (k >> 2)) * A2_CHUNK)) + 2 * (k & 3);
-                            const uint64_t b =
-                                make_kmajor_sw128_desc(smem_u32(sV + s * v_bytes + (k >> 2) * v_chunk)) + 2 * (k & 3);
-                            umma_bf16_ss(d_tmem, a, b, idesc_o, (j | k) != 0 ? 1u : 0u);
+                        if (jp[t] < nblk) done = false;
+                        // next score tile
+                        if (js[t] < nblk) {
+                            const int j = js[t];
+                            // (probes are non-blocking and each barrier is at most one phase ahead of the one probed)
+                            bool ok = mbar_test_wait(&kv_full[j & 1], (j >> 1) & 1);
+                            if (ok && j > 0) ok = mbar_test_wait(&s_free[t], (j - 1) & 1);
+                            if (ok && j == 0 && t == 1) ok = (js[0] >= 2) || (jp[0] >= 1);  // phase offset
+                            if (ok) {
+                                tc_fence_after();
+                                issue_S(t, j);
+                                js[t] = j + 1;
+                                progress = true;
+                            }
                         }
-                        umma_commit(&pv_done[t]);
+                        // next value product
+                        if (jp[t] < nblk && jp[t] < js[t]) {
+                            const int j = jp[t];
+                            if (mbar_test_wait(&p_full[t], j & 1)) {
+                                tc_fence_after();
+                                issue_PV(t, j);
+                                jp[t] = j + 1;
+                                progress = true;
+                                const int lo = ntiles == 2 ? min(jp[0], jp[1]) : jp[0];
+                                while (released < lo) {
+                                    umma_commit(&kv_empty[released & 1]);
+                                    ++released;
+                                }
+                            }
+                        }
                     }
-                    umma_commit(&kv_empty[s]);  // K(j) and V(j) have been consumed by every MMA issued so far
+                    if (done) break;
+                    if (!progress && clock64() - t_start > MOBI_WAIT_LIMIT_CYCLES) asm volatile("trap;");
                 }
             }
         }
@@ -201,10 +230,10 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                 if (j == 0) {
                     m_used = mx;
                 } else {
-                    // PV(j-1) complete: O is consistent for a rescale and the P buffer is free again
-                    mbar_wait(&pv_done[t], ph ^ 1);
                     const bool need = mx > m_used + 8.0f;
                     if (__any_sync(0xffffffffu, need)) {
+                        // PV(j-1) must be complete before O is rescaled in place
+                        mbar_wait(&pv_done[t], ph ^ 1);
                         tc_fence_after();
                         const float m_new = fmaxf(m_used, mx);
                         const float alpha = ex2_approx(m_used - m_new);
@@ -222,7 +251,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         tmem_st_wait();
                     }
                 }
-                // probabilities -> bf16, swizzled K-major tile (row = query, 64 keys per chunk)
+                // probabilities -> packed bf16 in registers (in place: sr[c/2] <- pack(p[c], p[c+1]))
                 float lsum = 0.f;
 #pragma unroll
                 for (int c = 0; c < BKV; c += 8) {
@@ -230,10 +259,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 #pragma unroll
                     for (int i = 0; i < 8; ++i) e[i] = ex2_approx(__uint_as_float(sr[c + i]) - m_used);
                     lsum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) sr[(c >> 1) + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+                }
+                // the P buffer is free once PV(j-1) has completed (it almost always has by now)
+                if (j > 0) mbar_wait(&pv_done[t], ph ^ 1);
+                // swizzled K-major tile (row = query, 64 keys per 128-byte row chunk)
+#pragma unroll
+                for (int c = 0; c < BKV; c += 8) {
                     const int unit = (c & 63) >> 3;  // 16-byte unit inside the 128-byte row
                     *reinterpret_cast<uint4*>(prow + (c >> 6) * A2_CHUNK + ((unit ^ (row & 7)) << 4)) =
-                        make_uint4(pack_bf16x2(e[0], e[1]), pack_bf16x2(e[2], e[3]), pack_bf16x2(e[4], e[5]),
-                                   pack_bf16x2(e[6], e[7]));
+                        make_uint4(sr[(c >> 1)], sr[(c >> 1) + 1], sr[(c >> 1) + 2], sr[(c >> 1) + 3]);
                 }
                 l += lsum;
                 fence_proxy_async();  // generic-proxy smem writes -> visible to the tensor-core (async) proxy

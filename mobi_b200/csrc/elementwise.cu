@@ -13,22 +13,26 @@ __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + __expf(-x)
 
 // ------------------------------------------------------------------------------------------------
 // GroupNorm: pass 1 = deterministic per-slab partial sums, pass 2 = finalize + normalise (+SiLU).
+// Both passes: warp <-> pixel, lane <-> 4-channel vectors (16-byte loads, 8-byte bf16 stores), GN_K vectors of a
+// pixel in flight per lane.
 // ------------------------------------------------------------------------------------------------
 constexpr int GN_THREADS = 256;
 constexpr int GN_WARPS = GN_THREADS / 32;
+constexpr int GN_K = 4;  // float4 vectors per lane per pass: 512 channels per pass
 
 template <bool IN_F32>
-__device__ __forceinline__ float2 gn_load2(const void* x1, const void* x2, int c1, int c2, long long pix, int c) {
-    // c is even; c1 is even, so a pair never straddles the concatenation boundary
+__device__ __forceinline__ float4 gn_load4(const void* x1, const void* x2, int c1, int c2, long long pix, int c) {
+    // c and c1 are multiples of 4, so a vector never straddles the concatenation boundary
     const void* src = (c < c1) ? x1 : x2;
     const int cc = (c < c1) ? c : c - c1;
     const int cw = (c < c1) ? c1 : c2;
     if (IN_F32) {
-        return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(src) + pix * cw + cc);
+        return *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(src) + pix * cw + cc);
     } else {
-        const __nv_bfloat162 v =
-            *reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(src) + pix * cw + cc);
-        return __bfloat1622float2(v);
+        const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const __nv_bfloat16*>(src) + pix * cw + cc);
+        const float2 lo = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.x));
+        const float2 hi = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&v.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
     }
 }
 
@@ -37,9 +41,9 @@ template <bool IN_F32>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const void* x1, const void* x2, float* partials, int hw, int c1, int c2, int groups,
                 int pix_per_slab) {
-    extern __shared__ float gn_smem[];  // [GN_WARPS][C/2][2]
+    extern __shared__ float gn_smem[];  // [GN_WARPS][C][2]
     const int C = c1 + c2;
-    const int half = C / 2;
+    const int nv = C >> 2;
     const int cpg = C / groups;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n = blockIdx.y;
@@ -47,71 +51,106 @@ gn_stats_kernel(const void* x1, const void* x2, float* partials, int hw, int c1,
     const int p1 = min(hw, p0 + pix_per_slab);
     const long long img_off = (long long)n * hw;
 
-    // each lane owns channel pairs v = lane + 32*k; accumulate over this warp's pixels
-    for (int vbase = 0; vbase < half; vbase += 32 * 4) {
-        float s[4] = {0.f, 0.f, 0.f, 0.f}, q[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int p = p0 + warp; p < p1; p += GN_WARPS) {
+    for (int vbase = 0; vbase < nv; vbase += 32 * GN_K) {
+        float4 s[GN_K], q[GN_K];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < GN_K; ++k) s[k] = q[k] = make_float4(0.f, 0.f, 0.f, 0.f);
+        // two pixels per iteration: 2 * GN_K independent 16-byte loads in flight per lane
+        for (int p = p0 + warp; p < p1; p += 2 * GN_WARPS) {
+            float4 f[2][GN_K];
+            const bool second = (p + GN_WARPS) < p1;
+#pragma unroll
+            for (int k = 0; k < GN_K; ++k) {
                 const int v = vbase + lane + 32 * k;
-                if (v < half) {
-                    const float2 f = gn_load2<IN_F32>(x1, x2, c1, c2, img_off + p, 2 * v);
-                    s[k] += f.x + f.y;
-                    q[k] += f.x * f.x + f.y * f.y;
+                f[0][k] = f[1][k] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (v < nv) {
+                    f[0][k] = gn_load4<IN_F32>(x1, x2, c1, c2, img_off + p, 4 * v);
+                    if (second) f[1][k] = gn_load4<IN_F32>(x1, x2, c1, c2, img_off + p + GN_WARPS, 4 * v);
                 }
             }
+#pragma unroll
+            for (int u = 0; u < 2; ++u)
+#pragma unroll
+                for (int k = 0; k < GN_K; ++k) {
+                    const float4 g = f[u][k];
+                    s[k].x += g.x; s[k].y += g.y; s[k].z += g.z; s[k].w += g.w;
+                    q[k].x += g.x * g.x; q[k].y += g.y * g.y; q[k].z += g.z * g.z; q[k].w += g.w * g.w;
+                }
         }
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
+        for (int k = 0; k < GN_K; ++k) {
             const int v = vbase + lane + 32 * k;
-            if (v < half) {
-                gn_smem[(warp * half + v) * 2 + 0] = s[k];
-                gn_smem[(warp * half + v) * 2 + 1] = q[k];
+            if (v < nv) {
+                float4* dst = reinterpret_cast<float4*>(gn_smem + ((size_t)warp * C + 4 * v) * 2);
+                dst[0] = make_float4(s[k].x, q[k].x, s[k].y, q[k].y);
+                dst[1] = make_float4(s[k].z, q[k].z, s[k].w, q[k].w);
             }
         }
     }
     __syncthreads();
-    if (threadIdx.x < groups) {
-        const int g = threadIdx.x;
+    // 8 threads per group: each sums a strided share of the group's (warp, channel) cells, then a shuffle reduce
+    {
+        const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
         float s = 0.f, q = 0.f;
-        const int v0 = g * cpg / 2, v1 = (g + 1) * cpg / 2;
-        for (int w = 0; w < GN_WARPS; ++w)
-            for (int v = v0; v < v1; ++v) {
-                s += gn_smem[(w * half + v) * 2 + 0];
-                q += gn_smem[(w * half + v) * 2 + 1];
+        if (g < groups) {
+            const int cells = GN_WARPS * cpg;
+            for (int i = part; i < cells; i += 8) {
+                const int w = i / cpg, c = g * cpg + (i - w * cpg);
+                s += gn_smem[((size_t)w * C + c) * 2 + 0];
+                q += gn_smem[((size_t)w * C + c) * 2 + 1];
             }
-        float* out = partials + (((long long)n * gridDim.x + blockIdx.x) * groups + g) * 2;
-        out[0] = s;
-        out[1] = q;
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && part == 0) {
+            float* out = partials + (((long long)n * gridDim.x + blockIdx.x) * groups + g) * 2;
+            out[0] = s;
+            out[1] = q;
+        }
     }
 }
 
 // grid (slabs2, n_img): each CTA finalises the statistics of its image (cheap) and normalises a slab.
-template <bool IN_F32>
+template <bool IN_F32, bool OUT_F32>
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma, const float* __restrict__ beta,
-                __nv_bfloat16* __restrict__ out, __nv_bfloat16* __restrict__ out_concat,
+                void* __restrict__ out_, __nv_bfloat16* __restrict__ out_concat,
                 const float* __restrict__ partials, int n_stat_slabs, int hw, int c1, int c2, int groups, float eps,
                 int silu, int pix_per_slab) {
     extern __shared__ float gn_smem[];  // scale[C], shift[C]
-    __shared__ float s_mean[64], s_rstd[64];
+    __shared__ float s_mean[32], s_rstd[32];
     const int C = c1 + c2;
+    const int nv = C >> 2;
     const int cpg = C / groups;
     const int n = blockIdx.y;
-    if (threadIdx.x < groups) {
-        const int g = threadIdx.x;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    {
+        // 8 threads per group over the stat slabs (groups <= 32)
+        const int g = threadIdx.x >> 3, part = threadIdx.x & 7;
         double s = 0.0, q = 0.0;
-        const float* pp = partials + ((long long)n * n_stat_slabs * groups + g) * 2;
-        for (int i = 0; i < n_stat_slabs; ++i) {
-            s += (double)pp[(long long)i * groups * 2 + 0];
-            q += (double)pp[(long long)i * groups * 2 + 1];
+        if (g < groups) {
+            const float* pp = partials + ((long long)n * n_stat_slabs * groups + g) * 2;
+            for (int i = part; i < n_stat_slabs; i += 8) {
+                s += (double)pp[(long long)i * groups * 2 + 0];
+                q += (double)pp[(long long)i * groups * 2 + 1];
+            }
         }
-        const double cnt = (double)hw * cpg;
-        const double mean = s / cnt;
-        double var = q / cnt - mean * mean;
-        if (var < 0.0) var = 0.0;
-        s_mean[g] = (float)mean;
-        s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            s += __shfl_xor_sync(0xffffffffu, s, o);
+            q += __shfl_xor_sync(0xffffffffu, q, o);
+        }
+        if (g < groups && part == 0) {
+            const double cnt = (double)hw * cpg;
+            const double mean = s / cnt;
+            double var = q / cnt - mean * mean;
+            if (var < 0.0) var = 0.0;
+            s_mean[g] = (float)mean;
+            s_rstd[g] = (float)(1.0 / sqrt(var + (double)eps));
+        }
     }
     __syncthreads();
     float* s_scale = gn_smem;
@@ -123,38 +162,58 @@ gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
         s_shift[c] = beta[c] - s_mean[g] * a;
     }
     __syncthreads();
-    const int half = C / 2;
     const int p0 = blockIdx.x * pix_per_slab;
     const int p1 = min(hw, p0 + pix_per_slab);
     const long long img_off = (long long)n * hw;
-    // thread -> (pixel, channel pair) without per-element division: the pair index advances by GN_THREADS mod half
-    const int step_p = GN_THREADS / half, step_v = GN_THREADS % half;
-    int p = p0 + (int)threadIdx.x / half;
-    int v = (int)threadIdx.x % half;
-    while (p < p1) {
-        const int c = 2 * v;
-        const float2 f = gn_load2<IN_F32>(x1, x2, c1, c2, img_off + p, c);
-        float y0 = f.x * s_scale[c] + s_shift[c];
-        float y1 = f.y * s_scale[c + 1] + s_shift[c + 1];
-        if (silu) {
-            y0 = silu_f(y0);
-            y1 = silu_f(y1);
-        }
-        const long long o = (img_off + p) * C + c;
-        *reinterpret_cast<__nv_bfloat162*>(out + o) = __floats2bfloat162_rn(y0, y1);
-        if (out_concat) *reinterpret_cast<__nv_bfloat162*>(out_concat + o) = __floats2bfloat162_rn(f.x, f.y);
-        p += step_p;
-        v += step_v;
-        if (v >= half) {
-            v -= half;
-            ++p;
+    for (int p = p0 + warp; p < p1; p += 2 * GN_WARPS) {
+        const bool second = (p + GN_WARPS) < p1;
+        for (int vbase = 0; vbase < nv; vbase += 32 * GN_K) {
+            float4 f[2][GN_K];
+#pragma unroll
+            for (int k = 0; k < GN_K; ++k) {
+                const int v = vbase + lane + 32 * k;
+                if (v < nv) {
+                    f[0][k] = gn_load4<IN_F32>(x1, x2, c1, c2, img_off + p, 4 * v);
+                    if (second) f[1][k] = gn_load4<IN_F32>(x1, x2, c1, c2, img_off + p + GN_WARPS, 4 * v);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                if (u == 1 && !second) break;
+                const long long pp = img_off + p + u * GN_WARPS;
+#pragma unroll
+                for (int k = 0; k < GN_K; ++k) {
+                    const int v = vbase + lane + 32 * k;
+                    if (v < nv) {
+                        const float4 sc = *reinterpret_cast<const float4*>(s_scale + 4 * v);
+                        const float4 sh = *reinterpret_cast<const float4*>(s_shift + 4 * v);
+                        const float4 g = f[u][k];
+                        float y0 = g.x * sc.x + sh.x, y1 = g.y * sc.y + sh.y;
+                        float y2 = g.z * sc.z + sh.z, y3 = g.w * sc.w + sh.w;
+                        if (silu) {
+                            y0 = silu_f(y0);
+                            y1 = silu_f(y1);
+                            y2 = silu_f(y2);
+                            y3 = silu_f(y3);
+                        }
+                        const long long o = pp * C + 4 * v;
+                        if (OUT_F32)
+                            *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + o) = make_float4(y0, y1, y2, y3);
+                        else
+                            *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_) + o) =
+                                make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+                        if (out_concat)
+                            *reinterpret_cast<uint2*>(out_concat + o) = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+                    }
+                }
+            }
         }
     }
 }
 
 static int gn_slabs(int hw, int C) {
-    // ~64 KB of fp32 input per slab, at least GN_WARPS pixels
-    long long pix = (64 * 1024) / ((long long)C * 4);
+    // ~128 KB of fp32 input per slab, at least GN_WARPS pixels
+    long long pix = (128 * 1024) / ((long long)C * 4);
     if (pix < GN_WARPS) pix = GN_WARPS;
     int slabs = (int)((hw + pix - 1) / pix);
     if (slabs > 256) slabs = 256;
@@ -429,6 +488,55 @@ __global__ void cast_bf16_kernel(const float* a, __nv_bfloat16* o, long long n) 
     if (i < n) o[i] = __float2bfloat16(a[i]);
 }
 
+// Row softmax of a score matrix that was produced by a GEMM (VAE AttnBlock, model.py:184-195: one head, d = C = 512,
+// too wide for the fused kernels' TMEM budget).  Scores are already scaled by C^-0.5 * log2(e) (folded into the q
+// projection), so p = 2^(s - max) / sum.  One CTA per row; the row is read three times (max, sum, write) out of L2.
+__global__ void __launch_bounds__(256)
+softmax_rows_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ p, int cols, long long ld_s, long long ld_p) {
+    __shared__ float red[8];
+    __shared__ float bcast;
+    const float* row = s + (long long)blockIdx.x * ld_s;
+    __nv_bfloat16* out = p + (long long)blockIdx.x * ld_p;
+    const int nv = cols >> 2;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float mx = -INFINITY;
+    for (int i = threadIdx.x; i < nv; i += 256) {
+        const float4 v = reinterpret_cast<const float4*>(row)[i];
+        mx = fmaxf(fmaxf(mx, fmaxf(v.x, v.y)), fmaxf(v.z, v.w));
+    }
+    mx = warp_max(mx);
+    if (lane == 0) red[warp] = mx;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float m = red[0];
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, red[i]);
+        bcast = m;
+    }
+    __syncthreads();
+    mx = bcast;
+    float sum = 0.f;
+    for (int i = threadIdx.x; i < nv; i += 256) {
+        const float4 v = reinterpret_cast<const float4*>(row)[i];
+        sum += (exp2f(v.x - mx) + exp2f(v.y - mx)) + (exp2f(v.z - mx) + exp2f(v.w - mx));
+    }
+    sum = warp_sum(sum);
+    __syncthreads();
+    if (lane == 0) red[warp] = sum;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float t = 0.f;
+        for (int i = 0; i < 8; ++i) t += red[i];
+        bcast = 1.0f / t;
+    }
+    __syncthreads();
+    const float inv = bcast;
+    for (int i = threadIdx.x; i < nv; i += 256) {
+        const float4 v = reinterpret_cast<const float4*>(row)[i];
+        reinterpret_cast<uint2*>(out)[i] = make_uint2(pack_bf16x2(exp2f(v.x - mx) * inv, exp2f(v.y - mx) * inv),
+                                                      pack_bf16x2(exp2f(v.z - mx) * inv, exp2f(v.w - mx) * inv));
+    }
+}
+
 static inline unsigned blocks_for(long long n, int threads) { return (unsigned)((n + threads - 1) / threads); }
 
 }  // namespace mobi
@@ -443,13 +551,13 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MOBI_CHECK(a && a->x1 && a->gamma && a->beta && a->out && a->partials, "mobi_groupnorm: null argument");
     const int C = a->c1 + a->c2;
-    MOBI_CHECK(a->groups > 0 && a->groups <= 64 && C % a->groups == 0, "mobi_groupnorm: C=%d groups=%d", C, a->groups);
-    MOBI_CHECK((C / a->groups) % 2 == 0 && a->c1 % 2 == 0 && a->c2 % 2 == 0,
-               "mobi_groupnorm: channels per group and concat halves must be even (C=%d c1=%d)", C, a->c1);
+    MOBI_CHECK(a->groups > 0 && a->groups <= 32 && C % a->groups == 0, "mobi_groupnorm: C=%d groups=%d", C, a->groups);
+    MOBI_CHECK(a->c1 % 4 == 0 && a->c2 % 4 == 0,
+               "mobi_groupnorm: channel counts of both inputs must be multiples of 4 (c1=%d c2=%d)", a->c1, a->c2);
     MOBI_CHECK(a->c2 == 0 || a->x2 != nullptr, "mobi_groupnorm: c2 > 0 needs x2");
     const int slabs = gn_slabs(a->hw, C);
     const int pix_per_slab = (a->hw + slabs - 1) / slabs;
-    const size_t smem1 = (size_t)GN_WARPS * (C / 2) * 2 * sizeof(float);
+    const size_t smem1 = (size_t)GN_WARPS * C * 2 * sizeof(float);
     const size_t smem2 = (size_t)2 * C * sizeof(float);
     const bool f32 = a->in_dtype == MOBI_DTYPE_F32;
     static bool configured = false;
@@ -468,21 +576,21 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
                                                                      a->groups, pix_per_slab);
     MOBI_CUDA(cudaGetLastError());
     // apply: finer slabs so small images still fill the machine
-    long long pix2 = (32 * 1024) / ((long long)C * 4);
-    if (pix2 < 1) pix2 = 1;
+    long long pix2 = (128 * 1024) / ((long long)C * 4);
+    if (pix2 < GN_WARPS) pix2 = GN_WARPS;
     int slabs2 = (int)((a->hw + pix2 - 1) / pix2);
     const int pix_per_slab2 = (a->hw + slabs2 - 1) / slabs2;
     dim3 grid2(slabs2, a->n_img);
-    if (f32)
-        gn_apply_kernel<true><<<grid2, GN_THREADS, smem2, stream>>>(
-            a->x1, a->x2, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out),
-            reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, a->hw, a->c1, a->c2, a->groups, a->eps,
-            a->silu, pix_per_slab2);
-    else
-        gn_apply_kernel<false><<<grid2, GN_THREADS, smem2, stream>>>(
-            a->x1, a->x2, a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out),
-            reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, a->hw, a->c1, a->c2, a->groups, a->eps,
-            a->silu, pix_per_slab2);
+#define GN_APPLY(INF, OUTF)                                                                                            \
+    gn_apply_kernel<INF, OUTF><<<grid2, GN_THREADS, smem2, stream>>>(                                                  \
+        a->x1, a->x2, a->gamma, a->beta, a->out, reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, \
+        a->hw, a->c1, a->c2, a->groups, a->eps, a->silu, pix_per_slab2)
+    const bool of32 = a->out_dtype == MOBI_DTYPE_F32;
+    if (f32 && of32) GN_APPLY(true, true);
+    else if (f32) GN_APPLY(true, false);
+    else if (of32) GN_APPLY(false, true);
+    else GN_APPLY(false, false);
+#undef GN_APPLY
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -577,6 +685,17 @@ extern "C" int mobi_ctx_attention(const mobi_ctx_attn_args* a, void* stream_) {
     const int warps = 8;
     ctx_attention_kernel<<<blocks_for(rows, warps), warps * 32, 0, stream>>>(
         reinterpret_cast<const __nv_bfloat16*>(a->xn), a->U, a->Z, a->zb, a->x, a->tokens, a->C, a->heads, a->keys, rows);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_softmax_rows(const float* s, void* p, int64_t rows, int32_t cols, int64_t ld_s, int64_t ld_p,
+                                 void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(s && p && rows > 0 && cols > 0, "mobi_softmax_rows: bad argument");
+    MOBI_CHECK(cols % 4 == 0 && ld_s % 4 == 0 && ld_p % 4 == 0 && rows < (1ll << 31),
+               "mobi_softmax_rows: cols=%d and row strides must be multiples of 4", cols);
+    softmax_rows_kernel<<<(unsigned)rows, 256, 0, stream>>>(s, reinterpret_cast<__nv_bfloat16*>(p), cols, ld_s, ld_p);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

@@ -54,6 +54,20 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// Non-blocking probe (try_wait may suspend the thread for a system-dependent time; event loops must not).
+__device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 P, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
 // Bounded wait: a protocol bug must trap (reported as a launch failure), never hang the GPU box.
 #ifndef MOBI_WAIT_LIMIT_CYCLES
 #define MOBI_WAIT_LIMIT_CYCLES 6000000000ll  /* ~3-4 s at B200 clocks */

@@ -213,7 +213,7 @@ def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0):
     return out
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_concat=False):
+def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_concat=False, out_dtype=torch.bfloat16):
     """x1 (and optionally x2, concatenated on channels): NHWC [N, H, W, C] f32|bf16 -> bf16 NHWC."""
     _cuda(x1, x2, gamma, beta)
     n = x1.shape[0]
@@ -223,8 +223,8 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_conca
     if x2 is not None:
         assert x2.dtype == x1.dtype and x2.shape[:-1] == x1.shape[:-1]
     c = c1 + c2
-    out = torch.empty(x1.shape[:-1] + (c,), device=x1.device, dtype=torch.bfloat16)
-    cat = torch.empty_like(out) if want_concat else None
+    out = torch.empty(x1.shape[:-1] + (c,), device=x1.device, dtype=out_dtype)
+    cat = torch.empty(out.shape, device=x1.device, dtype=torch.bfloat16) if want_concat else None
     lib = L.load()
     nbytes = lib.mobi_groupnorm_scratch_bytes(n, hw, c, groups)
     partials = torch.empty((nbytes // 4,), device=x1.device, dtype=torch.float32)
@@ -232,7 +232,7 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_conca
     a.x1, a.x2, a.gamma, a.beta = x1.data_ptr(), L.ptr(x2), gamma.data_ptr(), beta.data_ptr()
     a.out, a.out_concat, a.partials = out.data_ptr(), L.ptr(cat), partials.data_ptr()
     a.n_img, a.hw, a.c1, a.c2, a.groups = n, hw, c1, c2, groups
-    a.in_dtype, a.silu, a.eps = L.dt(x1), int(silu), eps
+    a.in_dtype, a.silu, a.eps, a.out_dtype = L.dt(x1), int(silu), eps, L.dt(out)
     with _timed("groupnorm", 0.0, x1.numel() * x1.element_size() * 2 + (x2.numel() * x2.element_size() * 2 if x2 is not None else 0)
                 + out.numel() * 2 * (2 if want_concat else 1), kernels=2):
         L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")
@@ -366,6 +366,18 @@ def ctx_attention(xn, U, Z, zb, x, batch, tokens, heads, keys):
     with _timed("ctx_attention", 0.0, xn.numel() * 2.0 + x.numel() * 8.0):
         L.check(L.load().mobi_ctx_attention(C.byref(a), L.stream()), "ctx_attention")
     return x
+
+
+def softmax_rows(s, out=None):
+    """s: f32 [rows, cols] scores in log2 units -> bf16 probabilities (see mobi_softmax_rows)."""
+    _cuda(s, out)
+    assert s.dtype == torch.float32 and s.dim() == 2
+    if out is None:
+        out = torch.empty(s.shape, device=s.device, dtype=torch.bfloat16)
+    with _timed("softmax", 0.0, s.numel() * 14.0):
+        L.check(L.load().mobi_softmax_rows(s.data_ptr(), out.data_ptr(), s.shape[0], s.shape[1], s.stride(0),
+                                           out.stride(0), L.stream()), "softmax_rows")
+    return out
 
 
 def add_f32(a, b, out=None):
