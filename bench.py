@@ -139,7 +139,7 @@ def run_reference(args):
 def run_native(args):
     import torch
     import torch.distributed as dist
-    from mobi_b200 import ops, synth
+    from mobi_b200 import ops, sharding, synth
     from mobi_b200.ddim import DDIMSampler
 
     if not torch.cuda.is_available():
@@ -153,12 +153,19 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.samples_per_gpu
     latent = args.latent
-    ldm = synth.build_synthetic_ldm(latent=latent, device=dev, seed=0)
+    ldm = synth.build_synthetic_ldm(latent=latent, device=dev, seed=0, with_vae=True)
     sampler = DDIMSampler(ldm, use_cuda_graph=not args.no_graph)
-    # per-rank inputs: sample index = rank * n + i  (results do not depend on the sharding)
-    host = synth.synthetic_inputs(n, latent, seed=1 + rank, pin=True)
+    # the job is n * world joint samples cut into per-rank shards between samples (mobi_b200/sharding.py); every
+    # sample's inputs and noise depend on its GLOBAL index only, so results do not depend on the number of GPUs
+    lo, hi = sharding.shard_bounds(n * world, world, rank)
+    full = synth.synthetic_inputs(n * world, latent, seed=1)
+    host = {k: sharding.shard_rows(v, world, rank).contiguous() for k, v in full.items()}
+    host["x_T"] = sharding.sample_noise((4, latent, latent), lo, hi, base_seed=1)
+    host = {k: v.pin_memory() for k, v in host.items()}
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
-    host_out = torch.empty((2 * n, 4, latent, latent), dtype=torch.float32).pin_memory()
+    px = 8 * latent
+    host_img = torch.empty((n, 3, px, px), dtype=torch.float32).pin_memory()
+    host_rng = torch.empty((n, 2, px, px), dtype=torch.float32).pin_memory()
 
     def sample_from(inp):
         return sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=2 * n, shape=[4, latent, latent],
@@ -171,9 +178,13 @@ def run_native(args):
         return sample_from(devin)
 
     def step_e2e():
+        """What a user of the reference runs per batch (scripts/inference_test_bench.py:414-464): inputs from pinned host
+        memory, sampler.sample, decode_sample, decode_first_stage for both modalities, decoded images back to the host."""
         inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
         out = sample_from(inp)
-        host_out.copy_(out, non_blocking=True)                                  # D2H of the result
+        h_cam, h_lid = ldm.decode_sample(out, out[1::2])
+        host_img.copy_(ldm.decode_first_stage(h_cam), non_blocking=True)       # D2H of the results
+        host_rng.copy_(ldm.decode_first_stage(h_lid, module_name="lidar_stage_model"), non_blocking=True)
         return out
 
     def barrier():
@@ -210,7 +221,7 @@ def run_native(args):
     value = total_samples / (ms / 1e3)
     e2e_value = total_samples / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = host_out.numel() * host_out.element_size()
+    d2h = host_img.numel() * 4 + host_rng.numel() * 4
 
     # ---- roofline of the dominant kernel class (tcgen05 GEMM / implicit conv), timed live with CUDA events on
     # the launching stream over one eager UNet evaluation of the same batch
@@ -220,7 +231,8 @@ def run_native(args):
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else "fallback 1.4 PFLOP/s sustained"
+    peak_src = "of measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else \
+        "of fallback (1.4 PFLOP/s sustained under the power cap; B200_PROFILING.md; burst 1.59)"
     roofline = None
     if rank == 0:
         x_in = torch.randn(4 * n, 9, latent, latent, device=dev)
@@ -239,7 +251,7 @@ def run_native(args):
         achieved = tc_fl / (tc_ms / 1e3) / 1e12
         step_flops = UNET_FLOPS_PER_JOINT.get(latent, 0) * 2 * n   # x2: CFG doubles the rows
         ms_unet = ms / args.steps / max(1, unet_evals // args.steps)
-        roofline = {"bound": "tensor", "kernel": "gemm_bf16_kernel (tcgen05 GEMM + implicit-GEMM conv3x3)",
+        roofline = {"bound": "tensor", "kernel": "gemm2_kernel (persistent tcgen05 GEMM + implicit-GEMM conv3x3)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
                     "peak_source": peak_src, "traffic": None,
                     "launches_per_unet_call": tc_n, "flops_per_launch_avg": tc_fl / max(1, tc_n),
@@ -270,7 +282,9 @@ def run_native(args):
             "config": {"workload": workload_name(args), "latent": latent, "rows_per_unet_call": 4 * n,
                        "ddim_steps": args.ddim_steps, "cfg_scale": CFG_SCALE, "sharding": "samples/%d GPUs, no collective" % world,
                        "l2": "inputs larger than L2 (2.1 GB bf16 weights streamed per UNet call)",
-                       "cuda_graph": not args.no_graph},
+                       "cuda_graph": not args.no_graph,
+                       "e2e_includes": "pinned H2D of latents/conditioning, sampling, camera + range-view VAE decode "
+                                       "to %dx%d, D2H of decoded images" % (px, px)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": gpu_launches, "unet_evals": unet_evals, "clocks": clock_info,

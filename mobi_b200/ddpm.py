@@ -130,9 +130,14 @@ class LatentDiffusion(nn.Module):
         assert not predict_cids
         module = getattr(self, module_name)
         sf = self.scale_factor if module_name == "first_stage_model" else self.lidar_scale_factor
-        z = 1.0 / sf * z
         if self.first_stage_key == "inpaint":
-            return module.decode(z[:, :4, :, :])
+            z = z[:, :4, :, :]
+        z = z.detach().float().contiguous()
+        if z.is_cuda:
+            from . import ops
+            z = ops.scale_f32(z, 1.0 / sf)       # z / scale_factor (ddpm.py:846-849)
+        else:
+            z = 1.0 / sf * z
         return module.decode(z)
 
     def decode_sample(self, sample, z_lidar=None):

@@ -283,11 +283,13 @@ class UNetModel(nn.Module):
         self._p = None
         self._ctx_key = None
         self._ctx_tabs = None
+        self._pack_serial = 0
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ------------------------------------------------------------------ packing
     def invalidate(self):
         """Drop packed weights (call after changing parameters in place)."""
+        self._pack_serial += 1  # samplers key their captured CUDA graphs on this
         self._p = None
         self._ctx_key = None
         self._ctx_tabs = None

@@ -57,7 +57,8 @@ class SamplerBase(object):
         self.ddpm_num_timesteps = model.num_timesteps
         self.schedule = schedule
         self.use_cuda_graph = use_cuda_graph
-        self._graph = None
+        self._graph = self._graph_ctx = None
+        self._static_key = None
         self.launches = 0  # UNet evaluations issued (for bench accounting)
 
     def register_buffer(self, name, attr):
@@ -102,22 +103,40 @@ class SamplerBase(object):
         return inner if isinstance(inner, UNetModel) else None
 
     def _setup_eval(self, b, shape_rest, cond, uc, scale):
-        """Static buffers for one sampling run (and, for the native UNet, a CUDA graph of apply_model)."""
+        """Static buffers for the sampling runs of one shape and, for the native UNet, two CUDA graphs that are captured
+        ONCE per (shape, CFG) and reused by every later sample() call of this sampler:
+          graph_ctx   context-only work (attn2 vectors, adapter tables) from the static conditioning buffer;
+          graph_unet  one apply_model evaluation reading the static x_in / t_in buffers and those tables."""
         dev = self.model.device
         self._cfg = not (uc is None or scale == 1.)
         rows = 2 * b if self._cfg else b
-        self._x_in = torch.empty((rows,) + tuple(shape_rest), device=dev, dtype=torch.float32)
-        self._t_in = torch.empty((rows,), device=dev, dtype=torch.long)
         if isinstance(cond, dict) or isinstance(cond, list):
             raise NotImplementedError("mobi_b200 samplers take the conditioning as one [B, n, ctx] tensor")
-        self._c_in = torch.cat([uc, cond]).contiguous() if self._cfg else cond.contiguous()
-        self._graph = None
-        self._eps = None
+        c_new = torch.cat([uc, cond]) if self._cfg else cond
+        c_new = c_new.to(dev).float()
         unet = self._native_unet()
         want_graph = self.use_cuda_graph if self.use_cuda_graph is not None else (unet is not None)
+        use_graph = bool(want_graph and unet is not None and dev.type == "cuda")
+        key = (rows, tuple(shape_rest), self._cfg, tuple(c_new.shape), use_graph, id(unet),
+               getattr(unet, "_pack_serial", None))
+        if getattr(self, "_static_key", None) == key:
+            self._c_in.copy_(c_new)
+            if self._graph_ctx is not None:
+                self._graph_ctx.replay()
+                unet._ctx_tabs = self._ctx_tabs_static
+                unet._ctx_key = (self._c_in.data_ptr(), self._c_in._version, tuple(self._c_in.shape))
+            elif unet is not None:
+                unet.prepare_context(self._c_in)
+            return
+        self._static_key = None
+        self._graph = self._graph_ctx = None
+        self._eps = None
+        self._x_in = torch.empty((rows,) + tuple(shape_rest), device=dev, dtype=torch.float32)
+        self._t_in = torch.empty((rows,), device=dev, dtype=torch.long)
+        self._c_in = c_new.contiguous().clone()
         if unet is not None:
-            unet.prepare_context(self._c_in.float())
-        if want_graph and unet is not None and dev.type == "cuda":
+            unet.prepare_context(self._c_in)
+        if use_graph:
             self._t_in.fill_(1)
             self._x_in.zero_()
             side = torch.cuda.Stream()
@@ -127,12 +146,17 @@ class SamplerBase(object):
                     self.model.apply_model(self._x_in, self._t_in, self._c_in)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
+            g_ctx = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g_ctx):
+                self._ctx_tabs_static = unet.prepare_context(self._c_in)
             g = torch.cuda.CUDAGraph()
             before = ops.Stats.launches
-            with torch.cuda.graph(g):
+            with torch.cuda.graph(g, pool=g_ctx.pool()):
                 self._eps = self.model.apply_model(self._x_in, self._t_in, self._c_in)
             self._graph_kernels = ops.Stats.launches - before  # kernels replayed per UNet evaluation
-            self._graph = g
+            self._graph, self._graph_ctx = g, g_ctx
+            g_ctx.replay()  # capture does not execute: fill the tables for this run
+        self._static_key = key
 
     def _eval_model(self, step):
         """eps for the current self._x_in at timestep `step` ([uncond ; cond] rows under CFG)."""

@@ -35,11 +35,23 @@ def mobi_unet_config(latent=64, use_lidar=True):
                 add_conv_in_front_of_unet=False, bbox_cond=True, use_camera=True, use_lidar=use_lidar)
 
 
-def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_cfg=None):
+def vae_ddconfig(latent=64, lidar=False):
+    """configs/mobi_nusc_512.yaml:84-127 (first_stage_config / lidar_stage_config ddconfig)."""
+    return dict(double_z=True, z_channels=4, resolution=8 * latent, in_channels=2 if lidar else 3,
+                out_ch=2 if lidar else 3, ch=128, ch_mult=[1, 2, 4, 4], num_res_blocks=2, attn_resolutions=[],
+                dropout=0.0, lidar_adapter=lidar)
+
+
+def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_cfg=None, with_vae=False):
     from .ddpm import LatentDiffusion
     cfg = unet_cfg or mobi_unet_config(latent, use_lidar)
+    vae = lambda lidar: dict(target="mobi_b200.autoencoder.AutoencoderKL",
+                             params=dict(ddconfig=vae_ddconfig(latent, lidar), embed_dim=4,
+                                         lossconfig=dict(target="torch.nn.Identity")))
     with torch.device("meta"):
         ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg),
+                              first_stage_config=vae(False) if with_vae else None,
+                              lidar_stage_config=vae(True) if (with_vae and use_lidar) else None,
                               linear_start=0.00085, linear_end=0.0120, timesteps=1000, first_stage_key="inpaint",
                               image_size=cfg["image_size"], channels=4, conditioning_key="crossattn",
                               scale_factor=0.18215, lidar_scale_factor=0.18215, use_camera=True, use_lidar=use_lidar)
@@ -47,6 +59,10 @@ def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_c
     ldm.register_schedule(linear_start=0.00085, linear_end=0.0120, timesteps=1000)  # buffers were meta: rebuild
     ldm = ldm.to(device)
     init_synthetic_(ldm.model.diffusion_model, seed)
+    if with_vae:
+        init_synthetic_(ldm.first_stage_model, seed + 1)
+        if ldm.lidar_stage_model is not None:
+            init_synthetic_(ldm.lidar_stage_model, seed + 2)
     return ldm.eval()
 
 
