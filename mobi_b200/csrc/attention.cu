@@ -270,7 +270,7 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     const long long BH = (long long)a->batch * a->heads;
     MOBI_CHECK(BH <= 65535, "mobi_attention: batch*heads=%lld exceeds grid.y", BH);
-    if (d <= 128 && a->kernel != 1) return attention2_dispatch(a, p, stream);
+    if (d <= 128 && (a->kernel & 15) != 1) return attention2_dispatch(a, p, stream);
     // shared memory plan: prefer double-buffered K/V and P; fall back to single buffers for wide heads
     auto smem_need = [&](int kvs, int pbs) {
         return (long long)p.nch * ATT_TILE * (1 + kvs) + (long long)kvs * 2 * att_v_tile_bytes(p.dn) +

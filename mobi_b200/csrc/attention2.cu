@@ -18,7 +18,7 @@
 // O += P V; scores and probabilities never touch HBM.
 //
 // Warp roles (384 threads): warps 0-3 softmax tile 0, warps 4-7 softmax tile 1, warp 8 TMA producer, warp 9 MMA
-// issuer + TMEM owner, warps 10-11 idle (they only donate registers: setmaxnreg).
+// issuer of tile 0 + TMEM owner, warp 10 MMA issuer of tile 1, warp 11 idle (warps 8-11 donate registers: setmaxnreg).
 #include "../../include/mobi_b200.h"
 #include "attention_common.cuh"
 #include "common.cuh"
@@ -27,6 +27,7 @@
 namespace mobi {
 
 constexpr int A2_CHUNK = 128 * 128;  // bytes of a 128-row x 64-col bf16 chunk
+constexpr int A2_KV_STAGES = 3;
 
 __device__ __forceinline__ float ex2_approx(float x) {
     float y;
@@ -34,8 +35,32 @@ __device__ __forceinline__ float ex2_approx(float x) {
     return y;
 }
 
+// 2^x for a pair of arguments on the FMA pipe instead of the MUFU (Cody-Waite split + degree-3 minimax polynomial,
+// relative error ~1e-4, far below the bf16 resolution of P): x = n + f with n = floor(x) taken from the mantissa of
+// x + 1.5*2^23 (round toward -inf), 2^f from the polynomial, and n added straight into the exponent field.
+// 2 FMNMX + 3 FADD2 + 3 FFMA2 + 2 LEA per pair.  Arguments are <= 8 here (stale running maximum) and clamped at -127.
+__device__ __forceinline__ void ex2_poly2(uint64_t x, float& e0, float& e1) {
+    float x0, x1;
+    unpack2(x, x0, x1);
+    const uint64_t magic = pack2(12582912.f, 12582912.f);
+    const uint64_t xc = pack2(fmaxf(x0, -127.f), fmaxf(x1, -127.f));
+    const uint64_t t = add2_rm(xc, magic);
+    const uint64_t f = sub2(xc, sub2(t, magic));
+    uint64_t pl = fma2(pack2(0.077119089663028717f, 0.077119089663028717f), f,
+                       pack2(0.227564394474029541f, 0.227564394474029541f));
+    pl = fma2(pl, f, pack2(0.695146143436431885f, 0.695146143436431885f));
+    pl = fma2(pl, f, pack2(1.f, 1.f));
+    float p0, p1, t0, t1;
+    unpack2(pl, p0, p1);
+    unpack2(t, t0, t1);
+    e0 = __uint_as_float(__float_as_uint(p0) + (__float_as_uint(t0) << 23));
+    e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
+}
+
 // MINB = 2: two CTAs per SM (BKV = 64, head_dim <= 64): four softmax warps per SM sub-partition instead of two.
-template <int BKV, int MINB>
+// POLY = how many of every 8 consecutive pairs of exponentials go to the FMA pipe (the rest use MUFU.EX2): the MUFU
+// (16/clk/SM) is the bottleneck of this kernel, so a fraction of the work is moved to where there are spare issue slots.
+template <int BKV, int MINB, int POLY>
 __global__ void __launch_bounds__(384, MINB)
 attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
@@ -44,6 +69,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr int TMEM_COLS = MINB == 2 ? 256 : 512;           // S: 2 x BKV columns, O: 2 x O_STRIDE columns
     constexpr int O_BASE = 2 * BKV;
     constexpr int K_CHUNK = BKV * 128;       // bytes of a BKV-row x 64-col bf16 chunk of K
+    constexpr int KVS = A2_KV_STAGES;        // K/V ring depth: the TMA round trip (~1 us) spans more than one block
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int q_tile_bytes = p.nch * A2_CHUNK;
@@ -52,17 +78,17 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const int v_bytes = KCH * v_chunk;
     uint8_t* sQ = smem;
     uint8_t* sK = sQ + 2 * q_tile_bytes;
-    uint8_t* sV = sK + 2 * k_bytes;
-    uint8_t* sP = sV + 2 * v_bytes;
+    uint8_t* sV = sK + KVS * k_bytes;
+    uint8_t* sP = sV + KVS * v_bytes;
     uint64_t* bars = reinterpret_cast<uint64_t*>(sP + 2 * KCH * A2_CHUNK);
     uint64_t* q_full = bars;         // 1
-    uint64_t* kv_full = bars + 1;    // 2
-    uint64_t* kv_empty = bars + 3;   // 2
-    uint64_t* s_full = bars + 5;     // 2 (per tile)
-    uint64_t* s_free = bars + 7;     // 2
-    uint64_t* p_full = bars + 9;     // 2
-    uint64_t* pv_done = bars + 11;   // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 13);
+    uint64_t* s_full = bars + 1;     // 2 (per tile)
+    uint64_t* s_free = bars + 3;     // 2
+    uint64_t* p_full = bars + 5;     // 2
+    uint64_t* pv_done = bars + 7;    // 2
+    uint64_t* kv_full = bars + 9;    // KVS
+    uint64_t* kv_empty = kv_full + KVS;  // KVS
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + KVS);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -77,9 +103,11 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tma_prefetch_desc(&tmK);
             tma_prefetch_desc(&tmV);
             mbar_init(q_full, 1);
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < KVS; ++i) {
                 mbar_init(&kv_full[i], 1);
-                mbar_init(&kv_empty[i], 1);
+                mbar_init(&kv_empty[i], ntiles);  // one tcgen05.commit per tile issuer
+            }
+            for (int i = 0; i < 2; ++i) {
                 mbar_init(&s_full[i], 1);
                 mbar_init(&s_free[i], 128);
                 mbar_init(&p_full[i], 128);
@@ -106,8 +134,8 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     for (int c = 0; c < p.nch; ++c)
                         tma_load_3d(sQ + t * q_tile_bytes + c * A2_CHUNK, &tmQ, q_full, c * 64, q0 + t * 128, bh);
                 for (int j = 0; j < nblk; ++j) {
-                    const int s = j & 1;
-                    mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                    const int s = j % KVS;
+                    mbar_wait(&kv_empty[s], ((j / KVS) & 1) ^ 1);
                     mbar_arrive_expect_tx(&kv_full[s], k_bytes + v_bytes);
                     for (int c = 0; c < p.nch; ++c)
                         tma_load_3d(sK + s * k_bytes + c * K_CHUNK, &tmK, &kv_full[s], c * 64, j * BKV, bh);
@@ -115,13 +143,16 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         tma_load_3d(sV + s * v_bytes + c * v_chunk, &tmV, &kv_full[s], j * BKV + c * 64, 0, bh);
                 }
             }
-        } else if (warp == 9) {
+        } else if (warp - 9 < ntiles) {
             if (elect_one()) {
-                // ---------------- MMA issuer
+                // ---------------- MMA issuer of tile t (warp 9: tile 0, warp 10: tile 1).  Each tile has its own issuing
+                // thread, so the two tiles never block each other; inside a tile the events arrive in program order
+                // (s_free(j) always precedes p_full(j)), so plain blocking waits have no head-of-line stalls.
+                const int t = warp - 9;
                 const uint32_t idesc_s = make_idesc_bf16(128, BKV);
                 const uint32_t idesc_o = make_idesc_bf16(128, p.dn);
-                auto issue_S = [&](int t, int j) {  // S_t(j) = Q_t K(j)^T
-                    const int s = j & 1;
+                auto issue_S = [&](int j) {  // S_t(j) = Q_t K(j)^T
+                    const int s = j % KVS;
                     const uint32_t d_tmem = tmem_base + t * BKV;
                     for (int k = 0; k < p.dk16; ++k) {
                         const uint64_t a =
@@ -132,8 +163,25 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     umma_commit(&s_full[t]);
                 };
-                auto issue_PV = [&](int t, int j) {  // O_t += P_t(j) V(j)
-                    const int s = j & 1;
+                mbar_wait(q_full, 0);
+                // tile 1 starts once tile 0 has pulled its first score tile into registers: the half-block phase offset
+                // keeps one warpgroup in its exponential phase while the other waits for TMEM loads
+                if (t == 1) mbar_wait(&s_free[0], 0);
+                mbar_wait(&kv_full[0], 0);
+                tc_fence_after();
+                issue_S(0);
+                for (int j = 0; j < nblk; ++j) {
+                    const int s = j % KVS;
+                    const uint32_t ph = j & 1;
+                    if (j + 1 < nblk) {
+                        // next score tile as soon as the softmax threads have S(j) in registers and K(j+1) has landed
+                        mbar_wait(&kv_full[(j + 1) % KVS], ((j + 1) / KVS) & 1);
+                        mbar_wait(&s_free[t], ph);
+                        tc_fence_after();
+                        issue_S(j + 1);
+                    }
+                    mbar_wait(&p_full[t], ph);
+                    tc_fence_after();
                     const uint32_t d_tmem = tmem_base + O_BASE + t * O_STRIDE;
                     for (int k = 0; k < BKV / 16; ++k) {
                         const uint64_t a =
@@ -143,54 +191,7 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         umma_bf16_ss(d_tmem, a, b, idesc_o, (j | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&pv_done[t]);
-                };
-                // Event loop: the two tiles advance independently (no head-of-line blocking between them).
-                //   S_t(j+1) is issued as soon as softmax t has pulled S_t(j) into registers (s_free) and K(j+1) landed;
-                //   PV_t(j)  is issued as soon as P_t(j) is in shared memory (p_full);
-                //   a K/V stage is released once both tiles have issued their PV on it.
-                // Tile 1 starts only after tile 0 has read its first score tile: the half-block phase offset keeps one
-                // warpgroup in its exponential phase while the other one waits for TMEM loads.
-                int js[2] = {0, 0};  // next score block to issue per tile
-                int jp[2] = {0, 0};  // next PV block to issue per tile
-                int released = 0;    // K/V blocks handed back to the producer
-                mbar_wait(q_full, 0);
-                const long long t_start = clock64();
-                for (;;) {
-                    bool done = true, progress = false;
-                    for (int t = 0; t < ntiles; ++t) {
-                        if (jp[t] < nblk) done = false;
-                        // next score tile
-                        if (js[t] < nblk) {
-                            const int j = js[t];
-                            // (probes are non-blocking and each barrier is at most one phase ahead of the one probed)
-                            bool ok = mbar_test_wait(&kv_full[j & 1], (j >> 1) & 1);
-                            if (ok && j > 0) ok = mbar_test_wait(&s_free[t], (j - 1) & 1);
-                            if (ok && j == 0 && t == 1) ok = (js[0] >= 2) || (jp[0] >= 1);  // phase offset
-                            if (ok) {
-                                tc_fence_after();
-                                issue_S(t, j);
-                                js[t] = j + 1;
-                                progress = true;
-                            }
-                        }
-                        // next value product
-                        if (jp[t] < nblk && jp[t] < js[t]) {
-                            const int j = jp[t];
-                            if (mbar_test_wait(&p_full[t], j & 1)) {
-                                tc_fence_after();
-                                issue_PV(t, j);
-                                jp[t] = j + 1;
-                                progress = true;
-                                const int lo = ntiles == 2 ? min(jp[0], jp[1]) : jp[0];
-                                while (released < lo) {
-                                    umma_commit(&kv_empty[released & 1]);
-                                    ++released;
-                                }
-                            }
-                        }
-                    }
-                    if (done) break;
-                    if (!progress && clock64() - t_start > MOBI_WAIT_LIMIT_CYCLES) asm volatile("trap;");
+                    umma_commit(&kv_empty[s]);  // this tile is done with K(j) / V(j)
                 }
             }
         }
@@ -252,16 +253,28 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                 }
                 // probabilities -> packed bf16 in registers (in place: sr[c/2] <- pack(p[c], p[c+1]))
-                float lsum = 0.f;
+                const uint64_t m2 = pack2(m_used, m_used);
+                uint64_t lsum2 = pack2(0.f, 0.f);
 #pragma unroll
-                for (int c = 0; c < BKV; c += 8) {
-                    float e[8];
-#pragma unroll
-                    for (int i = 0; i < 8; ++i) e[i] = ex2_approx(__uint_as_float(sr[c + i]) - m_used);
-                    lsum += ((e[0] + e[1]) + (e[2] + e[3])) + ((e[4] + e[5]) + (e[6] + e[7]));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) sr[(c >> 1) + i] = pack_bf16x2(e[2 * i], e[2 * i + 1]);
+                for (int c = 0; c < BKV; c += 2) {
+                    const uint64_t x = sub2(pack2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), m2);
+                    float e0, e1;
+                    // pair index within its group of 8 pairs decides the pipe (spread so the two pipes interleave)
+                    constexpr int kPolySlots[9] = {0x00, 0x08, 0x22, 0x2a, 0xaa, 0xab, 0xbb, 0xbf, 0xff};
+                    if ((kPolySlots[POLY] >> ((c >> 1) & 7)) & 1) {
+                        ex2_poly2(x, e0, e1);
+                    } else {
+                        float x0, x1;
+                        unpack2(x, x0, x1);
+                        e0 = ex2_approx(x0);
+                        e1 = ex2_approx(x1);
+                    }
+                    lsum2 = add2(lsum2, pack2(e0, e1));
+                    sr[c >> 1] = pack_bf16x2(e0, e1);
                 }
+                float lsum, lsum_hi;
+                unpack2(lsum2, lsum, lsum_hi);
+                lsum += lsum_hi;
                 // the P buffer is free once PV(j-1) has completed (it almost always has by now)
                 if (j > 0) mbar_wait(&pv_done[t], ph ^ 1);
                 // swizzled K-major tile (row = query, 64 keys per 128-byte row chunk)
@@ -312,12 +325,12 @@ attention2_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
 }
 
-template <int BKV, int MINB>
+template <int BKV, int MINB, int POLY>
 static int launch_attention2(const mobi_attn_args* a, AttnParams p, cudaStream_t stream) {
     const int d = a->head_dim;
     const long long BH = (long long)a->batch * a->heads;
-    const long long smem = 2ll * p.nch * A2_CHUNK + 2ll * p.nch * BKV * 128 + 2ll * (BKV / 64) * p.dn * 128 +
-                           2ll * (BKV / 64) * A2_CHUNK + 256 + 1024;
+    const long long smem = 2ll * p.nch * A2_CHUNK + (long long)A2_KV_STAGES * p.nch * BKV * 128 +
+                           (long long)A2_KV_STAGES * (BKV / 64) * p.dn * 128 + 2ll * (BKV / 64) * A2_CHUNK + 256 + 1024;
     const long long limit = 227 * 1024;
     MOBI_CHECK(smem <= limit, "mobi_attention: head_dim=%d needs %lld bytes of shared memory", d, smem);
     CUtensorMap tmQ, tmK, tmV;
@@ -341,19 +354,28 @@ static int launch_attention2(const mobi_attn_args* a, AttnParams p, cudaStream_t
     }
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(attention2_kernel<BKV, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
+        MOBI_CUDA(cudaFuncSetAttribute(attention2_kernel<BKV, MINB, POLY>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)limit));
         configured = true;
     }
     dim3 grid((a->tq + 255) / 256, (unsigned)BH, 1);
-    attention2_kernel<BKV, MINB><<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, p);
+    attention2_kernel<BKV, MINB, POLY><<<grid, 384, smem, stream>>>(tmQ, tmK, tmV, p);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
 
 int attention2_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream) {
-    if (a->head_dim <= 64 && a->kernel != 2) return launch_attention2<64, 2>(a, p, stream);
-    if (a->head_dim <= 64) return launch_attention2<128, 1>(a, p, stream);
-    return launch_attention2<64, 1>(a, p, stream);
+    const int poly = (a->kernel >> 4) & 15;  // tuning hook: 0 = default split, 1..8 = pairs of 8 on the FMA pipe, 9 = none
+    if (a->head_dim <= 64 && (a->kernel & 15) != 2) {
+        switch (poly) {
+            case 9: return launch_attention2<64, 2, 0>(a, p, stream);
+            case 2: return launch_attention2<64, 2, 2>(a, p, stream);
+            case 4: return launch_attention2<64, 2, 4>(a, p, stream);
+            case 3: return launch_attention2<64, 2, 3>(a, p, stream);
+            default: return launch_attention2<64, 2, 2>(a, p, stream);
+        }
+    }
+    if (a->head_dim <= 64) return launch_attention2<128, 1, 2>(a, p, stream);
+    return launch_attention2<64, 1, 2>(a, p, stream);
 }
 
 }  // namespace mobi

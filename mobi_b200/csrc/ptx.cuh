@@ -68,16 +68,36 @@ __device__ __forceinline__ bool mbar_test_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a protocol bug must trap (reported as a launch failure), never hang the GPU box.
+// try_wait with an explicit suspend-time hint (ns): the thread sleeps in hardware until the phase completes or the
+// hint expires, instead of coming back after the (short) system default and burning issue slots in a spin loop.
+__device__ __forceinline__ bool mbar_try_wait_hint(uint64_t* bar, uint32_t parity, uint32_t ns) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred P;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 P, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, P;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity), "r"(ns)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must trap (reported as a launch failure), never hang the GPU box.  The clock is only
+// consulted every 256 wake-ups so that waiting warps cost the SM sub-partition (almost) no issue slots.
 #ifndef MOBI_WAIT_LIMIT_CYCLES
 #define MOBI_WAIT_LIMIT_CYCLES 6000000000ll  /* ~3-4 s at B200 clocks */
 #endif
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
-    const long long start = clock64();
-    while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - start > MOBI_WAIT_LIMIT_CYCLES) {
-            asm volatile("trap;");
+    long long start = 0;
+#pragma unroll 1
+    for (uint32_t spins = 1;; ++spins) {
+        if (mbar_try_wait(bar, parity)) return;  // (a suspend-time hint was measured slower: wake-up latency)
+        if ((spins & 255u) == 0u) {
+            const long long now = clock64();
+            if (start == 0) start = now;
+            else if (now - start > MOBI_WAIT_LIMIT_CYCLES) asm volatile("trap;");
         }
     }
 }
@@ -199,6 +219,36 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
            | (1u << 10)                           // B format BF16
            | (static_cast<uint32_t>(N >> 3) << 17)
            | (static_cast<uint32_t>(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------- packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100)
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t d;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t add2_rm(uint64_t a, uint64_t b) {  // round toward -inf
+    uint64_t d;
+    asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
+}
+__device__ __forceinline__ uint64_t sub2(uint64_t a, uint64_t b) {
+    uint64_t d;
+    asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+    return d;
 }
 
 // ---------------------------------------------------------------- misc

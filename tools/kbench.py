@@ -55,9 +55,10 @@ def bench_attn():
         vt = rnd(rows * H, D, T)
         out = torch.empty(rows, T, H * D, device="cuda", dtype=torch.bfloat16)
         fl = 4.0 * rows * H * T * T * D
-        for kern in ((0, 1) if D <= 128 else (1,)):
+        kerns = (1,) if D > 128 else ((0, 0x90, 0x30, 0x40, 2, 1) if D <= 64 else (0, 1))
+        for kern in kerns:
             ms = timeit(lambda: ops.attention(q, k, vt, rows, H, D, T, T, out=out, kernel=kern))
-            report("attention %s d=%d T=%d kernel=%d" % (tag, D, T, kern), ms, fl, clk_per_tile=round(
+            report("attention %s d=%d T=%d kernel=0x%x" % (tag, D, T, kern), ms, fl, clk_per_tile=round(
                 ms * 1e-3 * 1.9e9 * 148 / (rows * H * (T / 128) ** 2), 0))
 
 
