@@ -296,10 +296,32 @@ def run_native(args):
 
 def main():
     args = parse()
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_native(args)
+    # stdout carries exactly ONE JSON line: anything libraries print there (e.g. NCCL's version banner) goes to stderr
+    sys.stdout.flush()
+    saved = os.dup(1)
+    os.dup2(2, 1)
+    real_stdout = os.fdopen(saved, "w")
+    sys.stdout = real_stdout_proxy = _Tee(real_stdout)
+    try:
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_native(args)
+    finally:
+        real_stdout_proxy.flush()
+
+
+class _Tee:
+    """print() target that writes to the saved stdout descriptor (fd 1 itself is pointed at stderr)."""
+
+    def __init__(self, f):
+        self.f = f
+
+    def write(self, s):
+        return self.f.write(s)
+
+    def flush(self):
+        self.f.flush()
 
 
 if __name__ == "__main__":

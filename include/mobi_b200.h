@@ -34,6 +34,8 @@ extern "C" {
 #define MOBI_EPI_HEADS_T 3 /* out[((m / tokens) * heads + n / d) , n % d, m % tokens]   (v transposed)  */
 #define MOBI_EPI_QKV 4     /* n / (heads*d) selects q (HEADS -> out), k (HEADS -> out2), v (HEADS_T -> out3) */
 #define MOBI_EPI_KV 5      /* n / (heads*d) selects k (HEADS -> out), v (HEADS_T -> out2)                     */
+#define MOBI_EPI_GEGLU2 6  /* columns come in (value, gate) PAIRS: out[m, n/2] = v * gelu(g); the layout the
+                              persistent kernel's vector epilogue handles without cross-lane traffic          */
 
 const char* mobi_last_error(void);
 int mobi_version(void);

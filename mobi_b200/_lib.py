@@ -11,7 +11,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libmobi_b200.so")
 
 DT_BF16, DT_F32 = 0, 1
-EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV, EPI_KV = 0, 1, 2, 3, 4, 5
+EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV, EPI_KV, EPI_GEGLU2 = 0, 1, 2, 3, 4, 5, 6
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 

@@ -17,7 +17,7 @@ import torch.nn as nn
 
 from . import _lib as L
 from . import ops
-from .packing import interleave_geglu
+from .packing import interleave_geglu_pairs
 
 LOG2E = math.log2(math.e)
 
@@ -140,7 +140,8 @@ class BasicTransformerBlock(nn.Module):
                 p[m + "_wq"] = _bf16(at.to_q.weight.float() * (sc * LOG2E))
                 p[m + "_wkv"] = _bf16(torch.cat([at.to_k.weight.float(), at.to_v.weight.float()], 0))
                 p[m + "_wf"], p[m + "_bf"] = fold(at, getattr(self, "cross_modal_connector_" + m))
-        w1, b1 = interleave_geglu(self.ff.net[0].proj.weight.detach().float(), self.ff.net[0].proj.bias.detach().float())
+        w1, b1 = interleave_geglu_pairs(self.ff.net[0].proj.weight.detach().float(),
+                                        self.ff.net[0].proj.bias.detach().float())
         p["w_ff1"], p["b_ff1"] = _bf16(w1), _f32(b1)
         p["w_ff2"], p["b_ff2"] = _bf16(self.ff.net[2].weight), _f32(self.ff.net[2].bias)
         for n in ("norm1", "norm2", "norm3", "cond_adapter_norm", "cross_modal_norm_camera", "cross_modal_norm_lidar"):
@@ -247,7 +248,7 @@ class BasicTransformerBlock(nn.Module):
         # 5. GEGLU feed-forward (attention.py:265)
         if xn is None:
             xn = ops.layernorm(x, *p["norm3"], add_vec=pending, add_rows_per_vec=T)
-        hmid = ops.gemm(xn, p["w_ff1"], bias=p["b_ff1"], epilogue=L.EPI_GEGLU)
+        hmid = ops.gemm(xn, p["w_ff1"], bias=p["b_ff1"], epilogue=L.EPI_GEGLU2)
         if out_bf16:
             return ops.gemm(hmid, p["w_ff2"], bias=p["b_ff2"], residual=x, out_dtype=torch.bfloat16)
         ops.gemm(hmid, p["w_ff2"], bias=p["b_ff2"], residual=x, out=x)

@@ -191,7 +191,7 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         tc_fence_after();
         const float* rb = (p.row_bias && row_ok) ? p.row_bias + (m / p.rows_per_group) * p.ld_row_bias : nullptr;
         // output row: identity, or gathered segments (camera-only / lidar-only rows of the interleaved batch)
-        const long long mo = (p.out_seg > 0 && p.mode <= MOBI_EPI_GEGLU)
+        const long long mo = (p.out_seg > 0 && (p.mode <= MOBI_EPI_GEGLU || p.mode == MOBI_EPI_GEGLU2))
                                  ? (m / p.out_seg) * p.out_seg_stride + p.out_seg_offset + (m % p.out_seg)
                                  : m;
 #pragma unroll 1
@@ -218,6 +218,16 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.act == 1) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+            }
+            if (p.mode == MOBI_EPI_GEGLU2) {
+                float o[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o[j] = v[2 * j] * gelu_erf(v[2 * j + 1]);
+                GemmParams q = p;
+                q.mode = MOBI_EPI_PLAIN;
+                q.N = p.N / 2;
+                store8(q, mo, n0 / 2, o);
+                continue;
             }
             if (p.mode == MOBI_EPI_GEGLU) {
                 float o[8];
@@ -310,12 +320,16 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     p.out_seg = a->out_seg;
     p.out_seg_stride = a->out_seg_stride;
     p.out_seg_offset = a->out_seg_offset;
-    MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_KV, "mobi_gemm: bad epilogue %d", p.mode);
+    MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_GEGLU2, "mobi_gemm: bad epilogue %d", p.mode);
     if (p.mode == MOBI_EPI_GEGLU) {
         MOBI_CHECK(a->N % 16 == 0, "mobi_gemm: GEGLU needs N %% 16 == 0 (N=%lld)", (long long)a->N);
         MOBI_CHECK(a->residual == nullptr, "mobi_gemm: GEGLU epilogue takes no residual");
     }
-    if (p.mode >= MOBI_EPI_HEADS) {
+    if (p.mode == MOBI_EPI_GEGLU2) {
+        MOBI_CHECK(a->N % 16 == 0, "mobi_gemm: GEGLU2 needs N %% 16 == 0 (N=%lld)", (long long)a->N);
+        MOBI_CHECK(a->residual == nullptr, "mobi_gemm: GEGLU epilogue takes no residual");
+    }
+    if (p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV) {
         MOBI_CHECK(p.heads > 0 && p.head_dim > 0 && p.tokens > 0 && p.head_dim % 8 == 0,
                    "mobi_gemm: head layouts need heads, head_dim %% 8 == 0, tokens");
         const long long inner = (long long)p.heads * p.head_dim;

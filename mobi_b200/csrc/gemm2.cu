@@ -48,6 +48,28 @@ __device__ __forceinline__ float erf_fast(float x) {
     return copysignf(y, x);
 }
 __device__ __forceinline__ float gelu_fast(float x) { return 0.5f * x * (1.0f + erf_fast(x * 0.70710678118654752f)); }
+// GELU(gate) * value for two (value, gate) pairs at once on the packed-fp32 pipe:
+//   gelu(x) = x * Phi(x),  Phi(x) ~= 0.5 * (1 + tanh(x * (k + a x^2 + b x^4)))
+// with (k, a, b) = (0.797507884, 0.0370056460, -0.000351516789) fitted to the exact erf form: max |error| of gelu over
+// the real line 2.5e-5 (the textbook tanh-GELU is 4.7e-4 off); x^2 is clamped at 64, where tanh has long saturated.
+// tanh.approx adds <= 2^-11 relative, i.e. everything stays ~8x below the bf16 resolution of the output.
+// 1 MUFU + 5.5 issue slots per output instead of 2 MUFU + ~18 for the erf formula: with K = 320 the GEGLU epilogue
+// would otherwise cost more cycles than the tile's MMAs.
+__device__ __forceinline__ uint32_t geglu_pair_bf16(float v0, float g0, float v1, float g1) {
+    const uint64_t x = pack2(g0, g1);
+    float q0, q1;
+    unpack2(mul2(x, x), q0, q1);
+    const uint64_t x2 = pack2(fminf(q0, 64.f), fminf(q1, 64.f));
+    uint64_t pl = fma2(pack2(-0.000351516789f, -0.000351516789f), x2, pack2(0.0370056460f, 0.0370056460f));
+    pl = fma2(pl, x2, pack2(0.797507884f, 0.797507884f));
+    float u0, u1;
+    unpack2(mul2(pl, x), u0, u1);
+    const uint64_t th = pack2(tanh_approx(u0), tanh_approx(u1));
+    const uint64_t phi = fma2(th, pack2(0.5f, 0.5f), pack2(0.5f, 0.5f));
+    float o0, o1;
+    unpack2(mul2(mul2(x, phi), pack2(v0, v1)), o0, o1);
+    return pack_bf16x2(o0, o1);
+}
 __device__ __forceinline__ float silu_fast(float x) { return __fdividef(x, 1.0f + __expf(-x)); }
 
 struct EpiRow {          // per-lane view of the 8 rows this lane serves in the transposed domain
@@ -64,7 +86,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
     const int rsub = lane >> 3;    // row inside a group of 4
     const int m_base = m_tile * BM + lg * 32;
     const int inner = p.heads * p.head_dim;
-    const bool head_mode = p.mode >= MOBI_EPI_HEADS;
+    const bool head_mode = p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV;
     const int nparts_last = p.mode == MOBI_EPI_QKV ? 2 : (p.mode == MOBI_EPI_KV ? 1 : (p.mode == MOBI_EPI_HEADS_T ? 0 : -1));
 
     EpiRow er;
@@ -177,7 +199,24 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
         }
         __syncwarp();
         // ---- transposed domain
-        if (out_units == 8) {
+        if (p.mode == MOBI_EPI_GEGLU2) {
+            // (value, gate) column pairs: two outputs per lane, no cross-lane traffic.  Branch-free math over the 8
+            // rows of this lane (16 independent GELUs in flight), only the stores are predicated.
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
+            uint32_t o[8];
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+                const int rr = it * 4 + rsub;
+                const float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + rr * 128 +
+                                                                  ((u ^ (rr & 7)) << 4));
+                o[it] = geglu_pair_bf16(v.x + b4.x, v.y + b4.y, v.z + b4.z, v.w + b4.w);
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+                if (col_ok && ((er.ok >> it) & 1))
+                    *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + er.off[it] + (n >> 1)) = o[it];
+        } else if (out_units == 8) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             // head-split column part
@@ -215,6 +254,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 if (p.act == 1) {
                     v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
                 }
+
                 if (p.residual) {
                     v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w;
                 }
@@ -407,6 +447,9 @@ bool gemm2_supported(const GemmParams& p) {
         if (p.out_seg >= (1ll << 31)) return false;
     } else if (p.mode == MOBI_EPI_GEGLU) {
         if (p.N % 32 != 0 || p.ldo % 4 != 0 || (reinterpret_cast<uintptr_t>(p.out) & 7)) return false;
+    } else if (p.mode == MOBI_EPI_GEGLU2) {
+        if (p.ldo % 2 != 0 || (reinterpret_cast<uintptr_t>(p.out) & 3)) return false;
+        if (p.bias && (reinterpret_cast<uintptr_t>(p.bias) & 15)) return false;
     } else {
         if (p.head_dim % 8 != 0) return false;
         if ((reinterpret_cast<uintptr_t>(p.out) & 7) || (p.out2 && (reinterpret_cast<uintptr_t>(p.out2) & 7)) ||

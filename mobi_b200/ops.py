@@ -99,7 +99,7 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     N = w.shape[0]
     if M is None:
         M = a.numel() // a.shape[-1]
-    if epilogue in (L.EPI_PLAIN, L.EPI_GEGLU):
+    if epilogue in (L.EPI_PLAIN, L.EPI_GEGLU, L.EPI_GEGLU2):
         n_out = N if epilogue == L.EPI_PLAIN else N // 2
         if out is None:
             out = torch.empty((M, n_out), device=a.device, dtype=out_dtype if epilogue == L.EPI_PLAIN else torch.bfloat16)

@@ -12,6 +12,14 @@ def interleave_geglu(w, b):
     return w[idx].contiguous(), (b[idx].contiguous() if b is not None else None)
 
 
+def interleave_geglu_pairs(w, b):
+    """[value | gate] halves -> (value, gate) column pairs [v0, g0, v1, g1, ...] for MOBI_EPI_GEGLU2."""
+    n2 = w.shape[0]
+    n = n2 // 2
+    idx = torch.arange(n2, device=w.device).reshape(2, n).t().reshape(-1)
+    return w[idx].contiguous(), (b[idx].contiguous() if b is not None else None)
+
+
 def pack_conv_weight(w, kpad=None):
     """OIHW -> [O, kh*kw*I] with K ordered (kh, kw, c), zero padded to kpad, bf16."""
     o, i, kh, kw = w.shape

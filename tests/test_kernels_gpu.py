@@ -97,11 +97,19 @@ def test_gemm_geglu():
     h = a.float() @ w.float().t() + b
     val, gate = h.chunk(2, dim=-1)
     ref = val * torch.nn.functional.gelu(gate)
-    from mobi_b200.packing import interleave_geglu
+    from mobi_b200.packing import interleave_geglu, interleave_geglu_pairs
     wp, bp = interleave_geglu(w, b)
     out = ops.gemm(a, wp, bias=bp, epilogue=L.EPI_GEGLU)
     assert out.shape == (M, 4 * C)
     assert relerr(out, ref) < 1e-2, describe(out, ref)
+    # (value, gate) pair layout: what the transformer blocks use; both kernels
+    w2, b2 = interleave_geglu_pairs(w, b)
+    for kernel in (0, 1):
+        out2 = ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU2, kernel=kernel)
+        assert out2.shape == (M, 4 * C)
+        assert relerr(out2, ref) < 1e-2, describe(out2, ref)
+    out1 = ops.gemm(a, wp, bias=bp, epilogue=L.EPI_GEGLU, kernel=1)
+    assert relerr(out1, ref) < 1e-2, describe(out1, ref)
 
 
 @pytest.mark.parametrize("B,T,H,D", [(2, 256, 8, 40), (1, 128, 2, 16), (2, 64, 8, 160), (1, 1024, 8, 80)])

@@ -86,11 +86,11 @@ def bench_gemm():
             fn = lambda: ops.gemm(a, w, bias=bias, residual=x, out=x, kernel=GK)
             nb = M * K * 2 + M * N * 8
         elif kind == "geglu":
-            from mobi_b200.packing import interleave_geglu
-            w2, b2 = interleave_geglu(w.float(), bias)
+            from mobi_b200.packing import interleave_geglu_pairs
+            w2, b2 = interleave_geglu_pairs(w.float(), bias)
             w2 = w2.to(torch.bfloat16)
             o = torch.empty(M, N // 2, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU, out=o, kernel=GK)
+            fn = lambda: ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU2, out=o, kernel=GK)
             nb = M * K * 2 + M * N
         else:
             o = torch.empty(M, N, device="cuda", dtype=torch.float32)
