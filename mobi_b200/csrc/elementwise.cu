@@ -315,7 +315,7 @@ __global__ void upsample2x_kernel(const void* __restrict__ x, void* __restrict__
         *reinterpret_cast<__nv_bfloat162*>(reinterpret_cast<__nv_bfloat16*>(out) + dst) = __floats2bfloat162_rn(f.x, f.y);
 }
 
-// im2col: one thread per output element of the [M, kpad] matrix (K order kh, kw, c)
+// im2col: K order (kh, kw, c).  Generic form: one thread per output element.
 template <bool IN_F32>
 __global__ void im2col_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, mobi_im2col_args a) {
     const long long total = (long long)a.n * a.ho * a.wo * a.kpad;
@@ -341,6 +341,41 @@ __global__ void im2col_kernel(const void* __restrict__ x, __nv_bfloat16* __restr
         }
     }
     out[i] = __float2bfloat16(v);
+}
+
+// Vector form for C % 8 == 0 (the strided Downsample convolutions): one thread per 8 channels of one filter tap of
+// one output pixel = one 16-byte store; a warp covers 256 consecutive channels, so loads are coalesced too.
+// grid.x = output pixels, threads loop over (tap, channel-octet).
+template <bool IN_F32>
+__global__ void __launch_bounds__(256)
+im2col_vec8_kernel(const void* __restrict__ x, __nv_bfloat16* __restrict__ out, mobi_im2col_args a) {
+    const int m = blockIdx.x;  // output pixel (b, oy, ox)
+    const int ox = m % a.wo;
+    const int t1 = m / a.wo;
+    const int oy = t1 % a.ho;
+    const int b = t1 / a.ho;
+    const int c8 = a.c >> 3;
+    const int units = a.kh * a.kw * c8;
+    uint4* orow = reinterpret_cast<uint4*>(out + (long long)m * a.kpad);
+    for (int u = threadIdx.x; u < units; u += blockDim.x) {
+        const int tap = u / c8, cc = (u - tap * c8) << 3;
+        const int ky = tap / a.kw, kx = tap - ky * a.kw;
+        const int iy = oy * a.stride + ky - a.pad_top;
+        const int ix = ox * a.stride + kx - a.pad_left;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (iy >= 0 && iy < a.h && ix >= 0 && ix < a.w) {
+            const long long s = (((long long)b * a.h + iy) * a.w + ix) * a.c + cc;
+            if (IN_F32) {
+                const float4 f0 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + s);
+                const float4 f1 = *reinterpret_cast<const float4*>(reinterpret_cast<const float*>(x) + s + 4);
+                v = make_uint4(pack_bf16x2(f0.x, f0.y), pack_bf16x2(f0.z, f0.w), pack_bf16x2(f1.x, f1.y),
+                               pack_bf16x2(f1.z, f1.w));
+            } else {
+                v = *reinterpret_cast<const uint4*>(reinterpret_cast<const __nv_bfloat16*>(x) + s);
+            }
+        }
+        orow[u] = v;
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -668,6 +703,16 @@ extern "C" int mobi_im2col(const mobi_im2col_args* a, void* stream_) {
     MOBI_CHECK(a && a->x && a->out, "mobi_im2col: null argument");
     MOBI_CHECK(a->kpad >= a->kh * a->kw * a->c && a->kpad % 8 == 0, "mobi_im2col: kpad=%d too small or not %%8", a->kpad);
     const long long total = (long long)a->n * a->ho * a->wo * a->kpad;
+    if (a->c % 8 == 0 && a->kpad == a->kh * a->kw * a->c && (reinterpret_cast<uintptr_t>(a->x) & 15) == 0 &&
+        (reinterpret_cast<uintptr_t>(a->out) & 15) == 0) {
+        const unsigned pixels = (unsigned)((long long)a->n * a->ho * a->wo);
+        if (a->in_dtype == MOBI_DTYPE_F32)
+            im2col_vec8_kernel<true><<<pixels, 256, 0, stream>>>(a->x, reinterpret_cast<__nv_bfloat16*>(a->out), *a);
+        else
+            im2col_vec8_kernel<false><<<pixels, 256, 0, stream>>>(a->x, reinterpret_cast<__nv_bfloat16*>(a->out), *a);
+        MOBI_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (a->in_dtype == MOBI_DTYPE_F32)
         im2col_kernel<true><<<blocks_for(total, 256), 256, 0, stream>>>(a->x, reinterpret_cast<__nv_bfloat16*>(a->out), *a);
     else
