@@ -34,6 +34,8 @@ extern "C" {
 #define MOBI_EPI_HEADS_T 3 /* out[((m / tokens) * heads + n / d) , n % d, m % tokens]   (v transposed)  */
 #define MOBI_EPI_QKV 4     /* n / (heads*d) selects q (HEADS -> out), k (HEADS -> out2), v (HEADS_T -> out3) */
 #define MOBI_EPI_KV 5      /* n / (heads*d) selects k (HEADS -> out), v (HEADS_T -> out2)                     */
+#define MOBI_EPI_QKV_ROW 7 /* like QKV but v is written like k: [BH, tokens, d] (mobi_attention v_rowmajor = 1)  */
+#define MOBI_EPI_KV_ROW 8  /* like KV  but v is written like k                                                 */
 #define MOBI_EPI_GEGLU2 6  /* columns come in (value, gate) PAIRS: out[m, n/2] = v * gelu(g); the layout the
                               persistent kernel's vector epilogue handles without cross-lane traffic          */
 
@@ -102,6 +104,8 @@ typedef struct {
     int64_t ld_out; /* row stride of out in elements (>= heads*head_dim) */
     int32_t kernel; /* 0 = choose (two-tile kernel for head_dim <= 128), 1 = force the one-tile kernel,
                        2 = two-tile kernel with 128-key blocks and one CTA per SM (head_dim <= 64) */
+    int32_t v_rowmajor; /* 1: `vt` holds V as [BH, Tk, d] (same layout as k; head_dim <= 128): consumed as an MN-major
+                           tcgen05 operand, no transposed copy needed.  0: `vt` is V^T [BH, d, Tk]. */
 } mobi_attn_args;
 
 int mobi_attention(const mobi_attn_args* args, void* stream);

@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(_HERE, "libmobi_b200.so")
 
 DT_BF16, DT_F32 = 0, 1
 EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV, EPI_KV, EPI_GEGLU2 = 0, 1, 2, 3, 4, 5, 6
+EPI_QKV_ROW, EPI_KV_ROW = 7, 8
 
 _vp, _i64, _i32, _f32 = C.c_void_p, C.c_int64, C.c_int32, C.c_float
 
@@ -35,7 +36,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", _vp), ("k", _vp), ("vt", _vp), ("out", _vp),
         ("batch", _i32), ("heads", _i32), ("head_dim", _i32), ("tq", _i32), ("tk", _i32),
-        ("ld_out", _i64), ("kernel", _i32),
+        ("ld_out", _i64), ("kernel", _i32), ("v_rowmajor", _i32),
     ]
 
 

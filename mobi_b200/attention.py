@@ -204,9 +204,11 @@ class BasicTransformerBlock(nn.Module):
         xn = ops.layernorm(x, *p["norm1"])
         q = torch.empty((R * H, T, D), device=dev, dtype=torch.bfloat16)
         k = torch.empty_like(q)
-        vt = torch.empty((R * H, D, T), device=dev, dtype=torch.bfloat16)
-        ops.gemm(xn, p["w_qkv"], epilogue=L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=vt)
-        o = ops.attention(q, k, vt, R, H, D, T, T)
+        rowv = D <= 128  # V in its natural layout (MN-major tcgen05 operand); wider heads use the transposed-V kernel
+        v = torch.empty_like(q) if rowv else torch.empty((R * H, D, T), device=dev, dtype=torch.bfloat16)
+        ops.gemm(xn, p["w_qkv"], epilogue=L.EPI_QKV_ROW if rowv else L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q,
+                 out2=k, out3=v)
+        o = ops.attention(q, k, v, R, H, D, T, T, v_rowmajor=rowv)
         ops.gemm(o.reshape(R * T, C), p["w_o"], bias=p["b_o"], residual=x, out=x)
         # 2. attn2 == broadcast add of tab["vec2"][row] (attention.py:235), fused into the next normalisation pass
         pending = tab["vec2"]
@@ -259,10 +261,12 @@ class BasicTransformerBlock(nn.Module):
         dev = x.device
         q = torch.empty((Rh * H, T, D), device=dev, dtype=torch.bfloat16)
         k = torch.empty_like(q)
-        vt = torch.empty((Rh * H, D, T), device=dev, dtype=torch.bfloat16)
+        rowv = D <= 128
+        v = torch.empty_like(q) if rowv else torch.empty((Rh * H, D, T), device=dev, dtype=torch.bfloat16)
         ops.gemm(qn, p[m + "_wq"], epilogue=L.EPI_HEADS, heads=H, head_dim=D, tokens=T, out=q)
-        ops.gemm(ctx, p[m + "_wkv"], epilogue=L.EPI_KV, heads=H, head_dim=D, tokens=T, out=k, out2=vt)
-        o = ops.attention(q, k, vt, Rh, H, D, T, T)
+        ops.gemm(ctx, p[m + "_wkv"], epilogue=L.EPI_KV_ROW if rowv else L.EPI_KV, heads=H, head_dim=D, tokens=T, out=k,
+                 out2=v)
+        o = ops.attention(q, k, v, Rh, H, D, T, T, v_rowmajor=rowv)
         ops.gemm(o.reshape(Rh * T, C), p[m + "_wf"], bias=p[m + "_bf"], residual=x, out=x, ldo=C, out_seg=T,
                  out_seg_stride=2 * T, out_seg_offset=row_off)
 

@@ -255,8 +255,8 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     MOBI_CHECK(a && a->q && a->k && a->vt && a->out, "mobi_attention: null argument");
     const int d = a->head_dim;
     MOBI_CHECK(d % 8 == 0 && d >= 8 && d <= 192, "mobi_attention: head_dim=%d must be a multiple of 8 in [8,192]", d);
-    MOBI_CHECK(a->tq > 0 && a->tk > 0 && a->tk % 8 == 0, "mobi_attention: tq=%d tk=%d (tk must be a multiple of 8)",
-               a->tq, a->tk);
+    MOBI_CHECK(a->tq > 0 && a->tk > 0 && (a->v_rowmajor || a->tk % 8 == 0),
+               "mobi_attention: tq=%d tk=%d (tk must be a multiple of 8 for the transposed V layout)", a->tq, a->tk);
     MOBI_CHECK(a->ld_out % 8 == 0 && a->ld_out >= (int64_t)a->heads * d, "mobi_attention: bad ld_out");
     AttnParams p{};
     p.heads = a->heads;
@@ -270,6 +270,10 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
     const long long BH = (long long)a->batch * a->heads;
     MOBI_CHECK(BH <= 65535, "mobi_attention: batch*heads=%lld exceeds grid.y", BH);
+    if (a->v_rowmajor) {
+        MOBI_CHECK(d <= 128, "mobi_attention: the row-major V layout needs head_dim <= 128 (got %d)", d);
+        return attention3_dispatch(a, p, stream);
+    }
     if (d <= 128 && (a->kernel & 15) != 1) return attention2_dispatch(a, p, stream);
     // shared memory plan: prefer double-buffered K/V and P; fall back to single buffers for wide heads
     auto smem_need = [&](int kvs, int pbs) {

@@ -20,5 +20,6 @@ struct AttnParams {
 };
 
 int attention2_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);
+int attention3_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);  // V row-major
 
 }  // namespace mobi

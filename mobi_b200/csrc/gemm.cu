@@ -70,6 +70,10 @@ __device__ __forceinline__ void store8(const GemmParams& p, long long m, int n0,
         n = n0 - which * inner;
         const int last = (mode == MOBI_EPI_QKV) ? 2 : 1;
         mode = (which == last) ? MOBI_EPI_HEADS_T : MOBI_EPI_HEADS;
+    } else if (mode == MOBI_EPI_QKV_ROW || mode == MOBI_EPI_KV_ROW) {
+        which = n0 / inner;
+        n = n0 - which * inner;
+        mode = MOBI_EPI_HEADS;
     }
     __nv_bfloat16* base = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
     const int h = n / p.head_dim;
@@ -320,7 +324,7 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     p.out_seg = a->out_seg;
     p.out_seg_stride = a->out_seg_stride;
     p.out_seg_offset = a->out_seg_offset;
-    MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_GEGLU2, "mobi_gemm: bad epilogue %d", p.mode);
+    MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_KV_ROW, "mobi_gemm: bad epilogue %d", p.mode);
     if (p.mode == MOBI_EPI_GEGLU) {
         MOBI_CHECK(a->N % 16 == 0, "mobi_gemm: GEGLU needs N %% 16 == 0 (N=%lld)", (long long)a->N);
         MOBI_CHECK(a->residual == nullptr, "mobi_gemm: GEGLU epilogue takes no residual");
@@ -329,16 +333,18 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         MOBI_CHECK(a->N % 16 == 0, "mobi_gemm: GEGLU2 needs N %% 16 == 0 (N=%lld)", (long long)a->N);
         MOBI_CHECK(a->residual == nullptr, "mobi_gemm: GEGLU epilogue takes no residual");
     }
-    if (p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV) {
+    if ((p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV) || p.mode >= MOBI_EPI_QKV_ROW) {
         MOBI_CHECK(p.heads > 0 && p.head_dim > 0 && p.tokens > 0 && p.head_dim % 8 == 0,
                    "mobi_gemm: head layouts need heads, head_dim %% 8 == 0, tokens");
         const long long inner = (long long)p.heads * p.head_dim;
-        const long long parts = p.mode == MOBI_EPI_QKV ? 3 : (p.mode == MOBI_EPI_KV ? 2 : 1);
+        const long long parts = (p.mode == MOBI_EPI_QKV || p.mode == MOBI_EPI_QKV_ROW)
+                                    ? 3
+                                    : ((p.mode == MOBI_EPI_KV || p.mode == MOBI_EPI_KV_ROW) ? 2 : 1);
         MOBI_CHECK(a->N == parts * inner, "mobi_gemm: N=%lld does not match heads*d", (long long)a->N);
         MOBI_CHECK(a->M % p.tokens == 0, "mobi_gemm: M must be a multiple of tokens");
         MOBI_CHECK(a->out_dtype == MOBI_DTYPE_BF16 && a->residual == nullptr, "mobi_gemm: head layouts are bf16");
-        if (p.mode == MOBI_EPI_QKV) MOBI_CHECK(a->out2 && a->out3, "mobi_gemm: QKV needs out2/out3");
-        if (p.mode == MOBI_EPI_KV) MOBI_CHECK(a->out2 != nullptr, "mobi_gemm: KV needs out2");
+        if (p.mode == MOBI_EPI_QKV || p.mode == MOBI_EPI_QKV_ROW) MOBI_CHECK(a->out2 && a->out3, "mobi_gemm: QKV needs out2/out3");
+        if (p.mode == MOBI_EPI_KV || p.mode == MOBI_EPI_KV_ROW) MOBI_CHECK(a->out2 != nullptr, "mobi_gemm: KV needs out2");
     }
 
     CUtensorMap tmA, tmB;

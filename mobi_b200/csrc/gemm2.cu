@@ -86,7 +86,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
     const int rsub = lane >> 3;    // row inside a group of 4
     const int m_base = m_tile * BM + lg * 32;
     const int inner = p.heads * p.head_dim;
-    const bool head_mode = p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV;
+    const bool head_mode = (p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV) || p.mode >= MOBI_EPI_QKV_ROW;
     const int nparts_last = p.mode == MOBI_EPI_QKV ? 2 : (p.mode == MOBI_EPI_KV ? 1 : (p.mode == MOBI_EPI_HEADS_T ? 0 : -1));
 
     EpiRow er;

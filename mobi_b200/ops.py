@@ -197,8 +197,9 @@ def im2col(x, kh, kw, stride, pad_top, pad_left, ho, wo):
     return out
 
 
-def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0):
-    """q,k: bf16 [batch*heads, T, d]; vt: bf16 [batch*heads, d, Tk]; returns bf16 [batch, tq, heads*d]."""
+def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0, v_rowmajor=False):
+    """q,k: bf16 [batch*heads, T, d]; vt: bf16 [batch*heads, d, Tk] (or V itself, [batch*heads, Tk, d], with
+    v_rowmajor=True, head_dim <= 128); returns bf16 [batch, tq, heads*d]."""
     _cuda(q, k, vt, out)
     assert q.dtype == k.dtype == vt.dtype == torch.bfloat16
     if out is None:
@@ -208,6 +209,7 @@ def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0):
     a.batch, a.heads, a.head_dim, a.tq, a.tk = batch, heads, head_dim, tq, tk
     a.ld_out = heads * head_dim
     a.kernel = kernel
+    a.v_rowmajor = int(v_rowmajor)
     with _timed("attention", 4.0 * batch * heads * tq * tk * head_dim):
         L.check(L.load().mobi_attention(C.byref(a), L.stream()), "attention")
     return out

@@ -130,6 +130,15 @@ def test_gemm_head_layouts(B, T, H, D):
     assert relerr(q, rq) < 1e-2, describe(q, rq)
     assert relerr(k, rk) < 1e-2, describe(k, rk)
     assert relerr(vt, rv) < 1e-2, describe(vt, rv)
+    # row-major V variants (v written like k)
+    v_row = torch.empty_like(q)
+    q3, k3 = torch.empty_like(q), torch.empty_like(q)
+    rvr = ref[:, :, 2].permute(0, 2, 1, 3).reshape(B * H, T, D)
+    for kernel in (0, 1):
+        ops.gemm(a, w, epilogue=L.EPI_QKV_ROW, heads=H, head_dim=D, tokens=T, out=q3, out2=k3, out3=v_row, kernel=kernel)
+        assert relerr(q3, rq) < 1e-2 and relerr(k3, rk) < 1e-2 and relerr(v_row, rvr) < 1e-2, describe(v_row, rvr)
+        ops.gemm(a, w[C:], epilogue=L.EPI_KV_ROW, heads=H, head_dim=D, tokens=T, out=k3, out2=v_row, kernel=kernel)
+        assert relerr(k3, rk) < 1e-2 and relerr(v_row, rvr) < 1e-2
     q2 = torch.empty_like(q)
     ops.gemm(a, w[:C], epilogue=L.EPI_HEADS, heads=H, head_dim=D, tokens=T, out=q2)
     assert relerr(q2, rq) < 1e-2
@@ -190,10 +199,17 @@ def test_conv_im2col(N, H, W, C, Cout, k, stride, pads):
     (1, 1, 64, 128, 128), (2, 8, 40, 256, 256), (1, 8, 40, 1024, 1024), (2, 8, 80, 256, 256),
     (2, 8, 160, 256, 256), (2, 8, 160, 64, 64), (1, 2, 16, 64, 64), (1, 2, 32, 16, 16),
     (1, 8, 40, 4096, 4096), (1, 4, 80, 384, 200), (2, 3, 40, 300, 136), (1, 2, 128, 512, 320), (1, 2, 64, 256, 1024),
+    (40, 8, 40, 1024, 1024), (1, 2, 48, 700, 100),
 ])
-@pytest.mark.parametrize("kernel", [0, 1])
+@pytest.mark.parametrize("kernel", [0, 1, 3, 4])
 def test_attention(B, H, D, Tq, Tk, kernel):
-    """kernel 0 = automatic (two-tile kernel for head_dim <= 128), 1 = the one-tile kernel."""
+    """kernel 0 = automatic (two-tile kernel for head_dim <= 128), 1 = the one-tile kernel (both take V^T);
+    3 = row-major V (MN-major tcgen05 operand; four query tiles per CTA for head_dim <= 64), 4 = same, two tiles."""
+    rowv = kernel >= 3
+    if rowv and D > 128:
+        pytest.skip("row-major V needs head_dim <= 128")
+    if not rowv and Tk % 8 != 0:
+        pytest.skip("transposed V needs Tk % 8 == 0")
     ops = _ops()
     q = rnd(B * H, Tq, D, seed=1, dtype=torch.float32)
     k = rnd(B * H, Tk, D, seed=2, dtype=torch.float32)
@@ -206,8 +222,8 @@ def test_attention(B, H, D, Tq, Tk, kernel):
     s = torch.einsum("bid,bjd->bij", qs.float(), kb.float()) * math.log(2.0)
     ref = torch.einsum("bij,bjd->bid", s.softmax(-1), vb.float())
     ref = ref.reshape(B, H, Tq, D).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
-    vt = vb.transpose(1, 2).contiguous()
-    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk, kernel=kernel)
+    vt = vb.contiguous() if rowv else vb.transpose(1, 2).contiguous()
+    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk, kernel={3: 0, 4: 2}.get(kernel, kernel), v_rowmajor=rowv)
     torch.cuda.synchronize()
     assert relerr(out, ref) < 1e-2, describe(out, ref)
 

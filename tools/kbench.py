@@ -53,11 +53,14 @@ def bench_attn():
                                  (R, 8, 160, 256, "self L2")]:
         q, k = rnd(rows * H, T, D), rnd(rows * H, T, D)
         vt = rnd(rows * H, D, T)
+        vrow = rnd(rows * H, T, D)
         out = torch.empty(rows, T, H * D, device="cuda", dtype=torch.bfloat16)
         fl = 4.0 * rows * H * T * T * D
-        kerns = (1,) if D > 128 else ((0, 0x90, 0x30, 0x40, 2, 1) if D <= 64 else (0, 1))
+        kerns = (1,) if D > 128 else ((0, 0x100, 0x102, 2, 1) if D <= 64 else (0, 0x100, 1))
         for kern in kerns:
-            ms = timeit(lambda: ops.attention(q, k, vt, rows, H, D, T, T, out=out, kernel=kern))
+            rowv = kern >= 0x100   # 0x100: row-major V (attention3), 0x102: its two-tile variant
+            ms = timeit(lambda: ops.attention(q, k, vrow if rowv else vt, rows, H, D, T, T, out=out, kernel=kern & 0xff,
+                                              v_rowmajor=rowv))
             report("attention %s d=%d T=%d kernel=0x%x" % (tag, D, T, kern), ms, fl, clk_per_tile=round(
                 ms * 1e-3 * 1.9e9 * 148 / (rows * H * (T / 128) ** 2), 0))
 
@@ -79,7 +82,10 @@ def bench_gemm():
             q = torch.empty(R * H, T, D, device="cuda", dtype=torch.bfloat16)
             k = torch.empty_like(q)
             vt = torch.empty(R * H, D, T, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: ops.gemm(a, w, epilogue=L.EPI_QKV, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=vt, kernel=GK)
+            vr = torch.empty_like(q)
+            ep = L.EPI_QKV_ROW if D <= 128 else L.EPI_QKV
+            fn = lambda: ops.gemm(a, w, epilogue=ep, heads=H, head_dim=D, tokens=T, out=q, out2=k,
+                                  out3=vr if D <= 128 else vt, kernel=GK)
             nb = M * K * 2 + M * N * 2
         elif kind == "res":
             x = rnd(M, N, dtype=torch.float32)
