@@ -306,6 +306,120 @@ int mobi_scale_f32(const float* x, float s, float* out, int64_t n, void* stream)
 /* f32 -> bf16 cast */
 int mobi_cast_bf16(const float* x, void* out, int64_t n, void* stream);
 
+/* ------------------------------------------------------------------------------------------------------------------
+ * Training step (config 5): LatentDiffusion.forward / p_losses (ldm/models/diffusion/ddpm.py:1040-1058, 1177-1217) and
+ * what torch.autograd executes behind `loss.backward()` for the UNet (trainable = cond_adapter_* and cross_modal_*
+ * parameters, ddpm.py:1686-1698).  The contractions of the backward pass (dgrad, wgrad, the five products of the
+ * attention backward) are mobi_gemm calls on transposed / flipped weight packs; the entries below are the rest.
+ * ------------------------------------------------------------------------------------------------------------------ */
+
+/* out[b][c, r] = bf16(in[b][r, c]); in f32 or bf16, row strides in elements.  Builds the K-major operands of
+ * wgrad (dW = dY^T X contracts over tokens) and of the attention backward (K^T, Q^T, dO^T). */
+int mobi_transpose_bf16(const void* in, int32_t in_dtype, void* out_bf16, int64_t batch, int32_t rows, int32_t cols,
+                        int64_t ld_in, int64_t in_batch_stride, int64_t ld_out, int64_t out_batch_stride, void* stream);
+
+/* Backward of nn.LayerNorm (attention.py:213-223) for the rows selected by the same segment gather as
+ * mobi_layernorm: dx[row] (+)= dLN(x[row], dy[i]); dgamma/dbeta (f32 [C], atomically accumulated) only for the
+ * trainable adapter norms.  gamma == NULL means unit gamma. */
+typedef struct {
+    const float* x;
+    const float* gamma;
+    const void* dy; /* [rows, C] compact, dy_dtype */
+    float* dx;      /* f32, addressed like x */
+    float* dgamma;
+    float* dbeta;
+    int64_t rows;
+    int32_t C;
+    int64_t seg, seg_stride, seg_offset;
+    float eps;
+    int32_t dy_dtype;
+    int32_t accumulate; /* 1: dx += ... */
+} mobi_layernorm_bwd_args;
+int mobi_layernorm_bwd(const mobi_layernorm_bwd_args* args, void* stream);
+
+/* Backward of GroupNorm (+SiLU) over an NHWC f32 image that may be the channel concatenation (x1 | x2)
+ * (GroupNorm32 + SiLU of ResBlock, openaimodel.py:190, 213, 892; SpatialTransformer.norm, attention.py:285):
+ * dx = dGN(dy) + dres, split back into dx1 [N,HW,c1] and dx2 [N,HW,c2].  The norms are frozen: no dgamma. */
+typedef struct {
+    const float* x1;
+    const float* x2;
+    const float* gamma;
+    const float* beta;
+    const void* dy;    /* [N, HW, C] dy_dtype: gradient w.r.t. the (SiLU'd) normalised output */
+    const float* dres; /* optional f32 [N, HW, C] added to dx (the identity branch of the residual) */
+    float* dx1;
+    float* dx2;
+    int32_t n_img, hw, c1, c2, groups, silu, dy_dtype;
+    float eps;
+} mobi_groupnorm_bwd_args;
+int mobi_groupnorm_bwd(const mobi_groupnorm_bwd_args* args, void* stream);
+
+/* GEGLU (attention.py:38-45) with exact erf GELU on (value, gate) column PAIRS: g bf16 [rows, 2*features] ->
+ * out bf16 [rows, features] = value * gelu(gate); backward: dg from g and dh. */
+int mobi_geglu(const void* g, void* out, int64_t rows, int64_t features, void* stream);
+int mobi_geglu_bwd(const void* g, const void* dh, void* dg, int64_t rows, int64_t features, void* stream);
+
+/* Softmax backward of CrossAttention.forward (attention.py:181-190) from materialised f32 tiles S = q' k^T (log2
+ * domain) and dP = dO V^T, both [batch, tq, tk]:  P = softmax2(S), dS = dscale * P * (dP - rowsum(P * dP)).
+ * Writes dS [tq, tk] and the transposed dS^T, P^T [tk, tq] (bf16): the A operands of dQ = dS k, dK = dS^T q',
+ * dV = P^T dO.  stats: scratch f32 [batch * tq * 3]. */
+typedef struct {
+    const float* S;
+    const float* dP;
+    void* dS;
+    void* dSt;
+    void* Pt;
+    float* stats;
+    int32_t batch, tq, tk;
+    float dscale;
+} mobi_attn_softmax_bwd_args;
+int mobi_attn_softmax_bwd(const mobi_attn_softmax_bwd_args* args, void* stream);
+
+/* cond_adapter_attn (attention.py:237-243, CrossAttention with `keys` <= 4 context tokens) on projected queries, for
+ * the training step where to_q/to_k/to_v are trainable and cannot be folded:
+ *   forward : o = softmax_j(<q, k_j>) v_j per head                                    (backward = 0)
+ *   backward: dq (bf16), dk / dv (f32 [batch, keys, C], atomically accumulated) from d_o (backward = 1)
+ * q, o, d_o, dq: bf16 [batch*tokens, C]; k, v: f32 [batch, keys, C]; the softmax scale is folded into q. */
+typedef struct {
+    const void* q;
+    const float* k;
+    const float* v;
+    void* o;
+    const void* d_o;
+    void* dq;
+    float* dk;
+    float* dv;
+    int32_t batch, tokens, C, heads, keys, backward;
+} mobi_ctx_attn_qspace_args;
+int mobi_ctx_attn_qspace(const mobi_ctx_attn_qspace_args* args, void* stream);
+
+/* out[g, c] += sum over the rows r of group g (r / rows_per_group) of x[r, c]: bias gradients (rows_per_group = rows)
+ * and per-batch-row sums.  out is f32 [rows / rows_per_group, cols], accumulated atomically. */
+int mobi_colsum(const void* x, int32_t dtype, int64_t rows, int32_t cols, int64_t ld, int64_t rows_per_group, float* out,
+                void* stream);
+/* out[n, k] += sum_m A[m, n] * B[m, k], all f32, tiny m (the context-token side of the adapter: to_k / to_v wgrad). */
+int mobi_wgrad_small(const float* A, const float* B, float* out, int32_t m, int32_t n, int32_t k, int64_t lda, int64_t ldb,
+                     int64_t ldo, void* stream);
+/* dst[segment row r] += src[r] (src compact [rows, C] f32/bf16): joins camera-only / lidar-only gradients
+ * (attention.py:246-261) into the interleaved residual-stream gradient. */
+int mobi_scatter_add_rows(const void* src, int32_t src_dtype, float* dst, int64_t rows, int32_t C, int64_t seg,
+                          int64_t seg_stride, int64_t seg_offset, void* stream);
+/* Adjoint of the stride-2 conv3x3 of Downsample (openaimodel.py:151-153): dy [n,h,w,c] -> bf16 [n,2h,2w,c] with dy at
+ * the even positions; a stride-1 conv with the flipped filter then gives dx. */
+int mobi_zero_insert2x(const void* dy, int32_t in_dtype, void* z_bf16, int32_t n, int32_t h, int32_t w, int32_t c,
+                       void* stream);
+/* Adjoint of nearest x2 upsampling (openaimodel.py:116): d f32 [n,2h,2w,c] -> out f32 [n,h,w,c]. */
+int mobi_sum2x2(const float* d, float* out, int32_t n, int32_t h, int32_t w, int32_t c, void* stream);
+/* q_sample on the first c_noised channels, the rest copied (ddpm.py:284-287, 1178-1182).  NCHW f32, t int64 [batch]. */
+int mobi_q_sample(const float* x0, const float* noise, const float* sqrt_ac, const float* sqrt_1mac, const int64_t* t,
+                  float* out, int32_t batch, int32_t c_total, int32_t c_noised, int32_t hw, void* stream);
+/* loss_sum += sum (pred - target)^2 ; grad = grad_scale * (pred - target)  (get_loss 'l2' + mean, ddpm.py:1196-1210). */
+int mobi_mse_grad(const float* pred, const float* target, float* grad, float* loss_sum, int64_t n, float grad_scale,
+                  void* stream);
+/* torch.optim.AdamW step over one flat f32 buffer (ddpm.py:1655): g is multiplied by grad_scale first. */
+int mobi_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
+               float weight_decay, float bias_corr1, float bias_corr2, float grad_scale, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -104,6 +104,37 @@ class AssembleArgs(C.Structure):
     ]
 
 
+class LayerNormBwdArgs(C.Structure):
+    _fields_ = [
+        ("x", _vp), ("gamma", _vp), ("dy", _vp), ("dx", _vp), ("dgamma", _vp), ("dbeta", _vp),
+        ("rows", _i64), ("C", _i32),
+        ("seg", _i64), ("seg_stride", _i64), ("seg_offset", _i64),
+        ("eps", _f32), ("dy_dtype", _i32), ("accumulate", _i32),
+    ]
+
+
+class GroupNormBwdArgs(C.Structure):
+    _fields_ = [
+        ("x1", _vp), ("x2", _vp), ("gamma", _vp), ("beta", _vp), ("dy", _vp), ("dres", _vp), ("dx1", _vp), ("dx2", _vp),
+        ("n_img", _i32), ("hw", _i32), ("c1", _i32), ("c2", _i32), ("groups", _i32), ("silu", _i32), ("dy_dtype", _i32),
+        ("eps", _f32),
+    ]
+
+
+class AttnSoftmaxBwdArgs(C.Structure):
+    _fields_ = [
+        ("S", _vp), ("dP", _vp), ("dS", _vp), ("dSt", _vp), ("Pt", _vp), ("stats", _vp),
+        ("batch", _i32), ("tq", _i32), ("tk", _i32), ("dscale", _f32),
+    ]
+
+
+class CtxAttnQspaceArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("d_o", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp),
+        ("batch", _i32), ("tokens", _i32), ("C", _i32), ("heads", _i32), ("keys", _i32), ("backward", _i32),
+    ]
+
+
 # name -> (restype, argtypes); also the list of symbols include/mobi_b200.h declares
 SIGNATURES = {
     "mobi_last_error": (C.c_char_p, []),
@@ -128,6 +159,22 @@ SIGNATURES = {
     "mobi_add_f32": (C.c_int, [_vp, _vp, _vp, _i64, _vp]),
     "mobi_scale_f32": (C.c_int, [_vp, _f32, _vp, _i64, _vp]),
     "mobi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
+    # training step
+    "mobi_transpose_bf16": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp]),
+    "mobi_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), _vp]),
+    "mobi_groupnorm_bwd": (C.c_int, [C.POINTER(GroupNormBwdArgs), _vp]),
+    "mobi_geglu": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
+    "mobi_geglu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
+    "mobi_attn_softmax_bwd": (C.c_int, [C.POINTER(AttnSoftmaxBwdArgs), _vp]),
+    "mobi_ctx_attn_qspace": (C.c_int, [C.POINTER(CtxAttnQspaceArgs), _vp]),
+    "mobi_colsum": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i64, _vp, _vp]),
+    "mobi_wgrad_small": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp]),
+    "mobi_scatter_add_rows": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i64, _i64, _i64, _vp]),
+    "mobi_zero_insert2x": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "mobi_sum2x2": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "mobi_q_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
+    "mobi_mse_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
+    "mobi_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
 }
 
 _lib = None

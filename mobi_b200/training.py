@@ -1,0 +1,542 @@
+"""Training step of MObI's latent-diffusion UNet on the C-ABI CUDA kernels (BASELINE.json config 5).
+
+What the reference runs per step (ldm/models/diffusion/ddpm.py):
+  LatentDiffusion.forward (1040-1058): t ~ randint, conditioning (dropout of the whole batch with p = u_cond_percent),
+  p_losses (1177-1217): noise ~ randn, x_noisy = cat(q_sample(x[:, :4], t, noise), x[:, 4:]), eps = apply_model(...),
+  loss = mean((eps - noise)^2)  (logvar = 0, l_simple_weight = 1, original_elbo_weight = 0);
+  loss.backward() through UNetModel with requires_grad only on parameters whose name contains "cond_adapter", "lidar"
+  or "cross_modal" (DiffusionWrapper.__init__, 1686-1698); DDP all-reduce of those gradients; AdamW (1655).
+
+Here the same computation is spelled out by hand, module by module: a training-mode forward that keeps what the backward
+needs (the inference path's algebraic folds of the adapters are NOT used, because their weights are the trainable
+ones), and a backward that mirrors it.  Every contraction is a tcgen05 GEMM / implicit conv (`ops.gemm`,
+`ops.conv_implicit`): dgrad with transposed / flipped weight packs, wgrad as dY^T X over the token dimension, the
+attention backward as five products per (row, head) around one softmax-backward kernel.  There is no autograd, no
+torch math on activations and no CPU fallback.
+
+The trainable parameters live in ONE flat fp32 buffer (their nn.Parameters are views into it), with a matching flat
+gradient buffer: the data-parallel exchange is a single NCCL all-reduce over that buffer and the optimizer a single
+fused AdamW launch.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import ops
+from . import train_ops as tops
+from .attention import LOG2E, BasicTransformerBlock, SpatialTransformer
+from .openaimodel import Conv3x3, Downsample, ResBlock, Upsample
+from .packing import pack_conv_weight
+
+TRAINABLE_KEYS = ("cond_adapter", "lidar", "cross_modal")  # ddpm.py:1686-1698
+
+
+def is_trainable(name):
+    return any(k in name for k in TRAINABLE_KEYS)
+
+
+# ------------------------------------------------------------------------------------------------ flat parameter store
+class FlatParams:
+    """Moves the selected parameters of `module` into one flat f32 buffer (views stay registered as the module's
+    nn.Parameters, so state_dict()/load_state_dict() keep working) and allocates the matching gradient buffer."""
+
+    ALIGN = 4  # elements: every view starts on a 16-byte boundary (vector epilogues of the wgrad GEMM)
+
+    def __init__(self, module, select=is_trainable, device=None):
+        named = [(n, p) for n, p in module.named_parameters() if select(n)]
+        if not named:
+            raise RuntimeError("no trainable parameters selected")
+        device = device or named[0][1].device
+        self.names = [n for n, _ in named]
+        self.offsets, self.shapes = {}, {}
+        off = 0
+        for n, p in named:
+            self.offsets[n] = off
+            self.shapes[n] = tuple(p.shape)
+            off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
+        self.numel = off
+        self.params = torch.zeros(off, device=device, dtype=torch.float32)
+        self.grads = torch.zeros(off, device=device, dtype=torch.float32)
+        with torch.no_grad():
+            for n, p in named:
+                v = self.view(self.params, n)
+                v.copy_(p.detach().to(device=device, dtype=torch.float32))
+                p.data = v
+                p.requires_grad_(True)
+        for n, p in module.named_parameters():
+            if not select(n):
+                p.requires_grad_(False)
+
+    def view(self, flat, name):
+        o = self.offsets[name]
+        shape = self.shapes[name]
+        return flat[o:o + math.prod(shape)].view(shape)
+
+    def grad(self, name):
+        return self.view(self.grads, name)
+
+    def pair_view(self, flat, first, second):
+        """One [2*rows, cols] view over two adjacent equal-shape matrices (to_k | to_v)."""
+        s = self.shapes[first]
+        assert self.shapes[second] == s and self.offsets[second] == self.offsets[first] + math.prod(s), \
+            "to_k / to_v are not adjacent in the flat buffer"
+        o = self.offsets[first]
+        return flat[o:o + 2 * math.prod(s)].view(2 * s[0], s[1])
+
+
+def allreduce_mean_(flat, group=None):
+    """Data-parallel gradient exchange: ONE all-reduce over the flat gradient buffer (NCCL over NVLink on the GPU box,
+    gloo in the CPU tests), then the mean.  Zero gradients of parameters unused this step (bbox_uncond_vector off the
+    cond-dropout steps) simply stay zero."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return flat
+    world = dist.get_world_size(group)
+    if world == 1:
+        return flat
+    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    flat.mul_(1.0 / world)
+    return flat
+
+
+def _bf16(t):
+    return t.detach().to(torch.bfloat16).contiguous()
+
+
+def _conv_dgrad_pack(conv):
+    """dX of a stride-1 'same' conv is the conv of dY with the spatially flipped, in/out-transposed filter."""
+    w = conv.weight.detach().float()
+    o, i, kh, kw = w.shape
+    wt = w.permute(1, 0, 2, 3).flip(2, 3).contiguous()  # [I, O, kh, kw]
+    k = kh * kw * o
+    return dict(w=pack_conv_weight(wt, (k + 7) // 8 * 8), b=None, kh=kh, kw=kw, cin=o, cout=i, stride=1,
+                pad=(kh // 2, kw // 2))
+
+
+class UNetTrainer:
+    """forward_backward(x_start, t, noise, context) -> loss; step() -> all-reduce + AdamW + repack."""
+
+    def __init__(self, ldm, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None):
+        self.ldm = ldm
+        self.unet = ldm.model.diffusion_model if hasattr(ldm, "model") else ldm
+        unet = self.unet
+        if not (unet.multimodal and all(b.bbox_cond for b in self._blocks())):
+            raise NotImplementedError("UNetTrainer: the training step is built for the joint camera+lidar UNet with "
+                                      "bbox_cond (configs/mobi_nusc_*.yaml), the only trained configuration")
+        dev = next(unet.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("UNetTrainer runs on CUDA only (no CPU fallback)")
+        self.device = dev
+        self.flat = FlatParams(unet, is_trainable, dev)
+        self.exp_avg = torch.zeros_like(self.flat.params)
+        self.exp_avg_sq = torch.zeros_like(self.flat.params)
+        self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
+        self.group = group
+        self.steps = 0
+        self.loss_sum = torch.zeros(1, device=dev, dtype=torch.float32)
+        self._names = {id(p): n for n, p in unet.named_parameters()}
+        self._ws = {}
+        unet.invalidate()
+        unet.pack()
+        self._pack_frozen_backward()
+        self.repack_trainable()
+
+    # ------------------------------------------------------------------ module lists / names
+    def _blocks(self):
+        return [m for m in self.unet.modules() if isinstance(m, BasicTransformerBlock)]
+
+    def _g(self, param):
+        return self.flat.grad(self._names[id(param)])
+
+    # ------------------------------------------------------------------ packs
+    @torch.no_grad()
+    def _pack_frozen_backward(self):
+        """Transposed (Linear) and flipped (conv) packs of the FROZEN weights for dgrad: built once."""
+        bp = {}
+        u = self.unet
+        for m in u.modules():
+            if isinstance(m, ResBlock):
+                d = dict(conv1=_conv_dgrad_pack(m.in_layers[2]), conv2=_conv_dgrad_pack(m.out_layers[3]))
+                if not isinstance(m.skip_connection, nn.Identity):
+                    d["w_skip_T"] = _bf16(m.skip_connection.weight.reshape(m.out_channels, m.channels).t())
+                bp[id(m)] = d
+            elif isinstance(m, SpatialTransformer):
+                bp[id(m)] = dict(w_in_T=_bf16(m.proj_in.weight.reshape(m.inner_dim, m.in_channels).t()),
+                                 w_out_T=_bf16(m.proj_out.weight.reshape(m.in_channels, m.inner_dim).t()))
+            elif isinstance(m, BasicTransformerBlock):
+                p = m._p
+                bp[id(m)] = dict(w_qkv_T=p["w_qkv"].t().contiguous(), w_o_T=p["w_o"].t().contiguous(),
+                                 w_ff1_T=p["w_ff1"].t().contiguous(), w_ff2_T=p["w_ff2"].t().contiguous())
+            elif isinstance(m, Upsample):
+                bp[id(m)] = dict(conv=_conv_dgrad_pack(m.conv))
+            elif isinstance(m, Downsample):
+                bp[id(m)] = dict(conv=_conv_dgrad_pack(m.op))
+        bp["conv_out"] = _conv_dgrad_pack(u.out[2])
+        self.bp = bp
+
+    def _pack_matrix(self, w, scale=1.0, transposed=True):
+        """f32 master weight [N, K] (a view of the flat buffer) -> bf16 [N, K] and bf16 [K, N], on the CUDA kernels."""
+        src = w if scale == 1.0 else ops.scale_f32(w, scale)
+        fwd = ops.cast_bf16(src)
+        wt = tops.transpose(src, rows=w.shape[0], cols=w.shape[1]).reshape(w.shape[1], w.shape[0]) if transposed else None
+        return fwd, wt
+
+    @torch.no_grad()
+    def repack_trainable(self):
+        """bf16 operand copies (and transposes for dgrad) of the TRAINABLE weights: after every optimizer step."""
+        tp = {}
+        self._qscales = []
+        for blk in self._blocks():
+            sc = blk.d_head ** -0.5
+            d = {}
+            ca = blk.cond_adapter_attn
+            d["a_wq"], d["a_wq_T"] = self._pack_matrix(ca.to_q.weight.data, sc)
+            d["a_wk"], _ = self._pack_matrix(ca.to_k.weight.data, transposed=False)
+            d["a_wv"], _ = self._pack_matrix(ca.to_v.weight.data, transposed=False)
+            d["a_wo"], d["a_wo_T"] = self._pack_matrix(ca.to_out[0].weight.data)
+            d["a_bo"] = ca.to_out[0].bias.data
+            d["a_wc"], d["a_wc_T"] = self._pack_matrix(blk.cond_adapter_connector.weight.data)
+            d["a_bc"] = blk.cond_adapter_connector.bias.data
+            self._qscales.append((self._g(ca.to_q.weight), sc))
+            for m in ("camera", "lidar"):
+                at = getattr(blk, "cross_modal_attn_" + m)
+                cn = getattr(blk, "cross_modal_connector_" + m)
+                d[m + "_wq"], d[m + "_wq_T"] = self._pack_matrix(at.to_q.weight.data, sc * LOG2E)
+                kv = self.flat.pair_view(self.flat.params, self._names[id(at.to_k.weight)], self._names[id(at.to_v.weight)])
+                d[m + "_wkv"], d[m + "_wkv_T"] = self._pack_matrix(kv)
+                d[m + "_wo"], d[m + "_wo_T"] = self._pack_matrix(at.to_out[0].weight.data)
+                d[m + "_bo"] = at.to_out[0].bias.data
+                d[m + "_wc"], d[m + "_wc_T"] = self._pack_matrix(cn.weight.data)
+                d[m + "_bc"] = cn.bias.data
+                self._qscales.append((self._g(at.to_q.weight), sc * LOG2E))
+            tp[id(blk)] = d
+        self.tp = tp
+        # the inference packs fold these weights: they are stale now
+        self.unet._ctx_key = None
+
+    # ------------------------------------------------------------------ attention helpers
+    def _attn_fwd(self, q, k, v, B, H, D, T):
+        if D <= 128:
+            return ops.attention(q, k, v, B, H, D, T, T, v_rowmajor=True)
+        vt = tops.transpose(v, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
+        return ops.attention(q, k, vt, B, H, D, T, T)
+
+    def _attn_ws(self, T):
+        ws = self._ws.get(T)
+        if ws is None:
+            dev = self.device
+            ws = dict(S=torch.empty((T, T), device=dev, dtype=torch.float32),
+                      dP=torch.empty((T, T), device=dev, dtype=torch.float32),
+                      dS=torch.empty((T, T), device=dev, dtype=torch.bfloat16),
+                      dSt=torch.empty((T, T), device=dev, dtype=torch.bfloat16),
+                      Pt=torch.empty((T, T), device=dev, dtype=torch.bfloat16),
+                      stats=torch.empty((3 * T,), device=dev, dtype=torch.float32))
+            self._ws[T] = ws
+        return ws
+
+    def _attn_bwd(self, q, k, v, do, B, H, D, T, dq_out, dq_col, dkv_out, dk_col, dv_col):
+        """Backward of softmax(q' k^T) v per (row, head) (CrossAttention.forward, attention.py:179-192).
+        q, k, v: bf16 [B*H, T, D] (q' carries scale*log2e); do: bf16 [B*T, C] token-major.  Writes dq', dk, dv as
+        [T, D] blocks at the given column offsets of the token-major outputs."""
+        C = H * D
+        kT = tops.transpose(k, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
+        qT = tops.transpose(q, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
+        doT = torch.empty((B * H, D, T), device=q.device, dtype=torch.bfloat16)
+        for b in range(B):
+            tops.transpose(do[b * T:(b + 1) * T], rows=T, cols=D, ld_in=C, batch=H, in_batch_stride=D,
+                           out=doT[b * H:(b + 1) * H])
+        ws = self._attn_ws(T)
+        f32 = torch.float32
+        for b in range(B):
+            rows = slice(b * T, (b + 1) * T)
+            for h in range(H):
+                bh = b * H + h
+                ops.gemm(q[bh], k[bh], out=ws["S"], out_dtype=f32)
+                ops.gemm(do[rows, h * D:(h + 1) * D], v[bh], out=ws["dP"], out_dtype=f32)
+                tops.attn_softmax_bwd(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2)
+                ops.gemm(ws["dS"], kT[bh], out=dq_out[rows, dq_col + h * D:dq_col + (h + 1) * D])
+                ops.gemm(ws["dSt"], qT[bh], out=dkv_out[rows, dk_col + h * D:dk_col + (h + 1) * D])
+                ops.gemm(ws["Pt"], doT[bh], out=dkv_out[rows, dv_col + h * D:dv_col + (h + 1) * D])
+
+    # ------------------------------------------------------------------ BasicTransformerBlock
+    def _block_forward(self, blk, x0, R, T, ctx_bf, ctx_f32):
+        """attention.py:230-266, x0: f32 [R*T, C] (kept).  Returns (x6, tape)."""
+        p, tp = blk._p, self.tp[id(blk)]
+        C, H, D = blk.dim, blk.n_heads, blk.d_head
+        dev, bf, f32 = x0.device, torch.bfloat16, torch.float32
+        nk = ctx_f32.shape[1]
+        t = dict(x0=x0)
+        # 1. self-attention
+        n1 = ops.layernorm(x0, *p["norm1"])
+        q = torch.empty((R * H, T, D), device=dev, dtype=bf)
+        k, v = torch.empty_like(q), torch.empty_like(q)
+        ops.gemm(n1, p["w_qkv"], epilogue=L.EPI_QKV_ROW, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=v)
+        o1 = self._attn_fwd(q, k, v, R, H, D, T).reshape(R * T, C)
+        x2 = ops.gemm(o1, p["w_o"], bias=p["b_o"], residual=x0, out_dtype=f32)
+        t.update(q=q, k=k, v=v)
+        # 2. attn2: one key -> the same vector to_out(to_v(c0)) for every token of a batch row (frozen weights)
+        c0 = ctx_bf.reshape(R, nk, -1)[:, 0].contiguous()
+        vec2 = ops.gemm(ops.gemm(c0, p["w_v2"]), p["w_o2"], bias=p["b_o2"], out_dtype=f32)
+        # 3. bbox / reference adapter (trainable): LN -> to_q ; to_k, to_v on the context ; 2-key attention ; to_out ;
+        #    connector.  The LayerNorm kernel adds vec2 to x2 in place first.
+        lna = blk.cond_adapter_norm
+        na = ops.layernorm(x2, lna.weight.data, lna.bias.data, add_vec=vec2, add_rows_per_vec=T)
+        qa = ops.gemm(na, tp["a_wq"])
+        ka = ops.gemm(ctx_bf, tp["a_wk"], out_dtype=f32).reshape(R, nk, C)
+        va = ops.gemm(ctx_bf, tp["a_wv"], out_dtype=f32).reshape(R, nk, C)
+        oa = tops.ctx_attn_qspace(qa, ka, va, R, T, H)
+        ua = ops.gemm(oa, tp["a_wo"], bias=tp["a_bo"])
+        x3 = ops.gemm(ua, tp["a_wc"], bias=tp["a_bc"], residual=x2, out_dtype=f32)
+        t.update(x2=x2, na=na, qa=qa, ka=ka, va=va, oa=oa, ua=ua, x3=x3)
+        # 4. cross-modal attention: camera rows (even) attend to the lidar rows, then lidar rows (odd) to the UPDATED
+        #    camera rows (attention.py:246-263)
+        Rh = R // 2
+        x5 = x3.clone()
+        seg = dict(rows=Rh * T, seg=T, seg_stride=2 * T)
+        for m, off in (("camera", 0), ("lidar", T)):
+            lnm = getattr(blk, "cross_modal_norm_" + m)
+            nq = ops.layernorm(x5, lnm.weight.data, lnm.bias.data, seg_offset=off, **seg)
+            ctx = ops.layernorm(x5, None, None, seg_offset=T - off, **seg)
+            qm = torch.empty((Rh * H, T, D), device=dev, dtype=bf)
+            km, vm = torch.empty_like(qm), torch.empty_like(qm)
+            ops.gemm(nq, tp[m + "_wq"], epilogue=L.EPI_HEADS, heads=H, head_dim=D, tokens=T, out=qm)
+            ops.gemm(ctx, tp[m + "_wkv"], epilogue=L.EPI_KV_ROW, heads=H, head_dim=D, tokens=T, out=km, out2=vm)
+            om = self._attn_fwd(qm, km, vm, Rh, H, D, T).reshape(Rh * T, C)
+            um = ops.gemm(om, tp[m + "_wo"], bias=tp[m + "_bo"])
+            ops.gemm(um, tp[m + "_wc"], bias=tp[m + "_bc"], residual=x5, out=x5, ldo=C, out_seg=T, out_seg_stride=2 * T,
+                     out_seg_offset=off)
+            t[m] = dict(nq=nq, ctx=ctx, q=qm, k=km, v=vm, o=om, u=um)
+        # 5. GEGLU feed-forward
+        n3 = ops.layernorm(x5, *p["norm3"])
+        g = ops.gemm(n3, p["w_ff1"], bias=p["b_ff1"])
+        x6 = ops.gemm(tops.geglu(g), p["w_ff2"], bias=p["b_ff2"], residual=x5, out_dtype=f32)
+        t.update(x5=x5, g=g)
+        return x6, t
+
+    def _linear_bwd(self, dy_bf, x_bf, w_T, weight, bias, M):
+        """y = x W^T + b: accumulates dW, db and returns dx = dy W (bf16)."""
+        n_out, k_in = weight.shape
+        if bias is not None:
+            tops.colsum(dy_bf, self._g(bias).reshape(1, n_out))
+        tops.wgrad(dy_bf, x_bf, self._g(weight), M=M, n_out=n_out, k_in=k_in)
+        return ops.gemm(dy_bf, w_T)
+
+    def _block_backward(self, blk, t, d, R, T, ctx_f32, need_dx0=True):
+        """d: f32 [R*T, C] gradient w.r.t. the block output; turned into the gradient w.r.t. x0 in place."""
+        p, tp, bp = blk._p, self.tp[id(blk)], self.bp[id(blk)]
+        C, H, D = blk.dim, blk.n_heads, blk.d_head
+        dev, bf = d.device, torch.bfloat16
+        M, Rh = R * T, R // 2
+        Mh = Rh * T
+        nk = ctx_f32.shape[1]
+        # 5. feed-forward
+        dh = ops.gemm(ops.cast_bf16(d), bp["w_ff2_T"])
+        dn3 = ops.gemm(tops.geglu_bwd(t["g"], dh), bp["w_ff1_T"])
+        tops.layernorm_bwd(t["x5"], p["norm3"][0], dn3, d)
+        # 4. cross-modal, in reverse order: lidar first (its context gradient lands on the camera rows)
+        for m, off in (("lidar", T), ("camera", 0)):
+            s = t[m]
+            at = getattr(blk, "cross_modal_attn_" + m)
+            cn = getattr(blk, "cross_modal_connector_" + m)
+            ln = getattr(blk, "cross_modal_norm_" + m)
+            seg = dict(seg=T, seg_stride=2 * T)
+            dm = ops.layernorm(d, None, None, rows=Mh, seg_offset=off, **seg)  # bf16 copy of this modality's rows
+            du = self._linear_bwd(dm, s["u"], tp[m + "_wc_T"], cn.weight, cn.bias, Mh)
+            do = self._linear_bwd(du, s["o"], tp[m + "_wo_T"], at.to_out[0].weight, at.to_out[0].bias, Mh)
+            dq = torch.empty((Mh, C), device=dev, dtype=bf)
+            dkv = torch.empty((Mh, 2 * C), device=dev, dtype=bf)
+            self._attn_bwd(s["q"], s["k"], s["v"], do, Rh, H, D, T, dq, 0, dkv, 0, C)
+            tops.wgrad(dq, s["nq"], self._g(at.to_q.weight), M=Mh, n_out=C, k_in=C)
+            dnq = ops.gemm(dq, tp[m + "_wq_T"])
+            gkv = self.flat.pair_view(self.flat.grads, self._names[id(at.to_k.weight)], self._names[id(at.to_v.weight)])
+            tops.wgrad(dkv, s["ctx"], gkv, M=Mh, n_out=2 * C, k_in=C)
+            dctx = ops.gemm(dkv, tp[m + "_wkv_T"])
+            # the LayerNorm input of this modality's rows is x3 (lidar rows are untouched by the camera update)
+            tops.layernorm_bwd(t["x3"], ln.weight.data, dnq, d, rows=Mh, seg_offset=off, dgamma=self._g(ln.weight),
+                               dbeta=self._g(ln.bias), **seg)
+            tops.scatter_add_rows(dctx, d, rows=Mh, Cc=C, seg_offset=T - off, **seg)
+        # 3. bbox / reference adapter
+        ca, cn, ln = blk.cond_adapter_attn, blk.cond_adapter_connector, blk.cond_adapter_norm
+        du = self._linear_bwd(ops.cast_bf16(d), t["ua"], tp["a_wc_T"], cn.weight, cn.bias, M)
+        do = self._linear_bwd(du, t["oa"], tp["a_wo_T"], ca.to_out[0].weight, ca.to_out[0].bias, M)
+        dqa, dka, dva = tops.ctx_attn_qspace(t["qa"], t["ka"], t["va"], R, T, H, d_o=do)
+        tops.wgrad(dqa, t["na"], self._g(ca.to_q.weight), M=M, n_out=C, k_in=C)
+        dna = ops.gemm(dqa, tp["a_wq_T"])
+        cflat = ctx_f32.reshape(R * nk, -1)
+        tops.wgrad_small(dka.reshape(R * nk, C), cflat, self._g(ca.to_k.weight))
+        tops.wgrad_small(dva.reshape(R * nk, C), cflat, self._g(ca.to_v.weight))
+        tops.layernorm_bwd(t["x2"], ln.weight.data, dna, d, dgamma=self._g(ln.weight), dbeta=self._g(ln.bias))
+        # 2. attn2 adds a per-row constant: identity for d.   1. self-attention (frozen weights: dgrad only)
+        if need_dx0:
+            do1 = ops.gemm(ops.cast_bf16(d), bp["w_o_T"])
+            dqkv = torch.empty((M, 3 * C), device=dev, dtype=bf)
+            self._attn_bwd(t["q"], t["k"], t["v"], do1, R, H, D, T, dqkv, 0, dqkv, C, 2 * C)
+            dn1 = ops.gemm(dqkv, bp["w_qkv_T"])
+            tops.layernorm_bwd(t["x0"], p["norm1"][0], dn1, d)
+        return d
+
+    # ------------------------------------------------------------------ SpatialTransformer / ResBlock / resampling
+    def _st_forward(self, st, h, ctx_bf, ctx_f32):
+        p = st._p
+        R, Hh, Ww, C = h.shape
+        T = Hh * Ww
+        hn = ops.groupnorm(h, p["gn"][0], p["gn"][1], 1e-6, silu=False)
+        x = ops.gemm(hn.reshape(R * T, C), p["w_in"], bias=p["b_in"], out_dtype=torch.float32)
+        tapes = []
+        for blk in st.transformer_blocks:
+            x, tb = self._block_forward(blk, x, R, T, ctx_bf, ctx_f32)
+            tapes.append(tb)
+        out = ops.gemm(ops.cast_bf16(x), p["w_out"], bias=p["b_out"], residual=h.reshape(R * T, C),
+                       out_dtype=torch.float32)
+        return out.reshape(R, Hh, Ww, C), dict(h=h, blocks=tapes)
+
+    def _st_backward(self, st, t, dout, ctx_f32, need_dx=True):
+        p, bp = st._p, self.bp[id(st)]
+        R, Hh, Ww, C = dout.shape
+        T = Hh * Ww
+        d = ops.gemm(ops.cast_bf16(dout).reshape(R * T, C), bp["w_out_T"], out_dtype=torch.float32)
+        n = len(st.transformer_blocks)
+        for i in range(n - 1, -1, -1):
+            d = self._block_backward(st.transformer_blocks[i], t["blocks"][i], d, R, T, ctx_f32,
+                                     need_dx0=need_dx or i > 0)
+        if not need_dx:
+            return None
+        dhn = ops.gemm(ops.cast_bf16(d), bp["w_in_T"])
+        dh, _ = tops.groupnorm_bwd(t["h"], p["gn"][0], p["gn"][1], dhn, 1e-6, silu=False, dres=dout)
+        return dh
+
+    def _res_forward(self, rb, h, emb_out, skip):
+        p = rb._p
+        R, Hh, Ww, _ = h.shape
+        need_raw = "w_skip" in p
+        g = ops.groupnorm(h, p["gn1"][0], p["gn1"][1], 1e-5, x2=skip, silu=True, want_concat=need_raw)
+        hn, raw = g if need_raw else (g, None)
+        h1 = Conv3x3.run(p["conv1"], hn, row_bias=emb_out)
+        hn2 = ops.groupnorm(h1, p["gn2"][0], p["gn2"][1], 1e-5, silu=True)
+        if need_raw:
+            res = ops.gemm(raw.reshape(R * Hh * Ww, -1), p["w_skip"], bias=p["b_skip"], out_dtype=torch.float32)
+            res = res.reshape(R, Hh, Ww, rb.out_channels)
+        else:
+            res = h
+        return Conv3x3.run(p["conv2"], hn2, residual=res), dict(h=h, skip=skip, h1=h1)
+
+    def _res_backward(self, rb, t, dout):
+        p, bp = rb._p, self.bp[id(rb)]
+        R, Hh, Ww, Co = dout.shape
+        dout_bf = ops.cast_bf16(dout)
+        dc = Conv3x3.run(bp["conv2"], dout_bf)
+        dh1, _ = tops.groupnorm_bwd(t["h1"], p["gn2"][0], p["gn2"][1], dc, 1e-5, silu=True)
+        da = Conv3x3.run(bp["conv1"], ops.cast_bf16(dh1))
+        if "w_skip_T" in bp:
+            dres = ops.gemm(dout_bf.reshape(R * Hh * Ww, Co), bp["w_skip_T"], out_dtype=torch.float32)
+        else:
+            dres = dout
+        return tops.groupnorm_bwd(t["h"], p["gn1"][0], p["gn1"][1], da, 1e-5, x2=t["skip"], silu=True, dres=dres)
+
+    def _seq_forward(self, seq, h, skip, emb_all, ctx_bf, ctx_f32):
+        tapes = []
+        for layer in seq:
+            if isinstance(layer, ResBlock):
+                off = self.unet._p["emb_offs"][id(layer)]
+                h, t = self._res_forward(layer, h, emb_all[:, off:off + layer.out_channels], skip)
+                skip = None
+            elif isinstance(layer, SpatialTransformer):
+                h, t = self._st_forward(layer, h, ctx_bf, ctx_f32)
+            elif isinstance(layer, Upsample):
+                h, t = layer.run(h), None
+            elif isinstance(layer, Downsample):
+                h, t = layer.run(h), None
+            else:
+                raise RuntimeError("unexpected layer %s" % type(layer))
+            tapes.append(t)
+        return h, tapes
+
+    def _seq_backward(self, seq, tapes, dh, ctx_f32, first=False):
+        """Returns (dh, dskip).  `first`: input_blocks[1] — nothing trainable upstream of its transformer."""
+        dskip = None
+        layers = list(seq)
+        for i in range(len(layers) - 1, -1, -1):
+            layer, t = layers[i], tapes[i]
+            if isinstance(layer, ResBlock):
+                if first:
+                    return None, None
+                dh, dskip = self._res_backward(layer, t, dh)
+            elif isinstance(layer, SpatialTransformer):
+                dh = self._st_backward(layer, t, dh, ctx_f32, need_dx=not first)
+            elif isinstance(layer, Upsample):
+                dup = Conv3x3.run(self.bp[id(layer)]["conv"], ops.cast_bf16(dh))
+                dh = tops.sum2x2(dup)
+            elif isinstance(layer, Downsample):
+                dh = Conv3x3.run(self.bp[id(layer)]["conv"], tops.zero_insert2x(dh))
+        return dh, dskip
+
+    # ------------------------------------------------------------------ the step
+    @torch.no_grad()
+    def forward_backward(self, x_start, t, noise, context):
+        """p_losses (ddpm.py:1177-1217) + backward.  x_start [R, 9, h, w] f32 (4 latent + 4 inpaint_image + mask channels),
+        t int64 [R], noise [R, 4, h, w], context [R, n_ctx, ctx_dim] (already dropped-out or not by the caller).
+        Gradients of the trainable parameters are left in self.flat.grads; returns the loss (0-dim tensor)."""
+        u, ldm = self.unet, self.ldm
+        p = u._p
+        for a in (x_start, noise, context):
+            if not a.is_cuda:
+                raise RuntimeError("UNetTrainer needs CUDA tensors (no CPU fallback)")
+        R = x_start.shape[0]
+        self.flat.grads.zero_()
+        self.loss_sum.zero_()
+        t = t.to(torch.int64).contiguous()
+        x_noisy = tops.q_sample(x_start.float().contiguous(), noise.float().contiguous(), ldm.sqrt_alphas_cumprod,
+                                ldm.sqrt_one_minus_alphas_cumprod, t, noise.shape[1])
+        ctx_f32 = context.detach().float().contiguous()
+        ctx_bf = ops.cast_bf16(ctx_f32).reshape(R * ctx_f32.shape[1], -1)
+        # ---- forward (openaimodel.py:861-898), keeping the tape
+        t_emb = ops.timestep_embedding(t, u.model_channels)
+        e1 = ops.gemm(t_emb, p["w_t0"], bias=p["b_t0"], act=1)
+        e2 = ops.gemm(e1, p["w_t2"], bias=p["b_t2"], act=1)
+        emb_all = ops.gemm(e2, p["w_emb"], bias=p["b_emb"], out_dtype=torch.float32)
+        h = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x_noisy))
+        hs, tapes_in, tapes_out = [h], [], []
+        for seq in list(u.input_blocks)[1:]:
+            h, tp_ = self._seq_forward(seq, h, None, emb_all, ctx_bf, ctx_f32)
+            hs.append(h)
+            tapes_in.append(tp_)
+        h, tape_mid = self._seq_forward(u.middle_block, h, None, emb_all, ctx_bf, ctx_f32)
+        for seq in u.output_blocks:
+            h, tp_ = self._seq_forward(seq, h, hs.pop(), emb_all, ctx_bf, ctx_f32)
+            tapes_out.append(tp_)
+        hn = ops.groupnorm(h, p["gn_out"][0], p["gn_out"][1], 1e-5, silu=True)
+        eps = Conv3x3.run(p["conv_out"], hn)                      # NHWC f32 [R, h, w, 4]
+        # ---- loss and its gradient (mean over all elements)
+        target = ops.nchw_to_nhwc(noise.float().contiguous())
+        d_eps = tops.mse_grad(eps, target, self.loss_sum, 2.0 / eps.numel())
+        self.eps_nhwc = eps
+        # ---- backward
+        dhn = Conv3x3.run(self.bp["conv_out"], ops.cast_bf16(d_eps))
+        dh, _ = tops.groupnorm_bwd(h, p["gn_out"][0], p["gn_out"][1], dhn, 1e-5, silu=True)
+        d_hs = []
+        for seq, tp_ in zip(reversed(list(u.output_blocks)), reversed(tapes_out)):
+            dh, dskip = self._seq_backward(seq, tp_, dh, ctx_f32)
+            d_hs.append(dskip)                                     # gradients of hs[0], hs[1], ... in order
+        dh, _ = self._seq_backward(u.middle_block, tape_mid, dh, ctx_f32)
+        inputs = list(u.input_blocks)
+        for i in range(len(inputs) - 1, 0, -1):
+            dh = ops.add_f32(dh, d_hs[i])
+            dh, _ = self._seq_backward(inputs[i], tapes_in[i - 1], dh, ctx_f32, first=(i == 1))
+        # gradients w.r.t. the scaled query projections -> w.r.t. to_q.weight
+        for gview, sc in self._qscales:
+            ops.scale_f32(gview, sc, out=gview)
+        return self.loss_sum[0] / eps.numel()
+
+    @torch.no_grad()
+    def step(self, lr=None):
+        """DDP gradient all-reduce (mean) + AdamW over the flat buffers + repack of the bf16 operand copies."""
+        allreduce_mean_(self.flat.grads, self.group)
+        self.steps += 1
+        tops.adamw(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=self.lr if lr is None else lr,
+                   beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self.steps)
+        self.repack_trainable()
+
+    def named_grads(self):
+        return {n: self.flat.grad(n) for n in self.flat.names}

@@ -9,6 +9,8 @@ What is pinned (all with the tiny topology-complete configs from oracle/*_oracle
   ddim_tiny.npz        DDIMSampler.sample, 4 steps of S=10, CFG 3.0, test_model_kwargs path (+ mask/x0 blend run)
   plms_tiny.npz        PLMSSampler.sample, 4 steps of S=10, CFG 3.0
   vae_tiny.npz         AutoencoderKL.decode / encode moments for the camera and the lidar-adapter autoencoder
+  train_tiny.npz       LatentDiffusion.p_losses loss + loss.backward() gradients of the trainable (adapter) parameters,
+                       and the parameters after one torch.optim.AdamW step
   schedule.npz         register_schedule + DDIM parameters for S=50 on the real (1000-step) schedule
   shapes_512.json      state_dict key -> shape of the real mobi_nusc_512 UNet (1,118 tensors) and both VAEs
 """
@@ -24,7 +26,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-from oracle import ref_shims, sampler_oracle, unet_oracle, vae_oracle  # noqa: E402
+from oracle import ref_shims, sampler_oracle, train_oracle, unet_oracle, vae_oracle  # noqa: E402
 
 
 def build_reference_ldm(unet_cfg, cam_dd=None, lid_dd=None):
@@ -132,6 +134,40 @@ def main():
     np.savez(os.path.join(GOLDEN, "vae_tiny.npz"), z=samples.numpy(), image=img.numpy(), range=rng_img.numpy(),
              cam_in=cam_in.numpy(), lid_in=lid_in.numpy(), cam_moments=cam_m.numpy(), lid_moments=lid_m.numpy())
     print("vae_tiny image std %.4f range std %.4f" % (img.std(), rng_img.std()))
+
+
+    # ---- training step: p_losses + backward + one AdamW step through the reference modules
+    tr = train_oracle.synth_train_inputs(2, 16, ucfg["context_dim"], seed=5)
+    with torch.enable_grad():
+        ldm.train()
+        for n_, p_ in ldm.model.diffusion_model.named_parameters():
+            assert p_.requires_grad == train_oracle.is_trainable(n_), n_   # DiffusionWrapper.__init__, ddpm.py:1686-1698
+        params = [p_ for p_ in ldm.model.diffusion_model.parameters() if p_.requires_grad]
+        opt = torch.optim.AdamW(params, lr=8e-5)                           # ddpm.py:1655
+        loss, _ = ldm.p_losses(tr["x_start"], tr["cond"], tr["t"], noise=tr["noise"])
+        loss.backward()
+        grads = {n_: p_.grad.detach().clone() for n_, p_ in ldm.model.diffusion_model.named_parameters()
+                 if p_.requires_grad}
+        opt.step()
+        after = {n_: p_.detach().clone() for n_, p_ in ldm.model.diffusion_model.named_parameters() if p_.requires_grad}
+        ldm.eval()
+    keep = ("input_blocks.1.1.", "middle_block.1.", "output_blocks.3.1.")
+    out = dict(x_start=tr["x_start"].numpy(), t=tr["t"].numpy(), noise=tr["noise"].numpy(), cond=tr["cond"].numpy(),
+               loss=np.float32(loss.item()), names=np.array(sorted(grads)),
+               grad_l2=np.array([grads[k].norm().item() for k in sorted(grads)], dtype=np.float64),
+               grad_sum=np.array([grads[k].double().sum().item() for k in sorted(grads)], dtype=np.float64))
+    for k in sorted(grads):
+        if k.startswith(keep):
+            out["g:" + k] = grads[k].numpy()
+            if "cross_modal_attn_camera.to_q" in k or "cond_adapter_norm" in k:
+                out["p1:" + k] = after[k].numpy()
+    np.savez_compressed(os.path.join(GOLDEN, "train_tiny.npz"), **out)
+    print("train_tiny loss %.6f, %d trainable tensors, %d stored in full" % (
+        loss.item(), len(grads), sum(1 for k in out if k.startswith("g:"))))
+    for p_ in ldm.model.diffusion_model.parameters():
+        p_.grad = None
+    load_synth(ldm.model.diffusion_model, unet_oracle.state_dict_shapes(ucfg), seed=0)   # undo the optimizer step
+    torch.set_grad_enabled(False)
 
     # ---- schedule buffers on the real schedule, S=50
     smp = DDIMSampler(ldm)

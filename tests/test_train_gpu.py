@@ -1,0 +1,331 @@
+"""Parity of the training step (BASELINE.json config 5) on the GPU, through the drop-in classes and the C ABI.
+
+Kernel level: every backward kernel against torch.autograd of the same fp32 math on seeded inputs.
+End to end: UNetTrainer.forward_backward on the tiny joint UNet against tests/golden/train_tiny.npz — loss and the
+gradients of the trainable (adapter) parameters produced by the UNMODIFIED reference's p_losses + loss.backward() — and
+one AdamW step against torch.optim.AdamW's result from the same file.
+
+Tolerances: the backward runs like the forward (bf16 GEMM operands, fp32 accumulation, fp32 statistics), and the
+gradient signal additionally passes through bf16-rounded activation gradients, so per-tensor gradients are held to
+max-abs error <= 5e-2 of the tensor's max (measured values are printed) and cosine similarity >= 0.999; fp32-only kernels
+(norm backward on fp32 dy, loss, AdamW) to <= 1e-4.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).abs().max() / b.abs().max().clamp_min(1e-30)).item()
+
+
+def cos(a, b):
+    a, b = a.double().reshape(-1), b.double().reshape(-1)
+    return (a @ b / (a.norm() * b.norm()).clamp_min(1e-30)).item()
+
+
+def rnd(*shape, seed=0, dtype=torch.float32, scale=1.0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    return (torch.randn(*shape, device="cuda", generator=g) * scale).to(dtype)
+
+
+# ---------------------------------------------------------------------------------------------- kernels
+def test_transpose_batched_strided():
+    from mobi_b200 import train_ops as tops
+    x = rnd(3, 70, 48, seed=1)
+    out = tops.transpose(x, rows=70, cols=48, batch=3, in_batch_stride=70 * 48)
+    assert torch.equal(out, x.transpose(1, 2).to(torch.bfloat16))
+    # head columns of a token-major matrix: batch = heads, stride = head_dim, ld = C
+    y = rnd(64, 96, seed=2, dtype=torch.bfloat16)
+    out = tops.transpose(y, rows=64, cols=24, ld_in=96, batch=4, in_batch_stride=24)
+    ref = y.reshape(64, 4, 24).permute(1, 2, 0)
+    assert torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("C,seg", [(64, False), (320, True), (1280, False)])
+def test_layernorm_bwd(C, seg):
+    from mobi_b200 import train_ops as tops
+    B, T = 4, 24
+    x = rnd(B * T, C, seed=3)
+    gamma, beta = 1 + 0.1 * rnd(C, seed=4), 0.1 * rnd(C, seed=5)
+    if seg:
+        rows = (B // 2) * T
+        idx = (torch.arange(rows, device="cuda") // T) * 2 * T + T + torch.arange(rows, device="cuda") % T  # odd rows
+    else:
+        rows, idx = B * T, torch.arange(B * T, device="cuda")
+    dy = rnd(rows, C, seed=6)
+    xr = x.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    F.layer_norm(xr[idx], (C,), gr, br, 1e-5).backward(dy)
+    d = rnd(B * T, C, seed=7)
+    d0 = d.clone()
+    dg, db = torch.zeros(C, device="cuda"), torch.zeros(C, device="cuda")
+    kw = dict(rows=rows, seg=T, seg_stride=2 * T, seg_offset=T) if seg else {}
+    tops.layernorm_bwd(x, gamma, dy, d, dgamma=dg, dbeta=db, **kw)
+    assert rel(d - d0, xr.grad) < 1e-4
+    assert rel(dg, gr.grad) < 1e-4 and rel(db, br.grad) < 1e-4
+    # bf16 dy, no parameter gradients, overwrite
+    d2 = torch.empty_like(d)
+    tops.layernorm_bwd(x, gamma, dy.to(torch.bfloat16), d2, accumulate=False, **kw)
+    xr.grad = None
+    F.layer_norm(xr[idx], (C,), gamma, beta, 1e-5).backward(dy.to(torch.bfloat16).float())
+    assert rel(d2[idx], xr.grad[idx]) < 1e-4
+
+
+@pytest.mark.parametrize("c1,c2,silu", [(64, 0, True), (96, 32, True), (320, 0, False), (1280, 640, True)])
+def test_groupnorm_bwd(c1, c2, silu):
+    from mobi_b200 import train_ops as tops
+    n, h, w = 2, 8, 8
+    x1 = rnd(n, h, w, c1, seed=1)
+    x2 = rnd(n, h, w, c2, seed=2) if c2 else None
+    C = c1 + c2
+    gamma, beta = 1 + 0.1 * rnd(C, seed=3), 0.1 * rnd(C, seed=4)
+    dy, dres = rnd(n, h, w, C, seed=5), rnd(n, h, w, C, seed=6)
+    eps = 1e-5 if silu else 1e-6
+    a1 = x1.clone().requires_grad_(True)
+    a2 = x2.clone().requires_grad_(True) if c2 else None
+    xin = torch.cat([a1, a2], -1) if c2 else a1
+    y = F.group_norm(xin.permute(0, 3, 1, 2), 32, gamma, beta, eps)
+    y = F.silu(y) if silu else y
+    (y.permute(0, 2, 3, 1) * dy).sum().backward()
+    dx1, dx2 = tops.groupnorm_bwd(x1, gamma, beta, dy, eps, x2=x2, silu=silu, dres=dres)
+    assert rel(dx1 - dres[..., :c1], a1.grad) < 1e-4
+    if c2:
+        assert rel(dx2 - dres[..., c1:], a2.grad) < 1e-4
+
+
+def test_geglu_fwd_bwd():
+    from mobi_b200 import train_ops as tops
+    M, Fh = 96, 128
+    g = rnd(M, 2 * Fh, seed=1, dtype=torch.bfloat16)
+    dh = rnd(M, Fh, seed=2, dtype=torch.bfloat16)
+    gf = g.float().requires_grad_(True)
+    val, gate = gf[:, 0::2], gf[:, 1::2]
+    out_ref = val * F.gelu(gate)
+    out_ref.backward(dh.float())
+    assert rel(tops.geglu(g).float(), out_ref.detach()) < 1e-2
+    assert rel(tops.geglu_bwd(g, dh).float(), gf.grad) < 1e-2
+
+
+@pytest.mark.parametrize("tq,tk", [(64, 64), (256, 256), (96, 160)])
+def test_attn_softmax_bwd(tq, tk):
+    from mobi_b200 import train_ops as tops
+    S = rnd(tq, tk, seed=1, scale=2.0)
+    dP = rnd(tq, tk, seed=2)
+    dS = torch.empty(tq, tk, device="cuda", dtype=torch.bfloat16)
+    dSt = torch.empty(tk, tq, device="cuda", dtype=torch.bfloat16)
+    Pt = torch.empty(tk, tq, device="cuda", dtype=torch.bfloat16)
+    stats = torch.empty(3 * tq, device="cuda")
+    tops.attn_softmax_bwd(S, dP, dS, dSt, Pt, stats, tq, tk, tops.LN2)
+    Sr = S.clone().requires_grad_(True)
+    P = torch.softmax(Sr * tops.LN2, -1)          # S is in the log2 domain
+    (P * dP).sum().backward()
+    assert rel(Pt.float().t(), P.detach()) < 1e-2
+    assert rel(dS.float(), Sr.grad) < 1e-2 and torch.equal(dSt.t(), dS)
+
+
+@pytest.mark.parametrize("keys", [1, 2])
+def test_ctx_attn_qspace_fwd_bwd(keys):
+    from mobi_b200 import train_ops as tops
+    B, T, H, D = 2, 200, 4, 16
+    C = H * D
+    q = rnd(B * T, C, seed=1, dtype=torch.bfloat16)
+    k, v = rnd(B, keys, C, seed=2), rnd(B, keys, C, seed=3)
+    do = rnd(B * T, C, seed=4, dtype=torch.bfloat16)
+    qr, kr, vr = q.float().requires_grad_(True), k.clone().requires_grad_(True), v.clone().requires_grad_(True)
+    qh = qr.reshape(B, T, H, D).permute(0, 2, 1, 3)
+    kh, vh = kr.reshape(B, keys, H, D).permute(0, 2, 1, 3), vr.reshape(B, keys, H, D).permute(0, 2, 1, 3)
+    o_ref = (torch.softmax(qh @ kh.transpose(-1, -2), -1) @ vh).permute(0, 2, 1, 3).reshape(B * T, C)
+    o_ref.backward(do.float())
+    o = tops.ctx_attn_qspace(q, k, v, B, T, H)
+    assert rel(o.float(), o_ref.detach()) < 1e-2
+    dq, dk, dv = tops.ctx_attn_qspace(q, k, v, B, T, H, d_o=do)
+    assert rel(dq.float(), qr.grad) < 1e-2
+    assert rel(dk, kr.grad) < 1e-3 and rel(dv, vr.grad) < 1e-3
+
+
+def test_small_reductions_and_adjoints():
+    from mobi_b200 import ops
+    from mobi_b200 import train_ops as tops
+    x = rnd(512, 72, seed=1)
+    out = torch.zeros(1, 72, device="cuda")
+    tops.colsum(x, out)
+    assert rel(out[0], x.sum(0)) < 1e-5
+    out = torch.zeros(4, 72, device="cuda")
+    tops.colsum(x.to(torch.bfloat16), out, rows_per_group=128)
+    assert rel(out, x.to(torch.bfloat16).float().reshape(4, 128, 72).sum(1)) < 1e-5
+    A, B = rnd(8, 40, seed=2), rnd(8, 24, seed=3)
+    acc = rnd(40, 24, seed=4)
+    ref = acc + A.t() @ B
+    tops.wgrad_small(A, B, acc)
+    assert rel(acc, ref) < 1e-5
+    # scatter-add into the lidar (odd) batch rows
+    T, C = 16, 32
+    dst = rnd(4 * T, C, seed=5)
+    src = rnd(2 * T, C, seed=6, dtype=torch.bfloat16)
+    ref = dst.clone().reshape(4, T, C)
+    ref[1::2] += src.float().reshape(2, T, C)
+    tops.scatter_add_rows(src, dst, rows=2 * T, Cc=C, seg=T, seg_stride=2 * T, seg_offset=T)
+    assert rel(dst, ref.reshape(4 * T, C)) < 1e-6
+    # nearest-upsample adjoint
+    d = rnd(2, 8, 8, 16, seed=7)
+    xr = rnd(2, 4, 4, 16, seed=8).requires_grad_(True)
+    up = F.interpolate(xr.permute(0, 3, 1, 2), scale_factor=2, mode="nearest").permute(0, 2, 3, 1)
+    (up * d).sum().backward()
+    assert rel(tops.sum2x2(d), xr.grad) < 1e-6
+    # q_sample / loss
+    x0, noise = rnd(4, 9, 8, 8, seed=9), rnd(4, 4, 8, 8, seed=10)
+    sa, s1 = torch.linspace(1, 0.1, 1000, device="cuda"), torch.linspace(0.05, 1, 1000, device="cuda")
+    t = torch.tensor([0, 999, 500, 21], device="cuda")
+    got = tops.q_sample(x0, noise, sa, s1, t, 4)
+    ref = x0.clone()
+    ref[:, :4] = sa[t].view(-1, 1, 1, 1) * x0[:, :4] + s1[t].view(-1, 1, 1, 1) * noise
+    assert rel(got, ref) < 1e-6
+    pred, tgt = rnd(5000, seed=11), rnd(5000, seed=12)
+    ls = torch.zeros(1, device="cuda")
+    gr = tops.mse_grad(pred, tgt, ls, 2.0 / 5000)
+    assert abs(ls.item() / 5000 - F.mse_loss(pred, tgt).item()) < 1e-5 and rel(gr, 2 * (pred - tgt) / 5000) < 1e-6
+
+
+def test_adamw_matches_torch():
+    from mobi_b200 import train_ops as tops
+    p = rnd(10001, seed=1)
+    ref = torch.nn.Parameter(p.clone())
+    opt = torch.optim.AdamW([ref], lr=8e-5)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in (1, 2, 3):
+        g = rnd(10001, seed=10 + step, scale=1e-3)
+        ref.grad = g.clone()
+        opt.step()
+        tops.adamw(p, g, m, v, lr=8e-5, step=step)
+    assert rel(p - rnd(10001, seed=1), ref.detach() - rnd(10001, seed=1)) < 1e-4
+
+
+@pytest.mark.parametrize("cin,cout,hw,stride", [(64, 128, 16, 1), (128, 64, 8, 1), (64, 4, 16, 1), (64, 64, 16, 2)])
+def test_conv_dgrad(cin, cout, hw, stride):
+    """dX of conv3x3 as a conv of dY (zero-inserted for stride 2) with the flipped, transposed filter."""
+    from mobi_b200 import ops
+    from mobi_b200 import train_ops as tops
+    from mobi_b200.openaimodel import Conv3x3
+    from mobi_b200.training import _conv_dgrad_pack
+    conv = torch.nn.Conv2d(cin, cout, 3, stride=stride, padding=1).cuda()
+    x = rnd(2, cin, hw, hw, seed=1).requires_grad_(True)
+    y = conv(x)
+    dy = rnd(*y.shape, seed=2)
+    y.backward(dy)
+    pack = _conv_dgrad_pack(conv)
+    dy_nhwc = dy.permute(0, 2, 3, 1).contiguous()
+    z = tops.zero_insert2x(dy_nhwc) if stride == 2 else ops.cast_bf16(dy_nhwc)
+    dx = Conv3x3.run(pack, z)
+    assert rel(dx, x.grad.permute(0, 2, 3, 1)) < 1e-2
+
+
+def test_wgrad_and_bias_grad():
+    from mobi_b200 import train_ops as tops
+    M, N, K = 512, 64, 128
+    dy, x = rnd(M, N, seed=1, dtype=torch.bfloat16), rnd(M, K, seed=2, dtype=torch.bfloat16)
+    acc = rnd(N, K, seed=3)
+    ref = acc + dy.float().t() @ x.float()
+    tops.wgrad(dy, x, acc, M=M, n_out=N, k_in=K)
+    assert rel(acc, ref) < 2e-3
+
+
+@pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256)])
+def test_attention_backward_composite(B, H, D, T):
+    """The five products + softmax backward per (row, head) against autograd of softmax(q k^T * scale) v."""
+    import math
+    from mobi_b200.training import UNetTrainer
+    C = H * D
+    sc = D ** -0.5
+    q = rnd(B * H, T, D, seed=1)
+    k, v = rnd(B * H, T, D, seed=2), rnd(B * H, T, D, seed=3)
+    do = rnd(B * T, C, seed=4, dtype=torch.bfloat16)
+    qb = (q * sc * math.log2(math.e)).to(torch.bfloat16)      # what the packed to_q produces
+    kb, vb = k.to(torch.bfloat16), v.to(torch.bfloat16)
+    qr = qb.float().requires_grad_(True)
+    kr, vr = kb.float().requires_grad_(True), vb.float().requires_grad_(True)
+    o = torch.softmax(qr @ kr.transpose(-1, -2) * math.log(2.0), -1) @ vr            # [BH, T, D]
+    o.reshape(B, H, T, D).permute(0, 2, 1, 3).reshape(B * T, C).backward(do.float())
+    tr = UNetTrainer.__new__(UNetTrainer)
+    tr.device, tr._ws = torch.device("cuda"), {}
+    dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
+    tr._attn_bwd(qb, kb, vb, do, B, H, D, T, dqkv, 0, dqkv, C, 2 * C)
+    heads = lambda g: g.reshape(B, H, T, D).permute(0, 2, 1, 3).reshape(B * T, C)
+    assert rel(dqkv[:, :C].float(), heads(qr.grad)) < 2e-2
+    assert rel(dqkv[:, C:2 * C].float(), heads(kr.grad)) < 2e-2
+    assert rel(dqkv[:, 2 * C:].float(), heads(vr.grad)) < 2e-2
+
+
+# ---------------------------------------------------------------------------------------------- end to end
+def _tiny_trainer():
+    from mobi_b200.ddpm import LatentDiffusion
+    from mobi_b200.training import UNetTrainer
+    from oracle import unet_oracle as uo
+    cfg = uo.tiny_unet_config()
+    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
+    ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg),
+                          linear_start=0.00085, linear_end=0.0120, timesteps=1000, first_stage_key="inpaint",
+                          image_size=16, channels=4, conditioning_key="crossattn", use_camera=True,
+                          use_lidar=True).cuda().eval()
+    ldm.model.diffusion_model.load_state_dict(sd, strict=True)
+    return UNetTrainer(ldm), cfg, sd
+
+
+def test_training_step_tiny_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    tr, cfg, sd = _tiny_trainer()
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    loss = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"))
+    torch.cuda.synchronize()
+    ref_loss = float(g["loss"])
+    print("tiny training step: loss %.6f (reference %.6f)" % (loss.item(), ref_loss))
+    assert abs(loss.item() - ref_loss) <= 1e-2 * ref_loss
+    grads = tr.named_grads()
+    names = [str(n) for n in g["names"]]
+    assert sorted(grads) == names
+    l2 = np.array([grads[n].norm().item() for n in names])
+    worst_l2 = np.abs(l2 - g["grad_l2"]) / np.maximum(g["grad_l2"], 1e-12)
+    worst, wcos, wname = 0.0, 1.0, None
+    for k in g.files:
+        if not k.startswith("g:"):
+            continue
+        ref = torch.from_numpy(g[k]).cuda()
+        e, c = rel(grads[k[2:]], ref), cos(grads[k[2:]], ref)
+        if e > worst:
+            worst, wname = e, k[2:]
+        wcos = min(wcos, c)
+    print("tiny training step: worst per-tensor grad max-abs-rel %.3e (%s), min cosine %.5f, worst L2-norm rel %.3e"
+          % (worst, wname, wcos, worst_l2.max()))
+    assert worst <= 5e-2 and wcos >= 0.999 and worst_l2.max() <= 5e-2
+
+
+def test_adamw_step_tiny_vs_reference_golden():
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    tr, cfg, sd = _tiny_trainer()
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"))
+    tr.step()
+    torch.cuda.synchronize()
+    params = dict(tr.unet.named_parameters())
+    n_checked = 0
+    for k in g.files:
+        if not k.startswith("p1:"):
+            continue
+        n = k[3:]
+        upd = params[n].detach() - sd[n].cuda()
+        upd_ref = torch.from_numpy(g[k]).cuda() - sd[n].cuda()
+        # Adam's first step is lr * sign(g) (up to eps): elements whose gradient is ~0 may flip, so compare in the mean
+        agree = (torch.sign(upd) == torch.sign(upd_ref)).float().mean().item()
+        assert agree > 0.98, (n, agree)
+        n_checked += 1
+    assert n_checked >= 4
+    # a second step runs on the repacked weights and lowers nothing structurally: the loss stays finite
+    loss2 = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"))
+    assert torch.isfinite(loss2).item()
