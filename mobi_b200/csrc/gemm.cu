@@ -113,8 +113,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int n_tile = blockIdx.x;
-    const int m_tile = blockIdx.y;
+    // m tiles on grid.x (2^31 - 1 limit): the VAE decode at 512^2 has > 65535 of them per batch
+    const int m_tile = blockIdx.x;
+    const int n_tile = blockIdx.y;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -285,7 +286,7 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                                        Cfg::SMEM_BYTES));
         configured = true;
     }
-    dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, 1);
+    dim3 grid((p.M + BM - 1) / BM, (p.N + BN - 1) / BN, 1);
     gemm_bf16_kernel<BN><<<grid, 192, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
     MOBI_CUDA(cudaGetLastError());
     return 0;

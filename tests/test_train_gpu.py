@@ -205,7 +205,9 @@ def test_adamw_matches_torch():
         ref.grad = g.clone()
         opt.step()
         tops.adamw(p, g, m, v, lr=8e-5, step=step)
-    assert rel(p - rnd(10001, seed=1), ref.detach() - rnd(10001, seed=1)) < 1e-4
+    # three steps move every weight by ~3 * lr = 2.4e-4; fp32 spacing of the O(1) weights is ~1e-7, i.e. 5e-4 of the update
+    assert rel(p - rnd(10001, seed=1), ref.detach() - rnd(10001, seed=1)) < 5e-3
+    assert (p - ref.detach()).abs().max().item() < 3e-6
 
 
 @pytest.mark.parametrize("cin,cout,hw,stride", [(64, 128, 16, 1), (128, 64, 8, 1), (64, 4, 16, 1), (64, 64, 16, 2)])
@@ -329,3 +331,46 @@ def test_adamw_step_tiny_vs_reference_golden():
     # a second step runs on the repacked weights and lowers nothing structurally: the loss stays finite
     loss2 = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"))
     assert torch.isfinite(loss2).item()
+
+
+def test_training_step_fullwidth_vs_oracle():
+    """The real 1.04 B-parameter joint UNet (181.6 M trainable), 2 joint samples (config 5's batch_size) at latent
+    32 x 32, against torch.autograd over the fp32 oracle on the same device (TF32 off)."""
+    from mobi_b200.ddpm import LatentDiffusion
+    from mobi_b200.training import UNetTrainer
+    from oracle import sampler_oracle as so
+    from oracle import train_oracle as to
+    from oracle import unet_oracle as uo
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    cfg = uo.default_unet_config(image_size=32)
+    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
+    with torch.device("meta"):
+        ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg),
+                              linear_start=0.00085, linear_end=0.0120, timesteps=1000, first_stage_key="inpaint",
+                              image_size=32, channels=4, conditioning_key="crossattn", use_camera=True, use_lidar=True)
+    ldm = ldm.to_empty(device="cuda")
+    ldm.register_schedule(linear_start=0.00085, linear_end=0.0120, timesteps=1000)
+    ldm = ldm.to("cuda").eval()
+    ldm.model.diffusion_model.load_state_dict(sd, strict=True)
+    tr = UNetTrainer(ldm)
+    assert tr.flat.numel >= 180_394_240 and len(tr.flat.names) == 16 * 27   # tests/golden/shapes_512.json
+    inp = to.synth_train_inputs(2, 32, 768, seed=5, device="cuda")
+    loss = tr.forward_backward(inp["x_start"], inp["t"], inp["noise"], inp["cond"])
+    torch.cuda.synchronize()
+    sdc = {k: v.cuda() for k, v in sd.items()}
+    sched = {k: v.cuda() for k, v in so.register_schedule().items()}
+    ref_loss, ref = to.loss_and_grads(sdc, cfg, sched, inp["x_start"], inp["t"], inp["noise"], inp["cond"])
+    grads = tr.named_grads()
+    worst, wname, wcos = 0.0, None, 1.0
+    for n, gr in ref.items():
+        e, c = rel(grads[n], gr), cos(grads[n], gr)
+        if e > worst:
+            worst, wname = e, n
+        wcos = min(wcos, c)
+    flat_ref = torch.cat([ref[n].reshape(-1) for n in tr.flat.names])
+    flat_got = torch.cat([grads[n].reshape(-1) for n in tr.flat.names])
+    print("full-width training step: loss %.6f (oracle %.6f); worst per-tensor grad max-abs-rel %.3e (%s), min cosine "
+          "%.5f, whole-gradient cosine %.6f" % (loss.item(), ref_loss.item(), worst, wname, wcos, cos(flat_got, flat_ref)))
+    assert abs(loss.item() - ref_loss.item()) <= 1e-2 * ref_loss.item()
+    assert worst <= 5e-2 and wcos >= 0.999 and cos(flat_got, flat_ref) >= 0.9995

@@ -1,0 +1,93 @@
+#!/usr/bin/env python
+"""Training-step timing (BASELINE.json config 5): mobi_nusc_512 UNet forward + backward + gradient all-reduce + AdamW on
+synthetic latents, one process per GPU (torchrun for N > 1, NCCL).  Prints one JSON line with the step time, the
+per-kernel-class breakdown of one step and the achieved tensor-core rate against SURVEY.md §8(d)'s FLOP counts.
+
+  python tools/train_bench.py [--samples-per-gpu 2] [--latent 64] [--steps 5] [--warmup 2]
+"""
+import argparse
+import json
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+FWD_FLOPS_PER_JOINT = {64: 2043895808000, 32: 419359047680}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--samples-per-gpu", type=int, default=2)   # configs/mobi_nusc_512.yaml:11 batch_size
+    ap.add_argument("--latent", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=2)
+    args = ap.parse_args()
+    import torch.distributed as dist
+    from mobi_b200 import ops, synth
+    from mobi_b200.training import UNetTrainer
+    world, rank, local = (int(os.environ.get(k, d)) for k, d in (("WORLD_SIZE", "1"), ("RANK", "0"), ("LOCAL_RANK", "0")))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.samples_per_gpu
+    ldm = synth.build_synthetic_ldm(latent=args.latent, device=dev, seed=0)
+    tr = UNetTrainer(ldm)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    R, h = 2 * n, args.latent
+    x_start = torch.randn(R, 9, h, h, device=dev, generator=g)
+    noise = torch.randn(R, 4, h, h, device=dev, generator=g)
+    cond = torch.randn(R, 2, 768, device=dev, generator=g)
+    t = torch.randint(0, 1000, (R,), device=dev, generator=g)
+
+    def step():
+        loss = tr.forward_backward(x_start, t, noise, cond)
+        tr.step()
+        return loss
+
+    for _ in range(args.warmup):
+        loss = step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.Stats.launches
+    e0.record()
+    for _ in range(args.steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    launches = (ops.Stats.launches - l0) // args.steps
+    ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ops.Stats.begin_profile()
+    step()
+    prof = ops.Stats.end_profile()
+    if rank == 0:
+        fwd = FWD_FLOPS_PER_JOINT[args.latent] * n
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = peaks.get("bf16_tflops_sustained", 1400.0)
+        tc = {k: v for k, v in prof.items() if k in ("gemm", "conv", "attention")}
+        tc_ms, tc_fl = sum(v["ms"] for v in tc.values()), sum(v["flops"] for v in tc.values())
+        line = {"metric": "training step (UNet fwd+bwd, adapter grads, all-reduce, AdamW)", "ms_per_step": ms.item(),
+                "samples_per_s": n * world / (ms.item() / 1e3), "n_gpus": world, "joint_samples_per_gpu": n,
+                "latent": args.latent, "loss": loss.item(), "trainable_params": tr.flat.numel,
+                "kernel_launches_per_step": launches,
+                "nominal_tflops_3x_forward": 3 * fwd / (ms.item() / 1e3) / 1e12,
+                "tensor_core_launch_tflops": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else None, "peak_tflops": peak,
+                "by_kernel_ms": {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
+                "by_kernel_launches": {k: v["launches"] for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
