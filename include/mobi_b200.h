@@ -83,6 +83,12 @@ typedef struct {
     int32_t n_img, H, W, C, KH, KW, pad_h, pad_w;
     int32_t tile_n; /* 0 = choose */
     int32_t kernel; /* 0 = choose (persistent kernel when its epilogue supports the problem), 1 = one-tile kernel */
+    /* Batched GEMM (PLAIN epilogue, persistent kernel only): `batch` independent problems of the same M, N, K whose
+     * operands / outputs are `*_batch_stride` ELEMENTS apart (A, B, out, residual; bias is shared).  batch <= 1 means
+     * one problem.  The per-(row, head) products of the attention backward (attention.py:179-192 under autograd)
+     * run as one launch per batch row with batch = heads. */
+    int32_t batch;
+    int64_t a_batch_stride, b_batch_stride, out_batch_stride;
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);

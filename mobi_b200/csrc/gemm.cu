@@ -326,6 +326,15 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     p.out_seg_stride = a->out_seg_stride;
     p.out_seg_offset = a->out_seg_offset;
     MOBI_CHECK(p.mode >= MOBI_EPI_PLAIN && p.mode <= MOBI_EPI_KV_ROW, "mobi_gemm: bad epilogue %d", p.mode);
+    const bool batched = a->batch > 1;
+    p.batch = batched ? a->batch : 1;
+    p.out_batch_stride = batched ? a->out_batch_stride : 0;
+    if (batched) {
+        MOBI_CHECK(p.mode == MOBI_EPI_PLAIN && !a->conv && a->out_seg == 0 && a->row_bias == nullptr,
+                   "mobi_gemm: batch needs the PLAIN epilogue without conv / row segments / row_bias");
+        MOBI_CHECK(a->a_batch_stride % 8 == 0 && a->b_batch_stride % 8 == 0 && a->out_batch_stride % 4 == 0,
+                   "mobi_gemm: batch strides must keep 16-byte alignment (A, B: %% 8, out: %% 4 elements)");
+    }
     if (p.mode == MOBI_EPI_GEGLU) {
         MOBI_CHECK(a->N % 16 == 0, "mobi_gemm: GEGLU needs N %% 16 == 0 (N=%lld)", (long long)a->N);
         MOBI_CHECK(a->residual == nullptr, "mobi_gemm: GEGLU epilogue takes no residual");
@@ -387,17 +396,17 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         MOBI_CHECK(a->K % 8 == 0 && a->lda % 8 == 0, "mobi_gemm: K=%lld and lda=%lld must be multiples of 8",
                    (long long)a->K, (long long)a->lda);
         p.num_k_blocks = (int)((K + BK - 1) / BK);
-        uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->M};
-        uint64_t strides[1] = {(uint64_t)a->lda * 2};
-        uint32_t box[2] = {BK, BM};
-        if (make_tensor_map_bf16(&tmA, a->A, 2, dims, strides, box)) return 1;
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)a->M, (uint64_t)p.batch};
+        uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_batch_stride * 2};
+        uint32_t box[3] = {BK, BM, 1};
+        if (make_tensor_map_bf16(&tmA, a->A, batched ? 3 : 2, dims, strides, box)) return 1;
     }
     MOBI_CHECK(a->ldb % 8 == 0 && a->ldb >= K, "mobi_gemm: ldb=%lld must be a multiple of 8 and >= K", (long long)a->ldb);
 
     int bn_tile = a->tile_n;
     if (bn_tile == 0) {
         // Largest tile that keeps waste low and still gives every SM at least one CTA.
-        const long long mt = (a->M + BM - 1) / BM;
+        const long long mt = (a->M + BM - 1) / BM * p.batch;
         const int cand[4] = {256, 160, 128, 64};
         bn_tile = 64;
         double best = 1e30;
@@ -416,12 +425,14 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         }
     }
     {
-        uint64_t dims[2] = {(uint64_t)K, (uint64_t)a->N};
-        uint64_t strides[1] = {(uint64_t)a->ldb * 2};
-        uint32_t box[2] = {BK, (uint32_t)bn_tile};
-        if (make_tensor_map_bf16(&tmB, a->B, 2, dims, strides, box)) return 1;
+        uint64_t dims[3] = {(uint64_t)K, (uint64_t)a->N, (uint64_t)p.batch};
+        uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)a->b_batch_stride * 2};
+        uint32_t box[3] = {BK, (uint32_t)bn_tile, 1};
+        if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
     }
     if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);
+    MOBI_CHECK(!batched, "mobi_gemm: this batched problem is outside the persistent kernel's epilogue (N %% 4, "
+                         "16-byte aligned out / residual / bias)");
     switch (bn_tile) {
         case 64: return launch_gemm<64>(tmA, tmB, p, stream);
         case 128: return launch_gemm<128>(tmA, tmB, p, stream);

@@ -80,7 +80,7 @@ struct EpiRow {          // per-lane view of the 8 rows this lane serves in the 
 
 template <int BN>
 __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc_tmem, float* stg, int m_tile,
-                                               int n_tile, int lg, int half, int lane) {
+                                               int n_tile, int lg, int half, int lane, long long batch_off) {
     using Cfg = Gemm2Cfg<BN>;
     const int u = lane & 7;        // 4-column unit inside a 32-column chunk
     const int rsub = lane >> 3;    // row inside a group of 4
@@ -104,7 +104,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 const int sg = m / (int)p.out_seg;
                 mo = (long long)sg * p.out_seg_stride + p.out_seg_offset + (m - sg * (int)p.out_seg);
             }
-            er.off[it] = mo * p.ldo;
+            er.off[it] = mo * p.ldo + batch_off;
         }
         er.rb[it] = p.row_bias ? (m / p.rows_per_group) * (int)p.ld_row_bias : 0;
     }
@@ -332,14 +332,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = p.num_k_blocks;
-    const int total = m_tiles * n_tiles;
+    const int per_batch = m_tiles * n_tiles;
+    const int total = per_batch * (p.batch > 1 ? p.batch : 1);
 
     if (warp == 0) {
         if (elect_one()) {
             // ---------------- TMA producer
             uint32_t it = 0;
             for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-                const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+                const int z = tile / per_batch, rem = tile - z * per_batch;
+                const int m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
                     const long long pix = (long long)m_tile * BM;
@@ -360,6 +362,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w,
                                     y0 + kh - p.pad_h, n0);
                         tma_load_2d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], tap * p.C + cb * BK, n_tile * BN);
+                    } else if (p.batch > 1) {
+                        tma_load_3d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
+                        tma_load_3d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], kb * BK, n_tile * BN, z);
                     } else {
                         tma_load_2d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], kb * BK, m_tile * BM);
                         tma_load_2d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], kb * BK, n_tile * BN);
@@ -399,11 +404,13 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         float* stg = staging + (warp - 2) * 1024;
         uint32_t lt = 0;
         for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
-            const int m_tile = tile / n_tiles, n_tile = tile - m_tile * n_tiles;
+            const int z = tile / per_batch, rem = tile - z * per_batch;
+            const int m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
             const uint32_t as = lt & 1;
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
-            gemm2_epilogue<BN>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane);
+            gemm2_epilogue<BN>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane,
+                               (long long)z * p.out_batch_stride);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(&tempty_bar[as]);
@@ -426,7 +433,8 @@ static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const 
         configured = true;
     }
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
-    const long long total = (long long)m_tiles * n_tiles;
+    const long long total = (long long)m_tiles * n_tiles * (p.batch > 1 ? p.batch : 1);
+    MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
     gemm2_kernel<BN><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
     MOBI_CUDA(cudaGetLastError());

@@ -27,6 +27,8 @@ struct GemmParams {
     int act;
     int heads, head_dim, tokens;
     long long out_seg, out_seg_stride, out_seg_offset;
+    int batch;                    // > 1: batched problem, A/B through 3-D tensor maps
+    long long out_batch_stride;   // elements
 };
 
 constexpr int BM = 128;

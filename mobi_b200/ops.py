@@ -79,7 +79,7 @@ def _rows_view(t, what):
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
          tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
-         kernel=0):
+         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
@@ -96,7 +96,7 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     lda = lda_v if lda is None else lda
     ldb = ldb_v if ldb is None else ldb
     K = w.shape[1] if K is None else K
-    N = w.shape[0]
+    N = w.shape[0] if N is None else N
     if M is None:
         M = a.numel() // a.shape[-1]
     if epilogue in (L.EPI_PLAIN, L.EPI_GEGLU, L.EPI_GEGLU2):
@@ -129,7 +129,9 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.conv = 0
     args.tile_n = tile_n
     args.kernel = kernel
-    with _timed("gemm", 2.0 * M * N * K):
+    args.batch = batch
+    args.a_batch_stride, args.b_batch_stride, args.out_batch_stride = a_batch_stride, b_batch_stride, out_batch_stride
+    with _timed("gemm", 2.0 * M * N * K * max(1, batch)):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
     return out
 

@@ -223,42 +223,48 @@ class UNetTrainer:
         vt = tops.transpose(v, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
         return ops.attention(q, k, vt, B, H, D, T, T)
 
-    def _attn_ws(self, T):
-        ws = self._ws.get(T)
+    def _attn_ws(self, H, T):
+        ws = self._ws.get((H, T))
         if ws is None:
             dev = self.device
-            ws = dict(S=torch.empty((T, T), device=dev, dtype=torch.float32),
-                      dP=torch.empty((T, T), device=dev, dtype=torch.float32),
-                      dS=torch.empty((T, T), device=dev, dtype=torch.bfloat16),
-                      dSt=torch.empty((T, T), device=dev, dtype=torch.bfloat16),
-                      Pt=torch.empty((T, T), device=dev, dtype=torch.bfloat16),
-                      stats=torch.empty((3 * T,), device=dev, dtype=torch.float32))
-            self._ws[T] = ws
+            ws = dict(S=torch.empty((H, T, T), device=dev, dtype=torch.float32),
+                      dP=torch.empty((H, T, T), device=dev, dtype=torch.float32),
+                      dS=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
+                      dSt=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
+                      Pt=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
+                      stats=torch.empty((3 * H * T,), device=dev, dtype=torch.float32))
+            self._ws[(H, T)] = ws
         return ws
 
     def _attn_bwd(self, q, k, v, do, B, H, D, T, dq_out, dq_col, dkv_out, dk_col, dv_col):
         """Backward of softmax(q' k^T) v per (row, head) (CrossAttention.forward, attention.py:179-192).
         q, k, v: bf16 [B*H, T, D] (q' carries scale*log2e); do: bf16 [B*T, C] token-major.  Writes dq', dk, dv as
-        [T, D] blocks at the given column offsets of the token-major outputs."""
+        [T, D] blocks at the given column offsets of the token-major outputs.  Per batch row: five BATCHED (batch = heads)
+        tcgen05 GEMMs around one batched softmax-backward launch; the score tiles of one batch row (S, dP in f32; dS,
+        dS^T, P^T in bf16) live in a reused workspace."""
         C = H * D
-        kT = tops.transpose(k, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
-        qT = tops.transpose(q, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
+        TD, TT = T * D, T * T
+        kT = tops.transpose(k, rows=T, cols=D, batch=B * H, in_batch_stride=TD)
+        qT = tops.transpose(q, rows=T, cols=D, batch=B * H, in_batch_stride=TD)
         doT = torch.empty((B * H, D, T), device=q.device, dtype=torch.bfloat16)
         for b in range(B):
             tops.transpose(do[b * T:(b + 1) * T], rows=T, cols=D, ld_in=C, batch=H, in_batch_stride=D,
                            out=doT[b * H:(b + 1) * H])
-        ws = self._attn_ws(T)
+        ws = self._attn_ws(H, T)
         f32 = torch.float32
         for b in range(B):
             rows = slice(b * T, (b + 1) * T)
-            for h in range(H):
-                bh = b * H + h
-                ops.gemm(q[bh], k[bh], out=ws["S"], out_dtype=f32)
-                ops.gemm(do[rows, h * D:(h + 1) * D], v[bh], out=ws["dP"], out_dtype=f32)
-                tops.attn_softmax_bwd(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2)
-                ops.gemm(ws["dS"], kT[bh], out=dq_out[rows, dq_col + h * D:dq_col + (h + 1) * D])
-                ops.gemm(ws["dSt"], qT[bh], out=dkv_out[rows, dk_col + h * D:dk_col + (h + 1) * D])
-                ops.gemm(ws["Pt"], doT[bh], out=dkv_out[rows, dv_col + h * D:dv_col + (h + 1) * D])
+            hs = slice(b * H, (b + 1) * H)
+            bat = dict(batch=H)
+            ops.gemm(q[hs], k[hs], out=ws["S"], out_dtype=f32, M=T, N=T, K=D, lda=D, ldb=D, ldo=T, a_batch_stride=TD,
+                     b_batch_stride=TD, out_batch_stride=TT, **bat)
+            ops.gemm(do[rows], v[hs], out=ws["dP"], out_dtype=f32, M=T, N=T, K=D, lda=C, ldb=D, ldo=T, a_batch_stride=D,
+                     b_batch_stride=TD, out_batch_stride=TT, **bat)
+            tops.attn_softmax_bwd(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2, batch=H)
+            for a_op, b_op, out, col in ((ws["dS"], kT, dq_out, dq_col), (ws["dSt"], qT, dkv_out, dk_col),
+                                         (ws["Pt"], doT, dkv_out, dv_col)):
+                ops.gemm(a_op, b_op[hs], out=out[rows, col:col + C], M=T, N=D, K=T, lda=T, ldb=T, a_batch_stride=TT,
+                         b_batch_stride=TD, out_batch_stride=D, **bat)
 
     # ------------------------------------------------------------------ BasicTransformerBlock
     def _block_forward(self, blk, x0, R, T, ctx_bf, ctx_f32):

@@ -239,6 +239,26 @@ def test_wgrad_and_bias_grad():
     assert rel(acc, ref) < 2e-3
 
 
+
+@pytest.mark.parametrize("M,N,K,H", [(256, 256, 40, 8), (64, 40, 64, 4), (200, 96, 136, 3)])
+def test_batched_gemm(M, N, K, H):
+    """mobi_gemm with a batch dimension: contiguous batches and head-column batches of token-major matrices."""
+    from mobi_b200 import ops
+    a = rnd(H, M, K, seed=1, dtype=torch.bfloat16)
+    b = rnd(H, N, K, seed=2, dtype=torch.bfloat16)
+    ref = torch.bmm(a.float(), b.float().transpose(1, 2))
+    out = torch.empty(H, M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out=out, M=M, N=N, K=K, lda=K, ldb=K, ldo=N, batch=H, a_batch_stride=M * K, b_batch_stride=N * K,
+             out_batch_stride=M * N)
+    assert rel(out, ref) < 1e-2
+    # A = head h columns of a token-major [M, H*K] matrix; output into head columns of a token-major [M, H*N] matrix
+    tok = a.permute(1, 0, 2).reshape(M, H * K).contiguous()
+    out2 = torch.zeros(M, H * N + 8, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(tok, b, out=out2[:, 8:], M=M, N=N, K=K, lda=H * K, ldb=K, batch=H, a_batch_stride=K, b_batch_stride=N * K,
+             out_batch_stride=N)
+    assert rel(out2[:, 8:].float().reshape(M, H, N).permute(1, 0, 2), ref) < 1e-2
+    assert out2[:, :8].abs().max().item() == 0.0
+
 @pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256)])
 def test_attention_backward_composite(B, H, D, T):
     """The five products + softmax backward per (row, head) against autograd of softmax(q k^T * scale) v."""
