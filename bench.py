@@ -37,6 +37,8 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step (config 5) measurement")
+    ap.add_argument("--train-samples-per-gpu", type=int, default=2)  # configs/mobi_nusc_512.yaml:11 batch_size
     return ap.parse_args()
 
 
@@ -133,6 +135,52 @@ def run_reference(args):
             "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------- training step
+def measure_train_step(ldm, dev, world, rank, n, latent, steps=3, warmup=1):
+    """BASELINE.json config 5: UNet forward + backward (adapter gradients) + ONE NCCL all-reduce of the flat gradient
+    buffer + AdamW, `n` joint samples per GPU, timed with CUDA events (max over ranks).  Runs after every inference
+    measurement because it re-homes the trainable parameters into the flat buffer."""
+    import torch
+    import torch.distributed as dist
+    from mobi_b200 import ops
+    from mobi_b200.training import UNetTrainer
+    tr = UNetTrainer(ldm)
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    R = 2 * n
+    x_start = torch.randn(R, 9, latent, latent, device=dev, generator=g)
+    noise = torch.randn(R, 4, latent, latent, device=dev, generator=g)
+    cond = torch.randn(R, 2, 768, device=dev, generator=g)
+    t = torch.randint(0, 1000, (R,), device=dev, generator=g)
+
+    def step():
+        loss = tr.forward_backward(x_start, t, noise, cond)
+        tr.step()
+        return loss
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    l0 = ops.Stats.launches
+    e0.record()
+    for _ in range(steps):
+        loss = step()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms = ms.item()
+    fwd = UNET_FLOPS_PER_JOINT.get(latent, 0) * n
+    return {"workload": "mobi_nusc_512 training step: UNet fwd+bwd bf16, %d trainable (adapter) parameters, "
+                        "flat-buffer all-reduce%s, AdamW" % (tr.flat.numel, " over NCCL" if world > 1 else " (1 rank: none)"),
+            "joint_samples_per_gpu": n, "ms_per_step": ms, "samples_per_s": n * world / (ms / 1e3),
+            "gpu_launches_per_step": (ops.Stats.launches - l0) // steps, "loss": float(loss.item()),
+            "nominal_tflops_3x_forward_per_gpu": 3 * fwd / (ms / 1e3) / 1e12 if fwd else None}
 
 
 # ---------------------------------------------------------------------------------------------- native arm
@@ -264,6 +312,14 @@ def run_native(args):
                     "unet_step_algorithmic_tflops": step_flops / (ms_unet / 1e3) / 1e12 if step_flops else None,
                     "unet_step_frac_of_peak": step_flops / (ms_unet / 1e3) / 1e12 / peak_tf if step_flops else None}
 
+    train = None
+    if not args.no_train:
+        try:
+            train = measure_train_step(ldm, dev, world, rank, args.train_samples_per_gpu, latent)
+        except Exception as exc:  # the headline line must survive a failure of this secondary measurement
+            train = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+            if world > 1:
+                raise
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -288,7 +344,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": gpu_launches, "unet_evals": unet_evals, "clocks": clock_info,
-            "roofline": roofline, "cpu_baseline": cpu_baseline}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "train_step": train}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

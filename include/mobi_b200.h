@@ -137,6 +137,8 @@ typedef struct {
     int32_t silu;
     float eps;
     int32_t out_dtype; /* dtype of `out`: MOBI_DTYPE_BF16 (default, a GEMM/conv operand) or MOBI_DTYPE_F32 */
+    int32_t force_two_pass; /* 1: always run the statistics + apply kernel pair (default 0: single-pass cluster kernel
+                               whenever one cluster's slab set fits L2) */
 } mobi_groupnorm_args;
 
 int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);

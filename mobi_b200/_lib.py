@@ -46,7 +46,7 @@ class GroupNormArgs(C.Structure):
         ("x1", _vp), ("x2", _vp), ("gamma", _vp), ("beta", _vp), ("out", _vp), ("out_concat", _vp),
         ("partials", _vp),
         ("n_img", _i32), ("hw", _i32), ("c1", _i32), ("c2", _i32), ("groups", _i32),
-        ("in_dtype", _i32), ("silu", _i32), ("eps", _f32), ("out_dtype", _i32),
+        ("in_dtype", _i32), ("silu", _i32), ("eps", _f32), ("out_dtype", _i32), ("force_two_pass", _i32),
     ]
 
 

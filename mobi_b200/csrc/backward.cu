@@ -8,6 +8,7 @@
 #include "../../include/mobi_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cooperative_groups.h>
 
 namespace mobi {
 
@@ -119,8 +120,9 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
 }
 
 // ------------------------------------------------------------------------------------------------
-// GroupNorm (+SiLU) backward over NHWC, one CTA per (image, group), three passes over the group's slice (which stays
-// in L1/L2 between passes): statistics; S1 = sum dz, S2 = sum dz * xh with dz = dy * silu'(y) * gamma; then
+// GroupNorm (+SiLU) backward over NHWC, one 8-CTA thread-block cluster per (image, group) (each CTA owns a pixel slab,
+// the two reductions go through distributed shared memory), three passes over the slab (which stays in L1/L2 between
+// passes): statistics; S1 = sum dz, S2 = sum dz * xh with dz = dy * silu'(y) * gamma; then
 //   dx = rstd * (dz - (S1 + xh * S2) / m) + dres
 // The input may be the channel concatenation of two tensors (skip connections, openaimodel.py:892): dx is split.
 // ------------------------------------------------------------------------------------------------
@@ -135,34 +137,63 @@ __device__ __forceinline__ float block_sum(float v, float* red) {
     return t;
 }
 
-__global__ void __launch_bounds__(256)
+constexpr int GNB_CLUSTER = 8;  // CTAs per (image, group): a thread-block cluster that reduces through DSMEM
+
+// Sum of (a, b) over all threads of all CTAs of the cluster; every thread gets the totals.
+__device__ __forceinline__ void cluster_sum2(float& a, float& b, float* red, float* slot) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    const float ta = block_sum(a, red);
+    const float tb = block_sum(b, red);
+    if (threadIdx.x == 0) {
+        slot[0] = ta;
+        slot[1] = tb;
+    }
+    cluster.sync();
+    float sa = 0.f, sb = 0.f;
+    for (unsigned r = 0; r < cluster.num_blocks(); ++r) {
+        const float* remote = cluster.map_shared_rank(slot, r);
+        sa += remote[0];
+        sb += remote[1];
+    }
+    cluster.sync();  // nobody overwrites its slot before every CTA has read it
+    a = sa;
+    b = sb;
+}
+
+__global__ void __cluster_dims__(GNB_CLUSTER, 1, 1) __launch_bounds__(256)
 gn_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ gamma,
               const float* __restrict__ beta, const void* __restrict__ dy, int dy_f32, const float* __restrict__ dres,
               float* dx1, float* dx2, int hw, int c1, int c2, int groups, int silu, float eps) {
     __shared__ float red[8];
+    __shared__ float slot[2];
     const int C = c1 + c2;
     const int cpg = C / groups;
-    const int n = blockIdx.y, g = blockIdx.x;
+    const int n = blockIdx.y, g = blockIdx.x / GNB_CLUSTER, part = blockIdx.x % GNB_CLUSTER;
     const int cbase = g * cpg;
     const long long img = (long long)n * hw;
-    const int total = hw * cpg;
+    const int pix_per = (hw + GNB_CLUSTER - 1) / GNB_CLUSTER;
+    const int pbeg = min(hw, part * pix_per), pend = min(hw, pbeg + pix_per);
+    const int total = (pend - pbeg) * cpg;
     auto load_x = [&](int p, int c) -> float {
         return c < c1 ? x1[(img + p) * c1 + c] : x2[(img + p) * c2 + (c - c1)];
     };
     float s = 0.f, q = 0.f;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int p = i / cpg, c = cbase + i - p * cpg;
-        const float v = load_x(p, c);
+        const int pl = i / cpg, c = cbase + i - pl * cpg;
+        const float v = load_x(pbeg + pl, c);
         s += v;
         q += v * v;
     }
-    const float m = (float)total;
-    const float mean = block_sum(s, red) / m;
-    const float var = fmaxf(block_sum(q, red) / m - mean * mean, 0.f);
+    cluster_sum2(s, q, red, slot);
+    const float m = (float)hw * cpg;
+    const float mean = s / m;
+    const float var = fmaxf(q / m - mean * mean, 0.f);
     const float rstd = rsqrtf(var + eps);
     float s1 = 0.f, s2 = 0.f;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int p = i / cpg, c = cbase + i - p * cpg;
+        const int pl = i / cpg, c = cbase + i - pl * cpg;
+        const int p = pbeg + pl;
         const float xh = (load_x(p, c) - mean) * rstd;
         float dz = ld_any(dy, dy_f32, (img + p) * C + c);
         if (silu) {
@@ -174,9 +205,11 @@ gn_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const 
         s1 += dz;
         s2 += dz * xh;
     }
-    const float S1 = block_sum(s1, red) / m, S2 = block_sum(s2, red) / m;
+    cluster_sum2(s1, s2, red, slot);
+    const float S1 = s1 / m, S2 = s2 / m;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
-        const int p = i / cpg, c = cbase + i - p * cpg;
+        const int pl = i / cpg, c = cbase + i - pl * cpg;
+        const int p = pbeg + pl;
         const float xh = (load_x(p, c) - mean) * rstd;
         float dz = ld_any(dy, dy_f32, (img + p) * C + c);
         if (silu) {
@@ -583,7 +616,7 @@ extern "C" int mobi_groupnorm_bwd(const mobi_groupnorm_bwd_args* a, void* stream
     MOBI_CHECK(a->c2 == 0 || (a->x2 && a->dx2), "mobi_groupnorm_bwd: second source / gradient missing");
     MOBI_CHECK(a->groups > 0 && (a->c1 + a->c2) % a->groups == 0, "mobi_groupnorm_bwd: C=%d not divisible by groups=%d",
                a->c1 + a->c2, a->groups);
-    dim3 grid(a->groups, a->n_img);
+    dim3 grid(a->groups * GNB_CLUSTER, a->n_img);  // clusters of GNB_CLUSTER CTAs along x
     gn_bwd_kernel<<<grid, 256, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->dy, a->dy_dtype == MOBI_DTYPE_F32,
                                             a->dres, a->dx1, a->dx2, a->hw, a->c1, a->c2, a->groups, a->silu, a->eps);
     MOBI_CUDA(cudaGetLastError());

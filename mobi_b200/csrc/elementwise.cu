@@ -6,6 +6,7 @@
 #include "../../include/mobi_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cooperative_groups.h>
 
 namespace mobi {
 
@@ -209,6 +210,165 @@ gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
             }
         }
     }
+}
+
+
+// ------------------------------------------------------------------------------------------------
+// Single-pass GroupNorm: one 8-CTA thread-block cluster per (image, chunk of `gpc` groups).  Each CTA owns a pixel slab:
+// it accumulates the statistics of its slab, the cluster combines them through distributed shared memory, and the CTA
+// normalises the SAME slab again — the second read comes from L2 (the host sizes the chunk so that the slabs of all
+// resident clusters fit), so HBM sees 4 B read + 2 B written per element instead of 8 + 2.
+// ------------------------------------------------------------------------------------------------
+constexpr int GNF_CLUSTER = 8;
+constexpr int GNF_THREADS = 512;
+constexpr int GNF_UNROLL = 4;  // pixels in flight per thread
+
+// Thread mapping: thread = (pixel lane pl, 4-channel vector v) with v = tid % nvc fixed for the whole kernel, so the
+// statistics accumulate in registers, the per-channel scale / shift of phase 2 live in registers, and consecutive
+// threads read consecutive 16-byte vectors of a pixel (every lane busy even for a 160-channel chunk).
+template <bool IN_F32, bool OUT_F32>
+__global__ void __cluster_dims__(GNF_CLUSTER, 1, 1) __launch_bounds__(GNF_THREADS)
+gn_fused_kernel(const void* x1, const void* x2, const float* __restrict__ gamma, const float* __restrict__ beta,
+                void* __restrict__ out_, __nv_bfloat16* __restrict__ out_concat, int hw, int c1, int c2, int groups,
+                int gpc, float eps, int silu) {
+    namespace cg = cooperative_groups;
+    cg::cluster_group cluster = cg::this_cluster();
+    __shared__ float part_s[GNF_THREADS * 8];  // [pixel lane][Cc][2], pixel lanes * Cc <= 4 * GNF_THREADS
+    __shared__ float slot[32][2];
+    __shared__ float s_mean[32], s_rstd[32];
+    const int C = c1 + c2;
+    const int cpg = C / groups;
+    const int Cc = gpc * cpg;
+    const int nvc = Cc >> 2;
+    const int lanes = GNF_THREADS / nvc;  // pixel lanes
+    const int v = threadIdx.x % nvc, pl = threadIdx.x / nvc;
+    const bool active = pl < lanes;
+    const int part = blockIdx.x % GNF_CLUSTER, chunk = blockIdx.x / GNF_CLUSTER;
+    const int cbeg = chunk * gpc * cpg;
+    const int ch = cbeg + 4 * v;  // first of this thread's 4 channels
+    const int n = blockIdx.y;
+    const int pix_per = (hw + GNF_CLUSTER - 1) / GNF_CLUSTER;
+    const int p0 = min(hw, part * pix_per), p1 = min(hw, p0 + pix_per);
+    const long long img_off = (long long)n * hw;
+
+    float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+    if (active) {
+        for (int p = p0 + pl; p < p1; p += GNF_UNROLL * lanes) {
+            float4 f[GNF_UNROLL];
+#pragma unroll
+            for (int u = 0; u < GNF_UNROLL; ++u) {
+                const int pp = p + u * lanes;
+                f[u] = pp < p1 ? gn_load4<IN_F32>(x1, x2, c1, c2, img_off + pp, ch) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < GNF_UNROLL; ++u) {
+                const float4 g = f[u];
+                s.x += g.x; s.y += g.y; s.z += g.z; s.w += g.w;
+                q.x += g.x * g.x; q.y += g.y * g.y; q.z += g.z * g.z; q.w += g.w * g.w;
+            }
+        }
+        float4* dst = reinterpret_cast<float4*>(part_s + ((size_t)pl * Cc + 4 * v) * 2);
+        dst[0] = make_float4(s.x, q.x, s.y, q.y);
+        dst[1] = make_float4(s.z, q.z, s.w, q.w);
+    }
+    __syncthreads();
+    {
+        const int g = threadIdx.x >> 3, sub = threadIdx.x & 7;
+        float ss = 0.f, qq = 0.f;
+        if (g < gpc) {
+            const int cells = lanes * cpg;
+            for (int i = sub; i < cells; i += 8) {
+                const int w = i / cpg, c = g * cpg + (i - w * cpg);
+                ss += part_s[((size_t)w * Cc + c) * 2 + 0];
+                qq += part_s[((size_t)w * Cc + c) * 2 + 1];
+            }
+        }
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            ss += __shfl_xor_sync(0xffffffffu, ss, o);
+            qq += __shfl_xor_sync(0xffffffffu, qq, o);
+        }
+        if (g < gpc && sub == 0) {
+            slot[g][0] = ss;
+            slot[g][1] = qq;
+        }
+    }
+    cluster.sync();
+    if (threadIdx.x < gpc) {
+        double ss = 0.0, qq = 0.0;
+        for (int r = 0; r < GNF_CLUSTER; ++r) {
+            const float* remote = cluster.map_shared_rank(&slot[0][0], r);
+            ss += (double)remote[2 * threadIdx.x];
+            qq += (double)remote[2 * threadIdx.x + 1];
+        }
+        const double cnt = (double)hw * cpg;
+        const double mean = ss / cnt;
+        double var = qq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    cluster.sync();  // every CTA has read every slot (nobody exits early); s_mean / s_rstd visible in the CTA
+    if (!active) return;
+    float sc[4], sh[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int g = (4 * v + j) / cpg;
+        const float a = gamma[ch + j] * s_rstd[g];
+        sc[j] = a;
+        sh[j] = beta[ch + j] - s_mean[g] * a;
+    }
+    for (int p = p0 + pl; p < p1; p += GNF_UNROLL * lanes) {
+        float4 f[GNF_UNROLL];
+#pragma unroll
+        for (int u = 0; u < GNF_UNROLL; ++u) {
+            const int pp = p + u * lanes;
+            if (pp < p1) f[u] = gn_load4<IN_F32>(x1, x2, c1, c2, img_off + pp, ch);
+        }
+#pragma unroll
+        for (int u = 0; u < GNF_UNROLL; ++u) {
+            const int pp = p + u * lanes;
+            if (pp >= p1) break;
+            const float4 g = f[u];
+            float y0 = g.x * sc[0] + sh[0], y1 = g.y * sc[1] + sh[1];
+            float y2 = g.z * sc[2] + sh[2], y3 = g.w * sc[3] + sh[3];
+            if (silu) {
+                y0 = silu_f(y0);
+                y1 = silu_f(y1);
+                y2 = silu_f(y2);
+                y3 = silu_f(y3);
+            }
+            const long long o = (img_off + pp) * C + ch;
+            if (OUT_F32)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + o) = make_float4(y0, y1, y2, y3);
+            else
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_) + o) =
+                    make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            if (out_concat)
+                *reinterpret_cast<uint2*>(out_concat + o) = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+        }
+    }
+}
+
+// Groups per cluster for the single-pass kernel, or 0 when the two-kernel path should run: the chunk's channel range
+// must be 16-byte aligned and at least 128 contiguous bytes per pixel, and one cluster's slab set ~3 MB so that the
+// ~18 clusters resident on 148 SMs re-read their data from L2.
+static int gn_fused_gpc(int hw, int C, int groups, int in_bytes) {
+    if (hw < GNF_CLUSTER || groups > 32) return 0;
+    const int cpg = C / groups;
+    const long long target = 3ll << 20;
+    int best = 0;
+    for (int gpc = 1; gpc <= groups; gpc <<= 1) {
+        if (groups % gpc) continue;
+        const long long cc = (long long)gpc * cpg;
+        if (cc % 4 || cc * in_bytes < 128) continue;
+        if (cc > 4 * GNF_THREADS) break;  // one thread per 4-channel vector
+        if (best == 0 || (long long)hw * cc * in_bytes <= target) best = gpc;
+    }
+    if (best == 0) return 0;
+    // a chunk that is far above the target even at the smallest usable size (e.g. VAE images at 512^2) gains nothing
+    if ((long long)hw * best * cpg * in_bytes > 4 * target) return 0;
+    return best;
 }
 
 static int gn_slabs(int hw, int C) {
@@ -590,17 +750,33 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
     MOBI_CHECK(a->c1 % 4 == 0 && a->c2 % 4 == 0,
                "mobi_groupnorm: channel counts of both inputs must be multiples of 4 (c1=%d c2=%d)", a->c1, a->c2);
     MOBI_CHECK(a->c2 == 0 || a->x2 != nullptr, "mobi_groupnorm: c2 > 0 needs x2");
-    const int slabs = gn_slabs(a->hw, C);
-    const int pix_per_slab = (a->hw + slabs - 1) / slabs;
-    const size_t smem1 = (size_t)GN_WARPS * C * 2 * sizeof(float);
-    const size_t smem2 = (size_t)2 * C * sizeof(float);
     const bool f32 = a->in_dtype == MOBI_DTYPE_F32;
+    const bool of32 = a->out_dtype == MOBI_DTYPE_F32;
     static bool configured = false;
     if (!configured) {
         MOBI_CUDA(cudaFuncSetAttribute(gn_stats_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         MOBI_CUDA(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         configured = true;
     }
+    const int gpc = a->force_two_pass ? 0 : gn_fused_gpc(a->hw, C, a->groups, f32 ? 4 : 2);
+    if (gpc > 0) {
+        dim3 grid(GNF_CLUSTER * (a->groups / gpc), a->n_img);
+#define GN_FUSED(INF, OUTF)                                                                                        \
+    gn_fused_kernel<INF, OUTF><<<grid, GNF_THREADS, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->out,          \
+                                                                   reinterpret_cast<__nv_bfloat16*>(a->out_concat), \
+                                                                   a->hw, a->c1, a->c2, a->groups, gpc, a->eps, a->silu)
+        if (f32 && of32) GN_FUSED(true, true);
+        else if (f32) GN_FUSED(true, false);
+        else if (of32) GN_FUSED(false, true);
+        else GN_FUSED(false, false);
+#undef GN_FUSED
+        MOBI_CUDA(cudaGetLastError());
+        return 0;
+    }
+    const int slabs = gn_slabs(a->hw, C);
+    const int pix_per_slab = (a->hw + slabs - 1) / slabs;
+    const size_t smem1 = (size_t)GN_WARPS * C * 2 * sizeof(float);
+    const size_t smem2 = (size_t)2 * C * sizeof(float);
     MOBI_CHECK(smem1 <= 160 * 1024, "mobi_groupnorm: C=%d too large", C);
     dim3 grid1(slabs, a->n_img);
     if (f32)
@@ -620,7 +796,6 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
     gn_apply_kernel<INF, OUTF><<<grid2, GN_THREADS, smem2, stream>>>(                                                  \
         a->x1, a->x2, a->gamma, a->beta, a->out, reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, \
         a->hw, a->c1, a->c2, a->groups, a->eps, a->silu, pix_per_slab2)
-    const bool of32 = a->out_dtype == MOBI_DTYPE_F32;
     if (f32 && of32) GN_APPLY(true, true);
     else if (f32) GN_APPLY(true, false);
     else if (of32) GN_APPLY(false, true);

@@ -78,16 +78,27 @@ struct EpiRow {          // per-lane view of the 8 rows this lane serves in the 
     unsigned ok;         // bit i: row i exists (m < M)
 };
 
-template <int BN>
+// MC = epilogue class fixed at compile time (the runtime `p.mode` branches, the integer divisions of the head-split
+// layouts and their registers disappear from the other classes): 0 = any mode (runtime), 1 = PLAIN, 2 = GEGLU2,
+// 3 = head-split layouts without a transposed part (HEADS, QKV_ROW, KV_ROW).
+template <int BN, int MC>
 __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc_tmem, float* stg, int m_tile,
                                                int n_tile, int lg, int half, int lane, long long batch_off) {
     using Cfg = Gemm2Cfg<BN>;
+    const int mode = MC == 1 ? MOBI_EPI_PLAIN : (MC == 2 ? MOBI_EPI_GEGLU2 : p.mode);
     const int u = lane & 7;        // 4-column unit inside a 32-column chunk
     const int rsub = lane >> 3;    // row inside a group of 4
     const int m_base = m_tile * BM + lg * 32;
     const int inner = p.heads * p.head_dim;
-    const bool head_mode = (p.mode >= MOBI_EPI_HEADS && p.mode <= MOBI_EPI_KV) || p.mode >= MOBI_EPI_QKV_ROW;
-    const int nparts_last = p.mode == MOBI_EPI_QKV ? 2 : (p.mode == MOBI_EPI_KV ? 1 : (p.mode == MOBI_EPI_HEADS_T ? 0 : -1));
+    const bool head_mode = MC == 3 || (mode >= MOBI_EPI_HEADS && mode <= MOBI_EPI_KV) || mode >= MOBI_EPI_QKV_ROW;
+    const int nparts_last =
+        MC == 3 ? -1 : (mode == MOBI_EPI_QKV ? 2 : (mode == MOBI_EPI_KV ? 1 : (mode == MOBI_EPI_HEADS_T ? 0 : -1)));
+    // exact integer division by a small runtime divisor without the ~25-instruction IDIV sequence:
+    // floor((x + 0.5) / d) in fp32 is exact while x < 2^21 (the fraction stays >= 0.5/d away from an integer)
+    const float inv_inner = head_mode ? 1.0f / (float)inner : 0.f;
+    const float inv_hd = head_mode ? 1.0f / (float)p.head_dim : 0.f;
+    const bool tile_in_one_row = head_mode && (p.tokens % BM) == 0;  // all 128 rows of the tile share the batch row
+    const int b_tile = tile_in_one_row ? (m_tile * BM) / p.tokens : 0;
 
     EpiRow er;
     er.ok = 0;
@@ -96,7 +107,8 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
         const int m = m_base + it * 4 + rsub;
         if (m < p.M) er.ok |= 1u << it;
         if (head_mode) {
-            const int b = m / p.tokens, t = m - b * p.tokens;
+            const int b = tile_in_one_row ? b_tile : m / p.tokens;
+            const int t = m - b * p.tokens;
             er.off[it] = ((long long)b * p.heads * p.tokens + t) * p.head_dim;  // + (h*tokens*d + dd) per column
         } else {
             long long mo = m;
@@ -111,7 +123,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
     // row-domain identity (thread = TMEM lane = row), needed for the transposed-V layout
     const int m_own = m_base + lane;
     long long vt_row = 0;
-    if (head_mode && m_own < p.M) {
+    if (nparts_last >= 0 && m_own < p.M) {
         const int b = m_own / p.tokens, t = m_own - b * p.tokens;
         vt_row = (long long)b * inner * p.tokens + t;
     }
@@ -126,9 +138,12 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
         if (n0 >= p.N) break;
         const int n = n0 + 4 * u;             // first of this lane's 4 columns (transposed domain)
         const bool col_ok = n < p.N;          // N % 4 == 0: the unit is entirely inside or outside
+        // bias of this lane's 4 columns: issued before the accumulator load so its latency hides under it
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (mode != MOBI_EPI_GEGLU && p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
         // ---- prefetch the residual of this chunk (transposed domain)
         float4 res[8];
-        if (p.residual != nullptr && p.mode == MOBI_EPI_PLAIN) {
+        if (p.residual != nullptr && mode == MOBI_EPI_PLAIN) {
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -150,7 +165,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
         tmem_ld32(acc_tmem + lane_addr + c * 32, r);
         tmem_ld_wait();
         int out_units = 8;  // 16-byte units per staged row
-        if (p.mode == MOBI_EPI_GEGLU) {
+        if (mode == MOBI_EPI_GEGLU) {
             // [8 value | 8 gate] groups: activation in the row domain, 16 outputs per chunk
             out_units = 4;
 #pragma unroll
@@ -199,11 +214,9 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
         }
         __syncwarp();
         // ---- transposed domain
-        if (p.mode == MOBI_EPI_GEGLU2) {
+        if (mode == MOBI_EPI_GEGLU2) {
             // (value, gate) column pairs: two outputs per lane, no cross-lane traffic.  Branch-free math over the 8
             // rows of this lane (16 independent GELUs in flight), only the stores are predicated.
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             uint32_t o[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -217,17 +230,15 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 if (col_ok && ((er.ok >> it) & 1))
                     *reinterpret_cast<uint32_t*>(reinterpret_cast<__nv_bfloat16*>(p.out) + er.off[it] + (n >> 1)) = o[it];
         } else if (out_units == 8) {
-            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias && col_ok) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + n));
             // head-split column part
             long long coloff = 0;
             __nv_bfloat16* hbase = nullptr;
             bool is_vt = false;
             if (head_mode && col_ok) {
-                const int which = n / inner;
+                const int which = (int)(((float)n + 0.5f) * inv_inner);
                 const int nn = n - which * inner;
                 is_vt = (which == nparts_last);
-                const int h = nn / p.head_dim, dd = nn - h * p.head_dim;
+                const int h = (int)(((float)nn + 0.5f) * inv_hd), dd = nn - h * p.head_dim;
                 coloff = (long long)h * p.tokens * p.head_dim + dd;
                 hbase = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
             }
@@ -289,14 +300,15 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
     }
 }
 
-template <int BN>
+template <int BN, int MC>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
              const int m_tiles, const int n_tiles) {
     using Cfg = Gemm2Cfg<BN>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    // align by OFFSET so the pointer keeps its shared address space (LDS/STS instead of generic LD/ST in the epilogue)
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sA = smem;
     uint8_t* sB = smem + STAGES * A_TILE_BYTES;
     float* staging = reinterpret_cast<float*>(sB + STAGES * Cfg::B_TILE_BYTES);
@@ -409,7 +421,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint32_t as = lt & 1;
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
-            gemm2_epilogue<BN>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane,
+            gemm2_epilogue<BN, MC>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane,
                                (long long)z * p.out_batch_stride);
             tc_fence_before();
             __syncwarp();
@@ -424,21 +436,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 }
 
-template <int BN>
-static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+template <int BN, int MC>
+static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
     using Cfg = Gemm2Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
         configured = true;
     }
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
     const long long total = (long long)m_tiles * n_tiles * (p.batch > 1 ? p.batch : 1);
     MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm2_kernel<BN><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
+    gemm2_kernel<BN, MC><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
     MOBI_CUDA(cudaGetLastError());
     return 0;
+}
+
+template <int BN>
+static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    if (p.mode == MOBI_EPI_PLAIN) return launch_gemm2_tm<BN, 1>(tmA, tmB, p, stream);
+    if (p.mode == MOBI_EPI_GEGLU2) return launch_gemm2_tm<BN, 2>(tmA, tmB, p, stream);
+    if (p.mode == MOBI_EPI_HEADS || p.mode == MOBI_EPI_QKV_ROW || p.mode == MOBI_EPI_KV_ROW)
+        return launch_gemm2_tm<BN, 3>(tmA, tmB, p, stream);
+    return launch_gemm2_tm<BN, 0>(tmA, tmB, p, stream);
 }
 
 bool gemm2_supported(const GemmParams& p) {

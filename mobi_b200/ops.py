@@ -217,7 +217,8 @@ def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0, v_ro
     return out
 
 
-def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_concat=False, out_dtype=torch.bfloat16):
+def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_concat=False, out_dtype=torch.bfloat16,
+              two_pass=False):
     """x1 (and optionally x2, concatenated on channels): NHWC [N, H, W, C] f32|bf16 -> bf16 NHWC."""
     _cuda(x1, x2, gamma, beta)
     n = x1.shape[0]
@@ -237,6 +238,7 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_conca
     a.out, a.out_concat, a.partials = out.data_ptr(), L.ptr(cat), partials.data_ptr()
     a.n_img, a.hw, a.c1, a.c2, a.groups = n, hw, c1, c2, groups
     a.in_dtype, a.silu, a.eps, a.out_dtype = L.dt(x1), int(silu), eps, L.dt(out)
+    a.force_two_pass = int(two_pass)
     with _timed("groupnorm", 0.0, x1.numel() * x1.element_size() * 2 + (x2.numel() * x2.element_size() * 2 if x2 is not None else 0)
                 + out.numel() * 2 * (2 if want_concat else 1), kernels=2):
         L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")

@@ -118,7 +118,7 @@ def _conv_dgrad_pack(conv):
 class UNetTrainer:
     """forward_backward(x_start, t, noise, context) -> loss; step() -> all-reduce + AdamW + repack."""
 
-    def __init__(self, ldm, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None):
+    def __init__(self, ldm, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None, use_cuda_graph=True):
         self.ldm = ldm
         self.unet = ldm.model.diffusion_model if hasattr(ldm, "model") else ldm
         unet = self.unet
@@ -138,6 +138,8 @@ class UNetTrainer:
         self.loss_sum = torch.zeros(1, device=dev, dtype=torch.float32)
         self._names = {id(p): n for n, p in unet.named_parameters()}
         self._ws = {}
+        self.use_cuda_graph = use_cuda_graph
+        self._fb_graph = self._fb_key = self._repack_graph = None
         unet.invalidate()
         unet.pack()
         self._pack_frozen_backward()
@@ -185,7 +187,26 @@ class UNetTrainer:
 
     @torch.no_grad()
     def repack_trainable(self):
-        """bf16 operand copies (and transposes for dgrad) of the TRAINABLE weights: after every optimizer step."""
+        """bf16 operand copies (and transposes for dgrad) of the TRAINABLE weights: after every optimizer step.  With
+        CUDA graphs the ~500 small cast / transpose launches are captured once (the packed tensors then live at fixed
+        addresses in the graph's pool, which is what lets the forward/backward graph read them) and replayed."""
+        if not self.use_cuda_graph:
+            return self._repack_trainable()
+        if self._repack_graph is None:
+            self._repack_trainable()                     # warm-up outside capture
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = ops.Stats.launches
+            with torch.cuda.graph(g):
+                self._repack_trainable()
+            self._repack_kernels = ops.Stats.launches - before
+            self._repack_graph = g
+            self._fb_graph = self._fb_key = None         # operand addresses changed
+        self._repack_graph.replay()
+        ops.Stats.launches += self._repack_kernels
+        self.unet._ctx_key = None
+
+    def _repack_trainable(self):
         tp = {}
         self._qscales = []
         for blk in self._blocks():
@@ -483,12 +504,44 @@ class UNetTrainer:
     def forward_backward(self, x_start, t, noise, context):
         """p_losses (ddpm.py:1177-1217) + backward.  x_start [R, 9, h, w] f32 (4 latent + 4 inpaint_image + mask channels),
         t int64 [R], noise [R, 4, h, w], context [R, n_ctx, ctx_dim] (already dropped-out or not by the caller).
-        Gradients of the trainable parameters are left in self.flat.grads; returns the loss (0-dim tensor)."""
-        u, ldm = self.unet, self.ldm
-        p = u._p
-        for a in (x_start, noise, context):
+        Gradients of the trainable parameters are left in self.flat.grads; returns the loss (0-dim tensor).
+        With use_cuda_graph the whole forward + backward (several thousand launches) is captured once per input shape
+        and replayed from static input buffers."""
+        for a in (x_start, noise, context, t):
             if not a.is_cuda:
                 raise RuntimeError("UNetTrainer needs CUDA tensors (no CPU fallback)")
+        if not self.use_cuda_graph:
+            return self._forward_backward(x_start, t, noise, context)
+        key = (tuple(x_start.shape), tuple(noise.shape), tuple(context.shape))
+        if self._fb_graph is None or self._fb_key != key:
+            self._static = dict(x=x_start.detach().float().contiguous().clone(), t=t.to(torch.int64).contiguous().clone(),
+                                noise=noise.detach().float().contiguous().clone(),
+                                ctx=context.detach().float().contiguous().clone())
+            st = self._static
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):                # warm-up: workspaces, cudaFuncSetAttribute, allocator pools
+                self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"])
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            before = ops.Stats.launches
+            with torch.cuda.graph(g):
+                self._static_loss = self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"])
+            self._fb_kernels = ops.Stats.launches - before
+            self._fb_graph, self._fb_key = g, key
+        st = self._static
+        st["x"].copy_(x_start)
+        st["t"].copy_(t)
+        st["noise"].copy_(noise)
+        st["ctx"].copy_(context)
+        self._fb_graph.replay()
+        ops.Stats.launches += self._fb_kernels
+        return self._static_loss
+
+    def _forward_backward(self, x_start, t, noise, context):
+        u, ldm = self.unet, self.ldm
+        p = u._p
         R = x_start.shape[0]
         self.flat.grads.zero_()
         self.loss_sum.zero_()

@@ -136,13 +136,15 @@ def bench_ln():
 
 
 def bench_gn():
-    for (C1, C2, S) in ((320, 0, 64), (640, 320, 64), (640, 0, 32), (1280, 1280, 16), (1280, 0, 8)):
+    for (C1, C2, S) in ((320, 0, 64), (640, 320, 64), (640, 0, 32), (1280, 640, 32), (1280, 1280, 16), (1280, 0, 8)):
         x1 = rnd(R, S, S, C1, dtype=torch.float32)
         x2 = rnd(R, S, S, C2, dtype=torch.float32) if C2 else None
         C = C1 + C2
         g, b = rnd(C, dtype=torch.float32), rnd(C, dtype=torch.float32)
         E = R * S * S * C
         report("groupnorm+silu C=%d+%d @%d" % (C1, C2, S), timeit(lambda: ops.groupnorm(x1, g, b, 1e-5, x2=x2)), 0, E * 10)
+        report("groupnorm+silu C=%d+%d @%d two-pass" % (C1, C2, S),
+               timeit(lambda: ops.groupnorm(x1, g, b, 1e-5, x2=x2, two_pass=True)), 0, E * 10)
 
 
 if __name__ == "__main__":

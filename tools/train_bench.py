@@ -23,6 +23,7 @@ def main():
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--no-graph", action="store_true")
     args = ap.parse_args()
     import torch.distributed as dist
     from mobi_b200 import ops, synth
@@ -34,7 +35,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = args.samples_per_gpu
     ldm = synth.build_synthetic_ldm(latent=args.latent, device=dev, seed=0)
-    tr = UNetTrainer(ldm)
+    tr = UNetTrainer(ldm, use_cuda_graph=not args.no_graph)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     R, h = 2 * n, args.latent
     x_start = torch.randn(R, 9, h, h, device=dev, generator=g)
@@ -63,6 +64,8 @@ def main():
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    tr.use_cuda_graph = False          # per-kernel CUDA events need eager launches
+    step()
     ops.Stats.begin_profile()
     step()
     prof = ops.Stats.end_profile()
@@ -78,7 +81,7 @@ def main():
         tc_ms, tc_fl = sum(v["ms"] for v in tc.values()), sum(v["flops"] for v in tc.values())
         line = {"metric": "training step (UNet fwd+bwd, adapter grads, all-reduce, AdamW)", "ms_per_step": ms.item(),
                 "samples_per_s": n * world / (ms.item() / 1e3), "n_gpus": world, "joint_samples_per_gpu": n,
-                "latent": args.latent, "loss": loss.item(), "trainable_params": tr.flat.numel,
+                "latent": args.latent, "cuda_graph": not args.no_graph, "loss": loss.item(), "trainable_params": tr.flat.numel,
                 "kernel_launches_per_step": launches,
                 "nominal_tflops_3x_forward": 3 * fwd / (ms.item() / 1e3) / 1e12,
                 "tensor_core_launch_tflops": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else None, "peak_tflops": peak,
