@@ -142,6 +142,8 @@ typedef struct {
 } mobi_groupnorm_args;
 
 int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);
+/* Kernels mobi_groupnorm launches for this shape: 1 (single-pass cluster kernel) or 2 (statistics + apply). */
+int32_t mobi_groupnorm_launches(int32_t hw, int32_t c, int32_t groups, int32_t in_dtype, int32_t force_two_pass);
 int mobi_groupnorm(const mobi_groupnorm_args* args, void* stream);
 
 /*

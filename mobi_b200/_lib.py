@@ -143,6 +143,7 @@ SIGNATURES = {
     "mobi_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
     "mobi_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "mobi_groupnorm_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32]),
+    "mobi_groupnorm_launches": (_i32, [_i32, _i32, _i32, _i32, _i32]),
     "mobi_groupnorm": (C.c_int, [C.POINTER(GroupNormArgs), _vp]),
     "mobi_layernorm": (C.c_int, [C.POINTER(LayerNormArgs), _vp]),
     "mobi_ln_dual": (C.c_int, [_vp, C.POINTER(LnDualSpec), _i32, _i32, _i32, _f32, _vp]),

@@ -742,6 +742,11 @@ extern "C" int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32
     return (int64_t)n_img * gn_slabs(hw, c) * groups * 2 * sizeof(float);
 }
 
+extern "C" int32_t mobi_groupnorm_launches(int32_t hw, int32_t c, int32_t groups, int32_t in_dtype, int32_t force_two_pass) {
+    if (groups <= 0 || c % groups) return 2;
+    return (!force_two_pass && gn_fused_gpc(hw, c, groups, in_dtype == MOBI_DTYPE_F32 ? 4 : 2) > 0) ? 1 : 2;
+}
+
 extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MOBI_CHECK(a && a->x1 && a->gamma && a->beta && a->out && a->partials, "mobi_groupnorm: null argument");

@@ -240,7 +240,8 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_conca
     a.in_dtype, a.silu, a.eps, a.out_dtype = L.dt(x1), int(silu), eps, L.dt(out)
     a.force_two_pass = int(two_pass)
     with _timed("groupnorm", 0.0, x1.numel() * x1.element_size() * 2 + (x2.numel() * x2.element_size() * 2 if x2 is not None else 0)
-                + out.numel() * 2 * (2 if want_concat else 1), kernels=2):
+                + out.numel() * 2 * (2 if want_concat else 1),
+                kernels=lib.mobi_groupnorm_launches(hw, c, groups, a.in_dtype, a.force_two_pass)):
         L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")
     return (out, cat) if want_concat else out
 
