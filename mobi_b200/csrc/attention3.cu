@@ -66,6 +66,8 @@ struct A3Cfg {
     static constexpr int SOFTMAX_REGS = NT == 4 ? 96 : 208;
 };
 
+constexpr uint32_t A3_ROLE_SLEEP_NS = 64;  // probe interval of the producer / issuer warps (see mbar_wait_backoff)
+
 template <int NT, int BKV, int KVS, int POLY>
 __global__ void __launch_bounds__(A3Cfg<NT>::THREADS, 1)
 attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -140,7 +142,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                         tma_load_3d(sQ + t * q_tile_bytes + c * A3_CHUNK, &tmQ, q_full, c * 64, q0 + t * 128, bh);
                 for (int j = 0; j < nblk; ++j) {
                     const int s = j % KVS;
-                    mbar_wait(&kv_empty[s], ((j / KVS) & 1) ^ 1);
+                    mbar_wait_backoff(&kv_empty[s], ((j / KVS) & 1) ^ 1, A3_ROLE_SLEEP_NS);
                     mbar_arrive_expect_tx(&kv_full[s], 2 * kv_bytes);
                     for (int c = 0; c < p.nch; ++c) {
                         tma_load_3d(sK + s * kv_bytes + c * K_CHUNK, &tmK, &kv_full[s], c * 64, j * BKV, bh);
@@ -167,23 +169,23 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     umma_commit(&s_full[t]);
                 };
-                mbar_wait(q_full, 0);
+                mbar_wait_backoff(q_full, 0, A3_ROLE_SLEEP_NS);
                 // staggered start: tile t begins once tile t-1 has pulled its first score tile into registers, so the
                 // warpgroups sit in different phases (TMEM load / exponentials / P store) at any time
-                if (t > 0) mbar_wait(&s_free[t - 1], 0);
-                mbar_wait(&kv_full[0], 0);
+                if (t > 0) mbar_wait_backoff(&s_free[t - 1], 0, A3_ROLE_SLEEP_NS);
+                mbar_wait_backoff(&kv_full[0], 0, A3_ROLE_SLEEP_NS);
                 tc_fence_after();
                 issue_S(0);
                 for (int j = 0; j < nblk; ++j) {
                     const int s = j % KVS;
                     const uint32_t ph = j & 1;
                     if (j + 1 < nblk) {
-                        mbar_wait(&kv_full[(j + 1) % KVS], ((j + 1) / KVS) & 1);
-                        mbar_wait(&s_free[t], ph);
+                        mbar_wait_backoff(&kv_full[(j + 1) % KVS], ((j + 1) / KVS) & 1, A3_ROLE_SLEEP_NS);
+                        mbar_wait_backoff(&s_free[t], ph, A3_ROLE_SLEEP_NS);
                         tc_fence_after();
                         issue_S(j + 1);
                     }
-                    mbar_wait(&p_full[t], ph);
+                    mbar_wait_backoff(&p_full[t], ph, A3_ROLE_SLEEP_NS);
                     tc_fence_after();
                     const uint32_t d_tmem = tmem_base + O_BASE + t * O_STRIDE;
                     for (int k = 0; k < BKV / 16; ++k) {  // 16 keys per MMA

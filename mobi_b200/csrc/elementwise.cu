@@ -7,6 +7,7 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cooperative_groups.h>
+#include <stdlib.h>
 
 namespace mobi {
 
@@ -220,20 +221,18 @@ gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
 // resident clusters fit), so HBM sees 4 B read + 2 B written per element instead of 8 + 2.
 // ------------------------------------------------------------------------------------------------
 constexpr int GNF_CLUSTER = 8;
-constexpr int GNF_THREADS = 512;
-constexpr int GNF_UNROLL = 4;  // pixels in flight per thread
 
 // Thread mapping: thread = (pixel lane pl, 4-channel vector v) with v = tid % nvc fixed for the whole kernel, so the
 // statistics accumulate in registers, the per-channel scale / shift of phase 2 live in registers, and consecutive
 // threads read consecutive 16-byte vectors of a pixel (every lane busy even for a 160-channel chunk).
-template <bool IN_F32, bool OUT_F32>
+template <bool IN_F32, bool OUT_F32, int GNF_THREADS, int GNF_UNROLL>
 __global__ void __cluster_dims__(GNF_CLUSTER, 1, 1) __launch_bounds__(GNF_THREADS)
 gn_fused_kernel(const void* x1, const void* x2, const float* __restrict__ gamma, const float* __restrict__ beta,
                 void* __restrict__ out_, __nv_bfloat16* __restrict__ out_concat, int hw, int c1, int c2, int groups,
                 int gpc, float eps, int silu) {
     namespace cg = cooperative_groups;
     cg::cluster_group cluster = cg::this_cluster();
-    __shared__ float part_s[GNF_THREADS * 8];  // [pixel lane][Cc][2], pixel lanes * Cc <= 4 * GNF_THREADS
+    __shared__ float part_s[GNF_THREADS * 8];  // [pixel lane][Cc][2], pixel lanes * Cc <= 4 * GNF_THREADS (<= 32 KB)
     __shared__ float slot[32][2];
     __shared__ float s_mean[32], s_rstd[32];
     const int C = c1 + c2;
@@ -353,7 +352,7 @@ gn_fused_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
 // Groups per cluster for the single-pass kernel, or 0 when the two-kernel path should run: the chunk's channel range
 // must be 16-byte aligned and at least 128 contiguous bytes per pixel, and one cluster's slab set ~3 MB so that the
 // ~18 clusters resident on 148 SMs re-read their data from L2.
-static int gn_fused_gpc(int hw, int C, int groups, int in_bytes) {
+static int gn_fused_gpc(int hw, int C, int groups, int in_bytes, int threads = 512) {
     if (hw < GNF_CLUSTER || groups > 32) return 0;
     const int cpg = C / groups;
     const long long target = 3ll << 20;
@@ -362,7 +361,7 @@ static int gn_fused_gpc(int hw, int C, int groups, int in_bytes) {
         if (groups % gpc) continue;
         const long long cc = (long long)gpc * cpg;
         if (cc % 4 || cc * in_bytes < 128) continue;
-        if (cc > 4 * GNF_THREADS) break;  // one thread per 4-channel vector
+        if (cc > 4 * threads) break;  // one thread per 4-channel vector
         if (best == 0 || (long long)hw * cc * in_bytes <= target) best = gpc;
     }
     if (best == 0) return 0;
@@ -766,15 +765,18 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
     const int gpc = a->force_two_pass ? 0 : gn_fused_gpc(a->hw, C, a->groups, f32 ? 4 : 2);
     if (gpc > 0) {
         dim3 grid(GNF_CLUSTER * (a->groups / gpc), a->n_img);
-#define GN_FUSED(INF, OUTF)                                                                                        \
-    gn_fused_kernel<INF, OUTF><<<grid, GNF_THREADS, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->out,          \
-                                                                   reinterpret_cast<__nv_bfloat16*>(a->out_concat), \
-                                                                   a->hw, a->c1, a->c2, a->groups, gpc, a->eps, a->silu)
+#define GN_FUSED_V(INF, OUTF, TH, UN)                                                                              \
+    gn_fused_kernel<INF, OUTF, TH, UN><<<grid, TH, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->out,           \
+                                                                reinterpret_cast<__nv_bfloat16*>(a->out_concat),    \
+                                                                a->hw, a->c1, a->c2, a->groups, gpc, a->eps, a->silu)
+    // 512 threads x 4 pixels in flight measured best of (256, 8), (512, 4), (512, 8), (1024, 2) at every UNet shape
+#define GN_FUSED(INF, OUTF) GN_FUSED_V(INF, OUTF, 512, 4)
         if (f32 && of32) GN_FUSED(true, true);
         else if (f32) GN_FUSED(true, false);
         else if (of32) GN_FUSED(false, true);
         else GN_FUSED(false, false);
 #undef GN_FUSED
+#undef GN_FUSED_V
         MOBI_CUDA(cudaGetLastError());
         return 0;
     }
