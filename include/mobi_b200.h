@@ -89,6 +89,8 @@ typedef struct {
      * run as one launch per batch row with batch = heads. */
     int32_t batch;
     int64_t a_batch_stride, b_batch_stride, out_batch_stride;
+    /* CTA pairs (tcgen05 cta_group::2, 256-row tiles): 0 = choose, 1 = force on (persistent kernel only), -1 = off. */
+    int32_t pair;
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);

@@ -424,10 +424,12 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
             }
         }
     }
+    p.pair = (a->kernel != 1 && gemm2_supported(p) && gemm2_pair_wanted(p, bn_tile, a->pair)) ? 1 : 0;
+    MOBI_CHECK(a->pair != 1 || p.pair, "mobi_gemm: pair = 1 needs a problem the persistent kernel supports");
     {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)a->N, (uint64_t)p.batch};
         uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)a->b_batch_stride * 2};
-        uint32_t box[3] = {BK, (uint32_t)bn_tile, 1};
+        uint32_t box[3] = {BK, (uint32_t)(p.pair ? bn_tile / 2 : bn_tile), 1};  // a CTA pair splits the B tile
         if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
     }
     if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);

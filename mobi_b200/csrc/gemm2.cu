@@ -24,9 +24,10 @@ namespace mobi {
 constexpr int G2_THREADS = 320;
 constexpr int G2_STAGING_BYTES = 8 * 4096;  // 8 epilogue warps x (32 rows x 128 B)
 
-template <int BN>
+template <int BN, bool PAIR = false>
 struct Gemm2Cfg {
-    static constexpr int B_TILE_BYTES = BN * BK * 2;
+    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of B this CTA stages per k-block
+    static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
     static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
     static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
@@ -300,11 +301,17 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
     }
 }
 
-template <int BN, int MC>
+// PAIR: the kernel runs as 2-CTA clusters (cta_group::2).  A pair owns a 256 x BN tile: CTA r computes rows
+// [m0 + 128 r, +128) into its own TMEM from its own A tile and HALF of the B tile (BN / 2 rows) — per MMA an SM reads
+// 4 KB of A + BN/2 * 32 B of B from shared memory instead of 4 KB + BN * 32 B, which lifts the 128 x 160 tiles of the
+// convolutions off the shared-memory read port.  The leader's warp 1 issues every MMA; TMA completions of both CTAs are
+// counted on the leader's `full` barriers, tcgen05.commit multicasts `empty` / `tfull` to both CTAs, and the epilogue
+// warps of both CTAs arrive on the leader's `tempty`.
+template <int BN, int MC, bool PAIR>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
              const int m_tiles, const int n_tiles) {
-    using Cfg = Gemm2Cfg<BN>;
+    using Cfg = Gemm2Cfg<BN, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // align by OFFSET so the pointer keeps its shared address space (LDS/STS instead of generic LD/ST in the epilogue)
@@ -320,6 +327,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
+    const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
+    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // persistent worker = CTA or CTA pair
+    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0) {
         if (elect_one()) {
@@ -331,19 +341,26 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tfull_bar[s], 1);
-                mbar_init(&tempty_bar[s], 8);  // one elected arrive per epilogue warp
+                mbar_init(&tempty_bar[s], PAIR ? 16 : 8);  // one elected arrive per epilogue warp (of both CTAs)
             }
             fence_barrier_init();
         }
     } else if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
-        tmem_relinquish();
+        if (PAIR) {
+            tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish_pair();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
+    else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = p.num_k_blocks;
+    // tiles are 128 x BN (or 256 x BN per pair: m_tiles then counts 256-row tiles)
     const int per_batch = m_tiles * n_tiles;
     const int total = per_batch * (p.batch > 1 ? p.batch : 1);
 
@@ -351,9 +368,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         if (elect_one()) {
             // ---------------- TMA producer
             uint32_t it = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+            for (int tile = worker; tile < total; tile += n_workers) {
                 const int z = tile / per_batch, rem = tile - z * per_batch;
-                const int m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
+                const int m_tile = PAIR ? (rem / n_tiles) * 2 + cta_rank : rem / n_tiles;   // this CTA's 128-row tile
+                const int n_tile = rem % n_tiles;
+                const int b_row0 = n_tile * BN + (PAIR ? cta_rank * (BN / 2) : 0);           // this CTA's rows of B
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
                     const long long pix = (long long)m_tile * BM;
@@ -365,31 +384,51 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
                     mbar_wait(&empty_bar[s], ph ^ 1);
+                    uint8_t* dA = sA + s * A_TILE_BYTES;
+                    uint8_t* dB = sB + s * Cfg::B_TILE_BYTES;
+                    if (PAIR) {
+                        // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
+                        if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_TILE_BYTES + Cfg::B_TILE_BYTES));
+                        if (p.conv) {
+                            const int tap = kb / p.cblocks;
+                            const int cb = kb - tap * p.cblocks;
+                            const int kh = tap / p.KW;
+                            const int kw = tap - kh * p.KW;
+                            tma_load_4d_pair(dA, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w, y0 + kh - p.pad_h, n0);
+                            tma_load_2d_pair(dB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0);
+                        } else if (p.batch > 1) {
+                            tma_load_3d_pair(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
+                            tma_load_3d_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0, z);
+                        } else {
+                            tma_load_2d_pair(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
+                            tma_load_2d_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0);
+                        }
+                        continue;
+                    }
                     mbar_arrive_expect_tx(&full_bar[s], A_TILE_BYTES + Cfg::B_TILE_BYTES);
                     if (p.conv) {
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
                         const int kh = tap / p.KW;
                         const int kw = tap - kh * p.KW;
-                        tma_load_4d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w,
-                                    y0 + kh - p.pad_h, n0);
-                        tma_load_2d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], tap * p.C + cb * BK, n_tile * BN);
+                        tma_load_4d(dA, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w, y0 + kh - p.pad_h, n0);
+                        tma_load_2d(dB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0);
                     } else if (p.batch > 1) {
-                        tma_load_3d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
-                        tma_load_3d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], kb * BK, n_tile * BN, z);
+                        tma_load_3d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
+                        tma_load_3d(dB, &tmB, &full_bar[s], kb * BK, b_row0, z);
                     } else {
-                        tma_load_2d(sA + s * A_TILE_BYTES, &tmA, &full_bar[s], kb * BK, m_tile * BM);
-                        tma_load_2d(sB + s * Cfg::B_TILE_BYTES, &tmB, &full_bar[s], kb * BK, n_tile * BN);
+                        tma_load_2d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
+                        tma_load_2d(dB, &tmB, &full_bar[s], kb * BK, b_row0);
                     }
                 }
             }
         }
     } else if (warp == 1) {
-        if (elect_one()) {
-            // ---------------- MMA issuer
-            constexpr uint32_t idesc = make_idesc_bf16(BM, BN);
+        if (cta_rank == 0 && elect_one()) {
+            // ---------------- MMA issuer (the leader CTA's for a pair)
+            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN);
             uint32_t it = 0, lt = 0;
-            for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+            for (int tile = worker; tile < total; tile += n_workers, ++lt) {
                 const uint32_t as = lt & 1;
                 mbar_wait(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
                 tc_fence_after();
@@ -402,11 +441,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + s * A_TILE_BYTES));
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES));
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k)
-                        umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                    umma_commit(&empty_bar[s]);
+                    for (int k = 0; k < BK / 16; ++k) {
+                        if (PAIR) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                    }
+                    if (PAIR) umma_commit_pair(&empty_bar[s]);
+                    else umma_commit(&empty_bar[s]);
                 }
-                umma_commit(&tfull_bar[as]);
+                if (PAIR) umma_commit_pair(&tfull_bar[as]);
+                else umma_commit(&tfull_bar[as]);
             }
         }
     } else {
@@ -415,9 +458,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         const int half = (warp - 2) >> 2;
         float* stg = staging + (warp - 2) * 1024;
         uint32_t lt = 0;
-        for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++lt) {
+        for (int tile = worker; tile < total; tile += n_workers, ++lt) {
             const int z = tile / per_batch, rem = tile - z * per_batch;
-            const int m_tile = rem / n_tiles, n_tile = rem - m_tile * n_tiles;
+            const int m_tile = PAIR ? (rem / n_tiles) * 2 + cta_rank : rem / n_tiles;
+            const int n_tile = rem % n_tiles;
             const uint32_t as = lt & 1;
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
@@ -425,30 +469,66 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                                (long long)z * p.out_batch_stride);
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[as]);
+            if (lane == 0) {
+                if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
+                else mbar_arrive(&tempty_bar[as]);
+            }
         }
     }
     tc_fence_before();
-    __syncthreads();
+    if (PAIR) cluster_sync_all();  // the leader's MMAs read the peer's shared memory: nobody leaves early
+    else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+        if (PAIR) tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+        else tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
     }
 }
 
 template <int BN, int MC>
+static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN, true>;
+    static bool configured = false;
+    if (!configured) {
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int m_tiles2 = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
+    const long long total = (long long)m_tiles2 * n_tiles * (p.batch > 1 ? p.batch : 1);
+    MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
+    const int pairs = (int)(total < sm_count() / 2 ? total : sm_count() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(G2_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, true>, tmA, tmB, p, m_tiles2, n_tiles));
+    return 0;
+}
+
+template <int BN, int MC>
 static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    if (p.pair) return launch_gemm2_pair<BN, MC>(tmA, tmB, p, stream);
     using Cfg = Gemm2Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
         configured = true;
     }
     const int m_tiles = (p.M + BM - 1) / BM, n_tiles = (p.N + BN - 1) / BN;
     const long long total = (long long)m_tiles * n_tiles * (p.batch > 1 ? p.batch : 1);
     MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm2_kernel<BN, MC><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
+    gemm2_kernel<BN, MC, false><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -486,6 +566,15 @@ bool gemm2_supported(const GemmParams& p) {
             return false;
     }
     return true;
+}
+
+bool gemm2_pair_wanted(const GemmParams& p, int bn_tile, int pair_request) {
+    if (pair_request < 0) return false;
+    if (pair_request > 0) return true;
+    // auto: long-K tensor-bound problems with at least one full wave of 256-row tiles (74 CTA pairs on 148 SMs)
+    const long long m2 = (p.M + 2 * BM - 1) / (2 * BM), nt = (p.N + bn_tile - 1) / bn_tile;
+    const long long tiles = m2 * nt * (p.batch > 1 ? p.batch : 1);
+    return p.num_k_blocks >= 16 && tiles >= sm_count() / 2;
 }
 
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn_tile, cudaStream_t stream) {

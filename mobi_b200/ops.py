@@ -79,7 +79,7 @@ def _rows_view(t, what):
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
          tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
-         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0):
+         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
@@ -131,13 +131,14 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.kernel = kernel
     args.batch = batch
     args.a_batch_stride, args.b_batch_stride, args.out_batch_stride = a_batch_stride, b_batch_stride, out_batch_stride
+    args.pair = pair
     with _timed("gemm", 2.0 * M * N * K * max(1, batch)):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
     return out
 
 
 def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_row_bias=0, residual=None, out=None,
-                  out_dtype=torch.float32, tile_n=0, kernel=0):
+                  out_dtype=torch.float32, tile_n=0, kernel=0, pair=0):
     """Stride-1 'same' convolution of an NHWC bf16 image by implicit GEMM.
 
     x: [N, H, W, C] bf16; w: [Cout, kh*kw*C] bf16 with K ordered (kh, kw, c). Returns [N, H, W, Cout].
@@ -167,6 +168,7 @@ def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_ro
     args.KH, args.KW, args.pad_h, args.pad_w = kh, kw, pad_h, pad_w
     args.tile_n = tile_n
     args.kernel = kernel
+    args.pair = pair
     with _timed("conv", 2.0 * n * h * wd * cout * kh * kw * c):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm(conv)")
     return out
