@@ -114,6 +114,8 @@ typedef struct {
                        2 = two-tile kernel with 128-key blocks and one CTA per SM (head_dim <= 64) */
     int32_t v_rowmajor; /* 1: `vt` holds V as [BH, Tk, d] (same layout as k; head_dim <= 128): consumed as an MN-major
                            tcgen05 operand, no transposed copy needed.  0: `vt` is V^T [BH, d, Tk]. */
+    float* lse;         /* optional f32 [BH, tq] (v_rowmajor = 1 only): log2-domain log-sum-exp of every score row,
+                           rowmax + log2(rowsum); the training step keeps it so that the backward needs no statistics pass */
 } mobi_attn_args;
 
 int mobi_attention(const mobi_attn_args* args, void* stream);
@@ -386,6 +388,11 @@ typedef struct {
     float dscale;
 } mobi_attn_softmax_bwd_args;
 int mobi_attn_softmax_bwd(const mobi_attn_softmax_bwd_args* args, void* stream);
+/* Same, with the row statistics taken from the forward instead of a pass over S and dP: `lse` f32 [batch, tq] from
+ * mobi_attention, Delta = rowsum(dO * O) computed here from the token-major bf16 o / d_o (row stride ld, head columns
+ * [h*d, (h+1)*d), batch entry = head h of one batch row).  args->stats is still the scratch it fills. */
+int mobi_attn_softmax_bwd_lse(const mobi_attn_softmax_bwd_args* args, const float* lse, const void* o, const void* d_o,
+                              int64_t ld, int32_t head_dim, void* stream);
 
 /* cond_adapter_attn (attention.py:237-243, CrossAttention with `keys` <= 4 context tokens) on projected queries, for
  * the training step where to_q/to_k/to_v are trainable and cannot be folded:

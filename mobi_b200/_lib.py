@@ -38,7 +38,7 @@ class AttnArgs(C.Structure):
     _fields_ = [
         ("q", _vp), ("k", _vp), ("vt", _vp), ("out", _vp),
         ("batch", _i32), ("heads", _i32), ("head_dim", _i32), ("tq", _i32), ("tk", _i32),
-        ("ld_out", _i64), ("kernel", _i32), ("v_rowmajor", _i32),
+        ("ld_out", _i64), ("kernel", _i32), ("v_rowmajor", _i32), ("lse", _vp),
     ]
 
 
@@ -169,6 +169,7 @@ SIGNATURES = {
     "mobi_geglu": (C.c_int, [_vp, _vp, _i64, _i64, _vp]),
     "mobi_geglu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "mobi_attn_softmax_bwd": (C.c_int, [C.POINTER(AttnSoftmaxBwdArgs), _vp]),
+    "mobi_attn_softmax_bwd_lse": (C.c_int, [C.POINTER(AttnSoftmaxBwdArgs), _vp, _vp, _vp, _i64, _i32, _vp]),
     "mobi_ctx_attn_qspace": (C.c_int, [C.POINTER(CtxAttnQspaceArgs), _vp]),
     "mobi_colsum": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i64, _vp, _vp]),
     "mobi_wgrad_small": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp]),

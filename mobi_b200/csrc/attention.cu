@@ -268,6 +268,8 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     p.dn = p.dk16 * 16;
     p.ld_out = a->ld_out;
     p.out = reinterpret_cast<__nv_bfloat16*>(a->out);
+    p.lse = a->lse;
+    MOBI_CHECK(a->lse == nullptr || a->v_rowmajor, "mobi_attention: lse output needs the row-major V kernel (head_dim <= 128)");
     const long long BH = (long long)a->batch * a->heads;
     MOBI_CHECK(BH <= 65535, "mobi_attention: batch*heads=%lld exceeds grid.y", BH);
     if (a->v_rowmajor) {

@@ -293,6 +293,7 @@ attention3_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             tc_fence_after();
             const float inv_l = 1.0f / l;
             const int tq_row = q0 + t * 128 + row;
+            if (p.lse != nullptr && tq_row < p.tq) p.lse[(long long)bh * p.tq + tq_row] = m_used + log2f(l);
             const int b = bh / p.heads, h = bh - b * p.heads;
             __nv_bfloat16* orow = p.out + ((long long)b * p.tq + tq_row) * p.ld_out + h * p.head_dim;
 #pragma unroll 1

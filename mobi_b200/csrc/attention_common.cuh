@@ -17,6 +17,7 @@ struct AttnParams {
     int p_bufs;     // 1 or 2            (attention.cu only)
     long long ld_out;
     __nv_bfloat16* out;
+    float* lse;     // optional [BH, tq]: row max + log2(row sum) in the log2 domain (attention3 only)
 };
 
 int attention2_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);

@@ -40,6 +40,34 @@ transpose_kernel(const void* in, int in_f32, __nv_bfloat16* out, int rows, int c
     }
 }
 
+// bf16 -> bf16 fast path: 64 x 64 tiles moved as 32-bit (bf16x2) words on both sides.
+__global__ void __launch_bounds__(256)
+transpose_bf16x2_kernel(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, int rows, int cols, long long ld_in,
+                        long long in_bs, long long ld_out, long long out_bs) {
+    __shared__ uint32_t t[64][33];  // [input row][input column pair]
+    const int b = blockIdx.z;
+    const int r0 = blockIdx.y * 64, c0 = blockIdx.x * 64;
+    const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t* src = in + (b * in_bs) / 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int r = r0 + ty + 8 * i, c = c0 + 2 * tx;
+        t[ty + 8 * i][tx] = (r < rows && c < cols) ? src[((long long)r * ld_in + c) >> 1] : 0u;
+    }
+    __syncthreads();
+    uint32_t* dst = out + (b * out_bs) / 2;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        const int oc = ty + 8 * i;            // output row = input column c0 + oc
+        const int r = r0 + 2 * tx;            // output column pair = input rows r, r + 1
+        if (c0 + oc < cols && r < rows) {
+            const uint32_t w0 = t[2 * tx][oc >> 1], w1 = t[2 * tx + 1][oc >> 1];
+            const uint32_t v = (oc & 1) ? __byte_perm(w0, w1, 0x7632) : __byte_perm(w0, w1, 0x5410);
+            dst[((long long)(c0 + oc) * ld_out + r) >> 1] = v;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // LayerNorm backward, one warp per token row (nn.LayerNorm, attention.py:213-223):
 //   xh = (x - mean) * rstd ; g = dy * gamma ; dx = rstd * (g - mean(g) - xh * mean(g * xh))
@@ -287,6 +315,27 @@ attn_bwd_stats_kernel(const float* __restrict__ S, const float* __restrict__ dP,
         o[0] = M;
         o[1] = 1.0f / l;
         o[2] = acc / l;
+    }
+}
+
+// stats[b, row] = (lse, 1, Delta) with Delta = <dO_row, O_row> over the head's d columns: one warp per (head, row)
+__global__ void __launch_bounds__(256)
+attn_bwd_stats_from_lse_kernel(const float* __restrict__ lse, const __nv_bfloat16* __restrict__ o,
+                               const __nv_bfloat16* __restrict__ d_o, float* __restrict__ stats, int tq, long long ld,
+                               int head_dim) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int row = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (row >= tq) return;
+    const long long b = blockIdx.y;
+    const long long base = (long long)row * ld + b * head_dim;
+    float acc = 0.f;
+    for (int j = lane; j < head_dim; j += 32) acc += __bfloat162float(o[base + j]) * __bfloat162float(d_o[base + j]);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+        float* st = stats + (b * tq + row) * 3;
+        st[0] = lse[b * tq + row];
+        st[1] = 1.0f;
+        st[2] = acc;
     }
 }
 
@@ -586,6 +635,16 @@ extern "C" int mobi_transpose_bf16(const void* in, int32_t in_dtype, void* out, 
                                    void* stream_) {
     MOBI_STREAM;
     MOBI_CHECK(in && out && batch > 0 && rows > 0 && cols > 0 && batch < 65536, "mobi_transpose_bf16: bad argument");
+    if (in_dtype == MOBI_DTYPE_BF16 && rows % 2 == 0 && cols % 2 == 0 && ld_in % 2 == 0 && in_batch_stride % 2 == 0 &&
+        ld_out % 2 == 0 && out_batch_stride % 2 == 0 && (reinterpret_cast<uintptr_t>(in) & 3) == 0 &&
+        (reinterpret_cast<uintptr_t>(out) & 3) == 0 && (rows + 63) / 64 < 65536) {
+        dim3 g64((cols + 63) / 64, (rows + 63) / 64, (unsigned)batch);
+        transpose_bf16x2_kernel<<<g64, 256, 0, stream>>>(reinterpret_cast<const uint32_t*>(in),
+                                                         reinterpret_cast<uint32_t*>(out), rows, cols, ld_in,
+                                                         in_batch_stride, ld_out, out_batch_stride);
+        MOBI_CUDA(cudaGetLastError());
+        return 0;
+    }
     dim3 grid((cols + 31) / 32, (rows + 31) / 32, (unsigned)batch);
     MOBI_CHECK(grid.y < 65536, "mobi_transpose_bf16: rows=%d too large", rows);
     transpose_kernel<<<grid, 256, 0, stream>>>(in, in_dtype == MOBI_DTYPE_F32, reinterpret_cast<__nv_bfloat16*>(out), rows,
@@ -654,6 +713,27 @@ extern "C" int mobi_attn_softmax_bwd(const mobi_attn_softmax_bwd_args* a, void* 
     MOBI_CUDA(cudaGetLastError());
     dim3 g2((a->tk + 31) / 32, (a->tq + 31) / 32, a->batch);
     MOBI_CHECK(g2.y < 65536, "mobi_attn_softmax_bwd: tq too large");
+    attn_bwd_apply_kernel<<<g2, 256, 0, stream>>>(a->S, a->dP, a->stats, reinterpret_cast<__nv_bfloat16*>(a->dS),
+                                                  reinterpret_cast<__nv_bfloat16*>(a->dSt),
+                                                  reinterpret_cast<__nv_bfloat16*>(a->Pt), a->tq, a->tk, a->dscale, bs);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_attn_softmax_bwd_lse(const mobi_attn_softmax_bwd_args* a, const float* lse, const void* o,
+                                         const void* d_o, int64_t ld, int32_t head_dim, void* stream_) {
+    MOBI_STREAM;
+    MOBI_CHECK(a && a->S && a->dP && a->dS && a->dSt && a->Pt && a->stats && lse && o && d_o,
+               "mobi_attn_softmax_bwd_lse: null argument");
+    MOBI_CHECK(a->tq > 0 && a->tk > 0 && a->batch > 0 && a->batch < 65536 && head_dim > 0, "mobi_attn_softmax_bwd_lse: bad shape");
+    const long long bs = (long long)a->tq * a->tk;
+    dim3 g1((a->tq + 7) / 8, a->batch);
+    attn_bwd_stats_from_lse_kernel<<<g1, 256, 0, stream>>>(lse, reinterpret_cast<const __nv_bfloat16*>(o),
+                                                           reinterpret_cast<const __nv_bfloat16*>(d_o), a->stats, a->tq, ld,
+                                                           head_dim);
+    MOBI_CUDA(cudaGetLastError());
+    dim3 g2((a->tk + 31) / 32, (a->tq + 31) / 32, a->batch);
+    MOBI_CHECK(g2.y < 65536, "mobi_attn_softmax_bwd_lse: tq too large");
     attn_bwd_apply_kernel<<<g2, 256, 0, stream>>>(a->S, a->dP, a->stats, reinterpret_cast<__nv_bfloat16*>(a->dS),
                                                   reinterpret_cast<__nv_bfloat16*>(a->dSt),
                                                   reinterpret_cast<__nv_bfloat16*>(a->Pt), a->tq, a->tk, a->dscale, bs);

@@ -201,7 +201,7 @@ def im2col(x, kh, kw, stride, pad_top, pad_left, ho, wo):
     return out
 
 
-def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0, v_rowmajor=False):
+def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0, v_rowmajor=False, lse=None):
     """q,k: bf16 [batch*heads, T, d]; vt: bf16 [batch*heads, d, Tk] (or V itself, [batch*heads, Tk, d], with
     v_rowmajor=True, head_dim <= 128); returns bf16 [batch, tq, heads*d]."""
     _cuda(q, k, vt, out)
@@ -214,6 +214,9 @@ def attention(q, k, vt, batch, heads, head_dim, tq, tk, out=None, kernel=0, v_ro
     a.ld_out = heads * head_dim
     a.kernel = kernel
     a.v_rowmajor = int(v_rowmajor)
+    if lse is not None:
+        assert lse.is_cuda and lse.dtype == torch.float32 and lse.numel() == batch * heads * tq and lse.is_contiguous()
+    a.lse = L.ptr(lse)
     with _timed("attention", 4.0 * batch * heads * tq * tk * head_dim):
         L.check(L.load().mobi_attention(C.byref(a), L.stream()), "attention")
     return out

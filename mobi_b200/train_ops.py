@@ -88,6 +88,17 @@ def attn_softmax_bwd(S, dP, dS, dSt, Pt, stats, tq, tk, dscale, batch=1):
         L.check(L.load().mobi_attn_softmax_bwd(C.byref(a), L.stream()), "attn_softmax_bwd")
 
 
+def attn_softmax_bwd_lse(S, dP, dS, dSt, Pt, stats, tq, tk, dscale, lse, o, d_o, ld, head_dim, batch=1):
+    """Like attn_softmax_bwd, with the row statistics from the forward's log-sum-exp and Delta = rowsum(dO * O)."""
+    a = L.AttnSoftmaxBwdArgs()
+    a.S, a.dP, a.dS, a.dSt, a.Pt, a.stats = (S.data_ptr(), dP.data_ptr(), dS.data_ptr(), dSt.data_ptr(), Pt.data_ptr(),
+                                             stats.data_ptr())
+    a.batch, a.tq, a.tk, a.dscale = batch, tq, tk, dscale
+    with _timed("attn_softmax_bwd", nbytes=batch * tq * tk * 14, kernels=2):
+        L.check(L.load().mobi_attn_softmax_bwd_lse(C.byref(a), lse.data_ptr(), o.data_ptr(), d_o.data_ptr(), ld, head_dim,
+                                                   L.stream()), "attn_softmax_bwd_lse")
+
+
 def ctx_attn_qspace(q, k, v, batch, tokens, heads, *, d_o=None):
     """Forward (d_o None): returns o.  Backward: returns (dq, dk, dv)."""
     _cuda(q, k, v, d_o)

@@ -277,12 +277,18 @@ def test_attention_backward_composite(B, H, D, T):
     o.reshape(B, H, T, D).permute(0, 2, 1, 3).reshape(B * T, C).backward(do.float())
     tr = UNetTrainer.__new__(UNetTrainer)
     tr.device, tr._ws = torch.device("cuda"), {}
-    dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
-    tr._attn_bwd(qb, kb, vb, do, B, H, D, T, dqkv, 0, dqkv, C, 2 * C)
     heads = lambda g: g.reshape(B, H, T, D).permute(0, 2, 1, 3).reshape(B * T, C)
-    assert rel(dqkv[:, :C].float(), heads(qr.grad)) < 2e-2
-    assert rel(dqkv[:, C:2 * C].float(), heads(kr.grad)) < 2e-2
-    assert rel(dqkv[:, 2 * C:].float(), heads(vr.grad)) < 2e-2
+    # (a) statistics recomputed from S and dP; (b) log-sum-exp from the forward kernel + Delta = rowsum(dO * O)
+    o_fwd, lse = tr._attn_fwd(qb, kb, vb, B, H, D, T)
+    assert rel(o_fwd.reshape(B * T, C).float(), heads(o.detach())) < 1e-2
+    lse_ref = torch.logsumexp(qr.detach() @ kr.detach().transpose(-1, -2) * math.log(2.0), -1) / math.log(2.0)
+    assert (lse - lse_ref).abs().max().item() < 2e-2
+    for kw in (dict(), dict(o=o_fwd.reshape(B * T, C), lse=lse)):
+        dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
+        tr._attn_bwd(qb, kb, vb, do, B, H, D, T, dqkv, 0, dqkv, C, 2 * C, **kw)
+        assert rel(dqkv[:, :C].float(), heads(qr.grad)) < 2e-2
+        assert rel(dqkv[:, C:2 * C].float(), heads(kr.grad)) < 2e-2
+        assert rel(dqkv[:, 2 * C:].float(), heads(vr.grad)) < 2e-2
 
 
 # ---------------------------------------------------------------------------------------------- end to end
