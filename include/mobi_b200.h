@@ -72,7 +72,8 @@ typedef struct {
     int64_t ld_row_bias;   /* row stride of row_bias in elements (0 = N) */
     int32_t out_dtype, res_dtype;
     int32_t epilogue;
-    int32_t act;           /* 0 = none, 1 = SiLU applied after bias (PLAIN only; time_embed, openaimodel.py:627-631) */
+    int32_t act;           /* applied after bias (PLAIN only): 0 = none, 1 = SiLU (time_embed, openaimodel.py:627-631;
+                              BBoxEmbedder, encoders/modules.py:195-201), 2 = exact-erf GELU (xf.py MLP, xf.py:49-60) */
     int32_t heads, head_dim, tokens;
     /* PLAIN only: output (and residual) row of GEMM row m is (m / out_seg) * out_seg_stride + out_seg_offset +
      * m % out_seg; out_seg = 0 means identity.  Writes the camera-only / lidar-only token rows of the
@@ -221,6 +222,12 @@ int mobi_ln_adapter(const mobi_ln_adapter_args* args, void* stream);
 /* timestep_embedding (ldm/modules/diffusionmodules/util.py:151-171): out bf16 [n, dim] = [cos | sin]. */
 int mobi_timestep_embedding(const int64_t* t, void* out_bf16, int32_t n, int32_t dim, float max_period,
                             void* stream);
+
+/* Fourier features of the BBoxEmbedder (ldm/modules/encoders/modules.py:203-206, 215-252): x f32 [rows, dims] ->
+ * out bf16 [rows, dims * (1 + 2 * num_freqs)] = [x, sin(x f_0), cos(x f_0), sin(x f_1), ...], f_i = 2^i, zero-padded to
+ * ld_out columns. */
+int mobi_fourier_embed(const float* x, void* out_bf16, int64_t rows, int32_t dims, int32_t num_freqs, int64_t ld_out,
+                       void* stream);
 
 /* y = silu(x) elementwise, f32 or bf16 in -> bf16 out (emb_layers[0], openaimodel.py:204). */
 int mobi_silu(const void* x, int32_t in_dtype, void* out_bf16, int64_t n, void* stream);

@@ -150,6 +150,7 @@ SIGNATURES = {
     "mobi_ln_dual": (C.c_int, [_vp, C.POINTER(LnDualSpec), _i32, _i32, _i32, _f32, _vp]),
     "mobi_ln_adapter": (C.c_int, [C.POINTER(LnAdapterArgs), _vp]),
     "mobi_timestep_embedding": (C.c_int, [_vp, _vp, _i32, _i32, _f32, _vp]),
+    "mobi_fourier_embed": (C.c_int, [_vp, _vp, _i64, _i32, _i32, _i64, _vp]),
     "mobi_silu": (C.c_int, [_vp, _i32, _vp, _i64, _vp]),
     "mobi_nchw_to_nhwc": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mobi_nhwc_to_nchw": (C.c_int, [_vp, _i32, _vp, _i32, _i32, _i32, _vp]),

@@ -823,6 +823,39 @@ extern "C" int mobi_timestep_embedding(const int64_t* t, void* out, int32_t n, i
     return 0;
 }
 
+namespace mobi {
+__global__ void fourier_embed_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int dims,
+                                     int num_freqs, long long ld_out) {
+    const int per_row = dims * (1 + 2 * num_freqs);
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= rows * ld_out) return;
+    const long long r = i / ld_out;
+    const int c = (int)(i - r * ld_out);
+    float v = 0.f;
+    if (c < per_row) {
+        const int blk = c / dims, d = c - blk * dims;   // block 0 = identity, then (sin, cos) per frequency
+        const float xv = x[r * dims + d];
+        if (blk == 0) v = xv;
+        else {
+            const float f = exp2f((float)((blk - 1) >> 1));
+            v = ((blk - 1) & 1) ? cosf(xv * f) : sinf(xv * f);
+        }
+    }
+    out[i] = __float2bfloat16(v);
+}
+}  // namespace mobi
+
+extern "C" int mobi_fourier_embed(const float* x, void* out, int64_t rows, int32_t dims, int32_t num_freqs, int64_t ld_out,
+                                  void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(x && out && rows > 0 && dims > 0 && num_freqs >= 0 && ld_out >= dims * (1 + 2 * num_freqs),
+               "mobi_fourier_embed: bad argument");
+    fourier_embed_kernel<<<blocks_for(rows * ld_out, 256), 256, 0, stream>>>(x, reinterpret_cast<__nv_bfloat16*>(out), rows,
+                                                                            dims, num_freqs, ld_out);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int mobi_silu(const void* x, int32_t in_dtype, void* out, int64_t n, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MOBI_CHECK(x && out, "mobi_silu: null argument");

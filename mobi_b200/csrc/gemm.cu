@@ -223,6 +223,9 @@ gemm_bf16_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.act == 1) {
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] = v[j] / (1.0f + __expf(-v[j]));
+            } else if (p.act == 2) {
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] = gelu_erf(v[j]);
             }
             if (p.mode == MOBI_EPI_GEGLU2) {
                 float o[8];
@@ -316,6 +319,7 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     p.rows_per_group = a->rows_per_group > 0 ? (int)a->rows_per_group : 1;
     p.ld_row_bias = a->ld_row_bias > 0 ? a->ld_row_bias : a->N;
     p.act = a->act;
+    MOBI_CHECK(a->act >= 0 && a->act <= 2, "mobi_gemm: act=%d (0 none, 1 SiLU, 2 GELU)", a->act);
     p.out_f32 = a->out_dtype == MOBI_DTYPE_F32;
     p.res_f32 = a->res_dtype == MOBI_DTYPE_F32;
     p.mode = a->epilogue;

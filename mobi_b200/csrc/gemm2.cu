@@ -265,6 +265,8 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 }
                 if (p.act == 1) {
                     v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
+                } else if (p.act == 2) {
+                    v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
                 }
 
                 if (p.residual) {

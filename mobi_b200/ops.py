@@ -329,6 +329,22 @@ def timestep_embedding(t, dim, max_period=10000.0):
     return out
 
 
+def fourier_embed(x, num_freqs, ld_out=None):
+    """x f32 [..., dims] -> bf16 [rows, ld_out]: [x, sin(x 2^i), cos(x 2^i) ...] per row of `dims` values (see
+    mobi_fourier_embed); ld_out pads the row (zeros) to a multiple of 8 for the GEMM that follows."""
+    _cuda(x)
+    assert x.dtype == torch.float32
+    dims = x.shape[-1]
+    rows = x.numel() // dims
+    per = dims * (1 + 2 * num_freqs)
+    ld_out = per if ld_out is None else ld_out
+    out = torch.empty((rows, ld_out), device=x.device, dtype=torch.bfloat16)
+    Stats.launches += 1
+    L.check(L.load().mobi_fourier_embed(x.data_ptr(), out.data_ptr(), rows, dims, num_freqs, ld_out, L.stream()),
+            "fourier_embed")
+    return out
+
+
 def silu(x):
     _cuda(x)
     out = torch.empty(x.shape, device=x.device, dtype=torch.bfloat16)

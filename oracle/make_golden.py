@@ -11,6 +11,9 @@ What is pinned (all with the tiny topology-complete configs from oracle/*_oracle
   vae_tiny.npz         AutoencoderKL.decode / encode moments for the camera and the lidar-adapter autoencoder
   train_tiny.npz       LatentDiffusion.p_losses loss + loss.backward() gradients of the trainable (adapter) parameters,
                        and the parameters after one torch.optim.AdamW step
+  cond_full.npz        conditioning tokens [B, 2, 768] from the reference's mapper Transformer + final_ln + proj_out and
+                       BBoxEmbedder at FULL size (weights are regenerated from the seed by tensor name, only inputs and
+                       outputs are stored)
   schedule.npz         register_schedule + DDIM parameters for S=50 on the real (1000-step) schedule
   shapes_512.json      state_dict key -> shape of the real mobi_nusc_512 UNet (1,118 tensors) and both VAEs
 """
@@ -26,7 +29,7 @@ ROOT = os.path.dirname(HERE)
 sys.path.insert(0, ROOT)
 GOLDEN = os.path.join(ROOT, "tests", "golden")
 
-from oracle import ref_shims, sampler_oracle, train_oracle, unet_oracle, vae_oracle  # noqa: E402
+from oracle import cond_oracle, ref_shims, sampler_oracle, train_oracle, unet_oracle, vae_oracle  # noqa: E402
 
 
 def build_reference_ldm(unet_cfg, cam_dd=None, lid_dd=None):
@@ -168,6 +171,30 @@ def main():
         p_.grad = None
     load_synth(ldm.model.diffusion_model, unet_oracle.state_dict_shapes(ucfg), seed=0)   # undo the optimizer step
     torch.set_grad_enabled(False)
+
+
+    # ---- conditioning encoders after the CLIP tower, full size, reference modules
+    from ldm.modules.encoders.modules import BBoxEmbedder
+    from ldm.modules.encoders.xf import LayerNorm as XfLayerNorm
+    from ldm.modules.encoders.xf import Transformer as XfTransformer
+    csd = unet_oracle.synth_state_dict(cond_oracle.shapes(), seed=30)
+    mapper, final_ln, bbox_emb = XfTransformer(1, 1024, 5, 1), XfLayerNorm(1024), BBoxEmbedder()   # modules.py:150-157
+    proj_out = torch.nn.Linear(1024, 768)                                                          # ddpm.py:492
+    pre = "cond_stage_model."
+    mapper.load_state_dict({k[len(pre + "mapper."):]: v for k, v in csd.items() if k.startswith(pre + "mapper.")})
+    final_ln.load_state_dict({k[len(pre + "final_ln."):]: v for k, v in csd.items() if k.startswith(pre + "final_ln.")})
+    bbox_emb.load_state_dict({k[len(pre + "bbox_embedder."):]: v for k, v in csd.items()
+                              if k.startswith(pre + "bbox_embedder.")})
+    proj_out.load_state_dict({"weight": csd["proj_out.weight"], "bias": csd["proj_out.bias"]})
+    gc = np.random.default_rng(11)
+    pooled = torch.from_numpy(gc.standard_normal((6, 1024), dtype=np.float32))     # CLIP pooler_output stand-in
+    bbox = torch.from_numpy(gc.uniform(-1.0, 1.0, (6, 8, 3)).astype(np.float32))   # normalised box corners
+    z = final_ln(mapper(pooled.unsqueeze(1)))                                      # modules.py:165-169
+    tok_img = proj_out(z)                                                          # ddpm.py:622
+    tok_box = bbox_emb(bbox)                                                       # modules.py:203-209
+    cond_ref = torch.cat([tok_img, tok_box], dim=1)                                # ddpm.py:623-630
+    np.savez(os.path.join(GOLDEN, "cond_full.npz"), pooled=pooled.numpy(), bbox=bbox.numpy(), cond=cond_ref.numpy())
+    print("cond_full cond std %.4f" % cond_ref.std())
 
     # ---- schedule buffers on the real schedule, S=50
     smp = DDIMSampler(ldm)
