@@ -446,6 +446,31 @@ int mobi_mse_grad(const float* pred, const float* target, float* grad, float* lo
 int mobi_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, float bias_corr1, float bias_corr2, float grad_scale, void* stream);
 
+/* Input assembly before the loop / the training step: one modality of
+ * LatentDiffusion.encode_all_stages (ldm/models/diffusion/ddpm.py:1010-1033) fused with the lidar alignment and the
+ * camera / lidar interleave of LatentDiffusion.get_input (ddpm.py:797-826):
+ *   z        = scale * (mean_gt + exp(0.5 * clamp(logvar_gt, -30, 20)) * noise_gt)       (distributions.py:24-37)
+ *   z_inp    = same from the inpaint posterior
+ *   mask     = nearest resize of the full-resolution keep mask to the latent size          (F.interpolate, ddpm.py:1020)
+ *   out[i * row_stride + row_offset, :, y, x] = [z | z_inp | mask][i, :, y - pad, x + left]  (zero outside: F.pad,
+ *   a negative pad crops rows), y, x in [0, S).
+ * moments: NCHW f32 [n, 8, hs, ws] (AutoencoderKL.encode(...).parameters); noise: [n, 4, hs, ws] or NULL (posterior mode);
+ * mask [n, 1, hm, wm]; out [*, 9, S, S].  Camera: left = pad = 0, row_offset 0; lidar: row_offset 1; row_stride 2. */
+typedef struct {
+    const float* moments_gt;
+    const float* noise_gt;
+    const float* moments_inpaint;
+    const float* noise_inpaint;
+    const float* mask;
+    float* out;
+    int32_t n, hs, ws, hm, wm, S, left, pad, row_stride, row_offset;
+    float scale;
+} mobi_latent_input_args;
+int mobi_assemble_latent_input(const mobi_latent_input_args* args, void* stream);
+/* In-place box-corner re-normalisation of get_input (ddpm.py:815-816): bbox f32 [n_points, 3];
+ * x = (x * W - left) / S ; y += pad / S. */
+int mobi_bbox_renorm(float* bbox, int64_t n_points, int32_t W, int32_t left, int32_t S, int32_t pad, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

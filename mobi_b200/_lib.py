@@ -137,6 +137,14 @@ class CtxAttnQspaceArgs(C.Structure):
     ]
 
 
+class LatentInputArgs(C.Structure):
+    _fields_ = [
+        ("moments_gt", _vp), ("noise_gt", _vp), ("moments_inpaint", _vp), ("noise_inpaint", _vp), ("mask", _vp), ("out", _vp),
+        ("n", _i32), ("hs", _i32), ("ws", _i32), ("hm", _i32), ("wm", _i32), ("S", _i32), ("left", _i32), ("pad", _i32),
+        ("row_stride", _i32), ("row_offset", _i32), ("scale", _f32),
+    ]
+
+
 # name -> (restype, argtypes); also the list of symbols include/mobi_b200.h declares
 SIGNATURES = {
     "mobi_last_error": (C.c_char_p, []),
@@ -179,6 +187,8 @@ SIGNATURES = {
     "mobi_sum2x2": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mobi_q_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "mobi_mse_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
+    "mobi_assemble_latent_input": (C.c_int, [C.POINTER(LatentInputArgs), _vp]),
+    "mobi_bbox_renorm": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "mobi_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
 }
 

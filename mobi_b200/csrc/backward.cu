@@ -624,6 +624,47 @@ __global__ void scatter_add_rows_kernel(const void* __restrict__ src, int is_f32
     dst[d * C + c] += ld_any(src, is_f32, i);
 }
 
+__global__ void latent_input_kernel(mobi_latent_input_args a) {
+    const long long total = (long long)a.n * 9 * a.S * a.S;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= total) return;
+    const int x = (int)(i % a.S);
+    long long r = i / a.S;
+    const int y = (int)(r % a.S);
+    r /= a.S;
+    const int c = (int)(r % 9);
+    const int img = (int)(r / 9);
+    const int ys = y - a.pad, xs = x + a.left;
+    float v = 0.f;
+    if (ys >= 0 && ys < a.hs && xs >= 0 && xs < a.ws) {
+        if (c < 8) {
+            const float* mom = c < 4 ? a.moments_gt : a.moments_inpaint;
+            const float* nz = c < 4 ? a.noise_gt : a.noise_inpaint;
+            const int cc = c & 3;
+            const long long plane = (long long)a.hs * a.ws;
+            const long long pix = (long long)ys * a.ws + xs;
+            const float mean = mom[((long long)img * 8 + cc) * plane + pix];
+            float lv = mom[((long long)img * 8 + 4 + cc) * plane + pix];
+            lv = fminf(fmaxf(lv, -30.0f), 20.0f);
+            const float eps = nz ? nz[((long long)img * 4 + cc) * plane + pix] : 0.f;
+            v = a.scale * (mean + expf(0.5f * lv) * eps);
+        } else {
+            // F.interpolate(mask, size=ws, mode="nearest"): src = floor(dst * in / out), output is ws x ws
+            const int my = min((int)floorf(ys * ((float)a.hm / a.ws)), a.hm - 1);
+            const int mx = min((int)floorf(xs * ((float)a.wm / a.ws)), a.wm - 1);
+            v = a.mask[((long long)img * a.hm + my) * a.wm + mx];
+        }
+    }
+    a.out[((((long long)img * a.row_stride + a.row_offset) * 9 + c) * a.S + y) * a.S + x] = v;
+}
+
+__global__ void bbox_renorm_kernel(float* bbox, long long n_points, float W, float left, float S, float pad) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_points) return;
+    bbox[3 * i] = (bbox[3 * i] * W - left) / S;
+    bbox[3 * i + 1] += pad / S;
+}
+
 }  // namespace mobi
 
 using namespace mobi;
@@ -850,6 +891,29 @@ extern "C" int mobi_scatter_add_rows(const void* src, int32_t src_dtype, float* 
     MOBI_CHECK(src && dst && rows > 0 && C > 0, "mobi_scatter_add_rows: bad argument");
     scatter_add_rows_kernel<<<bw_blocks(rows * C, 256), 256, 0, stream>>>(src, src_dtype == MOBI_DTYPE_F32, dst, rows, C,
                                                                          seg, seg_stride, seg_offset);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_assemble_latent_input(const mobi_latent_input_args* a, void* stream_) {
+    MOBI_STREAM;
+    MOBI_CHECK(a && a->moments_gt && a->moments_inpaint && a->mask && a->out, "mobi_assemble_latent_input: null argument");
+    MOBI_CHECK((a->noise_gt == nullptr) == (a->noise_inpaint == nullptr), "mobi_assemble_latent_input: noise_gt and noise_inpaint go together");
+    MOBI_CHECK(a->n > 0 && a->hs > 0 && a->ws > 0 && a->hm > 0 && a->wm > 0 && a->S > 0 && a->row_stride >= 1 &&
+                   a->row_offset >= 0 && a->row_offset < a->row_stride,
+               "mobi_assemble_latent_input: bad shape");
+    const long long total = (long long)a->n * 9 * a->S * a->S;
+    latent_input_kernel<<<bw_blocks(total, 256), 256, 0, stream>>>(*a);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_bbox_renorm(float* bbox, int64_t n_points, int32_t W, int32_t left, int32_t S, int32_t pad,
+                                void* stream_) {
+    MOBI_STREAM;
+    MOBI_CHECK(bbox && n_points > 0 && S > 0, "mobi_bbox_renorm: bad argument");
+    bbox_renorm_kernel<<<bw_blocks(n_points, 128), 128, 0, stream>>>(bbox, n_points, (float)W, (float)left, (float)S,
+                                                                    (float)pad);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

@@ -140,6 +140,105 @@ class LatentDiffusion(nn.Module):
             z = 1.0 / sf * z
         return module.decode(z)
 
+    # ------------------------------------------------------------------ input assembly
+    @torch.no_grad()
+    def encode_first_stage(self, x, module_name="first_stage_model"):
+        """ddpm.py:970-1008 (the patch-wise split_input_params branch is not used by MObI's configs)."""
+        assert module_name in ["first_stage_model", "lidar_stage_model"]
+        return getattr(self, module_name).encode(x)
+
+    def get_first_stage_encoding(self, encoder_posterior, scale_factor=1, noise=None):
+        """xf-less restatement of ddpm.py:600-608; `noise` overrides the posterior's RNG draw (parity tests)."""
+        from .autoencoder import DiagonalGaussianDistribution
+        if isinstance(encoder_posterior, DiagonalGaussianDistribution):
+            z = encoder_posterior.sample(noise)
+        elif isinstance(encoder_posterior, torch.Tensor):
+            z = encoder_posterior
+        else:
+            raise NotImplementedError("encoder_posterior of type '%s' not yet implemented" % type(encoder_posterior))
+        return scale_factor * z
+
+    def _sample_into(self, m_gt, m_in, noise, mask, scale, out, row_stride=1, row_offset=0, left=0, pad=0):
+        """ONE kernel: sample both posteriors, nearest-resize the mask, write the 9-channel rows (cropped / padded /
+        interleaved) in place (mobi_assemble_latent_input)."""
+        import ctypes as C
+
+        from . import _lib as L
+        n, _, hs, ws = m_gt.shape
+        assert hs == ws, "the reference resizes the mask to a square of the latent width (ddpm.py:1020, 1030)"
+        mask = mask.detach().float().contiguous()
+        a = L.LatentInputArgs()
+        a.moments_gt, a.moments_inpaint = m_gt.data_ptr(), m_in.data_ptr()
+        a.noise_gt, a.noise_inpaint = noise[0].data_ptr(), noise[1].data_ptr()
+        a.mask, a.out = mask.data_ptr(), out.data_ptr()
+        a.n, a.hs, a.ws, a.hm, a.wm = n, hs, ws, mask.shape[-2], mask.shape[-1]
+        a.S, a.left, a.pad, a.row_stride, a.row_offset, a.scale = out.shape[-1], left, pad, row_stride, row_offset, scale
+        L.check(L.load().mobi_assemble_latent_input(C.byref(a), L.stream()), "assemble_latent_input")
+        return out
+
+    def _encode_pair(self, module_name, gt, inpaint, noise):
+        m_gt = self.encode_first_stage(gt, module_name).parameters.contiguous()
+        m_in = self.encode_first_stage(inpaint, module_name).parameters.contiguous()
+        if noise is None:   # DiagonalGaussianDistribution.sample draws (distributions.py:35-37)
+            shape = (m_gt.shape[0], 4) + tuple(m_gt.shape[2:])
+            noise = (torch.randn(shape, device=m_gt.device), torch.randn(shape, device=m_gt.device))
+        return m_gt, m_in, tuple(t.detach().float().contiguous() for t in noise)
+
+    @torch.no_grad()
+    def encode_all_stages(self, image_gt, image_inpaint, image_mask, range_gt, range_inpaint, range_mask, noise=None):
+        """ddpm.py:1010-1033.  Returns (z_image, z_lidar), each [N, 9, h, w] = [z | z_inpaint | mask].  `noise` =
+        optional dict(camera=(n_gt, n_inpaint), lidar=(n_gt, n_inpaint)) replacing the posterior RNG draws."""
+        z_image = z_lidar = None
+        noise = noise or {}
+        if self.use_camera:
+            m_gt, m_in, nz = self._encode_pair("first_stage_model", image_gt, image_inpaint, noise.get("camera"))
+            z_image = torch.empty((m_gt.shape[0], 9) + tuple(m_gt.shape[2:]), device=m_gt.device, dtype=torch.float32)
+            self._sample_into(m_gt, m_in, nz, image_mask, self.scale_factor, z_image)
+        if self.use_lidar:
+            m_gt, m_in, nz = self._encode_pair("lidar_stage_model", range_gt, range_inpaint, noise.get("lidar"))
+            z_lidar = torch.empty((m_gt.shape[0], 9) + tuple(m_gt.shape[2:]), device=m_gt.device, dtype=torch.float32)
+            self._sample_into(m_gt, m_in, nz, range_mask, self.lidar_scale_factor, z_lidar)
+        return z_image, z_lidar
+
+    @torch.no_grad()
+    def get_input(self, batch, k="inpaint", force_c_encode=False, bs=None, return_vae_rec=False, noise=None):
+        """ddpm.py:758-834 for the joint camera + lidar model: batch = {"image": {GT, inpaint_image, inpaint_mask, cond},
+        "lidar": {range_data, range_data_inpaint, range_mask, cond}}.  Returns {"z": [2N, 9, S, S] rows interleaved
+        cam0, lid0, cam1, ..., "cond": {key: interleaved raw conditioning}, "z_lidar": [N, 4, hl, wl]}.  The lidar box
+        corners are re-normalised IN PLACE like the reference does (ddpm.py:815-816).  The conditioning encoders are a
+        separate step (mobi_b200.encoders.learned_conditioning)."""
+        from . import _lib as L
+        assert k == "inpaint" and self.use_camera and self.use_lidar, "get_input: joint camera + lidar model only"
+        assert not force_c_encode and not return_vae_rec, "get_input: encode conditioning / decode reconstructions separately"
+        image_data, lidar_data = batch["image"], batch["lidar"]
+        if bs is not None:
+            sel = lambda d: {kk: (sel(v) if isinstance(v, dict) else v[:bs]) for kk, v in d.items()}
+            image_data, lidar_data = sel(image_data), sel(lidar_data)
+        noise = noise or {}
+        n, S = image_data["GT"].shape[0], self.image_size
+        z = torch.empty((2 * n, 9, S, S), device=image_data["GT"].device, dtype=torch.float32)
+        m_gt, m_in, nz = self._encode_pair("first_stage_model", image_data["GT"], image_data["inpaint_image"],
+                                           noise.get("camera"))
+        assert m_gt.shape[-1] == S and m_gt.shape[-2] == S, "camera latent must have the UNet's image_size"
+        self._sample_into(m_gt, m_in, nz, image_data["inpaint_mask"], self.scale_factor, z, 2, 0)
+        # the lidar latent is centre-cropped in width and padded (cropped when negative) in height (ddpm.py:797-812)
+        m_gt, m_in, nz = self._encode_pair("lidar_stage_model", lidar_data["range_data"], lidar_data["range_data_inpaint"],
+                                           noise.get("lidar"))
+        hl, wl = m_gt.shape[-2], m_gt.shape[-1]
+        left, pad = wl // 2 - S // 2, (S - hl) // 2
+        self._sample_into(m_gt, m_in, nz, lidar_data["range_mask"], self.lidar_scale_factor, z, 2, 1, left, pad)
+        # un-cropped lidar latent for decode_sample (ddpm.py:819): same kernel, identity window
+        z_lidar = torch.empty((n, 9, hl, wl), device=z.device, dtype=torch.float32)
+        self._sample_into(m_gt, m_in, nz, lidar_data["range_mask"], self.lidar_scale_factor, z_lidar)
+        bbox = lidar_data["cond"]["ref_bbox"]
+        assert bbox.is_cuda and bbox.dtype == torch.float32 and bbox.is_contiguous()
+        L.check(L.load().mobi_bbox_renorm(bbox.data_ptr(), bbox.numel() // 3, wl, left, S, pad, L.stream()), "bbox_renorm")
+        cond = {}
+        for key in image_data["cond"]:
+            c, l = image_data["cond"][key], lidar_data["cond"][key]
+            cond[key] = torch.stack([c, l], dim=1).reshape((-1,) + tuple(c.shape[1:]))    # cat_interleave (ldm/util.py:213-221)
+        return {"z": z, "cond": cond, "z_lidar": z_lidar[:, :4]}
+
     def decode_sample(self, sample, z_lidar=None):
         """ddpm.py:1420-1447."""
         h_camera, h_lidar = None, None

@@ -11,6 +11,9 @@ What is pinned (all with the tiny topology-complete configs from oracle/*_oracle
   vae_tiny.npz         AutoencoderKL.decode / encode moments for the camera and the lidar-adapter autoencoder
   train_tiny.npz       LatentDiffusion.p_losses loss + loss.backward() gradients of the trainable (adapter) parameters,
                        and the parameters after one torch.optim.AdamW step
+  get_input_tiny.npz   LatentDiffusion.get_input (encode_all_stages: 4 VAE encodes + posterior samples + nearest mask resize +
+                       9-channel concat; lidar crop/pad to the image latent; bbox re-normalisation; cam/lidar interleave)
+                       with the tiny VAEs, a 32x32 camera image and a 48x48 range image (so crop AND negative pad run)
   cond_full.npz        conditioning tokens [B, 2, 768] from the reference's mapper Transformer + final_ln + proj_out and
                        BBoxEmbedder at FULL size (weights are regenerated from the seed by tensor name, only inputs and
                        outputs are stored)
@@ -172,6 +175,33 @@ def main():
     load_synth(ldm.model.diffusion_model, unet_oracle.state_dict_shapes(ucfg), seed=0)   # undo the optimizer step
     torch.set_grad_enabled(False)
 
+
+
+    # ---- get_input assembly through the unmodified LatentDiffusion.get_input
+    gi = np.random.default_rng(21)
+    f32 = lambda *s_: torch.from_numpy(gi.standard_normal(s_, dtype=np.float32))
+    nb = 2
+    mk = lambda h_: torch.from_numpy((gi.random((nb, 1, h_, h_)) > 0.3).astype(np.float32))
+    batch = dict(
+        image=dict(GT=f32(nb, 3, 32, 32), inpaint_image=f32(nb, 3, 32, 32), inpaint_mask=mk(32),
+                   cond=dict(ref_image=f32(nb, 3, 8, 8), ref_bbox=torch.from_numpy(gi.uniform(0, 1, (nb, 8, 3)).astype(np.float32)))),
+        lidar=dict(range_data=f32(nb, 2, 48, 48), range_data_inpaint=f32(nb, 2, 48, 48), range_mask=mk(48),
+                   cond=dict(ref_image=f32(nb, 3, 8, 8), ref_bbox=torch.from_numpy(gi.uniform(0, 1, (nb, 8, 3)).astype(np.float32)))))
+    bbox_lidar_in = batch["lidar"]["cond"]["ref_bbox"].clone()      # get_input re-normalises it IN PLACE (ddpm.py:815-816)
+    ldm.process_conditioning = lambda cond, force_c_encode=False: (cond, None)   # conditioning encoders: separate row
+    torch.manual_seed(77)
+    gout = ldm.get_input(batch, "inpaint")
+    torch.manual_seed(77)                                             # DiagonalGaussianDistribution.sample draws, in call order
+    noises = [torch.randn(nb, 4, 16, 16), torch.randn(nb, 4, 16, 16), torch.randn(nb, 4, 24, 24), torch.randn(nb, 4, 24, 24)]
+    np.savez(os.path.join(GOLDEN, "get_input_tiny.npz"),
+             image_gt=batch["image"]["GT"].numpy(), image_inpaint=batch["image"]["inpaint_image"].numpy(),
+             image_mask=batch["image"]["inpaint_mask"].numpy(), range_gt=batch["lidar"]["range_data"].numpy(),
+             range_inpaint=batch["lidar"]["range_data_inpaint"].numpy(), range_mask=batch["lidar"]["range_mask"].numpy(),
+             bbox_camera=batch["image"]["cond"]["ref_bbox"].numpy(), bbox_lidar_in=bbox_lidar_in.numpy(),
+             noise_cam_gt=noises[0].numpy(), noise_cam_inpaint=noises[1].numpy(), noise_lid_gt=noises[2].numpy(),
+             noise_lid_inpaint=noises[3].numpy(), z=gout["z"].numpy(), z_lidar=gout["z_lidar"].numpy(),
+             bbox_out=gout["cond"]["ref_bbox"].numpy())
+    print("get_input_tiny z", tuple(gout["z"].shape), "z_lidar", tuple(gout["z_lidar"].shape), "std %.4f" % gout["z"].std())
 
     # ---- conditioning encoders after the CLIP tower, full size, reference modules
     from ldm.modules.encoders.modules import BBoxEmbedder
