@@ -303,8 +303,8 @@ int mobi_sampler_update(const mobi_sampler_args* args, void* stream);
  * where x0_noised = sqrt_ac * x0 + sqrt_1mac * noise (q_sample, ddpm.py:284-287). */
 typedef struct {
     float* x;               /* [B,4,H,W]; updated in place when blend_mask != NULL */
-    const float* inpaint_image; /* [B,4,H,W] */
-    const float* inpaint_mask;  /* [B,1,H,W] */
+    const float* inpaint_image; /* [B,4,H,W]; or the whole `rest` tensor [B,rest_c,H,W] when inpaint_mask is NULL */
+    const float* inpaint_mask;  /* [B,1,H,W] or NULL (ddim.py:173-176: kwargs['rest']) */
     const float* blend_mask;    /* [B, blend_c, H, W], blend_c = 1 (broadcast over channels) or 4; NULL = no blend */
     const float* blend_x0;
     const float* blend_noise;

@@ -657,7 +657,7 @@ __global__ void assemble_input_kernel(mobi_assemble_args a) {
         float* dst = a.x_in + ((long long)(r * a.B + b) * ctot) * a.hw + p;
 #pragma unroll
         for (int c = 0; c < 4; ++c) dst[(long long)c * a.hw] = xv[c];
-        if (a.rest_c == 5) {
+        if (a.inpaint_mask != nullptr) {  // test_model_kwargs: 4 inpaint_image channels + 1 mask channel
 #pragma unroll
             for (int c = 0; c < 4; ++c) dst[(long long)(4 + c) * a.hw] = a.inpaint_image[((long long)b * 4 + c) * a.hw + p];
             dst[(long long)8 * a.hw] = a.inpaint_mask[(long long)b * a.hw + p];
@@ -971,7 +971,8 @@ extern "C" int mobi_sampler_update(const mobi_sampler_args* a, void* stream_) {
 extern "C" int mobi_assemble_input(const mobi_assemble_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MOBI_CHECK(a && a->x && a->x_in && a->inpaint_image, "mobi_assemble_input: null argument");
-    MOBI_CHECK(a->rest_c != 5 || a->inpaint_mask, "mobi_assemble_input: inpaint_mask missing");
+    MOBI_CHECK(a->inpaint_mask == nullptr || a->rest_c == 5, "mobi_assemble_input: image + mask means rest_c = 5 (got %d)",
+               a->rest_c);
     MOBI_CHECK(!a->blend_mask || (a->blend_x0 && a->blend_noise), "mobi_assemble_input: blend needs x0 and noise");
     const long long total = (long long)a->B * a->hw;
     assemble_input_kernel<<<blocks_for(total, 256), 256, 0, stream>>>(*a);
