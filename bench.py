@@ -299,9 +299,18 @@ def run_native(args):
         achieved = tc_fl / (tc_ms / 1e3) / 1e12
         step_flops = UNET_FLOPS_PER_JOINT.get(latent, 0) * 2 * n   # x2: CFG doubles the rows
         ms_unet = ms / args.steps / max(1, unet_evals // args.steps)
+        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one representative launch: the
+        # level-0 conv3x3), next to the algorithmic bytes of that same launch
+        traffic, traffic_note = None, None
+        try:
+            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))
+            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+            traffic_note = {"launch": tj["kernel"], "algorithmic_bytes": tj["algorithmic_bytes"], "source": tj["source"]}
+        except Exception:
+            pass
         roofline = {"bound": "tensor", "kernel": "gemm2_kernel (persistent tcgen05 GEMM + implicit-GEMM conv3x3)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
-                    "peak_source": peak_src, "traffic": None,
+                    "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                     "launches_per_unet_call": tc_n, "flops_per_launch_avg": tc_fl / max(1, tc_n),
                     "ms_per_launch_avg": tc_ms / max(1, tc_n),
                     "share_of_unet_time": tc_ms / all_ms if all_ms else None,
