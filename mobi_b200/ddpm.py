@@ -53,7 +53,7 @@ class LatentDiffusion(nn.Module):
                  timesteps=1000, beta_schedule="linear", linear_start=1e-4, linear_end=2e-2, cosine_s=8e-3,
                  conditioning_key="crossattn", parameterization="eps", first_stage_key="image", image_size=256,
                  channels=3, scale_factor=1.0, lidar_scale_factor=1.0, use_camera=True, use_lidar=False,
-                 v_posterior=0.0, **ignored):
+                 v_posterior=0.0, cond_stage_key="image", **ignored):
         super().__init__()
         assert parameterization == "eps"
         self.parameterization = parameterization
@@ -68,6 +68,10 @@ class LatentDiffusion(nn.Module):
         self.model = DiffusionWrapper(unet_config, conditioning_key)
         self.first_stage_model = instantiate_from_config(first_stage_config) if (first_stage_config and use_camera) else None
         self.lidar_stage_model = instantiate_from_config(lidar_stage_config) if (lidar_stage_config and use_lidar) else None
+        # conditioning stage (ddpm.py:564-586): "__is_unconditional__" / None -> no encoder (the path starts from tokens)
+        self.cond_stage_key = list(cond_stage_key) if isinstance(cond_stage_key, (list, tuple)) else cond_stage_key
+        self.cond_stage_model = instantiate_from_config(cond_stage_config) if isinstance(cond_stage_config, dict) else None
+        self.proj_out = nn.Linear(1024, 768).requires_grad_(False)                               # ddpm.py:479
         self.learnable_vector = nn.Parameter(torch.randn((1, 1, 768)), requires_grad=False)     # ddpm.py:476
         self.bbox_uncond_vector = nn.Parameter(torch.randn((1, 1, 768)), requires_grad=False)   # ddpm.py:477
         self.register_schedule(beta_schedule=beta_schedule, timesteps=timesteps, linear_start=linear_start,
@@ -139,6 +143,15 @@ class LatentDiffusion(nn.Module):
         else:
             z = 1.0 / sf * z
         return module.decode(z)
+
+    @torch.no_grad()
+    def get_learned_conditioning(self, c):
+        """ddpm.py:610-630: encode the raw conditioning dict, project the image token, concatenate -> [B, n, 768]."""
+        from . import encoders
+        if self.cond_stage_model is None:
+            raise RuntimeError("get_learned_conditioning: this LatentDiffusion was built without a cond_stage_config")
+        keys = self.cond_stage_key if isinstance(self.cond_stage_key, list) else ["ref_image"]
+        return encoders.learned_conditioning(self.cond_stage_model, self.proj_out, c, cond_stage_key=keys)
 
     # ------------------------------------------------------------------ input assembly (SURVEY.md §8(f) row 2)
     @torch.no_grad()

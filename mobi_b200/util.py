@@ -37,6 +37,8 @@ TARGET_MAP = {
     "ldm.modules.diffusionmodules.openaimodel.UNetModel": "mobi_b200.openaimodel.UNetModel",
     "ldm.models.autoencoder.AutoencoderKL": "mobi_b200.autoencoder.AutoencoderKL",
     "ldm.models.diffusion.ddpm.LatentDiffusion": "mobi_b200.ddpm.LatentDiffusion",
+    "ldm.modules.encoders.modules.FrozenCLIPImageEmbedder": "mobi_b200.encoders.FrozenCLIPImageEmbedder",
+    "ldm.modules.encoders.modules.BBoxEmbedder": "mobi_b200.encoders.BBoxEmbedder",
 }
 
 
