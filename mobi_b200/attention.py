@@ -40,6 +40,14 @@ def _f32(t):
     return t.detach().float().contiguous()
 
 
+def repeat_rows2(t):
+    """cat([t, t]) along the batch dimension as two device-to-device copies (data movement only)."""
+    out = torch.empty((2 * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
+    out[:t.shape[0]].copy_(t)
+    out[t.shape[0]:].copy_(t)
+    return out
+
+
 class GEGLU(nn.Module):
     """attention.py:38-45 (parameter container; the math is the GEGLU epilogue of mobi_gemm)."""
 
@@ -194,13 +202,12 @@ class BasicTransformerBlock(nn.Module):
         return tab
 
     # ------------------------------------------------------------------ execution
-    def run(self, x, R, T, tab, out_bf16=False):
-        """x: f32 [R*T, C] residual stream, updated in place.  Returns x (f32) or, with out_bf16, a bf16 copy
-        of the block output (what SpatialTransformer.proj_out consumes)."""
+    def run_attn1(self, x, R, T):
+        """Step 1 only (x = attn1(norm1(x)) + x, attention.py:234), in place: the part of the block that does not see
+        the context — under classifier-free guidance it is identical for the uncond and cond halves of the batch."""
         p = self._p
         C, H, D = self.dim, self.n_heads, self.d_head
         dev = x.device
-        # 1. self-attention (attention.py:234)
         xn = ops.layernorm(x, *p["norm1"])
         q = torch.empty((R * H, T, D), device=dev, dtype=torch.bfloat16)
         k = torch.empty_like(q)
@@ -210,6 +217,19 @@ class BasicTransformerBlock(nn.Module):
                  out2=k, out3=v)
         o = ops.attention(q, k, v, R, H, D, T, T, v_rowmajor=rowv)
         ops.gemm(o.reshape(R * T, C), p["w_o"], bias=p["b_o"], residual=x, out=x)
+        return x
+
+    def run(self, x, R, T, tab, out_bf16=False, attn1_done=False):
+        """x: f32 [R*T, C] residual stream, updated in place.  Returns x (f32) or, with out_bf16, a bf16 copy
+        of the block output (what SpatialTransformer.proj_out consumes)."""
+        if not attn1_done:
+            self.run_attn1(x, R, T)
+        return self._run_rest(x, R, T, tab, out_bf16)
+
+    def _run_rest(self, x, R, T, tab, out_bf16):
+        p = self._p
+        C, H, D = self.dim, self.n_heads, self.d_head
+        dev = x.device
         # 2. attn2 == broadcast add of tab["vec2"][row] (attention.py:235), fused into the next normalisation pass
         pending = tab["vec2"]
         cam = (ops.LN_NORM,) + p["cross_modal_norm_camera"] if self.multimodal else None
@@ -308,16 +328,25 @@ class SpatialTransformer(nn.Module):
     def context_tables(self, context):
         return [b.context_tables(context) for b in self.transformer_blocks]
 
-    def run(self, h, tabs):
-        """h: f32 NHWC [R, H, W, C] -> f32 NHWC."""
+    def run(self, h, tabs, duplicate=False):
+        """h: f32 NHWC [R, H, W, C] -> f32 NHWC.
+        duplicate: h holds ONE half of a classifier-free-guidance batch whose two halves are identical up to here
+        (DDIMSampler.p_sample_ddim feeds cat([x] * 2), ddim.py:180-183).  GroupNorm, proj_in and the first block's
+        self-attention do not see the context, so they run once on the half; the residual stream and h are then
+        repeated to both halves and the context-dependent rest runs on all rows.  Returns 2R rows."""
         p = self._p
         R, Hh, Ww, C = h.shape
         T = Hh * Ww
         hn = ops.groupnorm(h, p["gn"][0], p["gn"][1], 1e-6, silu=False)
         x = ops.gemm(hn.reshape(R * T, C), p["w_in"], bias=p["b_in"], out_dtype=torch.float32)
         n = len(self.transformer_blocks)
+        attn1_done = False
+        if duplicate:
+            self.transformer_blocks[0].run_attn1(x, R, T)
+            x, h = repeat_rows2(x), repeat_rows2(h)
+            R, attn1_done = 2 * R, True
         for i, blk in enumerate(self.transformer_blocks):
-            x = blk.run(x, R, T, tabs[i], out_bf16=(i == n - 1))
+            x = blk.run(x, R, T, tabs[i], out_bf16=(i == n - 1), attn1_done=(attn1_done and i == 0))
         out = ops.gemm(x, p["w_out"], bias=p["b_out"], residual=h.reshape(R * T, C), out_dtype=torch.float32)
         return out.reshape(R, Hh, Ww, C)
 

@@ -107,7 +107,8 @@ class DDIMSampler(SamplerBase):
         ops.assemble_input(x, rest_image, rest_mask, x_in, cfg=cfg)
         t_in = torch.cat([t] * 2) if cfg else t
         c_in = torch.cat([unconditional_conditioning, c]) if cfg else c
-        eps = self.model.apply_model(x_in, t_in, c_in).float().contiguous()
+        self._cfg = cfg
+        eps = self._apply_model(x_in, t_in, c_in).float().contiguous()
         k = StepCoefficients(self.ddim_alphas, self.ddim_alphas_prev, self.ddim_sqrt_one_minus_alphas, self.ddim_sigmas,
                              index)
         noise = torch.randn_like(x) if k.sigma != 0.0 else None

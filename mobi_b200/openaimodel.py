@@ -8,7 +8,7 @@ import torch
 import torch.nn as nn
 
 from . import ops
-from .attention import SpatialTransformer, _bf16, _f32, zero_module
+from .attention import SpatialTransformer, _bf16, _f32, repeat_rows2, zero_module
 from .packing import pack_conv_weight
 
 
@@ -284,6 +284,9 @@ class UNetModel(nn.Module):
         self._ctx_key = None
         self._ctx_tabs = None
         self._pack_serial = 0
+        # set by the samplers around their own calls: rows [0, R/2) and [R/2, R) of x and timesteps are identical
+        # (classifier-free guidance feeds cat([x] * 2), ddim.py:180-183); only the context differs between the halves
+        self.cfg_shared_halves = False
         self.register_load_state_dict_post_hook(lambda module, incompatible: module.invalidate())
 
     # ------------------------------------------------------------------ packing
@@ -362,11 +365,27 @@ class UNetModel(nn.Module):
         e2 = ops.gemm(e1, p["w_t2"], bias=p["b_t2"], act=1)                          # Linear, then emb_layers' SiLU
         emb_all = ops.gemm(e2, p["w_emb"], bias=p["b_emb"], out_dtype=torch.float32)  # [R, sum(out_channels)]
 
-        h = ops.nchw_to_nhwc(x.detach().float().contiguous())
+        R = x.shape[0]
+        blocks = list(self.input_blocks)[1:]
+        first = list(blocks[0]) if blocks else []
+        shared = bool(self.cfg_shared_halves) and R % (4 if self.multimodal else 2) == 0 and len(first) == 2 and isinstance(first[0], ResBlock) \
+            and isinstance(first[1], SpatialTransformer)
         hs = []
-        h = Conv3x3.run(p["conv_in"], h)
-        hs.append(h)
-        for seq in list(self.input_blocks)[1:]:
+        if shared:
+            # Everything before the first context injection is computed once for the identical halves: conv_in, the first
+            # ResBlock, the first SpatialTransformer's GroupNorm / proj_in and its first self-attention.
+            Rh = R // 2
+            h0 = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x[:Rh].detach().float().contiguous()))
+            hs.append(repeat_rows2(h0))
+            off = p["emb_offs"][id(first[0])]
+            hr = first[0].run(h0, emb_all[:Rh, off:off + first[0].out_channels])
+            h = first[1].run(hr, self._ctx_tabs[id(first[1])], duplicate=True)
+            hs.append(h)
+            blocks = blocks[1:]
+        else:
+            h = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x.detach().float().contiguous()))
+            hs.append(h)
+        for seq in blocks:
             h = self._run_block(seq, h, None, emb_all)
             hs.append(h)
         h = self._run_block(self.middle_block, h, None, emb_all)

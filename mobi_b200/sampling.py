@@ -143,7 +143,7 @@ class SamplerBase(object):
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):
                 for _ in range(2):  # warm-up: lazy packing, cudaFuncSetAttribute, allocator pools
-                    self.model.apply_model(self._x_in, self._t_in, self._c_in)
+                    self._apply_model(self._x_in, self._t_in, self._c_in)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g_ctx = torch.cuda.CUDAGraph()
@@ -152,11 +152,22 @@ class SamplerBase(object):
             g = torch.cuda.CUDAGraph()
             before = ops.Stats.launches
             with torch.cuda.graph(g, pool=g_ctx.pool()):
-                self._eps = self.model.apply_model(self._x_in, self._t_in, self._c_in)
+                self._eps = self._apply_model(self._x_in, self._t_in, self._c_in)
             self._graph_kernels = ops.Stats.launches - before  # kernels replayed per UNet evaluation
             self._graph, self._graph_ctx = g, g_ctx
             g_ctx.replay()  # capture does not execute: fill the tables for this run
         self._static_key = key
+
+    def _apply_model(self, x_in, t_in, c_in):
+        """apply_model with the native UNet told that the two CFG halves of x_in / t_in are identical copies."""
+        unet = self._native_unet()
+        if unet is not None:
+            unet.cfg_shared_halves = bool(self._cfg)
+        try:
+            return self.model.apply_model(x_in, t_in, c_in)
+        finally:
+            if unet is not None:
+                unet.cfg_shared_halves = False
 
     def _eval_model(self, step):
         """eps for the current self._x_in at timestep `step` ([uncond ; cond] rows under CFG)."""
@@ -166,7 +177,7 @@ class SamplerBase(object):
             self._graph.replay()
             ops.Stats.launches += self._graph_kernels
             return self._eps
-        return self.model.apply_model(self._x_in, self._t_in, self._c_in).float().contiguous()
+        return self._apply_model(self._x_in, self._t_in, self._c_in).float().contiguous()
 
     @staticmethod
     def _rest_from_kwargs(kwargs):

@@ -108,3 +108,22 @@ def test_wrong_device_and_missing_kwargs_fail_loudly(setup):
                                 x_T=inp["x_T"])
     with pytest.raises(RuntimeError):
         ldm.model.diffusion_model(torch.zeros(2, 9, 16, 16), torch.zeros(2, dtype=torch.long), context=torch.zeros(2, 2, 32))
+
+
+def test_cfg_shared_prefix_is_exact(setup):
+    """Under classifier-free guidance the two halves of the UNet batch are identical copies up to the first context
+    injection; computing that prefix once (UNetModel.cfg_shared_halves) must not change a single bit."""
+    ldm, cfg, apply_ref, sched, uo = setup
+    inp = uo.synth_inputs(2, 16, context_dim=cfg["context_dim"], seed=8, device="cuda")
+    x = torch.cat([inp["x_T"], inp["inpaint_image"], inp["inpaint_mask"]], 1)
+    x_in, t_in = torch.cat([x, x]), torch.full((8,), 481, device="cuda", dtype=torch.long)
+    c_in = torch.cat([inp["uc"], inp["cond"]]).contiguous()
+    unet = ldm.model.diffusion_model
+    ref = unet(x_in, t_in, context=c_in)
+    unet.cfg_shared_halves = True
+    try:
+        got = unet(x_in, t_in, context=c_in)
+    finally:
+        unet.cfg_shared_halves = False
+    assert torch.equal(got, ref)
+    assert not torch.equal(got[:4], got[4:])      # the halves do differ after the context enters
