@@ -442,6 +442,8 @@ int mobi_q_sample(const float* x0, const float* noise, const float* sqrt_ac, con
 /* loss_sum += sum (pred - target)^2 ; grad = grad_scale * (pred - target)  (get_loss 'l2' + mean, ddpm.py:1196-1210). */
 int mobi_mse_grad(const float* pred, const float* target, float* grad, float* loss_sum, int64_t n, float grad_scale,
                   void* stream);
+/* dx (f32) = dy * silu'(pre): backward of the SiLUs of the trainable BBoxEmbedder MLP (encoders/modules.py:195-201). */
+int mobi_silu_bwd(const void* pre, int32_t pre_dtype, const void* dy, int32_t dy_dtype, float* dx, int64_t n, void* stream);
 /* torch.optim.AdamW step over one flat f32 buffer (ddpm.py:1655): g is multiplied by grad_scale first. */
 int mobi_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, float bias_corr1, float bias_corr2, float grad_scale, void* stream);

@@ -189,6 +189,7 @@ SIGNATURES = {
     "mobi_mse_grad": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _vp]),
     "mobi_assemble_latent_input": (C.c_int, [C.POINTER(LatentInputArgs), _vp]),
     "mobi_bbox_renorm": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp]),
+    "mobi_silu_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mobi_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
 }
 

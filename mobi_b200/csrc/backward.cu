@@ -658,6 +658,16 @@ __global__ void latent_input_kernel(mobi_latent_input_args a) {
     a.out[((((long long)img * a.row_stride + a.row_offset) * 9 + c) * a.S + y) * a.S + x] = v;
 }
 
+// dx = dy * silu'(pre), silu'(a) = s (1 + a (1 - s)), s = sigmoid(a)   (BBoxEmbedder.second_linear, modules.py:195-201)
+__global__ void silu_bwd_kernel(const void* __restrict__ pre, int pre_f32, const void* __restrict__ dy, int dy_f32,
+                                float* __restrict__ dx, long long n) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float a = ld_any(pre, pre_f32, i);
+    const float sg = 1.0f / (1.0f + __expf(-a));
+    dx[i] = ld_any(dy, dy_f32, i) * sg * (1.0f + a * (1.0f - sg));
+}
+
 __global__ void bbox_renorm_kernel(float* bbox, long long n_points, float W, float left, float S, float pad) {
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n_points) return;
@@ -914,6 +924,16 @@ extern "C" int mobi_bbox_renorm(float* bbox, int64_t n_points, int32_t W, int32_
     MOBI_CHECK(bbox && n_points > 0 && S > 0, "mobi_bbox_renorm: bad argument");
     bbox_renorm_kernel<<<bw_blocks(n_points, 128), 128, 0, stream>>>(bbox, n_points, (float)W, (float)left, (float)S,
                                                                     (float)pad);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_silu_bwd(const void* pre, int32_t pre_dtype, const void* dy, int32_t dy_dtype, float* dx, int64_t n,
+                             void* stream_) {
+    MOBI_STREAM;
+    MOBI_CHECK(pre && dy && dx && n > 0, "mobi_silu_bwd: bad argument");
+    silu_bwd_kernel<<<bw_blocks(n, 256), 256, 0, stream>>>(pre, pre_dtype == MOBI_DTYPE_F32, dy, dy_dtype == MOBI_DTYPE_F32,
+                                                          dx, n);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

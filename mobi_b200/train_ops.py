@@ -192,6 +192,16 @@ def mse_grad(pred, target, loss_sum, grad_scale):
     return grad
 
 
+def silu_bwd(pre, dy):
+    """dx (f32) = dy * silu'(pre)."""
+    _cuda(pre, dy)
+    dx = torch.empty(pre.shape, device=pre.device, dtype=torch.float32)
+    with _timed("silu_bwd"):
+        L.check(L.load().mobi_silu_bwd(pre.data_ptr(), L.dt(pre), dy.data_ptr(), L.dt(dy), dx.data_ptr(), pre.numel(),
+                                       L.stream()), "silu_bwd")
+    return dx
+
+
 def adamw(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2, step=1, grad_scale=1.0):
     _cuda(p, g, m, v)
     bc1 = 1.0 - beta1 ** step

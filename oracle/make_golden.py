@@ -150,7 +150,8 @@ def main():
             assert p_.requires_grad == train_oracle.is_trainable(n_), n_   # DiffusionWrapper.__init__, ddpm.py:1686-1698
         params = [p_ for p_ in ldm.model.diffusion_model.parameters() if p_.requires_grad]
         opt = torch.optim.AdamW(params, lr=8e-5)                           # ddpm.py:1655
-        loss, _ = ldm.p_losses(tr["x_start"], tr["cond"], tr["t"], noise=tr["noise"])
+        cond_leaf = tr["cond"].clone().requires_grad_(True)        # d loss / d conditioning tokens: what trains bbox_embedder
+        loss, _ = ldm.p_losses(tr["x_start"], cond_leaf, tr["t"], noise=tr["noise"])
         loss.backward()
         grads = {n_: p_.grad.detach().clone() for n_, p_ in ldm.model.diffusion_model.named_parameters()
                  if p_.requires_grad}
@@ -159,7 +160,7 @@ def main():
         ldm.eval()
     keep = ("input_blocks.1.1.", "middle_block.1.", "output_blocks.3.1.")
     out = dict(x_start=tr["x_start"].numpy(), t=tr["t"].numpy(), noise=tr["noise"].numpy(), cond=tr["cond"].numpy(),
-               loss=np.float32(loss.item()), names=np.array(sorted(grads)),
+               loss=np.float32(loss.item()), d_cond=cond_leaf.grad.numpy(), names=np.array(sorted(grads)),
                grad_l2=np.array([grads[k].norm().item() for k in sorted(grads)], dtype=np.float64),
                grad_sum=np.array([grads[k].double().sum().item() for k in sorted(grads)], dtype=np.float64))
     for k in sorted(grads):

@@ -26,8 +26,10 @@ def p_losses(sd, cfg, sched, x_start, t, noise, cond):
     return loss_simple.mean(), eps
 
 
-def loss_and_grads(sd, cfg, sched, x_start, t, noise, cond):
-    """Returns (loss, {name: grad}) for the trainable tensors of the UNet state dict."""
+def loss_and_grads(sd, cfg, sched, x_start, t, noise, cond, want_d_cond=False):
+    """Returns (loss, {name: grad}) for the trainable tensors of the UNet state dict (and, with want_d_cond, the gradient
+    w.r.t. the conditioning tokens under the key "__d_cond__": it is what reaches the trainable bbox_embedder,
+    ddpm.py:580-586)."""
     leaves = {}
     work = {}
     for k, v in sd.items():
@@ -36,12 +38,15 @@ def loss_and_grads(sd, cfg, sched, x_start, t, noise, cond):
             work[k] = leaves[k]
         else:
             work[k] = v.detach()
+    cond_leaf = cond.detach().clone().requires_grad_(True)
     with torch.enable_grad():
-        loss, _ = p_losses(work, cfg, sched, x_start, t, noise, cond)
-        grads = torch.autograd.grad(loss, list(leaves.values()), allow_unused=True)
+        loss, _ = p_losses(work, cfg, sched, x_start, t, noise, cond_leaf)
+        grads = torch.autograd.grad(loss, list(leaves.values()) + [cond_leaf], allow_unused=True)
     out = {}
-    for (k, v), g in zip(leaves.items(), grads):
+    for (k, v), g in zip(leaves.items(), grads[:-1]):
         out[k] = torch.zeros_like(v) if g is None else g
+    if want_d_cond:
+        out["__d_cond__"] = grads[-1]
     return loss.detach(), out
 
 
