@@ -31,6 +31,7 @@ from .openaimodel import Conv3x3, Downsample, ResBlock, Upsample
 from .packing import pack_conv_weight
 
 TRAINABLE_KEYS = ("cond_adapter", "lidar", "cross_modal")  # ddpm.py:1686-1698
+BBOX_PREFIX = "cond_stage_model.bbox_embedder."             # checkpoint prefix of the trainable conditioning MLP
 
 
 def is_trainable(name):
@@ -44,8 +45,10 @@ class FlatParams:
 
     ALIGN = 4  # elements: every view starts on a 16-byte boundary (vector epilogues of the wgrad GEMM)
 
-    def __init__(self, module, select=is_trainable, device=None):
-        named = [(n, p) for n, p in module.named_parameters() if select(n)]
+    def __init__(self, module, select=is_trainable, device=None, extra=()):
+        """extra: further (name, parameter) pairs appended after the selected parameters of `module` (the trainable
+        bbox_embedder of the conditioning stage, ddpm.py:580-586)."""
+        named = [(n, p) for n, p in module.named_parameters() if select(n)] + list(extra)
         if not named:
             raise RuntimeError("no trainable parameters selected")
         device = device or named[0][1].device
@@ -119,7 +122,7 @@ class UNetTrainer:
     """forward_backward(x_start, t, noise, context) -> loss; step() -> all-reduce + AdamW + repack."""
 
     def __init__(self, ldm, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None, use_cuda_graph=True,
-                 lse_backward=False):
+                 lse_backward=False, bbox_embedder=None):
         self.ldm = ldm
         self.unet = ldm.model.diffusion_model if hasattr(ldm, "model") else ldm
         unet = self.unet
@@ -130,7 +133,11 @@ class UNetTrainer:
         if dev.type != "cuda":
             raise RuntimeError("UNetTrainer runs on CUDA only (no CPU fallback)")
         self.device = dev
-        self.flat = FlatParams(unet, is_trainable, dev)
+        # the reference also trains the bbox_embedder of the conditioning stage (ddpm.py:580-586, 1636-1641): its parameters
+        # join the same flat buffer under their checkpoint names
+        self.bbox_embedder = bbox_embedder
+        extra = [] if bbox_embedder is None else [(BBOX_PREFIX + n, p) for n, p in bbox_embedder.named_parameters()]
+        self.flat = FlatParams(unet, is_trainable, dev, extra=extra)
         self.exp_avg = torch.zeros_like(self.flat.params)
         self.exp_avg_sq = torch.zeros_like(self.flat.params)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
@@ -138,6 +145,7 @@ class UNetTrainer:
         self.steps = 0
         self.loss_sum = torch.zeros(1, device=dev, dtype=torch.float32)
         self._names = {id(p): n for n, p in unet.named_parameters()}
+        self._names.update({id(p): n for n, p in extra})
         self._ws = {}
         self.use_cuda_graph = use_cuda_graph
         # lse_backward: take the softmax row statistics of the attention backward from the forward kernel's log-sum-exp and
@@ -177,7 +185,8 @@ class UNetTrainer:
             elif isinstance(m, BasicTransformerBlock):
                 p = m._p
                 bp[id(m)] = dict(w_qkv_T=p["w_qkv"].t().contiguous(), w_o_T=p["w_o"].t().contiguous(),
-                                 w_ff1_T=p["w_ff1"].t().contiguous(), w_ff2_T=p["w_ff2"].t().contiguous())
+                                 w_ff1_T=p["w_ff1"].t().contiguous(), w_ff2_T=p["w_ff2"].t().contiguous(),
+                                 w_o2_T=p["w_o2"].t().contiguous(), w_v2_T=p["w_v2"].t().contiguous())
             elif isinstance(m, Upsample):
                 bp[id(m)] = dict(conv=_conv_dgrad_pack(m.conv))
             elif isinstance(m, Downsample):
@@ -221,8 +230,8 @@ class UNetTrainer:
             d = {}
             ca = blk.cond_adapter_attn
             d["a_wq"], d["a_wq_T"] = self._pack_matrix(ca.to_q.weight.data, sc)
-            d["a_wk"], _ = self._pack_matrix(ca.to_k.weight.data, transposed=False)
-            d["a_wv"], _ = self._pack_matrix(ca.to_v.weight.data, transposed=False)
+            d["a_wk"], d["a_wk_T"] = self._pack_matrix(ca.to_k.weight.data)
+            d["a_wv"], d["a_wv_T"] = self._pack_matrix(ca.to_v.weight.data)
             d["a_wo"], d["a_wo_T"] = self._pack_matrix(ca.to_out[0].weight.data)
             d["a_bo"] = ca.to_out[0].bias.data
             d["a_wc"], d["a_wc_T"] = self._pack_matrix(blk.cond_adapter_connector.weight.data)
@@ -240,6 +249,10 @@ class UNetTrainer:
                 d[m + "_bc"] = cn.bias.data
                 self._qscales.append((self._g(at.to_q.weight), sc * LOG2E))
             tp[id(blk)] = d
+        if self.bbox_embedder is not None:
+            be = self.bbox_embedder
+            lin = [be.bbox_proj, be.second_linear[0], be.second_linear[2], be.second_linear[4]]
+            tp["bbox"] = [self._pack_matrix(m.weight.data) + (m.bias.data,) for m in lin]
         self.tp = tp
         # the inference packs fold these weights: they are stale now
         self.unet._ctx_key = None
@@ -412,6 +425,16 @@ class UNetTrainer:
         tops.wgrad_small(dka.reshape(R * nk, C), cflat, self._g(ca.to_k.weight))
         tops.wgrad_small(dva.reshape(R * nk, C), cflat, self._g(ca.to_v.weight))
         tops.layernorm_bwd(t["x2"], ln.weight.data, dna, d, dgamma=self._g(ln.weight), dbeta=self._g(ln.bias))
+        # gradient w.r.t. the conditioning tokens (what trains the bbox_embedder): both tokens through the adapter's
+        # to_k / to_v, token 0 also through the frozen attn2 (vec2 = to_out(to_v(c0)) added to every token of a row)
+        dctx = self.d_context.reshape(R * nk, -1)
+        ops.gemm(ops.cast_bf16(dka.reshape(R * nk, C)), tp["a_wk_T"], residual=dctx, out=dctx)
+        ops.gemm(ops.cast_bf16(dva.reshape(R * nk, C)), tp["a_wv_T"], residual=dctx, out=dctx)
+        dvec2 = torch.zeros((R, C), device=dev, dtype=torch.float32)
+        tops.colsum(d, dvec2, rows_per_group=T)
+        dv0 = ops.gemm(ops.cast_bf16(dvec2), bp["w_o2_T"])
+        dc0 = self.d_context[:, 0]
+        ops.gemm(dv0, bp["w_v2_T"], residual=dc0, out=dc0)
         # 2. attn2 adds a per-row constant: identity for d.   1. self-attention (frozen weights: dgrad only)
         if need_dx0:
             do1 = ops.gemm(ops.cast_bf16(d), bp["w_o_T"])
@@ -518,33 +541,39 @@ class UNetTrainer:
 
     # ------------------------------------------------------------------ the step
     @torch.no_grad()
-    def forward_backward(self, x_start, t, noise, context):
+    def forward_backward(self, x_start, t, noise, context=None, *, bbox=None):
         """p_losses (ddpm.py:1177-1217) + backward.  x_start [R, 9, h, w] f32 (4 latent + 4 inpaint_image + mask channels),
         t int64 [R], noise [R, 4, h, w], context [R, n_ctx, ctx_dim] (already dropped-out or not by the caller).
-        Gradients of the trainable parameters are left in self.flat.grads; returns the loss (0-dim tensor).
+        With a trainable bbox_embedder (constructor) and `bbox` [R, 8, 3] given, token 1 of the context is recomputed
+        here from the box corners (get_learned_conditioning, ddpm.py:610-630) and its MLP receives gradients.
+        Gradients of the trainable parameters are left in self.flat.grads, the gradient w.r.t. the context in
+        self.d_context; returns the loss (0-dim tensor).
         With use_cuda_graph the whole forward + backward (several thousand launches) is captured once per input shape
         and replayed from static input buffers."""
-        for a in (x_start, noise, context, t):
+        for a in (x_start, noise, context, t) + ((bbox,) if bbox is not None else ()):
             if not a.is_cuda:
                 raise RuntimeError("UNetTrainer needs CUDA tensors (no CPU fallback)")
+        if bbox is not None and self.bbox_embedder is None:
+            raise RuntimeError("forward_backward(bbox=...) needs UNetTrainer(bbox_embedder=...)")
         if not self.use_cuda_graph:
-            return self._forward_backward(x_start, t, noise, context)
-        key = (tuple(x_start.shape), tuple(noise.shape), tuple(context.shape))
+            return self._forward_backward(x_start, t, noise, context, bbox)
+        key = (tuple(x_start.shape), tuple(noise.shape), tuple(context.shape), None if bbox is None else tuple(bbox.shape))
         if self._fb_graph is None or self._fb_key != key:
             self._static = dict(x=x_start.detach().float().contiguous().clone(), t=t.to(torch.int64).contiguous().clone(),
                                 noise=noise.detach().float().contiguous().clone(),
-                                ctx=context.detach().float().contiguous().clone())
+                                ctx=context.detach().float().contiguous().clone(),
+                                bbox=None if bbox is None else bbox.detach().float().contiguous().clone())
             st = self._static
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                # warm-up: workspaces, cudaFuncSetAttribute, allocator pools
-                self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"])
+                self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"])
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = ops.Stats.launches
             with torch.cuda.graph(g):
-                self._static_loss = self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"])
+                self._static_loss = self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"])
             self._fb_kernels = ops.Stats.launches - before
             self._fb_graph, self._fb_key = g, key
         st = self._static
@@ -552,11 +581,44 @@ class UNetTrainer:
         st["t"].copy_(t)
         st["noise"].copy_(noise)
         st["ctx"].copy_(context)
+        if bbox is not None:
+            st["bbox"].copy_(bbox)
         self._fb_graph.replay()
         ops.Stats.launches += self._fb_kernels
         return self._static_loss
 
-    def _forward_backward(self, x_start, t, noise, context):
+    # ------------------------------------------------------------------ trainable bbox_embedder (modules.py:181-213)
+    def _bbox_forward(self, bbox):
+        """bbox [R, 8, 3] -> (token f32 [R, 768], tape).  Same math as encoders.BBoxEmbedder.forward, keeping the
+        pre-activations of the two SiLUs."""
+        be, pk = self.bbox_embedder, self.tp["bbox"]
+        R = bbox.shape[0]
+        e = ops.fourier_embed(bbox.detach().float().contiguous(), be.num_freqs).reshape(R, 8 * be.out_dim)
+        a0 = ops.gemm(e, pk[0][0], bias=pk[0][2])                       # bbox_proj (no activation)
+        a1 = ops.gemm(a0, pk[1][0], bias=pk[1][2])                      # second_linear.0, SiLU follows
+        h1 = ops.silu(a1)
+        a2 = ops.gemm(h1, pk[2][0], bias=pk[2][2])                      # second_linear.2, SiLU follows
+        h2 = ops.silu(a2)
+        out = ops.gemm(h2, pk[3][0], bias=pk[3][2], out_dtype=torch.float32)
+        return out, dict(e=e, a0=a0, a1=a1, h1=h1, a2=a2, h2=h2)
+
+    def _bbox_backward(self, t, d_out):
+        """d_out f32 [R, 768]: gradient w.r.t. the bbox token.  R is tiny (2 rows per joint sample): the weight gradients
+        are plain outer-product sums (mobi_wgrad_small), the data gradients tensor-core GEMMs with 4-8 rows."""
+        be, pk = self.bbox_embedder, self.tp["bbox"]
+        lin = [be.bbox_proj, be.second_linear[0], be.second_linear[2], be.second_linear[4]]
+        acts = [t["e"], t["a0"], t["h1"], t["h2"]]                       # inputs of the four Linears
+        pre = [None, None, t["a1"], t["a2"]]                            # pre-activation feeding Linear i through a SiLU
+        d = d_out.contiguous()
+        for i in (3, 2, 1, 0):
+            tops.wgrad_small(d, acts[i].float(), self._g(lin[i].weight))
+            tops.colsum(d, self._g(lin[i].bias).reshape(1, -1))
+            if i == 0:
+                break
+            dx = ops.gemm(ops.cast_bf16(d), pk[i][1], out_dtype=torch.float32)    # d @ W_i
+            d = tops.silu_bwd(pre[i], dx) if pre[i] is not None else dx
+
+    def _forward_backward(self, x_start, t, noise, context, bbox=None):
         u, ldm = self.unet, self.ldm
         p = u._p
         R = x_start.shape[0]
@@ -566,6 +628,12 @@ class UNetTrainer:
         x_noisy = tops.q_sample(x_start.float().contiguous(), noise.float().contiguous(), ldm.sqrt_alphas_cumprod,
                                 ldm.sqrt_one_minus_alphas_cumprod, t, noise.shape[1])
         ctx_f32 = context.detach().float().contiguous()
+        bbox_tape = None
+        if bbox is not None:   # token 1 = bbox_embedder(bbox), computed here so that its MLP can be trained
+            tok, bbox_tape = self._bbox_forward(bbox)
+            ctx_f32 = ctx_f32.clone()
+            ctx_f32[:, 1].copy_(tok)
+        self.d_context = torch.zeros_like(ctx_f32)
         ctx_bf = ops.cast_bf16(ctx_f32).reshape(R * ctx_f32.shape[1], -1)
         # ---- forward (openaimodel.py:861-898), keeping the tape
         t_emb = ops.timestep_embedding(t, u.model_channels)
@@ -600,6 +668,8 @@ class UNetTrainer:
         for i in range(len(inputs) - 1, 0, -1):
             dh = ops.add_f32(dh, d_hs[i])
             dh, _ = self._seq_backward(inputs[i], tapes_in[i - 1], dh, ctx_f32, first=(i == 1))
+        if bbox_tape is not None:
+            self._bbox_backward(bbox_tape, self.d_context[:, 1])
         # gradients w.r.t. the scaled query projections -> w.r.t. to_q.weight
         for gview, sc in self._qscales:
             ops.scale_f32(gview, sc, out=gview)

@@ -400,3 +400,64 @@ def test_training_step_fullwidth_vs_oracle():
           "%.5f, whole-gradient cosine %.6f" % (loss.item(), ref_loss.item(), worst, wname, wcos, cos(flat_got, flat_ref)))
     assert abs(loss.item() - ref_loss.item()) <= 1e-2 * ref_loss.item()
     assert worst <= 5e-2 and wcos >= 0.999 and cos(flat_got, flat_ref) >= 0.9995
+
+
+def test_gradient_wrt_conditioning_tokens_vs_reference_golden():
+    """d loss / d cond (both tokens: through the adapter's to_k / to_v and, for token 0, the frozen attn2) against the
+    gradient the unmodified reference's loss.backward() leaves on the conditioning tensor."""
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    tr, cfg, sd = _tiny_trainer()
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"))
+    torch.cuda.synchronize()
+    ref = cu("d_cond")
+    e0, e1 = rel(tr.d_context[:, 0], ref[:, 0]), rel(tr.d_context[:, 1], ref[:, 1])
+    print("d loss / d cond max-abs-rel vs reference golden: ref-image token %.3e, bbox token %.3e; cosine %.5f"
+          % (e0, e1, cos(tr.d_context, ref)))
+    assert e0 < 5e-2 and e1 < 5e-2 and cos(tr.d_context, ref) > 0.999
+
+
+def test_bbox_embedder_training_path():
+    """The trainable BBoxEmbedder (ddpm.py:580-586): its token replaces context[:, 1] inside the step and its four
+    Linears receive d loss / d token through the SiLU MLP; checked against torch.autograd over the oracle's bbox_token
+    fed with the trainer's own d_context[:, 1]."""
+    from mobi_b200 import encoders
+    from mobi_b200.ddpm import LatentDiffusion
+    from mobi_b200.training import BBOX_PREFIX, UNetTrainer
+    from oracle import cond_oracle as co
+    from oracle import unet_oracle as uo
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    cfg = uo.tiny_unet_config()
+    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
+    ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg), linear_start=0.00085,
+                          linear_end=0.0120, timesteps=1000, first_stage_key="inpaint", image_size=16, channels=4,
+                          conditioning_key="crossattn", use_camera=True, use_lidar=True).cuda().eval()
+    ldm.model.diffusion_model.load_state_dict(sd, strict=True)
+    be = encoders.BBoxEmbedder(proj_dims=(48, 40, 40, 32)).cuda()          # token width = the tiny context_dim (32)
+    bsd = uo.synth_state_dict({k: tuple(v.shape) for k, v in be.state_dict().items()}, seed=40)
+    be.load_state_dict(bsd)
+    tr = UNetTrainer(ldm, bbox_embedder=be)
+    assert len(tr.flat.names) == 189 + 8 and tr.flat.names[-1].startswith(BBOX_PREFIX)
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    bbox = rnd(4, 8, 3, seed=50).clamp(-1, 1)
+    loss = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"), bbox=bbox)
+    torch.cuda.synchronize()
+    assert torch.isfinite(loss).item()
+    # oracle: token = bbox_token(weights, bbox); grads = autograd of <token, d_token> with the trainer's d_context[:, 1]
+    pre = "cond_stage_model.bbox_embedder."
+    leaves = {pre + k: v.cuda().clone().requires_grad_(True) for k, v in bsd.items()}
+    tok = co.bbox_token(leaves, bbox)[:, 0]
+    d_tok = tr.d_context[:, 1].clone()
+    tok.backward(d_tok)
+    # the forward token the trainer used is the embedder's own output
+    assert rel(be(bbox)[:, 0], tok.detach()) < 1e-2
+    grads = tr.named_grads()
+    worst = 0.0
+    for k, v in leaves.items():
+        e = rel(grads[k], v.grad)
+        worst = max(worst, e)
+        assert e < 3e-2 and cos(grads[k], v.grad) > 0.999, (k, e)
+    print("bbox_embedder gradients vs autograd over the oracle: worst max-abs-rel %.3e" % worst)
+    tr.step()
+    loss2 = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"), bbox=bbox)
+    assert torch.isfinite(loss2).item()
