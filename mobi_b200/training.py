@@ -137,6 +137,8 @@ class UNetTrainer:
         # join the same flat buffer under their checkpoint names
         self.bbox_embedder = bbox_embedder
         extra = [] if bbox_embedder is None else [(BBOX_PREFIX + n, p) for n, p in bbox_embedder.named_parameters()]
+        if bbox_embedder is not None and isinstance(getattr(ldm, "bbox_uncond_vector", None), nn.Parameter):
+            extra.append(("bbox_uncond_vector", ldm.bbox_uncond_vector))      # ddpm.py:477, 1643-1645
         self.flat = FlatParams(unet, is_trainable, dev, extra=extra)
         self.exp_avg = torch.zeros_like(self.flat.params)
         self.exp_avg_sq = torch.zeros_like(self.flat.params)
@@ -154,7 +156,7 @@ class UNetTrainer:
         # the cross-modal to_k / to_v weight gradients (27 % max-abs error on one tensor at full width, whole-gradient
         # cosine unchanged at 0.99992).  Off by default: the parity bar is per tensor.
         self.lse_backward = lse_backward
-        self._fb_graph = self._fb_key = self._repack_graph = None
+        self._fb_graphs, self._repack_graph = {}, None
         unet.invalidate()
         unet.pack()
         self._pack_frozen_backward()
@@ -217,7 +219,7 @@ class UNetTrainer:
                 self._repack_trainable()
             self._repack_kernels = ops.Stats.launches - before
             self._repack_graph = g
-            self._fb_graph = self._fb_key = None         # operand addresses changed
+            self._fb_graphs = {}                         # operand addresses changed
         self._repack_graph.replay()
         ops.Stats.launches += self._repack_kernels
         self.unet._ctx_key = None
@@ -541,51 +543,64 @@ class UNetTrainer:
 
     # ------------------------------------------------------------------ the step
     @torch.no_grad()
-    def forward_backward(self, x_start, t, noise, context=None, *, bbox=None):
+    def forward_backward(self, x_start, t, noise, context=None, *, bbox=None, uncond=False):
         """p_losses (ddpm.py:1177-1217) + backward.  x_start [R, 9, h, w] f32 (4 latent + 4 inpaint_image + mask channels),
-        t int64 [R], noise [R, 4, h, w], context [R, n_ctx, ctx_dim] (already dropped-out or not by the caller).
+        t int64 [R], noise [R, 4, h, w], context [R, n_ctx, ctx_dim].
         With a trainable bbox_embedder (constructor) and `bbox` [R, 8, 3] given, token 1 of the context is recomputed
         here from the box corners (get_learned_conditioning, ddpm.py:610-630) and its MLP receives gradients.
+        uncond=True is the reference's whole-batch conditioning dropout (ddpm.py:1052-1056): the context becomes
+        [learnable_vector, bbox_uncond_vector] for every row and bbox_uncond_vector receives its gradient.
         Gradients of the trainable parameters are left in self.flat.grads, the gradient w.r.t. the context in
         self.d_context; returns the loss (0-dim tensor).
-        With use_cuda_graph the whole forward + backward (several thousand launches) is captured once per input shape
-        and replayed from static input buffers."""
+        With use_cuda_graph the whole forward + backward (several thousand launches) is captured once per (input shapes,
+        mode) and replayed from static input buffers."""
+        if uncond:
+            context, bbox = self._uncond_context(x_start.shape[0]), None
         for a in (x_start, noise, context, t) + ((bbox,) if bbox is not None else ()):
             if not a.is_cuda:
                 raise RuntimeError("UNetTrainer needs CUDA tensors (no CPU fallback)")
         if bbox is not None and self.bbox_embedder is None:
             raise RuntimeError("forward_backward(bbox=...) needs UNetTrainer(bbox_embedder=...)")
         if not self.use_cuda_graph:
-            return self._forward_backward(x_start, t, noise, context, bbox)
-        key = (tuple(x_start.shape), tuple(noise.shape), tuple(context.shape), None if bbox is None else tuple(bbox.shape))
-        if self._fb_graph is None or self._fb_key != key:
-            self._static = dict(x=x_start.detach().float().contiguous().clone(), t=t.to(torch.int64).contiguous().clone(),
-                                noise=noise.detach().float().contiguous().clone(),
-                                ctx=context.detach().float().contiguous().clone(),
-                                bbox=None if bbox is None else bbox.detach().float().contiguous().clone())
-            st = self._static
+            return self._forward_backward(x_start, t, noise, context, bbox, uncond)
+        key = (tuple(x_start.shape), tuple(noise.shape), tuple(context.shape), None if bbox is None else tuple(bbox.shape),
+               bool(uncond))
+        entry = self._fb_graphs.get(key)
+        if entry is None:
+            st = dict(x=x_start.detach().float().contiguous().clone(), t=t.to(torch.int64).contiguous().clone(),
+                      noise=noise.detach().float().contiguous().clone(), ctx=context.detach().float().contiguous().clone(),
+                      bbox=None if bbox is None else bbox.detach().float().contiguous().clone())
             side = torch.cuda.Stream()
             side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(side):                # warm-up: workspaces, cudaFuncSetAttribute, allocator pools
-                self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"])
+                self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"], uncond)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
             g = torch.cuda.CUDAGraph()
             before = ops.Stats.launches
             with torch.cuda.graph(g):
-                self._static_loss = self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"])
-            self._fb_kernels = ops.Stats.launches - before
-            self._fb_graph, self._fb_key = g, key
-        st = self._static
+                loss = self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"], uncond)
+            entry = dict(graph=g, static=st, loss=loss, d_context=self.d_context, kernels=ops.Stats.launches - before)
+            self._fb_graphs[key] = entry
+        st = entry["static"]
         st["x"].copy_(x_start)
         st["t"].copy_(t)
         st["noise"].copy_(noise)
         st["ctx"].copy_(context)
         if bbox is not None:
             st["bbox"].copy_(bbox)
-        self._fb_graph.replay()
-        ops.Stats.launches += self._fb_kernels
-        return self._static_loss
+        entry["graph"].replay()
+        ops.Stats.launches += entry["kernels"]
+        self.d_context = entry["d_context"]
+        return entry["loss"]
+
+    def _uncond_context(self, R):
+        """[learnable_vector, bbox_uncond_vector] repeated for every row (ddpm.py:1053-1056)."""
+        ldm = self.ldm
+        ctx = torch.empty((R, 2, ldm.learnable_vector.shape[-1]), device=self.device, dtype=torch.float32)
+        ctx[:, 0].copy_(ldm.learnable_vector.detach().reshape(1, -1).expand(R, -1))
+        ctx[:, 1].copy_(ldm.bbox_uncond_vector.detach().reshape(1, -1).expand(R, -1))
+        return ctx
 
     # ------------------------------------------------------------------ trainable bbox_embedder (modules.py:181-213)
     def _bbox_forward(self, bbox):
@@ -618,7 +633,7 @@ class UNetTrainer:
             dx = ops.gemm(ops.cast_bf16(d), pk[i][1], out_dtype=torch.float32)    # d @ W_i
             d = tops.silu_bwd(pre[i], dx) if pre[i] is not None else dx
 
-    def _forward_backward(self, x_start, t, noise, context, bbox=None):
+    def _forward_backward(self, x_start, t, noise, context, bbox=None, uncond=False):
         u, ldm = self.unet, self.ldm
         p = u._p
         R = x_start.shape[0]
@@ -670,6 +685,8 @@ class UNetTrainer:
             dh, _ = self._seq_backward(inputs[i], tapes_in[i - 1], dh, ctx_f32, first=(i == 1))
         if bbox_tape is not None:
             self._bbox_backward(bbox_tape, self.d_context[:, 1])
+        if uncond and "bbox_uncond_vector" in self.flat.offsets:   # every row saw the same vector: sum over rows
+            tops.colsum(self.d_context[:, 1].contiguous(), self.flat.grad("bbox_uncond_vector").reshape(1, -1))
         # gradients w.r.t. the scaled query projections -> w.r.t. to_q.weight
         for gview, sc in self._qscales:
             ops.scale_f32(gview, sc, out=gview)

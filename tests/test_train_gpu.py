@@ -437,7 +437,8 @@ def test_bbox_embedder_training_path():
     bsd = uo.synth_state_dict({k: tuple(v.shape) for k, v in be.state_dict().items()}, seed=40)
     be.load_state_dict(bsd)
     tr = UNetTrainer(ldm, bbox_embedder=be)
-    assert len(tr.flat.names) == 189 + 8 and tr.flat.names[-1].startswith(BBOX_PREFIX)
+    assert len(tr.flat.names) == 189 + 8 + 1 and tr.flat.names[-2].startswith(BBOX_PREFIX) \
+        and tr.flat.names[-1] == "bbox_uncond_vector"
     cu = lambda k: torch.from_numpy(g[k]).cuda()
     bbox = rnd(4, 8, 3, seed=50).clamp(-1, 1)
     loss = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"), bbox=bbox)
@@ -461,3 +462,41 @@ def test_bbox_embedder_training_path():
     tr.step()
     loss2 = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"), bbox=bbox)
     assert torch.isfinite(loss2).item()
+
+
+def test_conditioning_dropout_step_trains_bbox_uncond_vector():
+    """u_cond_percent steps (ddpm.py:1052-1056): context = [learnable_vector, bbox_uncond_vector] for the whole batch;
+    bbox_uncond_vector is in the optimizer's parameter list (ddpm.py:1643-1645) and gets sum_rows d loss / d token_1."""
+    from mobi_b200 import encoders
+    from mobi_b200.ddpm import LatentDiffusion
+    from mobi_b200.training import UNetTrainer
+    from oracle import unet_oracle as uo
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    cfg = uo.tiny_unet_config()
+    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
+    ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg), linear_start=0.00085,
+                          linear_end=0.0120, timesteps=1000, first_stage_key="inpaint", image_size=16, channels=4,
+                          conditioning_key="crossattn", use_camera=True, use_lidar=True)
+    ldm.learnable_vector = torch.nn.Parameter(rnd(1, 1, 32, seed=60).cpu(), requires_grad=False)   # tiny context width
+    ldm.bbox_uncond_vector = torch.nn.Parameter(rnd(1, 1, 32, seed=61).cpu())
+    ldm = ldm.cuda().eval()
+    ldm.model.diffusion_model.load_state_dict(sd, strict=True)
+    be = encoders.BBoxEmbedder(proj_dims=(48, 40, 40, 32)).cuda()
+    tr = UNetTrainer(ldm, bbox_embedder=be)
+    assert "bbox_uncond_vector" in tr.flat.names
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    loss_u = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), uncond=True)
+    torch.cuda.synchronize()
+    gvec = tr.flat.grad("bbox_uncond_vector").reshape(-1)
+    assert torch.isfinite(loss_u).item() and gvec.abs().max().item() > 0
+    assert rel(gvec, tr.d_context[:, 1].sum(0)) < 1e-5
+    # the same step with the uncond context passed explicitly gives the same loss and leaves the vector's gradient at zero
+    ctx = torch.cat([ldm.learnable_vector, ldm.bbox_uncond_vector], 1).repeat(4, 1, 1).contiguous()
+    d_ctx_u = tr.d_context.clone()
+    loss_c = tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), ctx)
+    assert abs(loss_c.item() - loss_u.item()) < 1e-6 and rel(tr.d_context, d_ctx_u) < 1e-5
+    assert tr.flat.grad("bbox_uncond_vector").abs().max().item() == 0.0
+    v0 = ldm.bbox_uncond_vector.detach().clone()
+    tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), uncond=True)
+    tr.step()
+    assert not torch.equal(ldm.bbox_uncond_vector.detach(), v0)          # AdamW moved it (it is a view of the flat buffer)
