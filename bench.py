@@ -23,6 +23,7 @@ sys.path.insert(0, ROOT)
 
 # SURVEY.md §8(d) / BASELINE.md §2: algorithmic FLOPs of the REFERENCE forward per joint sample (2 rows), no CFG
 UNET_FLOPS_PER_JOINT = {64: 2043895808000, 32: 419359047680}
+UNET_FLOPS_PBE_ROW = {64: 835382476800}   # camera-only UNet (pbe.yaml), per row at latent 64
 CFG_SCALE = 5.0
 
 
@@ -37,6 +38,9 @@ def parse():
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--pbe", action="store_true",
+                    help="BASELINE.json config 4: camera-only Paint-by-Example UNet (pbe.yaml), 1 row per sample, 1 context "
+                         "token, camera VAE decode only (implies --no-train: that model has no adapters to train)")
     ap.add_argument("--no-train", action="store_true", help="skip the training-step (config 5) measurement")
     ap.add_argument("--train-samples-per-gpu", type=int, default=2)  # configs/mobi_nusc_512.yaml:11 batch_size
     return ap.parse_args()
@@ -85,6 +89,9 @@ class ClockSampler(threading.Thread):
 
 
 def workload_name(args):
+    if args.pbe:
+        return "pbe.yaml %d-step DDIM + CFG %.1f camera-only inpainting at latent %d, %d samples/GPU" % (
+            args.ddim_steps, CFG_SCALE, args.latent, args.samples_per_gpu)
     return ("mobi_nusc_512" if args.latent == 64 else "mobi_nusc_256") + \
         " %d-step DDIM + CFG %.1f joint camera+lidar inpainting, %d joint samples/GPU" % (
             args.ddim_steps, CFG_SCALE, args.samples_per_gpu)
@@ -201,14 +208,15 @@ def run_native(args):
         dist.init_process_group("nccl", device_id=dev)
     n = args.samples_per_gpu
     latent = args.latent
-    ldm = synth.build_synthetic_ldm(latent=latent, device=dev, seed=0, with_vae=True)
+    rps = 1 if args.pbe else 2                 # UNet rows per sample: camera only, or (camera, lidar)
+    ldm = synth.build_synthetic_ldm(latent=latent, use_lidar=not args.pbe, device=dev, seed=0, with_vae=True)
     sampler = DDIMSampler(ldm, use_cuda_graph=not args.no_graph)
     # the job is n * world joint samples cut into per-rank shards between samples (mobi_b200/sharding.py); every
     # sample's inputs and noise depend on its GLOBAL index only, so results do not depend on the number of GPUs
     lo, hi = sharding.shard_bounds(n * world, world, rank)
-    full = synth.synthetic_inputs(n * world, latent, seed=1)
-    host = {k: sharding.shard_rows(v, world, rank).contiguous() for k, v in full.items()}
-    host["x_T"] = sharding.sample_noise((4, latent, latent), lo, hi, base_seed=1)
+    full = synth.synthetic_inputs(n * world, latent, seed=1, rows_per_sample=rps, n_ctx=1 if args.pbe else 2)
+    host = {k: sharding.shard_rows(v, world, rank, rows_per_sample=rps).contiguous() for k, v in full.items()}
+    host["x_T"] = sharding.sample_noise((4, latent, latent), lo, hi, base_seed=1, rows_per_sample=rps)
     host = {k: v.pin_memory() for k, v in host.items()}
     devin = {k: v.to(dev, non_blocking=True) for k, v in host.items()}
     px = 8 * latent
@@ -216,7 +224,7 @@ def run_native(args):
     host_rng = torch.empty((n, 2, px, px), dtype=torch.float32).pin_memory()
 
     def sample_from(inp):
-        return sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=2 * n, shape=[4, latent, latent],
+        return sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=rps * n, shape=[4, latent, latent],
                               verbose=False, unconditional_guidance_scale=CFG_SCALE,
                               unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
                               test_model_kwargs=dict(inpaint_image=inp["inpaint_image"],
@@ -230,6 +238,9 @@ def run_native(args):
         memory, sampler.sample, decode_sample, decode_first_stage for both modalities, decoded images back to the host."""
         inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
         out = sample_from(inp)
+        if args.pbe:
+            host_img.copy_(ldm.decode_first_stage(out), non_blocking=True)
+            return out
         h_cam, h_lid = ldm.decode_sample(out, out[1::2])
         host_img.copy_(ldm.decode_first_stage(h_cam), non_blocking=True)       # D2H of the results
         host_rng.copy_(ldm.decode_first_stage(h_lid, module_name="lidar_stage_model"), non_blocking=True)
@@ -269,7 +280,7 @@ def run_native(args):
     value = total_samples / (ms / 1e3)
     e2e_value = total_samples / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = host_img.numel() * 4 + host_rng.numel() * 4
+    d2h = host_img.numel() * 4 + (0 if args.pbe else host_rng.numel() * 4)
 
     # ---- roofline of the dominant kernel class (tcgen05 GEMM / implicit conv), timed live with CUDA events on
     # the launching stream over one eager UNet evaluation of the same batch
@@ -283,8 +294,8 @@ def run_native(args):
         "of fallback (1.4 PFLOP/s sustained under the power cap; B200_PROFILING.md; burst 1.59)"
     roofline = None
     if rank == 0:
-        x_in = torch.randn(4 * n, 9, latent, latent, device=dev)
-        t_in = torch.full((4 * n,), 481, device=dev, dtype=torch.long)
+        x_in = torch.randn(2 * rps * n, 9, latent, latent, device=dev)
+        t_in = torch.full((2 * rps * n,), 481, device=dev, dtype=torch.long)
         c_in = torch.cat([devin["uc"], devin["cond"]]).contiguous()
         unet = ldm.model.diffusion_model
         unet(x_in, t_in, context=c_in)
@@ -297,7 +308,8 @@ def run_native(args):
         tc_n = sum(prof[k]["launches"] for k in ("gemm", "conv") if k in prof)
         all_ms = sum(v["ms"] for v in prof.values())
         achieved = tc_fl / (tc_ms / 1e3) / 1e12
-        step_flops = UNET_FLOPS_PER_JOINT.get(latent, 0) * 2 * n   # x2: CFG doubles the rows
+        per_sample = UNET_FLOPS_PBE_ROW.get(latent, 0) if args.pbe else UNET_FLOPS_PER_JOINT.get(latent, 0)
+        step_flops = per_sample * 2 * n   # x2: CFG doubles the rows
         ms_unet = ms / args.steps / max(1, unet_evals // args.steps)
         # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one representative launch: the
         # level-0 conv3x3), next to the algorithmic bytes of that same launch
@@ -322,7 +334,7 @@ def run_native(args):
                     "unet_step_frac_of_peak": step_flops / (ms_unet / 1e3) / 1e12 / peak_tf if step_flops else None}
 
     train = None
-    if not args.no_train:
+    if not args.no_train and not args.pbe:
         try:
             train = measure_train_step(ldm, dev, world, rank, args.train_samples_per_gpu, latent)
         except Exception as exc:  # the headline line must survive a failure of this secondary measurement
@@ -344,7 +356,7 @@ def run_native(args):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16 operands, fp32 accumulate/norms/residuals", "data": "synthetic",
-            "config": {"workload": workload_name(args), "latent": latent, "rows_per_unet_call": 4 * n,
+            "config": {"workload": workload_name(args), "latent": latent, "rows_per_unet_call": 2 * rps * n,
                        "ddim_steps": args.ddim_steps, "cfg_scale": CFG_SCALE, "sharding": "samples/%d GPUs, no collective" % world,
                        "l2": "inputs larger than L2 (2.1 GB bf16 weights streamed per UNet call)",
                        "cuda_graph": not args.no_graph,
