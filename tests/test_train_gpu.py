@@ -229,6 +229,17 @@ def test_conv_dgrad(cin, cout, hw, stride):
     assert rel(dx, x.grad.permute(0, 2, 3, 1)) < 1e-2
 
 
+@pytest.mark.parametrize("M,N,K", [(8192, 320, 320), (16384, 640, 320), (4096, 1280, 1280)])
+def test_wgrad_long_token_dimension(M, N, K):
+    """The real shapes of the adapter weight gradients: few output tiles, thousands of token rows to contract over."""
+    from mobi_b200 import train_ops as tops
+    dy, x = rnd(M, N, seed=1, dtype=torch.bfloat16), rnd(M, K, seed=2, dtype=torch.bfloat16)
+    acc = rnd(N, K, seed=3)
+    ref = acc.double() + dy.double().t() @ x.double()
+    tops.wgrad(dy, x, acc, M=M, n_out=N, k_in=K)
+    assert rel(acc, ref) < 1e-3
+
+
 def test_wgrad_and_bias_grad():
     from mobi_b200 import train_ops as tops
     M, N, K = 512, 64, 128
@@ -258,6 +269,11 @@ def test_batched_gemm(M, N, K, H):
              out_batch_stride=N)
     assert rel(out2[:, 8:].float().reshape(M, H, N).permute(1, 0, 2), ref) < 1e-2
     assert out2[:, :8].abs().max().item() == 0.0
+    # the same batched problem on CTA pairs (cta_group::2)
+    out3 = torch.empty(H, M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(a, b, out=out3, M=M, N=N, K=K, lda=K, ldb=K, ldo=N, batch=H, a_batch_stride=M * K, b_batch_stride=N * K,
+             out_batch_stride=M * N, pair=1)
+    assert rel(out3, ref) < 1e-2
 
 @pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256)])
 def test_attention_backward_composite(B, H, D, T):
