@@ -161,7 +161,7 @@ class LatentDiffusion(nn.Module):
         return getattr(self, module_name).encode(x)
 
     def get_first_stage_encoding(self, encoder_posterior, scale_factor=1, noise=None):
-        """xf-less restatement of ddpm.py:600-608; `noise` overrides the posterior's RNG draw (parity tests)."""
+        """ddpm.py:600-608; `noise` overrides the posterior's RNG draw (parity tests)."""
         from .autoencoder import DiagonalGaussianDistribution
         if isinstance(encoder_posterior, DiagonalGaussianDistribution):
             z = encoder_posterior.sample(noise)

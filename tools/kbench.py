@@ -6,7 +6,6 @@ enough buffers to exceed the 126 MB L2 where the real call would also miss) and 
 Usage: python tools/kbench.py [attn] [gemm] [conv] [ln] [gn]  -> also appends JSON lines to gpurun_out/kbench.jsonl
 """
 import json
-import math
 import os
 import sys
 
