@@ -401,6 +401,27 @@ int mobi_attn_softmax_bwd(const mobi_attn_softmax_bwd_args* args, void* stream);
 int mobi_attn_softmax_bwd_lse(const mobi_attn_softmax_bwd_args* args, const float* lse, const void* o, const void* d_o,
                               int64_t ld, int32_t head_dim, void* stream);
 
+/* Fused form of the two score products + mobi_attn_softmax_bwd for head_dim <= 128 and tokens % 128 == 0: S = q' k^T
+ * and dP = dO v^T are recomputed tile by tile on tcgen05 (two TMEM accumulators per 128 x 128 tile) in a statistics pass
+ * (rowmax, 1 / rowsum, Delta -> stats) and a main pass that writes dS, dS^T, P^T (bf16 [heads, tokens, tokens]) directly:
+ * the f32 T x T tiles never reach HBM.  q, k, v: bf16 [heads, tokens, head_dim] of ONE batch row (q' carries
+ * scale * log2(e)); d_o: bf16 token-major rows of that batch row, head h = columns [h * head_dim, (h + 1) * head_dim), row
+ * stride ld_do.  stats: f32 [heads, tokens, 3].  stats_only = 1 runs the first pass only. */
+typedef struct {
+    const void* q;
+    const void* k;
+    const void* v;
+    const void* d_o;
+    float* stats;
+    void* dS;
+    void* dSt;
+    void* Pt;
+    int32_t heads, tokens, head_dim, stats_only;
+    int64_t ld_do;
+    float dscale;
+} mobi_attn_bwd_tiles_args;
+int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* args, void* stream);
+
 /* cond_adapter_attn (attention.py:237-243, CrossAttention with `keys` <= 4 context tokens) on projected queries, for
  * the training step where to_q/to_k/to_v are trainable and cannot be folded:
  *   forward : o = softmax_j(<q, k_j>) v_j per head                                    (backward = 0)

@@ -130,6 +130,13 @@ class AttnSoftmaxBwdArgs(C.Structure):
     ]
 
 
+class AttnBwdTilesArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("k", _vp), ("v", _vp), ("d_o", _vp), ("stats", _vp), ("dS", _vp), ("dSt", _vp), ("Pt", _vp),
+        ("heads", _i32), ("tokens", _i32), ("head_dim", _i32), ("stats_only", _i32), ("ld_do", _i64), ("dscale", _f32),
+    ]
+
+
 class CtxAttnQspaceArgs(C.Structure):
     _fields_ = [
         ("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("d_o", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp),
@@ -179,6 +186,7 @@ SIGNATURES = {
     "mobi_geglu_bwd": (C.c_int, [_vp, _vp, _vp, _i64, _i64, _vp]),
     "mobi_attn_softmax_bwd": (C.c_int, [C.POINTER(AttnSoftmaxBwdArgs), _vp]),
     "mobi_attn_softmax_bwd_lse": (C.c_int, [C.POINTER(AttnSoftmaxBwdArgs), _vp, _vp, _vp, _i64, _i32, _vp]),
+    "mobi_attn_bwd_tiles": (C.c_int, [C.POINTER(AttnBwdTilesArgs), _vp]),
     "mobi_ctx_attn_qspace": (C.c_int, [C.POINTER(CtxAttnQspaceArgs), _vp]),
     "mobi_colsum": (C.c_int, [_vp, _i32, _i64, _i32, _i64, _i64, _vp, _vp]),
     "mobi_wgrad_small": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i64, _i64, _i64, _vp]),

@@ -269,17 +269,18 @@ class UNetTrainer:
         vt = tops.transpose(v, rows=T, cols=D, batch=B * H, in_batch_stride=T * D)
         return ops.attention(q, k, vt, B, H, D, T, T), None
 
-    def _attn_ws(self, H, T):
-        ws = self._ws.get((H, T))
+    def _attn_ws(self, H, T, fused=False):
+        ws = self._ws.get((H, T, fused))
         if ws is None:
             dev = self.device
-            ws = dict(S=torch.empty((H, T, T), device=dev, dtype=torch.float32),
-                      dP=torch.empty((H, T, T), device=dev, dtype=torch.float32),
+            f32_tiles = (0,) if fused else (H, T, T)      # the fused score-tile kernel never materialises S / dP
+            ws = dict(S=torch.empty(f32_tiles, device=dev, dtype=torch.float32),
+                      dP=torch.empty(f32_tiles, device=dev, dtype=torch.float32),
                       dS=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
                       dSt=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
                       Pt=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
                       stats=torch.empty((3 * H * T,), device=dev, dtype=torch.float32))
-            self._ws[(H, T)] = ws
+            self._ws[(H, T, fused)] = ws
         return ws
 
     def _attn_bwd(self, q, k, v, do, B, H, D, T, dq_out, dq_col, dkv_out, dk_col, dv_col, o=None, lse=None):
@@ -296,17 +297,26 @@ class UNetTrainer:
         for b in range(B):
             tops.transpose(do[b * T:(b + 1) * T], rows=T, cols=D, ld_in=C, batch=H, in_batch_stride=D,
                            out=doT[b * H:(b + 1) * H])
-        ws = self._attn_ws(H, T)
+        fused = D <= 128 and T % 128 == 0 and not (lse is not None and getattr(self, "lse_backward", False))
+        ws = self._attn_ws(H, T, fused)
         f32 = torch.float32
         for b in range(B):
             rows = slice(b * T, (b + 1) * T)
             hs = slice(b * H, (b + 1) * H)
             bat = dict(batch=H)
-            ops.gemm(q[hs], k[hs], out=ws["S"], out_dtype=f32, M=T, N=T, K=D, lda=D, ldb=D, ldo=T, a_batch_stride=TD,
-                     b_batch_stride=TD, out_batch_stride=TT, **bat)
-            ops.gemm(do[rows], v[hs], out=ws["dP"], out_dtype=f32, M=T, N=T, K=D, lda=C, ldb=D, ldo=T, a_batch_stride=D,
-                     b_batch_stride=TD, out_batch_stride=TT, **bat)
-            if lse is not None:
+            if fused:
+                # S and dP are recomputed on tcgen05 inside the statistics pass and the main pass: the f32 score tiles
+                # never reach HBM, only dS, dS^T and P^T (bf16) are written
+                tops.attn_bwd_tiles(q[hs], k[hs], v[hs], do[rows], ws["stats"], ws["dS"], ws["dSt"], ws["Pt"], heads=H,
+                                    tokens=T, head_dim=D, ld_do=C, dscale=tops.LN2)
+            else:
+                ops.gemm(q[hs], k[hs], out=ws["S"], out_dtype=f32, M=T, N=T, K=D, lda=D, ldb=D, ldo=T, a_batch_stride=TD,
+                         b_batch_stride=TD, out_batch_stride=TT, **bat)
+                ops.gemm(do[rows], v[hs], out=ws["dP"], out_dtype=f32, M=T, N=T, K=D, lda=C, ldb=D, ldo=T,
+                         a_batch_stride=D, b_batch_stride=TD, out_batch_stride=TT, **bat)
+            if fused:
+                pass
+            elif lse is not None:
                 tops.attn_softmax_bwd_lse(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2,
                                           lse[hs], o[rows], do[rows], C, D, batch=H)
             else:

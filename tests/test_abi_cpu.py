@@ -44,7 +44,8 @@ def test_ctypes_struct_sizes_match_the_header(tmp_path):
              ("mobi_ctx_attn_args", L.CtxAttnArgs), ("mobi_sampler_args", L.SamplerArgs),
              ("mobi_assemble_args", L.AssembleArgs), ("mobi_layernorm_bwd_args", L.LayerNormBwdArgs),
              ("mobi_groupnorm_bwd_args", L.GroupNormBwdArgs), ("mobi_attn_softmax_bwd_args", L.AttnSoftmaxBwdArgs),
-             ("mobi_ctx_attn_qspace_args", L.CtxAttnQspaceArgs), ("mobi_latent_input_args", L.LatentInputArgs)]
+             ("mobi_ctx_attn_qspace_args", L.CtxAttnQspaceArgs), ("mobi_latent_input_args", L.LatentInputArgs),
+             ("mobi_attn_bwd_tiles_args", L.AttnBwdTilesArgs)]
     prog = '#include <stdio.h>\n#include "%s"\nint main(void){' % HEADER
     prog += "".join('printf("%%zu\\n", sizeof(%s));' % c for c, _ in pairs) + "return 0;}\n"
     src = tmp_path / "sizes.c"

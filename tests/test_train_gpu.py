@@ -275,7 +275,7 @@ def test_batched_gemm(M, N, K, H):
              out_batch_stride=M * N, pair=1)
     assert rel(out3, ref) < 1e-2
 
-@pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256)])
+@pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256), (2, 8, 80, 1024), (1, 2, 128, 384)])
 def test_attention_backward_composite(B, H, D, T):
     """The five products + softmax backward per (row, head) against autograd of softmax(q k^T * scale) v."""
     import math
@@ -300,6 +300,7 @@ def test_attention_backward_composite(B, H, D, T):
     lse_ref = torch.logsumexp(qr.detach() @ kr.detach().transpose(-1, -2) * math.log(2.0), -1) / math.log(2.0)
     assert (lse - lse_ref).abs().max().item() < 2e-2
     for kw in (dict(), dict(o=o_fwd.reshape(B * T, C), lse=lse)):
+        tr.lse_backward = bool(kw)   # (a) runs the fused score-tile kernel when T % 128 == 0, else the materialised tiles
         dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
         tr._attn_bwd(qb, kb, vb, do, B, H, D, T, dqkv, 0, dqkv, C, 2 * C, **kw)
         assert rel(dqkv[:, :C].float(), heads(qr.grad)) < 2e-2
