@@ -22,7 +22,8 @@ namespace mobi {
 
 constexpr int AB_BM = 128, AB_BN = 128, AB_BK = 64;
 constexpr int AB_TILE = AB_BM * AB_BK * 2;  // 16 KB: one 128 x 64 bf16 tile
-constexpr int AB_THREADS = 320;
+constexpr int AB_EPI_WARPS = 16;                       // 4 per TMEM lane group: each takes 32 of the 128 key columns
+constexpr int AB_THREADS = 64 + 32 * AB_EPI_WARPS;
 constexpr int AB_MAX_NKB = 2;  // head_dim <= 128
 
 struct AttnBwdParams {
@@ -35,7 +36,7 @@ struct AttnBwdParams {
     int stages;
 };
 
-__device__ __forceinline__ void ab_bar_sync_epilogue() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void ab_bar_sync_epilogue() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <bool STATS>
 __global__ void __launch_bounds__(AB_THREADS, 1)
@@ -50,8 +51,8 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     uint8_t* sdO = sQ + nkb * AB_TILE;                   // nkb tiles
     uint8_t* sK = sdO + nkb * AB_TILE;                   // STAGES x nkb tiles
     uint8_t* sV = sK + STAGES * nkb * AB_TILE;           // STAGES x nkb tiles
-    float* part = reinterpret_cast<float*>(sV + STAGES * nkb * AB_TILE);  // [2][128][3] statistics of the column halves
-    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 2 * 128 * 3);
+    float* part = reinterpret_cast<float*>(sV + STAGES * nkb * AB_TILE);  // [4][128][3] statistics of the column quarters
+    uint64_t* bars = reinterpret_cast<uint64_t*>(part + 4 * 128 * 3);
     uint64_t* full_bar = bars;                // STAGES
     uint64_t* empty_bar = full_bar + 8;       // STAGES
     uint64_t* q_full = empty_bar + 8;         // 1
@@ -79,7 +80,7 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             mbar_init(q_empty, 1);
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tfull_bar[s], 1);
-                mbar_init(&tempty_bar[s], 8);
+                mbar_init(&tempty_bar[s], AB_EPI_WARPS);
             }
             fence_barrier_init();
         }
@@ -151,9 +152,9 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             }
         }
     } else {
-        // ---------------- epilogue warps 2..9: TMEM lane group = warp % 4, column half = (warp - 2) / 4
+        // ---------------- epilogue warps 2..17: TMEM lane group = warp % 4, column quarter = (warp - 2) / 4
         const int lg = warp & 3;
-        const int half = (warp - 2) >> 2;
+        const int half = (warp - 2) >> 2;  // 0..3: key columns [32 * half, 32 * half + 32) of the tile
         const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
         const int row_in_tile = lg * 32 + lane;
         uint32_t lt = 0;
@@ -172,9 +173,8 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 const uint32_t as = lt & 1;
                 mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
                 tc_fence_after();
-#pragma unroll 1
-                for (int c = 0; c < 2; ++c) {
-                    const int col0 = half * 64 + c * 32;  // first key column of this chunk inside the tile
+                {
+                    const int col0 = half * 32;  // first key column of this warp's chunk inside the tile
                     uint32_t s[32], d[32];
                     tmem_ld32(tmem_base + as * 256 + lane_addr + col0, s);
                     tmem_ld32(tmem_base + as * 256 + AB_BN + lane_addr + col0, d);
@@ -240,11 +240,17 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 mine[2] = acc;
                 ab_bar_sync_epilogue();
                 if (half == 0) {
-                    const float* oth = part + (128 + row_in_tile) * 3;
-                    const float M = fmaxf(m, oth[0]);
-                    const float r0 = exp2f(m - M), r1 = exp2f(oth[0] - M);
-                    const float L = l * r0 + oth[1] * r1;
-                    const float A = acc * r0 + oth[2] * r1;
+                    float M = m;
+#pragma unroll
+                    for (int h = 1; h < 4; ++h) M = fmaxf(M, part[(h * 128 + row_in_tile) * 3]);
+                    float L = l * exp2f(m - M), A = acc * exp2f(m - M);
+#pragma unroll
+                    for (int h = 1; h < 4; ++h) {
+                        const float* oth = part + (h * 128 + row_in_tile) * 3;
+                        const float r = exp2f(oth[0] - M);
+                        L += oth[1] * r;
+                        A += oth[2] * r;
+                    }
                     float* st = p.stats + ((long long)z * p.T + row) * 3;
                     st[0] = M;
                     st[1] = 1.0f / L;
@@ -285,7 +291,7 @@ extern "C" int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* a, void* stre
     p.dS = reinterpret_cast<__nv_bfloat16*>(a->dS);
     p.dSt = reinterpret_cast<__nv_bfloat16*>(a->dSt);
     p.Pt = reinterpret_cast<__nv_bfloat16*>(a->Pt);
-    const long long fixed = 2ll * p.nkb * AB_TILE + 2 * 128 * 3 * 4 + 512 + 1024;
+    const long long fixed = 2ll * p.nkb * AB_TILE + 4 * 128 * 3 * 4 + 512 + 1024;
     const long long per_stage = 2ll * p.nkb * AB_TILE;
     long long stages = (227 * 1024 - fixed) / per_stage;
     if (stages > 6) stages = 6;
