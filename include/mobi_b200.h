@@ -404,9 +404,10 @@ int mobi_attn_softmax_bwd_lse(const mobi_attn_softmax_bwd_args* args, const floa
 /* Fused form of the two score products + mobi_attn_softmax_bwd for head_dim <= 128 and tokens % 128 == 0: S = q' k^T
  * and dP = dO v^T are recomputed tile by tile on tcgen05 (two TMEM accumulators per 128 x 128 tile) in a statistics pass
  * (rowmax, 1 / rowsum, Delta -> stats) and a main pass that writes dS, dS^T, P^T (bf16 [heads, tokens, tokens]) directly:
- * the f32 T x T tiles never reach HBM.  q, k, v: bf16 [heads, tokens, head_dim] of ONE batch row (q' carries
- * scale * log2(e)); d_o: bf16 token-major rows of that batch row, head h = columns [h * head_dim, (h + 1) * head_dim), row
- * stride ld_do.  stats: f32 [heads, tokens, 3].  stats_only = 1 runs the first pass only. */
+ * the f32 T x T tiles never reach HBM.  q, k, v: bf16 [batch_rows * heads, tokens, head_dim] (q' carries
+ * scale * log2(e)); d_o: bf16 token-major [batch_rows * tokens, ld_do], head h = columns [h * head_dim, (h + 1) * head_dim).
+ * stats: f32 [batch_rows * heads, tokens, 3]; dS, dSt, Pt: bf16 [batch_rows * heads, tokens, tokens].
+ * stats_only = 1 runs the first pass only; batch_rows = 0 means 1. */
 typedef struct {
     const void* q;
     const void* k;
@@ -419,6 +420,7 @@ typedef struct {
     int32_t heads, tokens, head_dim, stats_only;
     int64_t ld_do;
     float dscale;
+    int32_t batch_rows;
 } mobi_attn_bwd_tiles_args;
 int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* args, void* stream);
 

@@ -134,6 +134,7 @@ class AttnBwdTilesArgs(C.Structure):
     _fields_ = [
         ("q", _vp), ("k", _vp), ("v", _vp), ("d_o", _vp), ("stats", _vp), ("dS", _vp), ("dSt", _vp), ("Pt", _vp),
         ("heads", _i32), ("tokens", _i32), ("head_dim", _i32), ("stats_only", _i32), ("ld_do", _i64), ("dscale", _f32),
+        ("batch_rows", _i32),
     ]
 
 

@@ -27,7 +27,7 @@ constexpr int AB_THREADS = 64 + 32 * AB_EPI_WARPS;
 constexpr int AB_MAX_NKB = 2;  // head_dim <= 128
 
 struct AttnBwdParams {
-    int T, D, nkb, Z;
+    int T, D, nkb, Z, H;   // Z = batch rows x H heads
     float dscale;
     float* stats;          // [Z, T, 3]
     __nv_bfloat16* dS;     // [Z, T, T]
@@ -103,7 +103,7 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 mbar_arrive_expect_tx(q_full, 2 * nkb * AB_TILE);
                 for (int c = 0; c < nkb; ++c) {
                     tma_load_3d(sQ + c * AB_TILE, &tmQ, q_full, c * AB_BK, m_tile * AB_BM, z);
-                    tma_load_3d(sdO + c * AB_TILE, &tmdO, q_full, c * AB_BK, m_tile * AB_BM, z);
+                    tma_load_4d(sdO + c * AB_TILE, &tmdO, q_full, c * AB_BK, m_tile * AB_BM, z % p.H, z / p.H);
                 }
                 for (int n = 0; n < n_tiles; ++n, ++it) {
                     const int s = it % STAGES;
@@ -285,7 +285,8 @@ extern "C" int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* a, void* stre
     p.T = a->tokens;
     p.D = a->head_dim;
     p.nkb = (a->head_dim + 63) / 64;
-    p.Z = a->heads;
+    p.Z = a->heads * (a->batch_rows > 0 ? a->batch_rows : 1);
+    p.H = a->heads;
     p.dscale = a->dscale;
     p.stats = a->stats;
     p.dS = reinterpret_cast<__nv_bfloat16*>(a->dS);
@@ -299,7 +300,7 @@ extern "C" int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* a, void* stre
     p.stages = (int)stages;
     const long long smem = fixed + stages * per_stage;
     CUtensorMap tmQ, tmK, tmV, tmdO;
-    const uint64_t T = a->tokens, D = a->head_dim, Z = a->heads;
+    const uint64_t T = a->tokens, D = a->head_dim, Z = (uint64_t)p.Z, Hh = a->heads;
     {
         uint64_t dims[3] = {D, T, Z};
         uint64_t strides[2] = {D * 2, T * D * 2};
@@ -309,10 +310,11 @@ extern "C" int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* a, void* stre
         if (make_tensor_map_bf16(&tmV, a->v, 3, dims, strides, box)) return 1;
     }
     {
-        uint64_t dims[3] = {D, T, Z};
-        uint64_t strides[2] = {(uint64_t)a->ld_do * 2, D * 2};  // token-major dO: head z = columns [z*D, (z+1)*D)
-        uint32_t box[3] = {AB_BK, AB_BM, 1};
-        if (make_tensor_map_bf16(&tmdO, a->d_o, 3, dims, strides, box)) return 1;
+        // token-major dO [batch_rows * T, ld_do]: head h of batch row b = rows [b*T, (b+1)*T), columns [h*D, (h+1)*D)
+        uint64_t dims[4] = {D, T, Hh, Z / Hh};
+        uint64_t strides[3] = {(uint64_t)a->ld_do * 2, D * 2, T * (uint64_t)a->ld_do * 2};
+        uint32_t box[4] = {AB_BK, AB_BM, 1, 1};
+        if (make_tensor_map_bf16(&tmdO, a->d_o, 4, dims, strides, box)) return 1;
     }
     static bool configured = false;
     if (!configured) {
@@ -320,7 +322,7 @@ extern "C" int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* a, void* stre
         MOBI_CUDA(cudaFuncSetAttribute(attn_bwd_tiles_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
         configured = true;
     }
-    const long long items = (long long)a->heads * (a->tokens / 128);
+    const long long items = (long long)p.Z * (a->tokens / 128);
     const int grid = (int)(items < sm_count() ? items : sm_count());
     attn_bwd_tiles_kernel<true><<<grid, AB_THREADS, smem, stream>>>(tmQ, tmK, tmdO, tmV, p);
     MOBI_CUDA(cudaGetLastError());

@@ -99,14 +99,15 @@ def attn_softmax_bwd_lse(S, dP, dS, dSt, Pt, stats, tq, tk, dscale, lse, o, d_o,
                                                    L.stream()), "attn_softmax_bwd_lse")
 
 
-def attn_bwd_tiles(q, k, v, d_o, stats, dS, dSt, Pt, *, heads, tokens, head_dim, ld_do, dscale):
-    """Fused S / dP recompute + softmax backward for the heads of one batch row (see mobi_attn_bwd_tiles)."""
+def attn_bwd_tiles(q, k, v, d_o, stats, dS, dSt, Pt, *, heads, tokens, head_dim, ld_do, dscale, batch_rows=1):
+    """Fused S / dP recompute + softmax backward for all heads of `batch_rows` batch rows (see mobi_attn_bwd_tiles)."""
     a = L.AttnBwdTilesArgs()
     a.q, a.k, a.v, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
     a.stats, a.dS, a.dSt, a.Pt = stats.data_ptr(), dS.data_ptr(), dSt.data_ptr(), Pt.data_ptr()
     a.heads, a.tokens, a.head_dim, a.stats_only, a.ld_do, a.dscale = heads, tokens, head_dim, 0, ld_do, dscale
-    fl = 2 * 2 * 2.0 * heads * tokens * tokens * head_dim      # S and dP, each computed in both passes
-    with _timed("attn_bwd_tiles", fl, nbytes=heads * tokens * tokens * 6.0, kernels=2):
+    a.batch_rows = batch_rows
+    fl = 2 * 2 * 2.0 * batch_rows * heads * tokens * tokens * head_dim      # S and dP, each computed in both passes
+    with _timed("attn_bwd_tiles", fl, nbytes=batch_rows * heads * tokens * tokens * 6.0, kernels=2):
         L.check(L.load().mobi_attn_bwd_tiles(C.byref(a), L.stream()), "attn_bwd_tiles")
 
 

@@ -298,17 +298,21 @@ class UNetTrainer:
             tops.transpose(do[b * T:(b + 1) * T], rows=T, cols=D, ld_in=C, batch=H, in_batch_stride=D,
                            out=doT[b * H:(b + 1) * H])
         fused = D <= 128 and T % 128 == 0 and not (lse is not None and getattr(self, "lse_backward", False))
-        ws = self._attn_ws(H, T, fused)
+        # fused: the score tiles of ALL batch rows come from one launch pair (more (head, query-tile) items per wave)
+        ws_all = self._attn_ws(B * H, T, True) if fused else None
+        ws = ws_all if fused else self._attn_ws(H, T, False)
         f32 = torch.float32
+        if fused:
+            # S and dP are recomputed on tcgen05 inside the statistics pass and the main pass: the f32 score tiles never
+            # reach HBM, only dS, dS^T and P^T (bf16) are written
+            tops.attn_bwd_tiles(q, k, v, do, ws_all["stats"], ws_all["dS"], ws_all["dSt"], ws_all["Pt"], heads=H, tokens=T,
+                                head_dim=D, ld_do=C, dscale=tops.LN2, batch_rows=B)
         for b in range(B):
             rows = slice(b * T, (b + 1) * T)
             hs = slice(b * H, (b + 1) * H)
             bat = dict(batch=H)
             if fused:
-                # S and dP are recomputed on tcgen05 inside the statistics pass and the main pass: the f32 score tiles
-                # never reach HBM, only dS, dS^T and P^T (bf16) are written
-                tops.attn_bwd_tiles(q[hs], k[hs], v[hs], do[rows], ws["stats"], ws["dS"], ws["dSt"], ws["Pt"], heads=H,
-                                    tokens=T, head_dim=D, ld_do=C, dscale=tops.LN2)
+                ws = {kk: (vv[hs] if kk != "stats" else vv) for kk, vv in ws_all.items()}
             else:
                 ops.gemm(q[hs], k[hs], out=ws["S"], out_dtype=f32, M=T, N=T, K=D, lda=D, ldb=D, ldo=T, a_batch_stride=TD,
                          b_batch_stride=TD, out_batch_stride=TT, **bat)
