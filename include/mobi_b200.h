@@ -496,6 +496,95 @@ int mobi_assemble_latent_input(const mobi_latent_input_args* args, void* stream)
  * x = (x * W - left) / S ; y += pad / S. */
 int mobi_bbox_renorm(float* bbox, int64_t n_points, int32_t W, int32_t left, int32_t S, int32_t pad, void* stream);
 
+/* ---- Range-view post-processing after the lidar decode --------------------------------------
+ * The reference runs this on the host, one sample at a time, in NumPy / cv2 / numba
+ * (scripts/inference_test_bench.py:567-629); these entry points keep it in HBM. */
+enum {
+    MOBI_RANGE_MAP_NONE = 0,
+    MOBI_RANGE_MAP_DEPTH_NORM = 1,   /* depth_normalization          ldm/data/utils.py:537-557 */
+    MOBI_RANGE_MAP_DEPTH_UNNORM = 2, /* inverse_depth_normalization  ldm/data/utils.py:560-580 */
+    MOBI_RANGE_MAP_INT_UNNORM = 3    /* clamp(-0.5 * log(1 - (x + 1) / 2) - 1, -1, 1)  ldm/models/diffusion/ddpm.py:1541 */
+};
+/* out[b, i] = map(in[b, i]) for f32 [batch, n] (strides in elements, 0 = n; in == out allowed).  The depth maps take the
+ * per-sample min_d / max_d [batch] of the object (nuscenes.py:439-442) and alpha (range_object_norm_scale);
+ * clamp_input applies torch.clamp(x, -1, 1) first (ddpm.py:1504). */
+typedef struct {
+    const float* in;
+    float* out;
+    const float* min_d;
+    const float* max_d;
+    int64_t n, in_stride, out_stride;
+    int32_t batch, mode, clamp_input;
+    double alpha; /* a Python float in the reference: 2 * alpha, alpha - 1, 1 - alpha are formed in double, then cast */
+} mobi_range_map_args;
+int mobi_range_map(const mobi_range_map_args* args, void* stream);
+
+/* LidarConverter.undo_default_transforms batched over samples as postprocess_range_depth_int does
+ * (ldm/data/lidar_converter.py:436-485, 230-287; ldm/data/utils.py:471-505), for one or two channels (depth, intensity):
+ * the [crop_h, crop_w] crop is resized to [H, width_crop[b]] — F.avg_pool2d when both sizes divide, else cv2's INTER_NEAREST
+ * rule — and pasted into a copy of the original [H, W] sweep at column crop_left[b] % W, wrapping the 360 degree seam.
+ * map[c] fuses one of the maps above into the crop load (what ddpm.py:1536, 1541 do to the decoded image before);
+ * zero_context replaces the original DEPTH by -1 (utils.py:486-487).  crop_left / width_crop: int64 [batch] on the device. */
+typedef struct {
+    const float* crop[2];
+    const float* orig[2];
+    float* out[2];
+    const float* min_d;
+    const float* max_d;
+    const int64_t* crop_left;
+    const int64_t* width_crop;
+    int64_t crop_batch_stride, orig_batch_stride, out_batch_stride; /* elements; 0 = dense */
+    int32_t batch, channels, crop_h, crop_w, H, W, zero_context, clamp_input;
+    int32_t map[2];
+    double alpha;
+} mobi_range_undo_args;
+int mobi_range_undo_transforms(const mobi_range_undo_args* args, void* stream);
+
+/* LidarConverter.range2pcd (ldm/data/lidar_converter.py:122-176) for [batch, H, W] sweeps at the base size:
+ * metres = (depth + 1) / 2 * depth_max; x = cos(yaw) cos(pitch) m, y = -sin(yaw) cos(pitch) m, z = sin(pitch) m; points
+ * with depth_min < m < depth_max are kept IN PIXEL ORDER.  points: f32 [batch, H*W, point_stride] (padded; [3] = label
+ * when point_stride > 3, [4] = beam index H-1-row when > 4), index (optional): flat pixel of each kept point
+ * (the `label = arange` use of inference_test_bench.py:587-588), count: int32 [batch]. */
+typedef struct {
+    const float* depth;
+    const float* pitch;
+    const float* yaw;
+    const float* label; /* optional f32 [batch, H*W] */
+    float* points;
+    int32_t* index; /* optional */
+    int32_t* count;
+    int32_t batch, H, W, point_stride;
+    float depth_min, depth_max;
+} mobi_range2pcd_args;
+int mobi_range2pcd(const mobi_range2pcd_args* args, void* stream);
+
+/* The save_samples sequence of scripts/inference_test_bench.py:580-629 for a batch in one launch: cloud of the generated
+ * sweep -> points inside the edited box (points_in_bbox_corners, one box [8, 3] per sample) -> pred_mask; paste where
+ * pred_mask | gt_mask; range_pred [batch, 4, H*W] = (depth, intensity, pitch, yaw); edited cloud
+ * points [batch, H*W, 5] = (x, y, z, intensity, beam index) in pixel order with count [batch]. */
+typedef struct {
+    const float* sample_depth;
+    const float* sample_int;
+    const float* depth_orig;
+    const float* int_orig;
+    const float* gt_mask; /* f32, non-zero = object (range_instance_mask_orig) */
+    const float* bbox;    /* f32 [batch, 8, 3] */
+    const float* pitch;
+    const float* yaw;
+    float* range_pred;
+    uint8_t* pred_mask;
+    float* points;
+    int32_t* count;
+    int32_t batch, H, W;
+    float depth_min, depth_max;
+} mobi_range_composite_args;
+int mobi_range_composite(const mobi_range_composite_args* args, void* stream);
+
+/* points_in_bbox_corners (ldm/data/box_np_ops.py:453-471, 406-427, 712-771): points f32 [n, point_stride >= 3],
+ * corners f32 [m, 8, 3] in center_to_corner_box3d order -> out u8 [n, m] (1 = inside every face). */
+int mobi_points_in_boxes(const float* points, int32_t point_stride, const float* corners, uint8_t* out, int32_t n, int32_t m,
+                         void* stream);
+
 #ifdef __cplusplus
 }
 #endif

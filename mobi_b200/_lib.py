@@ -153,6 +153,37 @@ class LatentInputArgs(C.Structure):
     ]
 
 
+class RangeMapArgs(C.Structure):
+    _fields_ = [
+        ("in_", _vp), ("out", _vp), ("min_d", _vp), ("max_d", _vp), ("n", _i64), ("in_stride", _i64), ("out_stride", _i64),
+        ("batch", _i32), ("mode", _i32), ("clamp_input", _i32), ("alpha", C.c_double),
+    ]
+
+
+class RangeUndoArgs(C.Structure):
+    _fields_ = [
+        ("crop", _vp * 2), ("orig", _vp * 2), ("out", _vp * 2), ("min_d", _vp), ("max_d", _vp), ("crop_left", _vp),
+        ("width_crop", _vp), ("crop_batch_stride", _i64), ("orig_batch_stride", _i64), ("out_batch_stride", _i64),
+        ("batch", _i32), ("channels", _i32), ("crop_h", _i32), ("crop_w", _i32), ("H", _i32), ("W", _i32),
+        ("zero_context", _i32), ("clamp_input", _i32), ("map", _i32 * 2), ("alpha", C.c_double),
+    ]
+
+
+class Range2PcdArgs(C.Structure):
+    _fields_ = [
+        ("depth", _vp), ("pitch", _vp), ("yaw", _vp), ("label", _vp), ("points", _vp), ("index", _vp), ("count", _vp),
+        ("batch", _i32), ("H", _i32), ("W", _i32), ("point_stride", _i32), ("depth_min", _f32), ("depth_max", _f32),
+    ]
+
+
+class RangeCompositeArgs(C.Structure):
+    _fields_ = [
+        ("sample_depth", _vp), ("sample_int", _vp), ("depth_orig", _vp), ("int_orig", _vp), ("gt_mask", _vp), ("bbox", _vp),
+        ("pitch", _vp), ("yaw", _vp), ("range_pred", _vp), ("pred_mask", _vp), ("points", _vp), ("count", _vp),
+        ("batch", _i32), ("H", _i32), ("W", _i32), ("depth_min", _f32), ("depth_max", _f32),
+    ]
+
+
 # name -> (restype, argtypes); also the list of symbols include/mobi_b200.h declares
 SIGNATURES = {
     "mobi_last_error": (C.c_char_p, []),
@@ -200,6 +231,11 @@ SIGNATURES = {
     "mobi_bbox_renorm": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "mobi_silu_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mobi_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "mobi_range_map": (C.c_int, [C.POINTER(RangeMapArgs), _vp]),
+    "mobi_range_undo_transforms": (C.c_int, [C.POINTER(RangeUndoArgs), _vp]),
+    "mobi_range2pcd": (C.c_int, [C.POINTER(Range2PcdArgs), _vp]),
+    "mobi_range_composite": (C.c_int, [C.POINTER(RangeCompositeArgs), _vp]),
+    "mobi_points_in_boxes": (C.c_int, [_vp, _i32, _vp, _vp, _i32, _i32, _vp]),
 }
 
 _lib = None
