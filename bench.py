@@ -190,6 +190,51 @@ def measure_train_step(ldm, dev, world, rank, n, latent, steps=3, warmup=1):
             "nominal_tflops_3x_forward_per_gpu": 3 * fwd / (ms / 1e3) / 1e12 if fwd else None}
 
 
+# ---------------------------------------------------------------------------------------------- range-view post-processing
+def measure_range_post(dev, n, px, cpu_samples=2, iters=20):
+    """decoded lidar image -> un-cropped sweep -> instance mask -> paste -> edited point cloud for `n`
+    samples (mobi_b200.lidar.postprocess_lidar_samples: two launches), against the NumPy port of the reference's per-sample
+    host code (scripts/inference_test_bench.py:567-629) timed on `cpu_samples` of the same inputs."""
+    import numpy as np
+    import torch
+    from mobi_b200 import lidar, synth
+    batch, dec, bbox = synth.synthetic_lidar_batch(n, px=px, device=dev)
+    out = lidar.postprocess_lidar_samples(dec, batch, bbox)
+    torch.cuda.synchronize()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    e = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+    for a, b in e:
+        flush.zero_()                                             # evict the inputs from L2 between timed iterations
+        a.record()
+        out = lidar.postprocess_lidar_samples(dec, batch, bbox)
+        b.record()
+    torch.cuda.synchronize()
+    ms = float(np.median([a.elapsed_time(b) for a, b in e]))
+    P = out["range_pred"].shape[-1] * out["range_pred"].shape[-2]
+    n_pts = out["n_points"].sum().item()
+    algo = n * (2 * px * px * 4 + P * (2 * 4 + 2 * 4 + 2 * 4 + 7 * 4 + 16 + 1)) + n_pts * 20
+    # CPU leg: the oracle port on the first samples of the SAME inputs (this is the one place bench may run oracle/)
+    from oracle import range_oracle as ro
+    k = min(cpu_samples, n)
+    host = {key: v[:k].cpu().numpy() for key, v in batch.items()}
+    inp = dict(range_depth=dec[:k, [0]].cpu().numpy(), range_int=dec[:k, [1]].cpu().numpy(),
+               range_depth_orig=host["range_depth_orig"], range_int_orig=host["range_int_orig"],
+               range_pitch=host["range_pitch"], range_yaw=host["range_yaw"],
+               range_instance_mask_orig=host["range_instance_mask_orig"], crop_left=host["range_shift_left"],
+               width_crop=host["width_crop"], min_depth_obj=host["min_depth_obj"], max_depth_obj=host["max_depth_obj"])
+    t0 = time.perf_counter()
+    want = ro.run_pipeline(inp, bbox[:k].cpu().numpy())
+    cpu_ms = (time.perf_counter() - t0) * 1e3 / k
+    same = bool(np.array_equal(out["pred_instance_mask"][:k].cpu().numpy(), want["pred_instance_mask"].astype(np.uint8))
+                and np.array_equal(out["range_pred"][:k].cpu().numpy(), want["range_pred"].astype(np.float32))
+                and out["n_points"][:k].cpu().tolist() == [len(p) for p in want["pred_points"]])
+    return {"workload": "%d decoded %dx%d range images -> 32x1096 sweeps, instance masks, edited clouds" % (n, px, px),
+            "ms_per_batch": ms, "samples_per_s": n / (ms / 1e3), "gpu_launches_per_batch": 2,
+            "algorithmic_bytes": algo, "achieved_GBps": algo / (ms / 1e3) / 1e9, "l2": "256 MB flush between iterations",
+            "points_per_sample": n_pts / n, "cpu_port_ms_per_sample": cpu_ms, "cpu_port_cores": 1,
+            "matches_cpu_port_bit_exact": same}
+
+
 # ---------------------------------------------------------------------------------------------- native arm
 def run_native(args):
     import torch
@@ -345,6 +390,12 @@ def run_native(args):
         if world > 1:
             dist.destroy_process_group()
         return
+    range_post = None
+    if not args.pbe and not args.no_cpu_baseline:
+        try:
+            range_post = measure_range_post(dev, n, px)
+        except Exception as exc:
+            range_post = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
     cpu_baseline = None
     if not args.no_cpu_baseline and world == 1:
         threads = os.cpu_count() or 1
@@ -365,7 +416,7 @@ def run_native(args):
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": gpu_launches, "unet_evals": unet_evals, "clocks": clock_info,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "train_step": train}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "train_step": train, "range_post": range_post}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -70,6 +70,83 @@ range_map_kernel(const float* __restrict__ in, float* __restrict__ out, const fl
         dst[i] = apply_map(src[i], mode, clamp, mn, mx, k);
 }
 
+// ---- window sums of the avg-pool shrink ---------------------------------------------------------------------------------
+// The per-pixel map of the pooled path with everything that is constant per sample hoisted: for the inverse depth map the
+// three pieces share ONE shape, base + (+-(x + off)) * mul / div, so a pixel costs a few selects and a single division.
+struct PixelMap {
+    int mode, clamp;
+    float mn, mx, a, two_a, a_m_1, one_m_a, span, mn_p1, one_m_mx;
+    static __device__ __forceinline__ PixelMap make(int mode, int clamp, float mn, float mx, const MapConst& k) {
+        PixelMap m;
+        m.mode = mode, m.clamp = clamp, m.mn = mn, m.mx = mx;
+        m.a = k.a, m.two_a = k.two_a, m.a_m_1 = k.a_m_1, m.one_m_a = k.one_m_a;
+        m.span = __fsub_rn(mx, mn), m.mn_p1 = __fadd_rn(mn, 1.f), m.one_m_mx = __fsub_rn(1.f, mx);
+        return m;
+    }
+    template <int MODE>
+    __device__ __forceinline__ float at(float x) const {
+        if (clamp) x = fminf(fmaxf(x, -1.f), 1.f);
+        if (MODE == MOBI_RANGE_MAP_DEPTH_UNNORM) {
+            const bool mid = x >= -a && x <= a, low = x >= -1.f && x < -a, high = x > a && x <= 1.f;
+            if (!(mid || low || high)) return x;
+            float t = __fadd_rn(x, mid ? a : (low ? 1.f : -a));  // x - a == x + (-a) exactly
+            t = low ? -t : t;
+            const float u = __fmul_rn(t, mid ? span : (low ? mn_p1 : one_m_mx));
+            return __fadd_rn(mid ? mn : (low ? -1.f : mx), __fdiv_rn(u, mid ? two_a : (low ? a_m_1 : one_m_a)));
+        }
+        if (MODE == MOBI_RANGE_MAP_DEPTH_NORM) return depth_norm_fwd(x, mn, mx, a, two_a, one_m_a);
+        if (MODE == MOBI_RANGE_MAP_INT_UNNORM) return int_unnorm(x);
+        return x;
+    }
+};
+
+// Sum of a kh x KW window in the order F.avg_pool2d's CPU kernel uses (row by row, one fp32 accumulator).  The adds keep
+// that order; the loads do not depend on them: a row is one or two 16-byte loads and four rows are in flight per thread.
+template <int KW, int MODE>
+__device__ __forceinline__ float window_sum(const float* __restrict__ win, int kh, int cw, int kw_rt, bool vec, const PixelMap& m) {
+    float acc = 0.f;
+    if (KW >= 4 && vec) {
+#pragma unroll 4
+        for (int i = 0; i < kh; ++i) {
+            const float4* row = reinterpret_cast<const float4*>(win + (long long)i * cw);
+#pragma unroll
+            for (int q = 0; q < KW / 4; ++q) {
+                const float4 v = __ldg(row + q);
+                acc = __fadd_rn(acc, m.at<MODE>(v.x));
+                acc = __fadd_rn(acc, m.at<MODE>(v.y));
+                acc = __fadd_rn(acc, m.at<MODE>(v.z));
+                acc = __fadd_rn(acc, m.at<MODE>(v.w));
+            }
+        }
+    } else if (KW == 2 && vec) {
+#pragma unroll 4
+        for (int i = 0; i < kh; ++i) {
+            const float2 v = __ldg(reinterpret_cast<const float2*>(win + (long long)i * cw));
+            acc = __fadd_rn(acc, m.at<MODE>(v.x));
+            acc = __fadd_rn(acc, m.at<MODE>(v.y));
+        }
+    } else {
+        const int kw = KW > 0 ? KW : kw_rt;
+#pragma unroll 4
+        for (int i = 0; i < kh; ++i) {
+            const float* row = win + (long long)i * cw;
+            for (int q = 0; q < kw; ++q) acc = __fadd_rn(acc, m.at<MODE>(__ldg(row + q)));
+        }
+    }
+    return acc;
+}
+
+template <int MODE>
+__device__ __forceinline__ float window_sum_kw(const float* __restrict__ win, int kh, int kw, int cw, bool vec, const PixelMap& m) {
+    switch (kw) {
+        case 1: return window_sum<1, MODE>(win, kh, cw, kw, vec, m);
+        case 2: return window_sum<2, MODE>(win, kh, cw, kw, vec, m);
+        case 4: return window_sum<4, MODE>(win, kh, cw, kw, vec, m);
+        case 8: return window_sum<8, MODE>(win, kh, cw, kw, vec, m);
+        default: return window_sum<0, MODE>(win, kh, cw, kw, false, m);
+    }
+}
+
 // ---- undo_default_transforms ------------------------------------------------------------------------------------------
 struct UndoParams {
     const float* crop[2];
@@ -80,7 +157,7 @@ struct UndoParams {
     const long long* crop_left;
     const long long* width_crop;
     long long crop_bs, orig_bs, out_bs;
-    int channels, ch, cw, H, W, zero_context, clamp;
+    int channels, ch, cw, H, W, zero_context, clamp, vec4;
     int map[2];
     MapConst k;
 };
@@ -108,10 +185,14 @@ __global__ void __launch_bounds__(256) range_undo_kernel(UndoParams p) {
         } else if (p.ch % p.H == 0 && p.cw % wc == 0) {
             // F.avg_pool2d: the window is summed row by row into ONE fp32 accumulator, then divided once
             const int kh = p.ch / p.H, kw = p.cw / wc;
-            float acc = 0.f;
-            for (int i = 0; i < kh; ++i) {
-                const float* row = src + (long long)(y * kh + i) * p.cw + (long long)j * kw;
-                for (int q = 0; q < kw; ++q) acc = __fadd_rn(acc, apply_map(row[q], mode, p.clamp, mn, mx, p.k));
+            const float* win = src + (long long)y * kh * p.cw + (long long)j * kw;
+            const PixelMap m = PixelMap::make(mode, p.clamp, mn, mx, p.k);
+            float acc;
+            switch (mode) {
+                case MOBI_RANGE_MAP_DEPTH_UNNORM: acc = window_sum_kw<MOBI_RANGE_MAP_DEPTH_UNNORM>(win, kh, kw, p.cw, p.vec4, m); break;
+                case MOBI_RANGE_MAP_DEPTH_NORM: acc = window_sum_kw<MOBI_RANGE_MAP_DEPTH_NORM>(win, kh, kw, p.cw, p.vec4, m); break;
+                case MOBI_RANGE_MAP_INT_UNNORM: acc = window_sum_kw<MOBI_RANGE_MAP_INT_UNNORM>(win, kh, kw, p.cw, p.vec4, m); break;
+                default: acc = window_sum_kw<MOBI_RANGE_MAP_NONE>(win, kh, kw, p.cw, p.vec4, m); break;
             }
             v = __fdiv_rn(acc, (float)(kh * kw));
         } else {
@@ -394,6 +475,8 @@ extern "C" int mobi_range_undo_transforms(const mobi_range_undo_args* a, void* s
     p.zero_context = a->zero_context;
     p.clamp = a->clamp_input;
     p.k = map_const(need_minmax ? a->alpha : 0.75);
+    p.vec4 = (p.cw % 4 == 0) && (p.crop_bs % 4 == 0);
+    for (int c = 0; c < a->channels; ++c) p.vec4 = p.vec4 && (reinterpret_cast<uintptr_t>(a->crop[c]) % 16 == 0);
     const unsigned gx = (unsigned)(a->H * ((a->W + 255) / 256));
     range_undo_kernel<<<dim3(gx, (unsigned)a->channels, (unsigned)a->batch), 256, 0, stream>>>(p);
     MOBI_CUDA(cudaGetLastError());

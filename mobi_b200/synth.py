@@ -4,6 +4,8 @@ Random init of the reference architecture is not usable as-is: `zero_module` (op
 attention.py:218-223, 296-300) makes a fresh UNet output exactly 0.  Every matrix/filter is therefore drawn
 N(0, 1/fan_in), biases N(0, 0.1^2), norm scales 1 + N(0, 0.1^2), on the device, from a seeded generator.
 """
+import math
+
 import torch
 
 
@@ -84,3 +86,39 @@ def synthetic_inputs(n_joint, latent, context_dim=768, seed=1, device="cpu", row
     if device != "cpu":
         out = {k: v.to(device) for k, v in out.items()}
     return out
+
+
+def synthetic_lidar_batch(n, px=512, H=32, W=1096, seed=3, device="cuda", obj_range_m=10.0):
+    """Synthetic stand-in for `batch["lidar"]` of the reference dataset (ldm/data/nuscenes.py:470-489), a decoded lidar
+    image [n, 3, px, px] and one edited box per sample [n, 8, 3] (corner order of box_np_ops.center_to_corner_box3d,
+    box_np_ops.py:48-78, 212-237), for the range-view post-processing bench: a box ~obj_range_m ahead whose direction sits
+    in the middle of the crop window, object-normalised depths in the middle of the crop, 15 % holes in the sweep."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    u = lambda *s: torch.rand(*s, generator=g)                                              # noqa: E731
+    beams = torch.tensor([0.0232 * x for x in range(-23, 9)])
+    col = torch.randint(0, W, (n,), generator=g)
+    wc = torch.tensor([64, 128, 256, 512])[torch.arange(n) % 4].clamp(max=px)
+    yaw0 = math.pi * (torch.arange(W, dtype=torch.float32) / W * 2 - 1)
+    pitch = beams.flip(0)[torch.linspace(0, 31, H).round().long()][None, :, None].expand(n, H, W) + (u(n, H, W) - 0.5) * 0.004
+    yaw = yaw0[None, None].expand(n, H, W) + (u(n, H, W) - 0.5) * 0.002
+    d_orig = u(n, H, W) * 1.85 - 0.95
+    d_orig[u(n, H, W) < 0.15] = -1
+    gt = torch.zeros(n, H, W)
+    for b in range(n):
+        gt[b, H // 2:H // 2 + 3, [(int(col[b]) + k) % W for k in range(-2, 3)]] = 1
+    d_obj = 2 * obj_range_m / 54 - 1
+    dec = u(n, 3, px, px) * 2.2 - 1.1                                                       # the clamp has work to do
+    dec[:, 0, :, int(px * 0.3):int(px * 0.7)] = u(n, px, int(px * 0.7) - int(px * 0.3)) * 1.5 - 0.75
+    yc = yaw0[col]
+    center = torch.stack([obj_range_m * torch.cos(yc), -obj_range_m * torch.sin(yc), torch.full((n,), -0.4)], 1)
+    norm = torch.tensor([[0, 0, 0], [0, 0, 1], [0, 1, 1], [0, 1, 0], [1, 0, 0], [1, 0, 1], [1, 1, 1], [1, 1, 0]],
+                        dtype=torch.float32) - 0.5
+    c = norm[None] * torch.tensor([4.6, 2.2, 1.8])
+    s, co = torch.sin(-yc), torch.cos(-yc)
+    z, o = torch.zeros(n), torch.ones(n)
+    rot_t = torch.stack([torch.stack([co, -s, z], 1), torch.stack([s, co, z], 1), torch.stack([z, z, o], 1)], 1)
+    bbox = torch.bmm(c.expand(n, 8, 3).contiguous(), rot_t) + center[:, None]
+    batch = dict(range_depth_orig=d_orig, range_int_orig=u(n, H, W) * 0.6, range_pitch=pitch.contiguous(),
+                 range_yaw=yaw.contiguous(), range_instance_mask_orig=gt, range_shift_left=(col - wc // 2) % W + W,
+                 width_crop=wc, min_depth_obj=torch.full((n,), d_obj - 0.03), max_depth_obj=torch.full((n,), d_obj + 0.03))
+    return ({k: v.to(device) for k, v in batch.items()}, dec.to(device), bbox.to(device))
