@@ -92,6 +92,13 @@ typedef struct {
     int64_t a_batch_stride, b_batch_stride, out_batch_stride;
     /* CTA pairs (tcgen05 cta_group::2, 256-row tiles): 0 = choose, 1 = force on (persistent kernel only), -1 = off. */
     int32_t pair;
+    /* MN-major ("transposed") operands, persistent kernel only, no conv / CTA pairs: with a_mn_major, A is given as the
+     * row-major [K, M] matrix (lda = its row stride >= M) and read as A^T by the tensor core (tcgen05 instruction-descriptor
+     * bit 15, MN-major shared-memory descriptors); with b_mn_major, B is given as row-major [K, N] (ldb >= N; tile_n a
+     * multiple of 64).  out = A_given^T . B_given is exactly the weight gradient dY^T X of a Linear over token rows and
+     * the dK / dV / dQ products of the attention backward, so none of them needs a transposed copy.  With both flags K
+     * may be any positive count (rows beyond K are zero-filled by TMA). */
+    int32_t a_mn_major, b_mn_major;
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);

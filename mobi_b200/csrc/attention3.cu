@@ -45,19 +45,6 @@ __device__ __forceinline__ void a3_ex2_poly2(uint64_t x, float& e0, float& e1) {
     e1 = __uint_as_float(__float_as_uint(p1) + (__float_as_uint(t1) << 23));
 }
 
-// Shared-memory descriptor of an MN-major operand stored as [K rows][64 MN elements = 128 bytes], 128B swizzle:
-// 8 K-rows form a 1024-byte swizzle atom (SBO = stride between atoms along K), the next 64 MN elements live
-// lbo_bytes further on (LBO).
-__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
-    uint64_t d = 0;
-    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
-    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
-    d |= static_cast<uint64_t>(1024 >> 4) << 32;
-    d |= static_cast<uint64_t>(1) << 46;
-    d |= static_cast<uint64_t>(2) << 61;
-    return d;
-}
-
 template <int NT>
 struct A3Cfg {
     static constexpr int ROLE_WARPS = NT <= 3 ? 4 : 8;

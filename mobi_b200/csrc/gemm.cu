@@ -396,6 +396,14 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         uint64_t strides[3] = {(uint64_t)a->C * 2, (uint64_t)a->W * a->C * 2, (uint64_t)a->H * a->W * a->C * 2};
         uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
         if (make_tensor_map_bf16(&tmA, a->A, 4, dims, strides, box)) return 1;
+    } else if (a->a_mn_major) {
+        MOBI_CHECK(a->lda % 8 == 0 && a->lda >= a->M, "mobi_gemm: MN-major A needs lda=%lld >= M and a multiple of 8",
+                   (long long)a->lda);
+        p.num_k_blocks = (int)((K + BK - 1) / BK);
+        uint64_t dims[3] = {(uint64_t)a->M, (uint64_t)K, (uint64_t)p.batch};
+        uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_batch_stride * 2};
+        uint32_t box[3] = {64, BK, 1};
+        if (make_tensor_map_bf16(&tmA, a->A, batched ? 3 : 2, dims, strides, box)) return 1;
     } else {
         MOBI_CHECK(a->K % 8 == 0 && a->lda % 8 == 0, "mobi_gemm: K=%lld and lda=%lld must be multiples of 8",
                    (long long)a->K, (long long)a->lda);
@@ -405,7 +413,14 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         uint32_t box[3] = {BK, BM, 1};
         if (make_tensor_map_bf16(&tmA, a->A, batched ? 3 : 2, dims, strides, box)) return 1;
     }
-    MOBI_CHECK(a->ldb % 8 == 0 && a->ldb >= K, "mobi_gemm: ldb=%lld must be a multiple of 8 and >= K", (long long)a->ldb);
+    p.a_mn = a->a_mn_major ? 1 : 0;
+    p.b_mn = a->b_mn_major ? 1 : 0;
+    if (p.a_mn || p.b_mn) {
+        MOBI_CHECK(!a->conv && a->kernel != 1 && a->pair != 1, "mobi_gemm: MN-major operands need the persistent kernel, no conv, no CTA pairs");
+        MOBI_CHECK(a->tile_n == 0 || !p.b_mn || a->tile_n % 64 == 0, "mobi_gemm: MN-major B needs tile_n %% 64 == 0");
+    }
+    if (p.b_mn) MOBI_CHECK(a->ldb % 8 == 0 && a->ldb >= a->N, "mobi_gemm: MN-major B needs ldb=%lld >= N and a multiple of 8", (long long)a->ldb);
+    else MOBI_CHECK(a->ldb % 8 == 0 && a->ldb >= K, "mobi_gemm: ldb=%lld must be a multiple of 8 and >= K", (long long)a->ldb);
 
     int bn_tile = a->tile_n;
     if (bn_tile == 0) {
@@ -416,6 +431,7 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         double best = 1e30;
         for (int i = 0; i < 4; ++i) {
             const int bnc = cand[i];
+            if (p.b_mn && bnc % 64 != 0) continue;  // MN-major B tiles are made of 64-column boxes
             const long long nt = (a->N + bnc - 1) / bnc;
             const long long ctas = mt * nt;
             const long long waves = (ctas + sm_count() - 1) / sm_count();
@@ -430,12 +446,18 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     }
     p.pair = (a->kernel != 1 && gemm2_supported(p) && gemm2_pair_wanted(p, bn_tile, a->pair)) ? 1 : 0;
     MOBI_CHECK(a->pair != 1 || p.pair, "mobi_gemm: pair = 1 needs a problem the persistent kernel supports");
-    {
+    if (p.b_mn) {
+        uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)K, (uint64_t)p.batch};
+        uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)a->b_batch_stride * 2};
+        uint32_t box[3] = {64, BK, 1};
+        if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
+    } else {
         uint64_t dims[3] = {(uint64_t)K, (uint64_t)a->N, (uint64_t)p.batch};
         uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)a->b_batch_stride * 2};
         uint32_t box[3] = {BK, (uint32_t)(p.pair ? bn_tile / 2 : bn_tile), 1};  // a CTA pair splits the B tile
         if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
     }
+    MOBI_CHECK(!(p.a_mn || p.b_mn) || gemm2_supported(p), "mobi_gemm: MN-major operands are outside the persistent kernel's epilogue here");
     if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);
     MOBI_CHECK(!batched, "mobi_gemm: this batched problem is outside the persistent kernel's epilogue (N %% 4, "
                          "16-byte aligned out / residual / bias)");

@@ -408,7 +408,30 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         continue;
                     }
                     mbar_arrive_expect_tx(&full_bar[s], A_TILE_BYTES + Cfg::B_TILE_BYTES);
-                    if (p.conv) {
+                    if (p.a_mn | p.b_mn) {
+                        // MN-major operands: the tile is [64 k-rows][64 MN elements = 128 B] boxes, one per 64 rows of
+                        // the tile; K-major operands keep their single [rows][64 k] box
+                        if (p.a_mn) {
+                            for (int c = 0; c < BM / 64; ++c) {
+                                if (p.batch > 1) tma_load_3d(dA + c * 8192, &tmA, &full_bar[s], m_tile * BM + c * 64, kb * BK, z);
+                                else tma_load_2d(dA + c * 8192, &tmA, &full_bar[s], m_tile * BM + c * 64, kb * BK);
+                            }
+                        } else if (p.batch > 1) {
+                            tma_load_3d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
+                        } else {
+                            tma_load_2d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
+                        }
+                        if (p.b_mn) {
+                            for (int c = 0; c < BN / 64; ++c) {
+                                if (p.batch > 1) tma_load_3d(dB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK, z);
+                                else tma_load_2d(dB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
+                            }
+                        } else if (p.batch > 1) {
+                            tma_load_3d(dB, &tmB, &full_bar[s], kb * BK, b_row0, z);
+                        } else {
+                            tma_load_2d(dB, &tmB, &full_bar[s], kb * BK, b_row0);
+                        }
+                    } else if (p.conv) {
                         const int tap = kb / p.cblocks;
                         const int cb = kb - tap * p.cblocks;
                         const int kh = tap / p.KW;
@@ -428,7 +451,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     } else if (warp == 1) {
         if (cta_rank == 0 && elect_one()) {
             // ---------------- MMA issuer (the leader CTA's for a pair)
-            constexpr uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN);
+            const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN) | (p.a_mn ? 1u << 15 : 0u) | (p.b_mn ? 1u << 16 : 0u);
             uint32_t it = 0, lt = 0;
             for (int tile = worker; tile < total; tile += n_workers, ++lt) {
                 const uint32_t as = lt & 1;
@@ -444,8 +467,16 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        if (PAIR) umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        else umma_bf16_ss(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (PAIR) {
+                            umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        } else {
+                            // MN-major: 16 k-rows = 2048 B into every 64-element chunk, chunks 8192 B apart (LBO)
+                            const uint64_t ad = p.a_mn ? make_mnmajor_sw128_desc(smem_u32(sA + s * A_TILE_BYTES) + k * 2048, 8192)
+                                                       : adesc + 2 * k;
+                            const uint64_t bd = p.b_mn ? make_mnmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES) + k * 2048, 8192)
+                                                       : bdesc + 2 * k;
+                            umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
+                        }
                     }
                     if (PAIR) umma_commit_pair(&empty_bar[s]);
                     else umma_commit(&empty_bar[s]);
@@ -571,7 +602,7 @@ bool gemm2_supported(const GemmParams& p) {
 }
 
 bool gemm2_pair_wanted(const GemmParams& p, int bn_tile, int pair_request) {
-    if (pair_request < 0) return false;
+    if (pair_request < 0 || p.a_mn || p.b_mn) return false;
     if (pair_request > 0) return true;
     // auto: long-K tensor-bound problems with at least one full wave of 256-row tiles (74 CTA pairs on 148 SMs)
     const long long m2 = (p.M + 2 * BM - 1) / (2 * BM), nt = (p.N + bn_tile - 1) / bn_tile;

@@ -307,6 +307,19 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
     return d;
 }
 // Instruction descriptor for kind::f16: bf16 x bf16 -> fp32, both operands K-major, dense.
+// Shared-memory descriptor of an MN-major operand stored as [K rows][64 MN elements = 128 bytes], 128B swizzle:
+// 8 K-rows form a 1024-byte swizzle atom (SBO = stride between atoms along K), the next 64 MN elements live
+// lbo_bytes further on (LBO).
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr, uint32_t lbo_bytes) {
+    uint64_t d = 0;
+    d |= static_cast<uint64_t>((smem_addr & 0x3FFFFu) >> 4);
+    d |= static_cast<uint64_t>((lbo_bytes >> 4) & 0x3FFFu) << 16;
+    d |= static_cast<uint64_t>(1024 >> 4) << 32;
+    d |= static_cast<uint64_t>(1) << 46;
+    d |= static_cast<uint64_t>(2) << 61;
+    return d;
+}
+
 __host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
     return (1u << 4)                              // C format F32
            | (1u << 7)                            // A format BF16

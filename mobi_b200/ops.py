@@ -79,11 +79,13 @@ def _rows_view(t, what):
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
          tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
-         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0):
+         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0, a_mn=False, b_mn=False):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
     may be column slices of wider matrices (row strides are taken from the views or given explicitly).
+    a_mn / b_mn: the operand is given MN-major, i.e. a is the row-major [K, M] matrix / w the row-major [K, N] matrix
+    (out = a^T @ w): pass M, N, K explicitly.
     """
     _cuda(bias, out2, out3)
     if row_bias is not None:  # may be a column slice of a wider matrix (ld_row_bias = its row stride)
@@ -91,6 +93,7 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
         if ld_row_bias == 0 and row_bias.dim() == 2:
             ld_row_bias = row_bias.stride(0)
     assert a.dtype == torch.bfloat16 and w.dtype == torch.bfloat16, "gemm operands must be bf16"
+    assert not (a_mn or b_mn) or None not in (M, N, K), "MN-major operands: pass M, N and K explicitly"
     lda_v = _rows_view(a, "a")
     ldb_v = _rows_view(w, "w")
     lda = lda_v if lda is None else lda
@@ -132,6 +135,7 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.batch = batch
     args.a_batch_stride, args.b_batch_stride, args.out_batch_stride = a_batch_stride, b_batch_stride, out_batch_stride
     args.pair = pair
+    args.a_mn_major, args.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
     with _timed("gemm", 2.0 * M * N * K * max(1, batch)):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
     return out

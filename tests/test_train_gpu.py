@@ -275,6 +275,51 @@ def test_batched_gemm(M, N, K, H):
              out_batch_stride=M * N, pair=1)
     assert rel(out3, ref) < 1e-2
 
+
+@pytest.mark.parametrize("M,N,K", [(256, 128, 512), (320, 320, 4096), (200, 72, 100), (64, 40, 264), (1280, 640, 256)])
+def test_gemm_mn_major_operands(M, N, K):
+    """out = A_given^T B_given with A given as row-major [K, M] and / or B as row-major [K, N] (tcgen05 MN-major operands):
+    the weight-gradient form dY^T X, ragged M / N / K (K need not be a multiple of 8 when both operands are MN-major)."""
+    from mobi_b200 import ops
+    at = rnd(K, M + 8, seed=1, dtype=torch.bfloat16)[:, :M]            # column slices: row stride > extent
+    bt = rnd(K, N + 16, seed=2, dtype=torch.bfloat16)[:, 8:8 + N]
+    ref = at.float().t() @ bt.float()
+    out = torch.empty(M, N, device="cuda", dtype=torch.float32)
+    ops.gemm(at, bt, out=out, M=M, N=N, K=K, lda=M + 8, ldb=N + 16, a_mn=True, b_mn=True)
+    assert rel(out, ref) < 1e-2
+    # accumulate into an f32 gradient (residual = out), as wgrad does
+    acc = rnd(M, N, seed=3)
+    want = acc + ref
+    ops.gemm(at, bt, out=acc, residual=acc, M=M, N=N, K=K, lda=M + 8, ldb=N + 16, a_mn=True, b_mn=True)
+    assert rel(acc, want) < 1e-2
+    if K % 8 == 0:
+        a_k = at.t().contiguous()                                      # [M, K] K-major
+        b_k = bt.t().contiguous()                                      # [N, K] K-major
+        o1 = ops.gemm(a_k, bt, M=M, N=N, K=K, ldb=N + 16, b_mn=True, out_dtype=torch.float32)
+        o2 = ops.gemm(at, b_k, M=M, N=N, K=K, lda=M + 8, a_mn=True, out_dtype=torch.float32)
+        assert rel(o1, ref) < 1e-2 and rel(o2, ref) < 1e-2
+
+
+@pytest.mark.parametrize("H,T,D", [(8, 256, 40), (4, 128, 80), (2, 128, 160)])
+def test_gemm_mn_major_batched_heads(H, T, D):
+    """The dK = dS^T q' and dV = P^T dO products of the attention backward without transposed copies: A = dS [Tq, Tk]
+    read MN-major, B = head columns of a token-major [T, H*D] matrix read MN-major with batch stride D."""
+    from mobi_b200 import ops
+    ds = rnd(H, T, T, seed=1, dtype=torch.bfloat16)
+    tok = rnd(T, H * D, seed=2, dtype=torch.bfloat16)
+    ref = torch.bmm(ds.float().transpose(1, 2), tok.float().reshape(T, H, D).permute(1, 0, 2))       # [H, Tk, D]
+    out = torch.zeros(T, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ds, tok, out=out, M=T, N=D, K=T, lda=T, ldb=H * D, a_mn=True, b_mn=True, batch=H, a_batch_stride=T * T,
+             b_batch_stride=D, out_batch_stride=D)
+    assert rel(out.float().reshape(T, H, D).permute(1, 0, 2), ref) < 1e-2
+    # dQ = dS k: A K-major, B = k [H, Tk, D] contiguous read MN-major
+    kk = rnd(H, T, D, seed=3, dtype=torch.bfloat16)
+    ref2 = torch.bmm(ds.float(), kk.float())
+    out2 = torch.zeros(T, H * D, device="cuda", dtype=torch.bfloat16)
+    ops.gemm(ds, kk, out=out2, M=T, N=D, K=T, lda=T, ldb=D, b_mn=True, batch=H, a_batch_stride=T * T, b_batch_stride=T * D,
+             out_batch_stride=D)
+    assert rel(out2.float().reshape(T, H, D).permute(1, 0, 2), ref2) < 1e-2
+
 @pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256), (2, 8, 80, 1024), (1, 2, 128, 384)])
 def test_attention_backward_composite(B, H, D, T):
     """The five products + softmax backward per (row, head) against autograd of softmax(q k^T * scale) v."""
