@@ -413,7 +413,9 @@ int mobi_attn_softmax_bwd_lse(const mobi_attn_softmax_bwd_args* args, const floa
  * (rowmax, 1 / rowsum, Delta -> stats) and a main pass that writes dS, dS^T, P^T (bf16 [heads, tokens, tokens]) directly:
  * the f32 T x T tiles never reach HBM.  q, k, v: bf16 [batch_rows * heads, tokens, head_dim] (q' carries
  * scale * log2(e)); d_o: bf16 token-major [batch_rows * tokens, ld_do], head h = columns [h * head_dim, (h + 1) * head_dim).
- * stats: f32 [batch_rows * heads, tokens, 3]; dS, dSt, Pt: bf16 [batch_rows * heads, tokens, tokens].
+ * stats: f32 [batch_rows * heads, tokens, 3]; dS, dSt, Pt: bf16 [batch_rows * heads, tokens, tokens].  With dSt == NULL
+ * the kernel writes P ROW-MAJOR into Pt and no transposed tiles at all: dK = dS^T q' and dV = P^T dO then read dS / P as
+ * MN-major GEMM operands (mobi_gemm a_mn_major).
  * stats_only = 1 runs the first pass only; batch_rows = 0 means 1. */
 typedef struct {
     const void* q;

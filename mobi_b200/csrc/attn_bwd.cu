@@ -212,6 +212,13 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
                         for (int q = 0; q < 4; ++q)
                             drow[q] = make_uint4(ds2[4 * q], ds2[4 * q + 1], ds2[4 * q + 2], ds2[4 * q + 3]);
+                        if (p.dSt == nullptr) {
+                            // P row-major (the dK / dV GEMMs read dS and P as MN-major operands: no transposed tiles)
+                            uint4* prow = reinterpret_cast<uint4*>(p.Pt + ((long long)z * p.T + row) * p.T + key0);
+#pragma unroll
+                            for (int q = 0; q < 4; ++q)
+                                prow[q] = make_uint4(p2[4 * q], p2[4 * q + 1], p2[4 * q + 2], p2[4 * q + 3]);
+                        } else {
                         // dS^T / P^T: for key column j the 32 lanes hold 32 consecutive query rows; even lanes pair with
                         // their odd neighbour and write one bf16x2 word -> 64 contiguous bytes per (warp, column)
                         const long long tbase = ((long long)z * p.T + key0) * p.T + m_tile * AB_BM + lg * 32 + (lane & ~1);
@@ -226,6 +233,7 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                                 *reinterpret_cast<uint32_t*>(p.dSt + tbase + (long long)j * p.T) = mine_ds | (oth_ds << 16);
                                 *reinterpret_cast<uint32_t*>(p.Pt + tbase + (long long)j * p.T) = mine_p | (oth_p << 16);
                             }
+                        }
                         }
                     }
                 }
@@ -275,7 +283,7 @@ using namespace mobi;
 extern "C" int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MOBI_CHECK(a && a->q && a->k && a->v && a->d_o && a->stats, "mobi_attn_bwd_tiles: null argument");
-    MOBI_CHECK(a->stats_only || (a->dS && a->dSt && a->Pt), "mobi_attn_bwd_tiles: the main pass needs dS, dSt, Pt");
+    MOBI_CHECK(a->stats_only || (a->dS && a->Pt), "mobi_attn_bwd_tiles: the main pass needs dS and Pt (P^T with dSt, row-major P without)");
     MOBI_CHECK(a->tokens > 0 && a->tokens % 128 == 0, "mobi_attn_bwd_tiles: tokens=%d must be a multiple of 128", a->tokens);
     MOBI_CHECK(a->head_dim % 8 == 0 && a->head_dim >= 8 && a->head_dim <= 64 * AB_MAX_NKB,
                "mobi_attn_bwd_tiles: head_dim=%d must be a multiple of 8 in [8, 128]", a->head_dim);

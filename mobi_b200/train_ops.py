@@ -100,14 +100,15 @@ def attn_softmax_bwd_lse(S, dP, dS, dSt, Pt, stats, tq, tk, dscale, lse, o, d_o,
 
 
 def attn_bwd_tiles(q, k, v, d_o, stats, dS, dSt, Pt, *, heads, tokens, head_dim, ld_do, dscale, batch_rows=1):
-    """Fused S / dP recompute + softmax backward for all heads of `batch_rows` batch rows (see mobi_attn_bwd_tiles)."""
+    """Fused S / dP recompute + softmax backward for all heads of `batch_rows` batch rows (see mobi_attn_bwd_tiles).
+    dSt None: `Pt` receives P row-major and no transposed tiles are written."""
     a = L.AttnBwdTilesArgs()
     a.q, a.k, a.v, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
-    a.stats, a.dS, a.dSt, a.Pt = stats.data_ptr(), dS.data_ptr(), dSt.data_ptr(), Pt.data_ptr()
+    a.stats, a.dS, a.dSt, a.Pt = stats.data_ptr(), dS.data_ptr(), L.ptr(dSt), Pt.data_ptr()
     a.heads, a.tokens, a.head_dim, a.stats_only, a.ld_do, a.dscale = heads, tokens, head_dim, 0, ld_do, dscale
     a.batch_rows = batch_rows
     fl = 2 * 2 * 2.0 * batch_rows * heads * tokens * tokens * head_dim      # S and dP, each computed in both passes
-    with _timed("attn_bwd_tiles", fl, nbytes=batch_rows * heads * tokens * tokens * 6.0, kernels=2):
+    with _timed("attn_bwd_tiles", fl, nbytes=batch_rows * heads * tokens * tokens * (4.0 if dSt is None else 6.0), kernels=2):
         L.check(L.load().mobi_attn_bwd_tiles(C.byref(a), L.stream()), "attn_bwd_tiles")
 
 
@@ -225,14 +226,11 @@ def adamw(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2
 
 # ------------------------------------------------------------------------------------------------ composites
 def wgrad(dy_bf, x_bf, out, *, M, n_out, k_in):
-    """out[n_out, k_in] += dy^T x over M token rows (dy_bf [M, n_out], x_bf [M, k_in], bf16, contiguous): two
-    transposes build the K-major operands, then one tcgen05 GEMM accumulates into the f32 gradient.  (Splitting the
-    token dimension into batched partial products + a fold was measured: no gain on the 85 ms step.)"""
-    if M % 8:  # K of the GEMM must be a multiple of 8: only the tiny test shapes could get here
-        raise RuntimeError("wgrad: token count %d must be a multiple of 8" % M)
-    dyT = transpose(dy_bf, rows=M, cols=n_out).reshape(n_out, M)
-    xT = transpose(x_bf, rows=M, cols=k_in).reshape(k_in, M)
-    return ops.gemm(dyT, xT, out=out, residual=out, out_dtype=torch.float32, M=n_out, K=M)
+    """out[n_out, k_in] += dy^T x over M token rows (dy_bf [M, n_out], x_bf [M, k_in], bf16; row strides taken from the
+    views): ONE tcgen05 GEMM that reads both operands MN-major (no transposed copies) and accumulates into the f32
+    gradient.  (Splitting the token dimension into batched partial products + a fold was measured: no gain.)"""
+    return ops.gemm(dy_bf, x_bf, out=out, residual=out, out_dtype=torch.float32, M=n_out, N=k_in, K=M,
+                    lda=dy_bf.stride(-2), ldb=x_bf.stride(-2), a_mn=True, b_mn=True)
 
 
 LN2 = math.log(2.0)

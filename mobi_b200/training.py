@@ -118,6 +118,14 @@ def _conv_dgrad_pack(conv):
                 pad=(kh // 2, kw // 2))
 
 
+class _MnMajorB:
+    """Tag: a forward weight pack [n_out, k_in] to be read as the MN-major B operand of dx = dy W."""
+    __slots__ = ("w",)
+
+    def __init__(self, w):
+        self.w = w
+
+
 class UNetTrainer:
     """forward_backward(x_start, t, noise, context) -> loss; step() -> all-reduce + AdamW + repack."""
 
@@ -197,11 +205,21 @@ class UNetTrainer:
         self.bp = bp
 
     def _pack_matrix(self, w, scale=1.0, transposed=True):
-        """f32 master weight [N, K] (a view of the flat buffer) -> bf16 [N, K] and bf16 [K, N], on the CUDA kernels."""
+        """f32 master weight [N, K] (a view of the flat buffer) -> bf16 [N, K] for the forward, and the SAME bf16 copy
+        tagged for the dgrad GEMM dx = dy W, which reads it as an MN-major B operand (no transposed pack to rebuild after
+        every optimizer step)."""
         src = w if scale == 1.0 else ops.scale_f32(w, scale)
         fwd = ops.cast_bf16(src)
-        wt = tops.transpose(src, rows=w.shape[0], cols=w.shape[1]).reshape(w.shape[1], w.shape[0]) if transposed else None
-        return fwd, wt
+        return fwd, (_MnMajorB(fwd) if transposed else None)
+
+    @staticmethod
+    def _dgemm(dy, w_t, **kw):
+        """dx = dy W for a weight given either as a transposed K-major pack [k_in, n_out] (frozen weights, packed once)
+        or as the forward pack [n_out, k_in] read MN-major (trainable weights)."""
+        if isinstance(w_t, _MnMajorB):
+            w = w_t.w
+            return ops.gemm(dy, w, M=dy.numel() // dy.shape[-1], N=w.shape[1], K=w.shape[0], ldb=w.stride(0), b_mn=True, **kw)
+        return ops.gemm(dy, w_t, **kw)
 
     @torch.no_grad()
     def repack_trainable(self):
@@ -277,7 +295,7 @@ class UNetTrainer:
             ws = dict(S=torch.empty(f32_tiles, device=dev, dtype=torch.float32),
                       dP=torch.empty(f32_tiles, device=dev, dtype=torch.float32),
                       dS=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
-                      dSt=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
+                      dSt=torch.empty((0,) if fused else (H, T, T), device=dev, dtype=torch.bfloat16),
                       Pt=torch.empty((H, T, T), device=dev, dtype=torch.bfloat16),
                       stats=torch.empty((3 * H * T,), device=dev, dtype=torch.float32))
             self._ws[(H, T, fused)] = ws
@@ -291,12 +309,6 @@ class UNetTrainer:
         dS^T, P^T in bf16) live in a reused workspace."""
         C = H * D
         TD, TT = T * D, T * T
-        kT = tops.transpose(k, rows=T, cols=D, batch=B * H, in_batch_stride=TD)
-        qT = tops.transpose(q, rows=T, cols=D, batch=B * H, in_batch_stride=TD)
-        doT = torch.empty((B * H, D, T), device=q.device, dtype=torch.bfloat16)
-        for b in range(B):
-            tops.transpose(do[b * T:(b + 1) * T], rows=T, cols=D, ld_in=C, batch=H, in_batch_stride=D,
-                           out=doT[b * H:(b + 1) * H])
         fused = D <= 128 and T % 128 == 0 and not (lse is not None and getattr(self, "lse_backward", False))
         # fused: the score tiles of ALL batch rows come from one launch pair (more (head, query-tile) items per wave)
         ws_all = self._attn_ws(B * H, T, True) if fused else None
@@ -304,8 +316,8 @@ class UNetTrainer:
         f32 = torch.float32
         if fused:
             # S and dP are recomputed on tcgen05 inside the statistics pass and the main pass: the f32 score tiles never
-            # reach HBM, only dS, dS^T and P^T (bf16) are written
-            tops.attn_bwd_tiles(q, k, v, do, ws_all["stats"], ws_all["dS"], ws_all["dSt"], ws_all["Pt"], heads=H, tokens=T,
+            # reach HBM, only dS and P (bf16, both row-major) are written
+            tops.attn_bwd_tiles(q, k, v, do, ws_all["stats"], ws_all["dS"], None, ws_all["Pt"], heads=H, tokens=T,
                                 head_dim=D, ld_do=C, dscale=tops.LN2, batch_rows=B)
         for b in range(B):
             rows = slice(b * T, (b + 1) * T)
@@ -318,18 +330,22 @@ class UNetTrainer:
                          b_batch_stride=TD, out_batch_stride=TT, **bat)
                 ops.gemm(do[rows], v[hs], out=ws["dP"], out_dtype=f32, M=T, N=T, K=D, lda=C, ldb=D, ldo=T,
                          a_batch_stride=D, b_batch_stride=TD, out_batch_stride=TT, **bat)
-            if fused:
-                pass
-            elif lse is not None:
-                tops.attn_softmax_bwd_lse(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2,
-                                          lse[hs], o[rows], do[rows], C, D, batch=H)
-            else:
-                tops.attn_softmax_bwd(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2,
-                                      batch=H)
-            for a_op, b_op, out, col in ((ws["dS"], kT, dq_out, dq_col), (ws["dSt"], qT, dkv_out, dk_col),
-                                         (ws["Pt"], doT, dkv_out, dv_col)):
-                ops.gemm(a_op, b_op[hs], out=out[rows, col:col + C], M=T, N=D, K=T, lda=T, ldb=T, a_batch_stride=TT,
-                         b_batch_stride=TD, out_batch_stride=D, **bat)
+                if lse is not None:
+                    tops.attn_softmax_bwd_lse(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2,
+                                              lse[hs], o[rows], do[rows], C, D, batch=H)
+                else:
+                    tops.attn_softmax_bwd(ws["S"], ws["dP"], ws["dS"], ws["dSt"], ws["Pt"], ws["stats"], T, T, tops.LN2,
+                                          batch=H)
+            # dq' = dS k ; dk = dS^T q' ; dv = P^T dO.  k, q' and the head columns of dO are read as MN-major B operands
+            # (no transposed copies); the fused path also reads dS / P as MN-major A operands instead of writing dS^T / P^T
+            a_dk, a_dv = (ws["dS"], ws["Pt"]) if fused else (ws["dSt"], ws["Pt"])
+            mn = dict(a_mn=True) if fused else {}
+            ops.gemm(ws["dS"], k[hs], out=dq_out[rows, dq_col:dq_col + C], M=T, N=D, K=T, lda=T, ldb=D, b_mn=True,
+                     a_batch_stride=TT, b_batch_stride=TD, out_batch_stride=D, **bat)
+            ops.gemm(a_dk, q[hs], out=dkv_out[rows, dk_col:dk_col + C], M=T, N=D, K=T, lda=T, ldb=D, b_mn=True,
+                     a_batch_stride=TT, b_batch_stride=TD, out_batch_stride=D, **bat, **mn)
+            ops.gemm(a_dv, do[rows], out=dkv_out[rows, dv_col:dv_col + C], M=T, N=D, K=T, lda=T, ldb=C, b_mn=True,
+                     a_batch_stride=TT, b_batch_stride=D, out_batch_stride=D, **bat, **mn)
 
     # ------------------------------------------------------------------ BasicTransformerBlock
     def _block_forward(self, blk, x0, R, T, ctx_bf, ctx_f32):
@@ -394,7 +410,7 @@ class UNetTrainer:
         if bias is not None:
             tops.colsum(dy_bf, self._g(bias).reshape(1, n_out))
         tops.wgrad(dy_bf, x_bf, self._g(weight), M=M, n_out=n_out, k_in=k_in)
-        return ops.gemm(dy_bf, w_T)
+        return self._dgemm(dy_bf, w_T)
 
     def _block_backward(self, blk, t, d, R, T, ctx_f32, need_dx0=True):
         """d: f32 [R*T, C] gradient w.r.t. the block output; turned into the gradient w.r.t. x0 in place."""
@@ -422,10 +438,10 @@ class UNetTrainer:
             dkv = torch.empty((Mh, 2 * C), device=dev, dtype=bf)
             self._attn_bwd(s["q"], s["k"], s["v"], do, Rh, H, D, T, dq, 0, dkv, 0, C, o=s["o"], lse=s["lse"])
             tops.wgrad(dq, s["nq"], self._g(at.to_q.weight), M=Mh, n_out=C, k_in=C)
-            dnq = ops.gemm(dq, tp[m + "_wq_T"])
+            dnq = self._dgemm(dq, tp[m + "_wq_T"])
             gkv = self.flat.pair_view(self.flat.grads, self._names[id(at.to_k.weight)], self._names[id(at.to_v.weight)])
             tops.wgrad(dkv, s["ctx"], gkv, M=Mh, n_out=2 * C, k_in=C)
-            dctx = ops.gemm(dkv, tp[m + "_wkv_T"])
+            dctx = self._dgemm(dkv, tp[m + "_wkv_T"])
             # the LayerNorm input of this modality's rows is x3 (lidar rows are untouched by the camera update)
             tops.layernorm_bwd(t["x3"], ln.weight.data, dnq, d, rows=Mh, seg_offset=off, dgamma=self._g(ln.weight),
                                dbeta=self._g(ln.bias), **seg)
@@ -436,7 +452,7 @@ class UNetTrainer:
         do = self._linear_bwd(du, t["oa"], tp["a_wo_T"], ca.to_out[0].weight, ca.to_out[0].bias, M)
         dqa, dka, dva = tops.ctx_attn_qspace(t["qa"], t["ka"], t["va"], R, T, H, d_o=do)
         tops.wgrad(dqa, t["na"], self._g(ca.to_q.weight), M=M, n_out=C, k_in=C)
-        dna = ops.gemm(dqa, tp["a_wq_T"])
+        dna = self._dgemm(dqa, tp["a_wq_T"])
         cflat = ctx_f32.reshape(R * nk, -1)
         tops.wgrad_small(dka.reshape(R * nk, C), cflat, self._g(ca.to_k.weight))
         tops.wgrad_small(dva.reshape(R * nk, C), cflat, self._g(ca.to_v.weight))
@@ -444,8 +460,8 @@ class UNetTrainer:
         # gradient w.r.t. the conditioning tokens (what trains the bbox_embedder): both tokens through the adapter's
         # to_k / to_v, token 0 also through the frozen attn2 (vec2 = to_out(to_v(c0)) added to every token of a row)
         dctx = self.d_context.reshape(R * nk, -1)
-        ops.gemm(ops.cast_bf16(dka.reshape(R * nk, C)), tp["a_wk_T"], residual=dctx, out=dctx)
-        ops.gemm(ops.cast_bf16(dva.reshape(R * nk, C)), tp["a_wv_T"], residual=dctx, out=dctx)
+        self._dgemm(ops.cast_bf16(dka.reshape(R * nk, C)), tp["a_wk_T"], residual=dctx, out=dctx)
+        self._dgemm(ops.cast_bf16(dva.reshape(R * nk, C)), tp["a_wv_T"], residual=dctx, out=dctx)
         dvec2 = torch.zeros((R, C), device=dev, dtype=torch.float32)
         tops.colsum(d, dvec2, rows_per_group=T)
         dv0 = ops.gemm(ops.cast_bf16(dvec2), bp["w_o2_T"])
@@ -644,7 +660,7 @@ class UNetTrainer:
             tops.colsum(d, self._g(lin[i].bias).reshape(1, -1))
             if i == 0:
                 break
-            dx = ops.gemm(ops.cast_bf16(d), pk[i][1], out_dtype=torch.float32)    # d @ W_i
+            dx = self._dgemm(ops.cast_bf16(d), pk[i][1], out_dtype=torch.float32)  # d @ W_i
             d = tops.silu_bwd(pre[i], dx) if pre[i] is not None else dx
 
     def _forward_backward(self, x_start, t, noise, context, bbox=None, uncond=False):
