@@ -99,6 +99,10 @@ typedef struct {
      * the dK / dV / dQ products of the attention backward, so none of them needs a transposed copy.  With both flags K
      * may be any positive count (rows beyond K are zero-filled by TMA). */
     int32_t a_mn_major, b_mn_major;
+    /* out (f32, PLAIN epilogue, no bias / activation / residual) is accumulated with fp32 atomic adds instead of stored:
+     * with batch > 1 and out_batch_stride = 0 the batch entries are K-slices of ONE product (split-K), e.g. a weight
+     * gradient over 16,384 token rows whose 6 output tiles would otherwise occupy 6 of 148 SMs. */
+    int32_t atomic_out;
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);

@@ -30,7 +30,7 @@ class GemmArgs(C.Structure):
         ("conv", _i32), ("n_img", _i32), ("H", _i32), ("W", _i32), ("C", _i32),
         ("KH", _i32), ("KW", _i32), ("pad_h", _i32), ("pad_w", _i32), ("tile_n", _i32), ("kernel", _i32),
         ("batch", _i32), ("a_batch_stride", _i64), ("b_batch_stride", _i64), ("out_batch_stride", _i64),
-        ("pair", _i32), ("a_mn_major", _i32), ("b_mn_major", _i32),
+        ("pair", _i32), ("a_mn_major", _i32), ("b_mn_major", _i32), ("atomic_out", _i32),
     ]
 
 

@@ -8,6 +8,8 @@
 #include "../../include/mobi_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
+#include <algorithm>
+#include <cstdlib>
 #include <cooperative_groups.h>
 
 namespace mobi {
@@ -139,6 +141,115 @@ ln_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma, cons
         }
     }
     if (dgamma) {
+        __syncthreads();
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            atomicAdd(dgamma + c, lnb_smem[c]);
+            atomicAdd(dbeta + c, lnb_smem[C + c]);
+        }
+    }
+}
+
+// Width- and dtype-specialised LayerNorm backward: a lane owns channel PAIRS (c, c + 1) = 2 * lane + 64 * j, so x / dx move
+// as 8-byte and bf16 dy as 4-byte words (256 / 128 contiguous bytes per warp load); NP = pairs per lane (5 / 10 / 20 for
+// C <= 320 / 640 / 1280); the dgamma / dbeta partial sums of all rows a warp visits stay in registers (NP <= 5: C <= 320, where most token rows live) and
+// reach shared memory once per warp; the dx read of the accumulate path is issued together with the x / dy loads.
+template <int NP, bool DY_F32>
+__global__ void __launch_bounds__(256)
+ln_bwd2_kernel(const float* __restrict__ x, const float* __restrict__ gamma, const void* __restrict__ dy,
+               float* dx, float* dgamma, float* dbeta, long long rows, int C, long long seg, long long seg_stride,
+               long long seg_offset, float eps, int accumulate) {
+    extern __shared__ float lnb_smem[];  // [2][C] when dgamma
+    constexpr bool REG_ACC = NP <= 5;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nwarps = blockDim.x >> 5;
+    if (dgamma) {
+        for (int c = threadIdx.x; c < 2 * C; c += blockDim.x) lnb_smem[c] = 0.f;
+        __syncthreads();
+    }
+    float2 ag[REG_ACC ? NP : 1], ab[REG_ACC ? NP : 1];
+#pragma unroll
+    for (int i = 0; i < (REG_ACC ? NP : 1); ++i) ag[i] = ab[i] = make_float2(0.f, 0.f);
+    const float inv_c = 1.0f / C;
+    for (long long row = (long long)blockIdx.x * nwarps + warp; row < rows; row += (long long)gridDim.x * nwarps) {
+        const long long src = seg > 0 ? (row / seg) * seg_stride + seg_offset + row % seg : row;
+        const float2* xr = reinterpret_cast<const float2*>(x + src * C);
+        float2* dr = reinterpret_cast<float2*>(dx + src * C);
+        float2 xv[NP], gv[NP], acc[NP];
+        float s = 0.f;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int pidx = lane + 32 * j;  // pair index: channels 2 * pidx, 2 * pidx + 1
+            const bool ok = 2 * pidx < C;
+            xv[j] = ok ? xr[pidx] : make_float2(0.f, 0.f);
+            if (DY_F32) {
+                gv[j] = ok ? reinterpret_cast<const float2*>(reinterpret_cast<const float*>(dy) + row * C)[pidx] : make_float2(0.f, 0.f);
+            } else {
+                gv[j] = ok ? __bfloat1622float2(reinterpret_cast<const __nv_bfloat162*>(
+                                 reinterpret_cast<const __nv_bfloat16*>(dy) + row * C)[pidx])
+                           : make_float2(0.f, 0.f);
+            }
+            acc[j] = (accumulate && ok) ? dr[pidx] : make_float2(0.f, 0.f);
+            s += xv[j].x + xv[j].y;
+        }
+        const float mean = warp_sum(s) * inv_c;
+        float q = 0.f;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const bool ok = 2 * (lane + 32 * j) < C;
+            xv[j].x = ok ? xv[j].x - mean : 0.f;
+            xv[j].y = ok ? xv[j].y - mean : 0.f;
+            q += xv[j].x * xv[j].x + xv[j].y * xv[j].y;
+        }
+        const float rstd = rsqrtf(warp_sum(q) * inv_c + eps);
+        float sg = 0.f, sgx = 0.f;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int pidx = lane + 32 * j;
+            const bool ok = 2 * pidx < C;
+            const float2 dyv = gv[j];
+            xv[j].x *= rstd;  // xhat (0 beyond C)
+            xv[j].y *= rstd;
+            if (dgamma) {
+                if (REG_ACC) {
+                    ag[j].x = fmaf(dyv.x, xv[j].x, ag[j].x);
+                    ag[j].y = fmaf(dyv.y, xv[j].y, ag[j].y);
+                    ab[j].x += dyv.x;
+                    ab[j].y += dyv.y;
+                } else if (ok) {
+                    atomicAdd(&lnb_smem[2 * pidx], dyv.x * xv[j].x);
+                    atomicAdd(&lnb_smem[2 * pidx + 1], dyv.y * xv[j].y);
+                    atomicAdd(&lnb_smem[C + 2 * pidx], dyv.x);
+                    atomicAdd(&lnb_smem[C + 2 * pidx + 1], dyv.y);
+                }
+            }
+            const float2 gm = (gamma && ok) ? reinterpret_cast<const float2*>(gamma)[pidx] : make_float2(1.f, 1.f);
+            gv[j].x = dyv.x * gm.x;
+            gv[j].y = dyv.y * gm.y;
+            sg += gv[j].x + gv[j].y;
+            sgx += gv[j].x * xv[j].x + gv[j].y * xv[j].y;
+        }
+        const float mg = warp_sum(sg) * inv_c, mgx = warp_sum(sgx) * inv_c;
+#pragma unroll
+        for (int j = 0; j < NP; ++j) {
+            const int pidx = lane + 32 * j;
+            if (2 * pidx < C)
+                dr[pidx] = make_float2(acc[j].x + rstd * (gv[j].x - mg - xv[j].x * mgx),
+                                       acc[j].y + rstd * (gv[j].y - mg - xv[j].y * mgx));
+        }
+    }
+    if (dgamma) {
+        if (REG_ACC) {
+#pragma unroll
+            for (int j = 0; j < NP; ++j) {
+                const int pidx = lane + 32 * j;
+                if (2 * pidx < C) {
+                    atomicAdd(&lnb_smem[2 * pidx], ag[j].x);
+                    atomicAdd(&lnb_smem[2 * pidx + 1], ag[j].y);
+                    atomicAdd(&lnb_smem[C + 2 * pidx], ab[j].x);
+                    atomicAdd(&lnb_smem[C + 2 * pidx + 1], ab[j].y);
+                }
+            }
+        }
         __syncthreads();
         for (int c = threadIdx.x; c < C; c += blockDim.x) {
             atomicAdd(dgamma + c, lnb_smem[c]);
@@ -487,6 +598,136 @@ ctx_attn_qspace_kernel(const __nv_bfloat16* __restrict__ q, const float* __restr
     }
 }
 
+// Vectorised version for D % 8 == 0 (every level of the UNet: D = 40 / 80 / 160): a thread owns one token of one head and
+// moves its q / dO / o / dq segments as 16-byte words (D / 8 of them) held in registers; the backward also parks q and dO
+// of the 128 tokens in shared memory so that the dk / dv block sums read them there instead of walking global columns.
+template <bool BWD, int DV>  // DV = D / 8
+__global__ void __launch_bounds__(CA_TOK)
+ctx_attn_qspace_vec_kernel(const __nv_bfloat16* __restrict__ q, const float* __restrict__ k, const float* __restrict__ v,
+                           __nv_bfloat16* __restrict__ o, const __nv_bfloat16* __restrict__ d_o,
+                           __nv_bfloat16* __restrict__ dq, float* dk, float* dv, int tokens, int C, int heads, int keys) {
+    extern __shared__ __align__(16) float ca_smem[];  // k[keys][D], v[keys][D], p[keys][128], ds[keys][128], q/dO tiles (bf16)
+    constexpr int D = DV * 8;
+    const int b = blockIdx.z, h = blockIdx.y;
+    const int t = blockIdx.x * CA_TOK + threadIdx.x;
+    float* sk = ca_smem;
+    float* sv = sk + keys * D;
+    float* sp = sv + keys * D;
+    float* sds = sp + keys * CA_TOK;
+    // bf16 tiles [128][D + 8] (row pitch padded by 16 bytes: conflict-free 16-byte row writes and column reads)
+    constexpr int PITCH = D + 8;
+    __nv_bfloat16* sq = reinterpret_cast<__nv_bfloat16*>(sds + keys * CA_TOK);
+    __nv_bfloat16* sdo = sq + CA_TOK * PITCH;
+    for (int i = threadIdx.x; i < keys * D; i += blockDim.x) {
+        const int j = i / D, dd = i - j * D;
+        sk[i] = k[((long long)b * keys + j) * C + h * D + dd];
+        sv[i] = v[((long long)b * keys + j) * C + h * D + dd];
+    }
+    __syncthreads();
+    const bool ok = t < tokens;
+    const long long row = ((long long)b * tokens + t) * C + h * D;
+    float p[CA_MAXK], ds[CA_MAXK];
+#pragma unroll
+    for (int j = 0; j < CA_MAXK; ++j) p[j] = ds[j] = 0.f;
+    uint4 qv[DV], dov[DV];
+#pragma unroll
+    for (int i = 0; i < DV; ++i) qv[i] = dov[i] = make_uint4(0u, 0u, 0u, 0u);
+    if (ok) {
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+            qv[i] = __ldg(reinterpret_cast<const uint4*>(q + row) + i);
+            if (BWD) dov[i] = __ldg(reinterpret_cast<const uint4*>(d_o + row) + i);
+        }
+        float s[CA_MAXK], dp[CA_MAXK];
+#pragma unroll
+        for (int j = 0; j < CA_MAXK; ++j) s[j] = dp[j] = 0.f;
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+            const uint32_t qw[4] = {qv[i].x, qv[i].y, qv[i].z, qv[i].w};
+            const uint32_t dw[4] = {dov[i].x, dov[i].y, dov[i].z, dov[i].w};
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const float q0 = __uint_as_float(qw[w] << 16), q1 = __uint_as_float(qw[w] & 0xffff0000u);
+                const float d0 = __uint_as_float(dw[w] << 16), d1 = __uint_as_float(dw[w] & 0xffff0000u);
+                const int dd = i * 8 + w * 2;
+#pragma unroll
+                for (int j = 0; j < CA_MAXK; ++j)
+                    if (j < keys) {
+                        s[j] = fmaf(q0, sk[j * D + dd], fmaf(q1, sk[j * D + dd + 1], s[j]));
+                        if (BWD) dp[j] = fmaf(d0, sv[j * D + dd], fmaf(d1, sv[j * D + dd + 1], dp[j]));
+                    }
+            }
+        }
+        float m = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < CA_MAXK; ++j)
+            if (j < keys) m = fmaxf(m, s[j]);
+        float l = 0.f;
+#pragma unroll
+        for (int j = 0; j < CA_MAXK; ++j)
+            if (j < keys) {
+                p[j] = __expf(s[j] - m);
+                l += p[j];
+            }
+        const float inv = 1.0f / l;
+#pragma unroll
+        for (int j = 0; j < CA_MAXK; ++j) p[j] *= inv;
+        if (BWD) {
+            float delta = 0.f;
+#pragma unroll
+            for (int j = 0; j < CA_MAXK; ++j) delta += p[j] * dp[j];
+#pragma unroll
+            for (int j = 0; j < CA_MAXK; ++j) ds[j] = p[j] * (dp[j] - delta);
+        }
+        // o = sum_j p_j v_j (forward) / dq = sum_j ds_j k_j (backward), 8 channels per 16-byte store
+        const float* coef = BWD ? ds : p;
+        const float* tab = BWD ? sk : sv;
+        __nv_bfloat16* dst = (BWD ? dq : o) + row;
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+            uint32_t wds[4];
+#pragma unroll
+            for (int w = 0; w < 4; ++w) {
+                const int dd = i * 8 + w * 2;
+                float a0 = 0.f, a1 = 0.f;
+#pragma unroll
+                for (int j = 0; j < CA_MAXK; ++j)
+                    if (j < keys) {
+                        a0 = fmaf(coef[j], tab[j * D + dd], a0);
+                        a1 = fmaf(coef[j], tab[j * D + dd + 1], a1);
+                    }
+                wds[w] = pack_bf16x2(a0, a1);
+            }
+            reinterpret_cast<uint4*>(dst)[i] = make_uint4(wds[0], wds[1], wds[2], wds[3]);
+        }
+    }
+    if (BWD) {
+#pragma unroll
+        for (int j = 0; j < CA_MAXK; ++j)
+            if (j < keys) {
+                sp[j * CA_TOK + threadIdx.x] = p[j];    // zero for tokens beyond the end
+                sds[j * CA_TOK + threadIdx.x] = ds[j];
+            }
+#pragma unroll
+        for (int i = 0; i < DV; ++i) {
+            *reinterpret_cast<uint4*>(sq + threadIdx.x * PITCH + i * 8) = qv[i];
+            *reinterpret_cast<uint4*>(sdo + threadIdx.x * PITCH + i * 8) = dov[i];
+        }
+        __syncthreads();
+        for (int i = threadIdx.x; i < keys * D; i += blockDim.x) {
+            const int j = i / D, dd = i - j * D;
+            float ak = 0.f, av = 0.f;
+#pragma unroll 8
+            for (int tt = 0; tt < CA_TOK; ++tt) {
+                ak = fmaf(sds[j * CA_TOK + tt], __bfloat162float(sq[tt * PITCH + dd]), ak);
+                av = fmaf(sp[j * CA_TOK + tt], __bfloat162float(sdo[tt * PITCH + dd]), av);
+            }
+            atomicAdd(dk + ((long long)b * keys + j) * C + h * D + dd, ak);
+            atomicAdd(dv + ((long long)b * keys + j) * C + h * D + dd, av);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // out[g, c] += sum over the rows of group g of x[r, c]   (bias gradients; per-batch-row sums)
 // grid (ceil(cols / 32), row chunks); block 32 x 8.
@@ -713,6 +954,19 @@ extern "C" int mobi_layernorm_bwd(const mobi_layernorm_bwd_args* a, void* stream
     long long blocks = (a->rows + warps - 1) / warps;
     if (blocks > 4 * sm_count()) blocks = 4 * sm_count();
     const size_t smem = a->dgamma ? 2 * a->C * sizeof(float) : 0;
+    const bool aligned = a->C % 2 == 0 && reinterpret_cast<uintptr_t>(a->x) % 8 == 0 && reinterpret_cast<uintptr_t>(a->dx) % 8 == 0 &&
+                         reinterpret_cast<uintptr_t>(a->dy) % 8 == 0 && (!a->gamma || reinterpret_cast<uintptr_t>(a->gamma) % 8 == 0);
+    if (aligned) {
+        const bool f32 = a->dy_dtype == MOBI_DTYPE_F32;
+#define LNB_LAUNCH(NP, F)                                                                                                \
+    ln_bwd2_kernel<NP, F><<<(unsigned)blocks, warps * 32, smem, stream>>>(a->x, a->gamma, a->dy, a->dx, a->dgamma, a->dbeta, \
+                                                                         a->rows, a->C, a->seg, a->seg_stride,             \
+                                                                         a->seg_offset, a->eps, a->accumulate)
+        if (a->C <= 320) { if (f32) LNB_LAUNCH(5, true); else LNB_LAUNCH(5, false); }
+        else if (a->C <= 640) { if (f32) LNB_LAUNCH(10, true); else LNB_LAUNCH(10, false); }
+        else { if (f32) LNB_LAUNCH(20, true); else LNB_LAUNCH(20, false); }
+#undef LNB_LAUNCH
+    } else
     ln_bwd_kernel<<<(unsigned)blocks, warps * 32, smem, stream>>>(a->x, a->gamma, a->dy, a->dy_dtype == MOBI_DTYPE_F32,
                                                                  a->dx, a->dgamma, a->dbeta, a->rows, a->C, a->seg,
                                                                  a->seg_stride, a->seg_offset, a->eps, a->accumulate);
@@ -800,6 +1054,39 @@ extern "C" int mobi_ctx_attn_qspace(const mobi_ctx_attn_qspace_args* a, void* st
     const int D = a->C / a->heads;
     dim3 grid((a->tokens + CA_TOK - 1) / CA_TOK, a->heads, a->batch);
     const size_t smem = (2 * a->keys * D + 2 * a->keys * CA_TOK) * sizeof(float);
+    MOBI_CHECK(!a->backward || (a->d_o && a->dq && a->dk && a->dv), "mobi_ctx_attn_qspace: backward needs d_o, dq, dk, dv");
+    MOBI_CHECK(a->backward || a->o != nullptr, "mobi_ctx_attn_qspace: forward needs o");
+    const bool al16 = a->C % 8 == 0 && reinterpret_cast<uintptr_t>(a->q) % 16 == 0 &&
+                      (a->backward ? (reinterpret_cast<uintptr_t>(a->d_o) % 16 == 0 && reinterpret_cast<uintptr_t>(a->dq) % 16 == 0)
+                                   : reinterpret_cast<uintptr_t>(a->o) % 16 == 0);
+    if (al16 && (D == 40 || D == 80 || D == 160)) {
+        const size_t smem_v = smem + (a->backward ? 2 * (size_t)CA_TOK * (D + 8) * sizeof(__nv_bfloat16) : 0);
+#define CA_LAUNCH(B, DVv)                                                                                                   \
+    do {                                                                                                                    \
+        static bool attr_set = false;                                                                                       \
+        if (!attr_set) {                                                                                                    \
+            MOBI_CUDA(cudaFuncSetAttribute(ctx_attn_qspace_vec_kernel<B, DVv>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                           100 * 1024));                                                                    \
+            attr_set = true;                                                                                                \
+        }                                                                                                                   \
+        ctx_attn_qspace_vec_kernel<B, DVv><<<grid, CA_TOK, smem_v, stream>>>(                                               \
+            reinterpret_cast<const __nv_bfloat16*>(a->q), a->k, a->v, reinterpret_cast<__nv_bfloat16*>(a->o),               \
+            reinterpret_cast<const __nv_bfloat16*>(a->d_o), reinterpret_cast<__nv_bfloat16*>(a->dq), a->dk, a->dv,         \
+            a->tokens, a->C, a->heads, a->keys);                                                                            \
+    } while (0)
+        if (a->backward) {
+            if (D == 40) CA_LAUNCH(true, 5);
+            else if (D == 80) CA_LAUNCH(true, 10);
+            else CA_LAUNCH(true, 20);
+        } else {
+            if (D == 40) CA_LAUNCH(false, 5);
+            else if (D == 80) CA_LAUNCH(false, 10);
+            else CA_LAUNCH(false, 20);
+        }
+#undef CA_LAUNCH
+        MOBI_CUDA(cudaGetLastError());
+        return 0;
+    }
     if (a->backward) {
         MOBI_CHECK(a->d_o && a->dq && a->dk && a->dv, "mobi_ctx_attn_qspace: backward needs d_o, dq, dk, dv");
         ctx_attn_qspace_kernel<true><<<grid, CA_TOK, smem, stream>>>(

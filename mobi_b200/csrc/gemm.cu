@@ -413,6 +413,11 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         uint32_t box[3] = {BK, BM, 1};
         if (make_tensor_map_bf16(&tmA, a->A, batched ? 3 : 2, dims, strides, box)) return 1;
     }
+    p.atomic_out = a->atomic_out ? 1 : 0;
+    if (p.atomic_out)
+        MOBI_CHECK(p.out_f32 && p.mode == MOBI_EPI_PLAIN && !a->bias && !a->row_bias && !a->residual && a->act == 0 &&
+                       a->kernel != 1 && a->out_seg == 0,
+                   "mobi_gemm: atomic_out needs a plain f32 output without bias / activation / residual");
     p.a_mn = a->a_mn_major ? 1 : 0;
     p.b_mn = a->b_mn_major ? 1 : 0;
     if (p.a_mn || p.b_mn) {
@@ -457,7 +462,8 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         uint32_t box[3] = {BK, (uint32_t)(p.pair ? bn_tile / 2 : bn_tile), 1};  // a CTA pair splits the B tile
         if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
     }
-    MOBI_CHECK(!(p.a_mn || p.b_mn) || gemm2_supported(p), "mobi_gemm: MN-major operands are outside the persistent kernel's epilogue here");
+    MOBI_CHECK(!(p.a_mn || p.b_mn || p.atomic_out) || gemm2_supported(p),
+               "mobi_gemm: MN-major operands / atomic_out are outside the persistent kernel's epilogue here");
     if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);
     MOBI_CHECK(!batched, "mobi_gemm: this batched problem is outside the persistent kernel's epilogue (N %% 4, "
                          "16-byte aligned out / residual / bias)");

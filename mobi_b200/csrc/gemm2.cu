@@ -273,7 +273,15 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                     v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w;
                 }
                 if (p.out_f32) {
-                    *reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + er.off[it] + n) = v;
+                    float* dst = reinterpret_cast<float*>(p.out) + er.off[it] + n;
+                    if (p.atomic_out) {
+                        atomicAdd(dst, v.x);
+                        atomicAdd(dst + 1, v.y);
+                        atomicAdd(dst + 2, v.z);
+                        atomicAdd(dst + 3, v.w);
+                    } else {
+                        *reinterpret_cast<float4*>(dst) = v;
+                    }
                 } else {
                     uint2 pk;
                     pk.x = pack_bf16x2(v.x, v.y);

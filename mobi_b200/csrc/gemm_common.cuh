@@ -30,6 +30,7 @@ struct GemmParams {
     int pair;                     // 1: run as 2-CTA clusters (cta_group::2, 256-row tiles, B box = BN / 2 rows)
     int batch;                    // > 1: batched problem, A/B through 3-D tensor maps
     long long out_batch_stride;   // elements
+    int atomic_out;               // f32 output accumulated with atomic adds (split-K over the batch index)
     int a_mn, b_mn;               // operand given MN-major ([K, M] / [K, N] row-major): 64 x 64 TMA boxes, UMMA major bits
 };
 

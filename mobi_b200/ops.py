@@ -3,9 +3,14 @@ torch.empty (the library never allocates) and launch on PyTorch's current stream
 """
 import ctypes as C
 
+import os
+
 import torch
 
 from . import _lib as L
+
+
+_SHAPE_KINDS = os.environ.get("MOBI_GEMM_SHAPES", "0") == "1"
 
 
 class Stats:
@@ -79,7 +84,8 @@ def _rows_view(t, what):
 def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, residual=None, out=None,
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
          tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
-         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0, a_mn=False, b_mn=False):
+         kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0, a_mn=False, b_mn=False,
+         atomic_out=False):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
@@ -136,7 +142,12 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.a_batch_stride, args.b_batch_stride, args.out_batch_stride = a_batch_stride, b_batch_stride, out_batch_stride
     args.pair = pair
     args.a_mn_major, args.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
-    with _timed("gemm", 2.0 * M * N * K * max(1, batch)):
+    args.atomic_out = 1 if atomic_out else 0
+    kind = "gemm"
+    if _SHAPE_KINDS:   # MOBI_GEMM_SHAPES=1: per-shape accounting for tools/train_bench.py
+        kind = "gemm M%d N%d K%d b%d%s%s%s" % (M, N, K, batch, " amn" if a_mn else "", " bmn" if b_mn else "",
+                                                " atomic" if atomic_out else "")
+    with _timed(kind, 2.0 * M * N * K * max(1, batch)):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
     return out
 

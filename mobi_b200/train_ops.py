@@ -225,12 +225,30 @@ def adamw(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2
 
 
 # ------------------------------------------------------------------------------------------------ composites
+def wgrad_splits(M, n_out, k_in, sms=148):
+    """How many K-slices a weight gradient over M token rows is cut into: enough that tiles x slices fill the SMs, slices
+    of at least 512 rows, a power of two that divides M."""
+    tiles = ((n_out + 127) // 128) * ((k_in + 159) // 160)
+    s = 1
+    while s < 32 and tiles * s < sms and M % (2 * s) == 0 and M // (2 * s) >= 512:
+        s *= 2
+    return s
+
+
 def wgrad(dy_bf, x_bf, out, *, M, n_out, k_in):
     """out[n_out, k_in] += dy^T x over M token rows (dy_bf [M, n_out], x_bf [M, k_in], bf16; row strides taken from the
-    views): ONE tcgen05 GEMM that reads both operands MN-major (no transposed copies) and accumulates into the f32
-    gradient.  (Splitting the token dimension into batched partial products + a fold was measured: no gain.)"""
-    return ops.gemm(dy_bf, x_bf, out=out, residual=out, out_dtype=torch.float32, M=n_out, N=k_in, K=M,
-                    lda=dy_bf.stride(-2), ldb=x_bf.stride(-2), a_mn=True, b_mn=True)
+    views): ONE tcgen05 GEMM that reads both operands MN-major (no transposed copies).  Few output tiles and a long token
+    dimension (320 x 320 over 16,384 rows = 6 tiles) would leave most SMs idle, so the token rows are cut into K-slices
+    that run as the batch entries of one launch and meet in the f32 gradient through atomic adds."""
+    lda, ldb = dy_bf.stride(-2), x_bf.stride(-2)
+    s = wgrad_splits(M, n_out, k_in)
+    if s == 1:
+        return ops.gemm(dy_bf, x_bf, out=out, residual=out, out_dtype=torch.float32, M=n_out, N=k_in, K=M, lda=lda, ldb=ldb,
+                        a_mn=True, b_mn=True)
+    ks = M // s
+    return ops.gemm(dy_bf, x_bf, out=out, out_dtype=torch.float32, M=n_out, N=k_in, K=ks, lda=lda, ldb=ldb, a_mn=True,
+                    b_mn=True, batch=s, a_batch_stride=ks * lda, b_batch_stride=ks * ldb, out_batch_stride=0,
+                    atomic_out=True)
 
 
 LN2 = math.log(2.0)

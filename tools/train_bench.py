@@ -77,7 +77,7 @@ def main():
         except Exception:
             pass
         peak = peaks.get("bf16_tflops_sustained", 1400.0)
-        tc = {k: v for k, v in prof.items() if k in ("gemm", "conv", "attention")}
+        tc = {k: v for k, v in prof.items() if k.split(" ")[0] in ("gemm", "conv", "attention")}
         tc_ms, tc_fl = sum(v["ms"] for v in tc.values()), sum(v["flops"] for v in tc.values())
         line = {"metric": "training step (UNet fwd+bwd, adapter grads, all-reduce, AdamW)", "ms_per_step": ms.item(),
                 "samples_per_s": n * world / (ms.item() / 1e3), "n_gpus": world, "joint_samples_per_gpu": n,
@@ -87,6 +87,10 @@ def main():
                 "tensor_core_launch_tflops": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else None, "peak_tflops": peak,
                 "by_kernel_ms": {k: round(v["ms"], 2) for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])},
                 "by_kernel_launches": {k: v["launches"] for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])}}
+        if os.environ.get("MOBI_GEMM_SHAPES", "0") == "1":   # per-shape table on stderr: kind, launches, ms, TFLOP/s
+            for k, v in sorted(prof.items(), key=lambda kv: -kv[1]["ms"])[:45]:
+                tf = v["flops"] / (v["ms"] / 1e3) / 1e12 if v["ms"] and v["flops"] else 0.0
+                print("%-44s %5d %8.3f ms %8.1f TF/s" % (k, v["launches"], v["ms"], tf), file=sys.stderr)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
