@@ -437,6 +437,28 @@ typedef struct {
 } mobi_attn_bwd_tiles_args;
 int mobi_attn_bwd_tiles(const mobi_attn_bwd_tiles_args* args, void* stream);
 
+/* Flash-style attention backward (attention.py:179-192 under autograd) for head_dim <= 128, tokens % 128 == 0: given the
+ * row statistics of mobi_attn_bwd_tiles (stats_only = 1) it recomputes S = q' k^T and dP = dO v^T per 128 x 128 tile on
+ * tcgen05, forms P and dS in registers, stages them as bf16 in shared memory and accumulates
+ *   dQ' = dS k (one kernel, CTA = 128 query rows)   and   dK = dS^T q', dV = P^T dO (second kernel, CTA = 128 key rows)
+ * in TMEM: no T x T tile ever reaches HBM.  q, k, v: bf16 [batch_rows * heads, tokens, head_dim]; d_o and the outputs are
+ * token-major [batch_rows * tokens, ld] matrices whose head h occupies columns [h * head_dim, (h + 1) * head_dim) of the
+ * given base pointers (which may point into wider rows: QKV gradient buffers). */
+typedef struct {
+    const void* q;
+    const void* k;
+    const void* v;
+    const void* d_o;
+    const float* stats;
+    void* dq;
+    void* dk;
+    void* dv;
+    int64_t ld_do, ld_dq, ld_dk, ld_dv;
+    int32_t heads, tokens, head_dim, batch_rows;
+    float dscale;
+} mobi_attn_bwd_flash_args;
+int mobi_attn_bwd_flash(const mobi_attn_bwd_flash_args* args, void* stream);
+
 /* cond_adapter_attn (attention.py:237-243, CrossAttention with `keys` <= 4 context tokens) on projected queries, for
  * the training step where to_q/to_k/to_v are trainable and cannot be folded:
  *   forward : o = softmax_j(<q, k_j>) v_j per head                                    (backward = 0)

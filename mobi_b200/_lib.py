@@ -138,6 +138,14 @@ class AttnBwdTilesArgs(C.Structure):
     ]
 
 
+class AttnBwdFlashArgs(C.Structure):
+    _fields_ = [
+        ("q", _vp), ("k", _vp), ("v", _vp), ("d_o", _vp), ("stats", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp),
+        ("ld_do", _i64), ("ld_dq", _i64), ("ld_dk", _i64), ("ld_dv", _i64),
+        ("heads", _i32), ("tokens", _i32), ("head_dim", _i32), ("batch_rows", _i32), ("dscale", _f32),
+    ]
+
+
 class CtxAttnQspaceArgs(C.Structure):
     _fields_ = [
         ("q", _vp), ("k", _vp), ("v", _vp), ("o", _vp), ("d_o", _vp), ("dq", _vp), ("dk", _vp), ("dv", _vp),
@@ -231,6 +239,7 @@ SIGNATURES = {
     "mobi_bbox_renorm": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "mobi_silu_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mobi_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "mobi_attn_bwd_flash": (C.c_int, [C.POINTER(AttnBwdFlashArgs), _vp]),
     "mobi_range_map": (C.c_int, [C.POINTER(RangeMapArgs), _vp]),
     "mobi_range_undo_transforms": (C.c_int, [C.POINTER(RangeUndoArgs), _vp]),
     "mobi_range2pcd": (C.c_int, [C.POINTER(Range2PcdArgs), _vp]),

@@ -99,6 +99,26 @@ def attn_softmax_bwd_lse(S, dP, dS, dSt, Pt, stats, tq, tk, dscale, lse, o, d_o,
                                                    L.stream()), "attn_softmax_bwd_lse")
 
 
+def attn_bwd_flash(q, k, v, d_o, stats, dq, dk, dv, *, heads, tokens, head_dim, dscale, batch_rows=1):
+    """Statistics pass + flash-style dQ' / dK / dV (see mobi_attn_bwd_flash): q, k, v bf16 [batch_rows * heads, T, D]; d_o,
+    dq, dk, dv token-major bf16 matrix VIEWS [batch_rows * T, heads * D] (row strides taken from the views)."""
+    a = L.AttnBwdTilesArgs()
+    a.q, a.k, a.v, a.d_o = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr()
+    a.stats = stats.data_ptr()
+    a.heads, a.tokens, a.head_dim, a.stats_only, a.ld_do, a.dscale = heads, tokens, head_dim, 1, d_o.stride(0), dscale
+    a.batch_rows = batch_rows
+    z = batch_rows * heads
+    with _timed("attn_bwd_stats", 2 * 2.0 * z * tokens * tokens * head_dim):
+        L.check(L.load().mobi_attn_bwd_tiles(C.byref(a), L.stream()), "attn_bwd_tiles(stats)")
+    f = L.AttnBwdFlashArgs()
+    f.q, f.k, f.v, f.d_o, f.stats = q.data_ptr(), k.data_ptr(), v.data_ptr(), d_o.data_ptr(), stats.data_ptr()
+    f.dq, f.dk, f.dv = dq.data_ptr(), dk.data_ptr(), dv.data_ptr()
+    f.ld_do, f.ld_dq, f.ld_dk, f.ld_dv = d_o.stride(0), dq.stride(0), dk.stride(0), dv.stride(0)
+    f.heads, f.tokens, f.head_dim, f.batch_rows, f.dscale = heads, tokens, head_dim, batch_rows, dscale
+    with _timed("attn_bwd_flash", 7 * 2.0 * z * tokens * tokens * head_dim, kernels=2):
+        L.check(L.load().mobi_attn_bwd_flash(C.byref(f), L.stream()), "attn_bwd_flash")
+
+
 def attn_bwd_tiles(q, k, v, d_o, stats, dS, dSt, Pt, *, heads, tokens, head_dim, ld_do, dscale, batch_rows=1):
     """Fused S / dP recompute + softmax backward for all heads of `batch_rows` batch rows (see mobi_attn_bwd_tiles).
     dSt None: `Pt` receives P row-major and no transposed tiles are written."""

@@ -130,7 +130,7 @@ class UNetTrainer:
     """forward_backward(x_start, t, noise, context) -> loss; step() -> all-reduce + AdamW + repack."""
 
     def __init__(self, ldm, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None, use_cuda_graph=True,
-                 lse_backward=False, bbox_embedder=None):
+                 lse_backward=False, bbox_embedder=None, flash_backward=True):
         self.ldm = ldm
         self.unet = ldm.model.diffusion_model if hasattr(ldm, "model") else ldm
         unet = self.unet
@@ -164,6 +164,10 @@ class UNetTrainer:
         # the cross-modal to_k / to_v weight gradients (27 % max-abs error on one tensor at full width, whole-gradient
         # cosine unchanged at 0.99992).  Off by default: the parity bar is per tensor.
         self.lse_backward = lse_backward
+        # flash_backward: dQ' / dK / dV of every attention with head_dim <= 128 and tokens % 128 == 0 come from the two
+        # flash-style kernels (attn_bwd_flash.cu) after the exact statistics pass; off = score tiles (dS, P) through HBM +
+        # three batched GEMMs (kept as the A/B reference and for other shapes)
+        self.flash_backward = flash_backward
         self._fb_graphs, self._repack_graph = {}, None
         unet.invalidate()
         unet.pack()
@@ -310,6 +314,15 @@ class UNetTrainer:
         C = H * D
         TD, TT = T * D, T * T
         fused = D <= 128 and T % 128 == 0 and not (lse is not None and getattr(self, "lse_backward", False))
+        if fused and getattr(self, "flash_backward", True):
+            # statistics pass + two flash-style kernels: dQ' (CTA = 128 query rows) and dK / dV (CTA = 128 key rows)
+            # accumulate in TMEM from dS / P tiles staged in shared memory; no T x T tile is written to HBM
+            stats = self._ws.get(("stats", B * H, T))
+            if stats is None:
+                stats = self._ws[("stats", B * H, T)] = torch.empty((3 * B * H * T,), device=q.device, dtype=torch.float32)
+            tops.attn_bwd_flash(q, k, v, do, stats, dq_out[:, dq_col:dq_col + C], dkv_out[:, dk_col:dk_col + C],
+                                dkv_out[:, dv_col:dv_col + C], heads=H, tokens=T, head_dim=D, dscale=tops.LN2, batch_rows=B)
+            return
         # fused: the score tiles of ALL batch rows come from one launch pair (more (head, query-tile) items per wave)
         ws_all = self._attn_ws(B * H, T, True) if fused else None
         ws = ws_all if fused else self._attn_ws(H, T, False)

@@ -320,7 +320,8 @@ def test_gemm_mn_major_batched_heads(H, T, D):
              out_batch_stride=D)
     assert rel(out2.float().reshape(T, H, D).permute(1, 0, 2), ref2) < 1e-2
 
-@pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256), (2, 8, 80, 1024), (1, 2, 128, 384)])
+@pytest.mark.parametrize("B,H,D,T", [(2, 4, 16, 64), (1, 4, 32, 256), (1, 8, 40, 256), (2, 8, 80, 1024), (1, 2, 128, 384),
+                                     (2, 8, 40, 4096)])
 def test_attention_backward_composite(B, H, D, T):
     """The five products + softmax backward per (row, head) against autograd of softmax(q k^T * scale) v."""
     import math
@@ -344,9 +345,11 @@ def test_attention_backward_composite(B, H, D, T):
     assert rel(o_fwd.reshape(B * T, C).float(), heads(o.detach())) < 1e-2
     lse_ref = torch.logsumexp(qr.detach() @ kr.detach().transpose(-1, -2) * math.log(2.0), -1) / math.log(2.0)
     assert (lse - lse_ref).abs().max().item() < 2e-2
-    for kw in (dict(), dict(o=o_fwd.reshape(B * T, C), lse=lse)):
+    # (c) flash-style kernels (dS / P staged in shared memory, accumulators in TMEM) when T % 128 == 0 and D <= 128
+    for kw, flash in ((dict(), False), (dict(o=o_fwd.reshape(B * T, C), lse=lse), False), (dict(), True)):
         tr.lse_backward = bool(kw)   # (a) runs the fused score-tile kernel when T % 128 == 0, else the materialised tiles
-        dqkv = torch.empty(B * T, 3 * C, device="cuda", dtype=torch.bfloat16)
+        tr.flash_backward = flash
+        dqkv = torch.full((B * T, 3 * C), float("nan"), device="cuda", dtype=torch.bfloat16)
         tr._attn_bwd(qb, kb, vb, do, B, H, D, T, dqkv, 0, dqkv, C, 2 * C, **kw)
         assert rel(dqkv[:, :C].float(), heads(qr.grad)) < 2e-2
         assert rel(dqkv[:, C:2 * C].float(), heads(kr.grad)) < 2e-2
