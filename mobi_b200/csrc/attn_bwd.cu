@@ -134,15 +134,15 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     for (int c = 0; c < nkb; ++c) {
                         const uint64_t qd = make_kmajor_sw128_desc(smem_u32(sQ + c * AB_TILE));
                         const uint64_t kd = make_kmajor_sw128_desc(smem_u32(sK + (s * nkb + c) * AB_TILE));
-#pragma unroll
-                        for (int k = 0; k < AB_BK / 16; ++k)
+                        const int ks = (min(AB_BK, p.D - c * AB_BK) + 15) >> 4;  // k-steps that hold head-dim columns
+                        for (int k = 0; k < ks; ++k)
                             umma_bf16_ss(dS_t, qd + 2 * k, kd + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
                     }
                     for (int c = 0; c < nkb; ++c) {
                         const uint64_t od = make_kmajor_sw128_desc(smem_u32(sdO + c * AB_TILE));
                         const uint64_t vd = make_kmajor_sw128_desc(smem_u32(sV + (s * nkb + c) * AB_TILE));
-#pragma unroll
-                        for (int k = 0; k < AB_BK / 16; ++k)
+                        const int ks = (min(AB_BK, p.D - c * AB_BK) + 15) >> 4;
+                        for (int k = 0; k < ks; ++k)
                             umma_bf16_ss(dP_t, od + 2 * k, vd + 2 * k, idesc, (c | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(&empty_bar[s]);

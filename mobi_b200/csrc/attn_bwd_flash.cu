@@ -136,7 +136,7 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             // ---------------- MMA issuer
             constexpr uint32_t idesc_s = make_idesc_bf16(FB_BM, 128);
             // accumulate products: N = padded head dim; B always MN-major, A MN-major when it is a transposed tile
-            const uint32_t idesc_acc = make_idesc_bf16(FB_BM, p.dpad) | (1u << 16) | (KEY_OUTER ? 1u << 15 : 0u);
+            const uint32_t idesc_acc = make_idesc_bf16(FB_BM, (p.D + 15) & ~15) | (1u << 16) | (KEY_OUTER ? 1u << 15 : 0u);
             const uint32_t S_t = tmem_base, dP_t = tmem_base + 128, acc0_t = tmem_base + 256, acc1_t = tmem_base + 384;
             uint32_t it = 0, li = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
@@ -154,17 +154,18 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     const uint8_t* k_t = KEY_OUTER ? sR0 : w0;
                     const uint8_t* do_t = KEY_OUTER ? w1 : sR1;
                     const uint8_t* v_t = KEY_OUTER ? sR1 : w1;
+                    // only the 16-column k-steps that hold head-dim columns (3 of 4 at D = 40; the rest is TMA zero fill)
                     for (int c = 0; c < nkb; ++c) {
                         const uint64_t qd = make_kmajor_sw128_desc(smem_u32(q_t + c * FB_TILE));
                         const uint64_t kd = make_kmajor_sw128_desc(smem_u32(k_t + c * FB_TILE));
-#pragma unroll
-                        for (int k = 0; k < FB_BK / 16; ++k) umma_bf16_ss(S_t, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+                        const int ks = (min(FB_BK, p.D - c * FB_BK) + 15) >> 4;
+                        for (int k = 0; k < ks; ++k) umma_bf16_ss(S_t, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
                     }
                     for (int c = 0; c < nkb; ++c) {
                         const uint64_t od = make_kmajor_sw128_desc(smem_u32(do_t + c * FB_TILE));
                         const uint64_t vd = make_kmajor_sw128_desc(smem_u32(v_t + c * FB_TILE));
-#pragma unroll
-                        for (int k = 0; k < FB_BK / 16; ++k) umma_bf16_ss(dP_t, od + 2 * k, vd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+                        const int ks = (min(FB_BK, p.D - c * FB_BK) + 15) >> 4;
+                        for (int k = 0; k < ks; ++k) umma_bf16_ss(dP_t, od + 2 * k, vd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
                     }
                     umma_commit(sdp_full);
                     // the epilogue turns S / dP into bf16 dS (and P) tiles in shared memory
