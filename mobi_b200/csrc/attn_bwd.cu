@@ -36,6 +36,13 @@ struct AttnBwdParams {
     int stages;
 };
 
+// 2^x on the MUFU pipe without exp2f's range fix-up instructions (inputs are <= 0 here; tiny results flush to zero)
+__device__ __forceinline__ float ab_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 __device__ __forceinline__ void ab_bar_sync_epilogue() { asm volatile("bar.sync 1, 512;" ::: "memory"); }
 
 template <bool STATS>
@@ -184,14 +191,14 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 #pragma unroll
                         for (int j = 1; j < 32; ++j) cm = fmaxf(cm, __uint_as_float(s[j]));
                         if (cm > m) {
-                            const float r = exp2f(m - cm);  // 0 when m == -inf
+                            const float r = ab_ex2(m - cm);  // 0 when m == -inf
                             l *= r;
                             acc *= r;
                             m = cm;
                         }
 #pragma unroll
                         for (int j = 0; j < 32; ++j) {
-                            const float e = exp2f(__uint_as_float(s[j]) - m);
+                            const float e = ab_ex2(__uint_as_float(s[j]) - m);
                             l += e;
                             acc = fmaf(e, __uint_as_float(d[j]), acc);
                         }
@@ -200,8 +207,8 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                         uint32_t ds2[16], p2[16];
 #pragma unroll
                         for (int j = 0; j < 32; j += 2) {
-                            const float p0 = exp2f(__uint_as_float(s[j]) - st_m) * st_il;
-                            const float p1 = exp2f(__uint_as_float(s[j + 1]) - st_m) * st_il;
+                            const float p0 = ab_ex2(__uint_as_float(s[j]) - st_m) * st_il;
+                            const float p1 = ab_ex2(__uint_as_float(s[j + 1]) - st_m) * st_il;
                             const float g0 = p.dscale * p0 * (__uint_as_float(d[j]) - st_d);
                             const float g1 = p.dscale * p1 * (__uint_as_float(d[j + 1]) - st_d);
                             ds2[j >> 1] = pack_bf16x2(g0, g1);
@@ -251,11 +258,11 @@ attn_bwd_tiles_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                     float M = m;
 #pragma unroll
                     for (int h = 1; h < 4; ++h) M = fmaxf(M, part[(h * 128 + row_in_tile) * 3]);
-                    float L = l * exp2f(m - M), A = acc * exp2f(m - M);
+                    float L = l * ab_ex2(m - M), A = acc * ab_ex2(m - M);
 #pragma unroll
                     for (int h = 1; h < 4; ++h) {
                         const float* oth = part + (h * 128 + row_in_tile) * 3;
-                        const float r = exp2f(oth[0] - M);
+                        const float r = ab_ex2(oth[0] - M);
                         L += oth[1] * r;
                         A += oth[2] * r;
                     }

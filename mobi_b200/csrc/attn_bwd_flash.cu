@@ -35,6 +35,12 @@ struct FlashBwdParams {
     long long ld0, ld1;
 };
 
+__device__ __forceinline__ float fb_ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
 template <bool KEY_OUTER>
 __global__ void __launch_bounds__(FB_THREADS, 1)
 attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -138,36 +144,50 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
             // accumulate products: N = padded head dim; B always MN-major, A MN-major when it is a transposed tile
             const uint32_t idesc_acc = make_idesc_bf16(FB_BM, (p.D + 15) & ~15) | (1u << 16) | (KEY_OUTER ? 1u << 15 : 0u);
             const uint32_t S_t = tmem_base, dP_t = tmem_base + 128, acc0_t = tmem_base + 256, acc1_t = tmem_base + 384;
+            // S = q' k^T and dP = dO v^T of walked tile `t` (global tile counter) into TMEM columns 0-255
+            auto issue_scores = [&](uint32_t t) {
+                const int s = t % STAGES;
+                mbar_wait(&full_bar[s], (t / STAGES) & 1);
+                mbar_wait(sdp_empty, (t & 1) ^ 1);  // the epilogue holds the previous tile's S / dP in registers
+                tc_fence_after();
+                const uint8_t* w0 = sW0 + s * nkb * FB_TILE;
+                const uint8_t* w1 = sW1 + s * nkb * FB_TILE;
+                const uint8_t* q_t = KEY_OUTER ? w0 : sR0;
+                const uint8_t* k_t = KEY_OUTER ? sR0 : w0;
+                const uint8_t* do_t = KEY_OUTER ? w1 : sR1;
+                const uint8_t* v_t = KEY_OUTER ? sR1 : w1;
+                // only the 16-column k-steps that hold head-dim columns (3 of 4 at D = 40; the rest is TMA zero fill)
+                for (int c = 0; c < nkb; ++c) {
+                    const uint64_t qd = make_kmajor_sw128_desc(smem_u32(q_t + c * FB_TILE));
+                    const uint64_t kd = make_kmajor_sw128_desc(smem_u32(k_t + c * FB_TILE));
+                    const int ks = (min(FB_BK, p.D - c * FB_BK) + 15) >> 4;
+                    for (int k = 0; k < ks; ++k) umma_bf16_ss(S_t, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+                }
+                for (int c = 0; c < nkb; ++c) {
+                    const uint64_t od = make_kmajor_sw128_desc(smem_u32(do_t + c * FB_TILE));
+                    const uint64_t vd = make_kmajor_sw128_desc(smem_u32(v_t + c * FB_TILE));
+                    const int ks = (min(FB_BK, p.D - c * FB_BK) + 15) >> 4;
+                    for (int k = 0; k < ks; ++k) umma_bf16_ss(dP_t, od + 2 * k, vd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
+                }
+                umma_commit(sdp_full);
+            };
+            // With a ring of >= 2 stages the scores of tile i + 1 are issued BEFORE the accumulate products of tile i: the
+            // S / dP columns are free as soon as the epilogue has loaded them into registers, so the tensor core computes
+            // the next scores while the epilogue still exponentiates / packs / stages the current tile.  (With one ring
+            // stage tile i + 1 cannot be loaded before the accumulate products of tile i release the stage.)
+            const bool ahead = STAGES >= 2;
             uint32_t it = 0, li = 0;
             for (int item = blockIdx.x; item < items; item += gridDim.x, ++li) {
                 mbar_wait(r_full, li & 1);
                 mbar_wait(acc_empty, (li & 1) ^ 1);  // the epilogue has drained the previous item's accumulators
                 tc_fence_after();
+                if (ahead) issue_scores(it);
                 for (int i = 0; i < tiles; ++i, ++it) {
                     const int s = it % STAGES;
-                    mbar_wait(&full_bar[s], (it / STAGES) & 1);
-                    mbar_wait(sdp_empty, (it & 1) ^ 1);
-                    tc_fence_after();
+                    if (!ahead) issue_scores(it);
+                    else if (i + 1 < tiles) issue_scores(it + 1);
                     const uint8_t* w0 = sW0 + s * nkb * FB_TILE;
                     const uint8_t* w1 = sW1 + s * nkb * FB_TILE;
-                    const uint8_t* q_t = KEY_OUTER ? w0 : sR0;
-                    const uint8_t* k_t = KEY_OUTER ? sR0 : w0;
-                    const uint8_t* do_t = KEY_OUTER ? w1 : sR1;
-                    const uint8_t* v_t = KEY_OUTER ? sR1 : w1;
-                    // only the 16-column k-steps that hold head-dim columns (3 of 4 at D = 40; the rest is TMA zero fill)
-                    for (int c = 0; c < nkb; ++c) {
-                        const uint64_t qd = make_kmajor_sw128_desc(smem_u32(q_t + c * FB_TILE));
-                        const uint64_t kd = make_kmajor_sw128_desc(smem_u32(k_t + c * FB_TILE));
-                        const int ks = (min(FB_BK, p.D - c * FB_BK) + 15) >> 4;
-                        for (int k = 0; k < ks; ++k) umma_bf16_ss(S_t, qd + 2 * k, kd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
-                    }
-                    for (int c = 0; c < nkb; ++c) {
-                        const uint64_t od = make_kmajor_sw128_desc(smem_u32(do_t + c * FB_TILE));
-                        const uint64_t vd = make_kmajor_sw128_desc(smem_u32(v_t + c * FB_TILE));
-                        const int ks = (min(FB_BK, p.D - c * FB_BK) + 15) >> 4;
-                        for (int k = 0; k < ks; ++k) umma_bf16_ss(dP_t, od + 2 * k, vd + 2 * k, idesc_s, (c | k) != 0 ? 1u : 0u);
-                    }
-                    umma_commit(sdp_full);
                     // the epilogue turns S / dP into bf16 dS (and P) tiles in shared memory
                     mbar_wait(stg_full, it & 1);
                     tc_fence_after();
@@ -234,13 +254,16 @@ attn_bwd_flash_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
                 tc_fence_before();
                 __syncwarp();
                 if (lane == 0) mbar_arrive(sdp_empty);
+                // P = 2^(S - m) / l = 2^(S - (m + log2 l)); dS = P * (dscale * dP - dscale * Delta): one add, one MUFU, one
+                // FMA and one multiply per element
+                const float m_l = st_m - __log2f(st_il), neg_sd = -p.dscale * st_d;
                 uint32_t ds2[16], p2[16];
 #pragma unroll
                 for (int j = 0; j < 32; j += 2) {
-                    const float p0 = exp2f(__uint_as_float(s[j]) - st_m) * st_il;
-                    const float p1 = exp2f(__uint_as_float(s[j + 1]) - st_m) * st_il;
-                    const float g0 = p.dscale * p0 * (__uint_as_float(d[j]) - st_d);
-                    const float g1 = p.dscale * p1 * (__uint_as_float(d[j + 1]) - st_d);
+                    const float p0 = fb_ex2(__uint_as_float(s[j]) - m_l);
+                    const float p1 = fb_ex2(__uint_as_float(s[j + 1]) - m_l);
+                    const float g0 = p0 * fmaf(p.dscale, __uint_as_float(d[j]), neg_sd);
+                    const float g1 = p1 * fmaf(p.dscale, __uint_as_float(d[j + 1]), neg_sd);
                     ds2[j >> 1] = pack_bf16x2(g0, g1);
                     p2[j >> 1] = pack_bf16x2(p0, p1);
                 }
