@@ -49,7 +49,7 @@ def test_transpose_batched_strided():
     assert torch.equal(out, ref)
 
 
-@pytest.mark.parametrize("C,seg", [(64, False), (320, True), (1280, False)])
+@pytest.mark.parametrize("C,seg", [(64, False), (320, True), (640, True), (1280, False), (66, False), (65, False)])
 def test_layernorm_bwd(C, seg):
     from mobi_b200 import train_ops as tops
     B, T = 4, 24
@@ -131,10 +131,12 @@ def test_attn_softmax_bwd(tq, tk):
     assert rel(dS.float(), Sr.grad) < 1e-2 and torch.equal(dSt.t(), dS)
 
 
-@pytest.mark.parametrize("keys", [1, 2])
-def test_ctx_attn_qspace_fwd_bwd(keys):
+@pytest.mark.parametrize("keys,H,D", [(1, 4, 16), (2, 4, 16), (2, 8, 40), (2, 8, 80), (1, 8, 160), (2, 5, 40)])
+def test_ctx_attn_qspace_fwd_bwd(keys, H, D):
+    """D = 16: generic kernel; D = 40 / 80 / 160 (the UNet's head dims): the 16-byte vectorised kernel with the
+    shared-memory dk / dv block sums; T = 200 leaves a ragged last chunk of 128 tokens."""
     from mobi_b200 import train_ops as tops
-    B, T, H, D = 2, 200, 4, 16
+    B, T = 2, 200
     C = H * D
     q = rnd(B * T, C, seed=1, dtype=torch.bfloat16)
     k, v = rnd(B, keys, C, seed=2), rnd(B, keys, C, seed=3)
