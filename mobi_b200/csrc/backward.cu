@@ -364,6 +364,110 @@ gn_bwd_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const 
     }
 }
 
+// Channel-pair version (every UNet shape: channels per group and c1 are even): a thread owns ONE channel pair of the group
+// for the whole kernel (gamma / beta / source tensor fixed in registers, no per-element division or dtype branch) and
+// walks pixels, four in flight, with 8-byte accesses.  Same three passes, same cluster reductions.
+template <bool DY_F32>
+__global__ void __cluster_dims__(GNB_CLUSTER, 1, 1) __launch_bounds__(256)
+gn_bwd2_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ gamma,
+               const float* __restrict__ beta, const void* __restrict__ dy, const float* __restrict__ dres,
+               float* dx1, float* dx2, int hw, int c1, int c2, int groups, int silu, float eps) {
+    __shared__ float red[8];
+    __shared__ float slot[2];
+    const int C = c1 + c2;
+    const int cpg = C / groups;
+    const int npairs = cpg >> 1;
+    const int n = blockIdx.y, g = blockIdx.x / GNB_CLUSTER, part = blockIdx.x % GNB_CLUSTER;
+    const int pv = threadIdx.x % npairs, lane_p = threadIdx.x / npairs;
+    const int lanes = blockDim.x / npairs;
+    const bool active = lane_p < lanes;
+    const int c = g * cpg + 2 * pv;  // first channel of this thread's pair
+    const long long img = (long long)n * hw;
+    const int pix_per = (hw + GNB_CLUSTER - 1) / GNB_CLUSTER;
+    const int pbeg = min(hw, part * pix_per), pend = min(hw, pbeg + pix_per);
+    // source / destination of this pair: x1 | x2 are the two halves of a channel concatenation
+    const bool first = c < c1;
+    const float* xs = first ? x1 + c : x2 + (c - c1);
+    float* dxs = first ? dx1 + c : dx2 + (c - c1);
+    const int cs = first ? c1 : c2;
+    const float2 gm = *reinterpret_cast<const float2*>(gamma + c);
+    const float2 bt = *reinterpret_cast<const float2*>(beta + c);
+    auto ld_x = [&](int p) { return *reinterpret_cast<const float2*>(xs + (img + p) * cs); };
+    auto ld_dy = [&](int p) {
+        if (DY_F32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(dy) + (img + p) * C + c);
+        return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(dy) + (img + p) * C + c));
+    };
+    constexpr int U = 4;
+    float s = 0.f, q = 0.f;
+    if (active) {
+        for (int p = pbeg + lane_p; p < pend; p += U * lanes) {
+            float2 v[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) v[u] = (p + u * lanes < pend) ? ld_x(p + u * lanes) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                s += v[u].x + v[u].y;
+                q += v[u].x * v[u].x + v[u].y * v[u].y;
+            }
+        }
+    }
+    cluster_sum2(s, q, red, slot);
+    const float m = (float)hw * cpg;
+    const float mean = s / m;
+    const float var = fmaxf(q / m - mean * mean, 0.f);
+    const float rstd = rsqrtf(var + eps);
+    // dz = dy * silu'(y) * gamma for one element
+    auto dz_of = [&](float xh, float dyv, float gmc, float btc) {
+        float dz = dyv;
+        if (silu) {
+            const float y = xh * gmc + btc;
+            const float sg = 1.0f / (1.0f + __expf(-y));
+            dz *= sg * (1.0f + y * (1.0f - sg));
+        }
+        return dz * gmc;
+    };
+    float s1 = 0.f, s2 = 0.f;
+    if (active) {
+        for (int p = pbeg + lane_p; p < pend; p += U * lanes) {
+            float2 v[U], d[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const bool ok = p + u * lanes < pend;
+                v[u] = ok ? ld_x(p + u * lanes) : make_float2(mean, mean);
+                d[u] = ok ? ld_dy(p + u * lanes) : make_float2(0.f, 0.f);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+                const float xh0 = (v[u].x - mean) * rstd, xh1 = (v[u].y - mean) * rstd;
+                const float dz0 = dz_of(xh0, d[u].x, gm.x, bt.x), dz1 = dz_of(xh1, d[u].y, gm.y, bt.y);
+                s1 += dz0 + dz1;
+                s2 += dz0 * xh0 + dz1 * xh1;
+            }
+        }
+    }
+    cluster_sum2(s1, s2, red, slot);
+    const float S1 = s1 / m, S2 = s2 / m;
+    if (!active) return;
+    for (int p = pbeg + lane_p; p < pend; p += U * lanes) {
+        float2 v[U], d[U], r[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const bool ok = p + u * lanes < pend;
+            v[u] = ok ? ld_x(p + u * lanes) : make_float2(mean, mean);
+            d[u] = ok ? ld_dy(p + u * lanes) : make_float2(0.f, 0.f);
+            r[u] = (ok && dres) ? *reinterpret_cast<const float2*>(dres + (img + p + u * lanes) * C + c) : make_float2(0.f, 0.f);
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (p + u * lanes >= pend) break;
+            const float xh0 = (v[u].x - mean) * rstd, xh1 = (v[u].y - mean) * rstd;
+            const float dz0 = dz_of(xh0, d[u].x, gm.x, bt.x), dz1 = dz_of(xh1, d[u].y, gm.y, bt.y);
+            *reinterpret_cast<float2*>(dxs + (img + p + u * lanes) * cs) =
+                make_float2(rstd * (dz0 - S1 - xh0 * S2) + r[u].x, rstd * (dz1 - S1 - xh1 * S2) + r[u].y);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // GEGLU (attention.py:38-45) on (value, gate) column pairs, exact erf GELU (F.gelu default).
 // ------------------------------------------------------------------------------------------------
@@ -981,6 +1085,22 @@ extern "C" int mobi_groupnorm_bwd(const mobi_groupnorm_bwd_args* a, void* stream
     MOBI_CHECK(a->groups > 0 && (a->c1 + a->c2) % a->groups == 0, "mobi_groupnorm_bwd: C=%d not divisible by groups=%d",
                a->c1 + a->c2, a->groups);
     dim3 grid(a->groups * GNB_CLUSTER, a->n_img);  // clusters of GNB_CLUSTER CTAs along x
+    {
+        const int cpg = (a->c1 + a->c2) / a->groups;
+        auto al8 = [](const void* p) { return reinterpret_cast<uintptr_t>(p) % 8 == 0; };
+        const bool pairs = cpg % 2 == 0 && cpg / 2 <= 256 && a->c1 % 2 == 0 && a->c2 % 2 == 0 && al8(a->x1) && al8(a->x2) &&
+                           al8(a->gamma) && al8(a->beta) && al8(a->dy) && al8(a->dres) && al8(a->dx1) && al8(a->dx2);
+        if (pairs) {
+            if (a->dy_dtype == MOBI_DTYPE_F32)
+                gn_bwd2_kernel<true><<<grid, 256, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->dy, a->dres, a->dx1, a->dx2,
+                                                               a->hw, a->c1, a->c2, a->groups, a->silu, a->eps);
+            else
+                gn_bwd2_kernel<false><<<grid, 256, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->dy, a->dres, a->dx1, a->dx2,
+                                                                a->hw, a->c1, a->c2, a->groups, a->silu, a->eps);
+            MOBI_CUDA(cudaGetLastError());
+            return 0;
+        }
+    }
     gn_bwd_kernel<<<grid, 256, 0, stream>>>(a->x1, a->x2, a->gamma, a->beta, a->dy, a->dy_dtype == MOBI_DTYPE_F32,
                                             a->dres, a->dx1, a->dx2, a->hw, a->c1, a->c2, a->groups, a->silu, a->eps);
     MOBI_CUDA(cudaGetLastError());
