@@ -857,6 +857,44 @@ colsum_kernel(const void* __restrict__ x, int is_f32, long long rows, int cols, 
     }
 }
 
+// Column-pair version: a warp reads 64 consecutive column pairs of a row (128 / 256 contiguous bytes for bf16 / f32), a
+// block covers 128 columns x `chunk` rows with 4 row lanes and eight rows in flight per thread.
+template <bool F32>
+__global__ void __launch_bounds__(256)
+colsum2_kernel(const void* __restrict__ x, long long rows, int cols, long long ld, long long rows_per_group, int chunk,
+               float* out) {
+    __shared__ float2 red[4][64];
+    const int tx = threadIdx.x & 63, ty = threadIdx.x >> 6;
+    const int c = blockIdx.x * 128 + 2 * tx;
+    const long long r0 = (long long)blockIdx.y * chunk;
+    const long long r1 = min(rows, r0 + chunk);
+    float2 acc = make_float2(0.f, 0.f);
+    if (c < cols) {
+        auto ld2 = [&](long long r) {
+            if (F32) return *reinterpret_cast<const float2*>(reinterpret_cast<const float*>(x) + r * ld + c);
+            return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(reinterpret_cast<const __nv_bfloat16*>(x) + r * ld + c));
+        };
+        for (long long r = r0 + ty; r < r1; r += 32) {
+            float2 v[8];
+#pragma unroll
+            for (int u = 0; u < 8; ++u) v[u] = (r + 4 * u < r1) ? ld2(r + 4 * u) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                acc.x += v[u].x;
+                acc.y += v[u].y;
+            }
+        }
+    }
+    red[ty][tx] = acc;
+    __syncthreads();
+    if (ty == 0 && c < cols) {
+        const float2 a = red[0][tx], b = red[1][tx], d = red[2][tx], e = red[3][tx];
+        float* dst = out + (r0 / rows_per_group) * cols + c;
+        atomicAdd(dst, (a.x + b.x) + (d.x + e.x));
+        atomicAdd(dst + 1, (a.y + b.y) + (d.y + e.y));
+    }
+}
+
 // out[n, k] += sum_m A[m, n] * B[m, k] for tiny m (the context-token side of the adapters: m = batch * keys)
 __global__ void wgrad_small_kernel(const float* __restrict__ A, const float* __restrict__ B, float* out, int m, int n,
                                    int k, long long lda, long long ldb, long long ldo) {
@@ -1231,9 +1269,20 @@ extern "C" int mobi_colsum(const void* x, int32_t dtype, int64_t rows, int32_t c
     MOBI_CHECK(rows % rows_per_group == 0, "mobi_colsum: rows must be a multiple of rows_per_group");
     int chunk = 256;
     while (rows_per_group % chunk != 0) chunk >>= 1;  // a chunk never straddles two groups
-    dim3 grid((cols + 31) / 32, (unsigned)(rows / chunk));
     MOBI_CHECK(rows / chunk < 65536, "mobi_colsum: too many row chunks");
-    colsum_kernel<<<grid, 256, 0, stream>>>(x, dtype == MOBI_DTYPE_F32, rows, cols, ld, rows_per_group, chunk, out);
+    const bool f32 = dtype == MOBI_DTYPE_F32;
+    if (cols % 2 == 0 && ld % 2 == 0 && reinterpret_cast<uintptr_t>(x) % (f32 ? 8 : 4) == 0) {
+        // enough blocks to fill the machine: halve the chunk while there are fewer than ~2 blocks per SM
+        while (chunk > 32 && (long long)((cols + 127) / 128) * (rows / chunk) < 2ll * sm_count()) chunk >>= 1;
+        dim3 grid2((cols + 127) / 128, (unsigned)(rows / chunk));
+        MOBI_CHECK(rows / chunk < 65536, "mobi_colsum: too many row chunks");
+        if (f32) colsum2_kernel<true><<<grid2, 256, 0, stream>>>(x, rows, cols, ld, rows_per_group, chunk, out);
+        else colsum2_kernel<false><<<grid2, 256, 0, stream>>>(x, rows, cols, ld, rows_per_group, chunk, out);
+        MOBI_CUDA(cudaGetLastError());
+        return 0;
+    }
+    dim3 grid((cols + 31) / 32, (unsigned)(rows / chunk));
+    colsum_kernel<<<grid, 256, 0, stream>>>(x, f32, rows, cols, ld, rows_per_group, chunk, out);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

@@ -1,5 +1,5 @@
 """LayerNorm-backward micro-benchmark (events, warm, inputs re-used: L2-resident above ~60 MB is not possible, so sizes
-at L0 stream from HBM).  Usage: MOBI_LNB_VARIANT=0|1|2 python tools/ln_bwd_bench.py"""
+at L0 stream from HBM).  Usage: python tools/ln_bwd_bench.py"""
 import os
 import sys
 
@@ -28,6 +28,5 @@ for rows, C in ((16384, 320), (8192, 320), (4096, 640), (1024, 1280)):
             torch.cuda.synchronize()
             us = e0.elapsed_time(e1) / 20 * 1e3
             nbytes = rows * C * (4 + dy.element_size() + 8)
-            print("variant %s rows %6d C %4d dgamma %d dy %s: %7.1f us  %6.0f GB/s" % (
-                os.environ.get("MOBI_LNB_VARIANT", "0"), rows, C, int(train), "f32" if dy_dt == torch.float32 else "bf16", us,
-                nbytes / us / 1e3))
+            print("rows %6d C %4d dgamma %d dy %s: %7.1f us  %6.0f GB/s" % (
+                rows, C, int(train), "f32" if dy_dt == torch.float32 else "bf16", us, nbytes / us / 1e3))
