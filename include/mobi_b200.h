@@ -337,6 +337,12 @@ int mobi_add_f32(const float* a, const float* b, float* out, int64_t n, void* st
 int mobi_scale_f32(const float* x, float s, float* out, int64_t n, void* stream);
 /* f32 -> bf16 cast */
 int mobi_cast_bf16(const float* x, void* out, int64_t n, void* stream);
+/* dst[i] = bf16(src[i] * seg_scale[j]) for i in [seg_start[j], seg_start[j + 1]) (sorted starts, multiples of 4, seg_start[0]
+ * = 0; the last segment runs to n): the whole flat f32 master-weight buffer of the training step becomes the bf16 operand
+ * packs of the next forward / backward in ONE launch, with the attention scale (and log2 e) folded into the to_q
+ * matrices (attention.py:171-177; what torch autocast / .to(bf16) would do per tensor). */
+int mobi_cast_bf16_segments(const float* src, void* dst, int64_t n, const int64_t* seg_start, const float* seg_scale,
+                            int32_t nseg, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Training step (config 5): LatentDiffusion.forward / p_losses (ldm/models/diffusion/ddpm.py:1040-1058, 1177-1217) and

@@ -994,6 +994,51 @@ extern "C" int mobi_scale_f32(const float* x, float s, float* out, int64_t n, vo
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
+namespace mobi {
+// dst[i] = bf16(src[i] * scale of the segment that holds i): segment j covers [seg_start[j], seg_start[j + 1]) (the last one
+// runs to n); starts are sorted and multiples of 4.  One thread = one 16-byte load; a block first checks whether its 1024
+// elements lie in a single segment (nearly always: segments are whole weight matrices).
+__global__ void __launch_bounds__(256)
+cast_bf16_segments_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ dst, long long n,
+                          const long long* __restrict__ seg_start, const float* __restrict__ seg_scale, int nseg) {
+    auto find = [&](long long i) {  // last segment whose start is <= i
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seg_start[mid] <= i) lo = mid;
+            else hi = mid - 1;
+        }
+        return lo;
+    };
+    __shared__ int s_seg;
+    __shared__ int s_uniform;
+    const long long b0 = (long long)blockIdx.x * 1024;
+    if (threadIdx.x == 0) {
+        const int j = find(b0);
+        s_seg = j;
+        s_uniform = (j + 1 >= nseg) || (seg_start[j + 1] >= min(n, b0 + 1024));
+    }
+    __syncthreads();
+    const long long i = b0 + 4 * threadIdx.x;
+    if (i >= n) return;
+    const float sc = seg_scale[s_uniform ? s_seg : find(i)];
+    const float4 v = *reinterpret_cast<const float4*>(src + i);
+    *reinterpret_cast<uint2*>(dst + i) = make_uint2(pack_bf16x2(v.x * sc, v.y * sc), pack_bf16x2(v.z * sc, v.w * sc));
+}
+}  // namespace mobi
+
+extern "C" int mobi_cast_bf16_segments(const float* src, void* dst, int64_t n, const int64_t* seg_start, const float* seg_scale,
+                                       int32_t nseg, void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(src && dst && seg_start && seg_scale && nseg > 0 && n > 0 && n % 4 == 0, "mobi_cast_bf16_segments: bad argument");
+    MOBI_CHECK(reinterpret_cast<uintptr_t>(src) % 16 == 0 && reinterpret_cast<uintptr_t>(dst) % 8 == 0,
+               "mobi_cast_bf16_segments: buffers must be 16-byte (src) / 8-byte (dst) aligned");
+    mobi::cast_bf16_segments_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(
+        src, reinterpret_cast<__nv_bfloat16*>(dst), n, reinterpret_cast<const long long*>(seg_start), seg_scale, nseg);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int mobi_cast_bf16(const float* x, void* out, int64_t n, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     if (n == 0) return 0;

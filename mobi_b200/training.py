@@ -168,7 +168,7 @@ class UNetTrainer:
         # flash-style kernels (attn_bwd_flash.cu) after the exact statistics pass; off = score tiles (dS, P) through HBM +
         # three batched GEMMs (kept as the A/B reference and for other shapes)
         self.flash_backward = flash_backward
-        self._fb_graphs, self._repack_graph = {}, None
+        self._fb_graphs, self._seg_start = {}, None
         unet.invalidate()
         unet.pack()
         self._pack_frozen_backward()
@@ -209,11 +209,13 @@ class UNetTrainer:
         self.bp = bp
 
     def _pack_matrix(self, w, scale=1.0, transposed=True):
-        """f32 master weight [N, K] (a view of the flat buffer) -> bf16 [N, K] for the forward, and the SAME bf16 copy
-        tagged for the dgrad GEMM dx = dy W, which reads it as an MN-major B operand (no transposed pack to rebuild after
-        every optimizer step)."""
-        src = w if scale == 1.0 else ops.scale_f32(w, scale)
-        fwd = ops.cast_bf16(src)
+        """f32 master weight [N, K] (a view of the flat parameter buffer) -> its bf16 operand pack: a VIEW of the flat bf16
+        mirror at the same offset (refreshed for all weights by one segmented-cast launch, `scale` folded in), and the same
+        view tagged for the dgrad GEMM dx = dy W, which reads it as an MN-major B operand (no transposed pack)."""
+        off = (w.data_ptr() - self.flat.params.data_ptr()) // 4
+        assert 0 <= off and off + w.numel() <= self.flat.numel and w.is_contiguous(), "not a view of the flat parameter buffer"
+        self._segments.append((off, w.numel(), float(scale)))
+        fwd = self._mirror[off:off + w.numel()].view(w.shape)
         return fwd, (_MnMajorB(fwd) if transposed else None)
 
     @staticmethod
@@ -227,24 +229,30 @@ class UNetTrainer:
 
     @torch.no_grad()
     def repack_trainable(self):
-        """bf16 operand copies (and transposes for dgrad) of the TRAINABLE weights: after every optimizer step.  With
-        CUDA graphs the ~500 small cast / transpose launches are captured once (the packed tensors then live at fixed
-        addresses in the graph's pool, which is what lets the forward/backward graph read them) and replayed."""
-        if not self.use_cuda_graph:
-            return self._repack_trainable()
-        if self._repack_graph is None:
-            self._repack_trainable()                     # warm-up outside capture
-            torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
-            before = ops.Stats.launches
-            with torch.cuda.graph(g):
-                self._repack_trainable()
-            self._repack_kernels = ops.Stats.launches - before
-            self._repack_graph = g
-            self._fb_graphs = {}                         # operand addresses changed
-        self._repack_graph.replay()
-        ops.Stats.launches += self._repack_kernels
+        """bf16 operand packs of the TRAINABLE weights after every optimizer step: ONE launch casts the whole flat f32
+        parameter buffer into its bf16 mirror (attention scales folded into the to_q segments); the packs are views of
+        the mirror, so their addresses never change and the captured forward/backward graphs keep reading them."""
+        if self._seg_start is None:
+            self._build_packs()
+        ops.Stats.launches += 1
+        L.check(L.load().mobi_cast_bf16_segments(self.flat.params.data_ptr(), self._mirror.data_ptr(), self.flat.numel,
+                                                   self._seg_start.data_ptr(), self._seg_scale.data_ptr(),
+                                                   self._seg_start.numel(), L.stream()), "cast_bf16_segments")
         self.unet._ctx_key = None
+
+    def _build_packs(self):
+        """Once: the pack views (self.tp) and the (start, scale) table of the segmented cast."""
+        self._mirror = torch.empty(self.flat.numel, device=self.device, dtype=torch.bfloat16)
+        self._segments = []
+        self._repack_trainable()
+        bounds = {0: 1.0}
+        for off, n, sc in sorted(self._segments):
+            bounds[off] = sc
+            bounds.setdefault(off + n, 1.0)          # what follows a scaled matrix is cast unscaled unless it is a pack itself
+        starts = sorted(b for b in bounds if b < self.flat.numel)
+        assert all(b % 4 == 0 for b in starts)
+        self._seg_start = torch.tensor(starts, device=self.device, dtype=torch.int64)
+        self._seg_scale = torch.tensor([bounds[b] for b in starts], device=self.device, dtype=torch.float32)
 
     def _repack_trainable(self):
         tp = {}
