@@ -343,6 +343,9 @@ int mobi_cast_bf16(const float* x, void* out, int64_t n, void* stream);
  * matrices (attention.py:171-177; what torch autocast / .to(bf16) would do per tensor). */
 int mobi_cast_bf16_segments(const float* src, void* dst, int64_t n, const int64_t* seg_start, const float* seg_scale,
                             int32_t nseg, void* stream);
+/* x[i] *= seg_scale[j] over the same kind of segment table, in place, skipping the blocks whose scale is 1: the chain rule
+ * through the scale folded into the packed to_q matrices (gradients w.r.t. W_q * scale -> w.r.t. W_q), one launch. */
+int mobi_scale_segments(float* x, int64_t n, const int64_t* seg_start, const float* seg_scale, int32_t nseg, void* stream);
 
 /* ------------------------------------------------------------------------------------------------------------------
  * Training step (config 5): LatentDiffusion.forward / p_losses (ldm/models/diffusion/ddpm.py:1040-1058, 1177-1217) and

@@ -219,6 +219,7 @@ SIGNATURES = {
     "mobi_scale_f32": (C.c_int, [_vp, _f32, _vp, _i64, _vp]),
     "mobi_cast_bf16": (C.c_int, [_vp, _vp, _i64, _vp]),
     "mobi_cast_bf16_segments": (C.c_int, [_vp, _vp, _i64, _vp, _vp, _i32, _vp]),
+    "mobi_scale_segments": (C.c_int, [_vp, _i64, _vp, _vp, _i32, _vp]),
     # training step
     "mobi_transpose_bf16": (C.c_int, [_vp, _i32, _vp, _i64, _i32, _i32, _i64, _i64, _i64, _i64, _vp]),
     "mobi_layernorm_bwd": (C.c_int, [C.POINTER(LayerNormBwdArgs), _vp]),

@@ -1027,6 +1027,52 @@ cast_bf16_segments_kernel(const float* __restrict__ src, __nv_bfloat16* __restri
 }
 }  // namespace mobi
 
+namespace mobi {
+// x[i] *= scale of the segment that holds i, touching only the blocks whose segment scale differs from 1 (same segment
+// table as the cast above): turns the gradients w.r.t. the scaled query projections into gradients w.r.t. to_q.weight.
+__global__ void __launch_bounds__(256)
+scale_segments_kernel(float* __restrict__ x, long long n, const long long* __restrict__ seg_start,
+                      const float* __restrict__ seg_scale, int nseg) {
+    auto find = [&](long long i) {
+        int lo = 0, hi = nseg - 1;
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (seg_start[mid] <= i) lo = mid;
+            else hi = mid - 1;
+        }
+        return lo;
+    };
+    __shared__ int s_seg;
+    __shared__ int s_uniform;
+    const long long b0 = (long long)blockIdx.x * 1024;
+    if (threadIdx.x == 0) {
+        const int j = find(b0);
+        s_seg = j;
+        s_uniform = (j + 1 >= nseg) || (seg_start[j + 1] >= min(n, b0 + 1024));
+    }
+    __syncthreads();
+    if (s_uniform && seg_scale[s_seg] == 1.0f) return;
+    const long long i = b0 + 4 * threadIdx.x;
+    if (i >= n) return;
+    const float sc = seg_scale[s_uniform ? s_seg : find(i)];
+    if (sc == 1.0f) return;
+    float4 v = *reinterpret_cast<float4*>(x + i);
+    v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+    *reinterpret_cast<float4*>(x + i) = v;
+}
+}  // namespace mobi
+
+extern "C" int mobi_scale_segments(float* x, int64_t n, const int64_t* seg_start, const float* seg_scale, int32_t nseg,
+                                   void* stream_) {
+    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+    MOBI_CHECK(x && seg_start && seg_scale && nseg > 0 && n > 0 && n % 4 == 0, "mobi_scale_segments: bad argument");
+    MOBI_CHECK(reinterpret_cast<uintptr_t>(x) % 16 == 0, "mobi_scale_segments: buffer must be 16-byte aligned");
+    mobi::scale_segments_kernel<<<(unsigned)((n + 1023) / 1024), 256, 0, stream>>>(
+        x, n, reinterpret_cast<const long long*>(seg_start), seg_scale, nseg);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
 extern "C" int mobi_cast_bf16_segments(const float* src, void* dst, int64_t n, const int64_t* seg_start, const float* seg_scale,
                                        int32_t nseg, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);

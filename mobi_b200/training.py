@@ -253,10 +253,12 @@ class UNetTrainer:
         assert all(b % 4 == 0 for b in starts)
         self._seg_start = torch.tensor(starts, device=self.device, dtype=torch.int64)
         self._seg_scale = torch.tensor([bounds[b] for b in starts], device=self.device, dtype=torch.float32)
+        # the same table for the gradients: the flat gradient buffer shares the parameter offsets, and only the to_q
+        # segments carry a scale (every other pack is cast with scale 1)
+        self._gseg_scale = self._seg_scale.clone()
 
     def _repack_trainable(self):
         tp = {}
-        self._qscales = []
         for blk in self._blocks():
             sc = blk.d_head ** -0.5
             d = {}
@@ -268,7 +270,6 @@ class UNetTrainer:
             d["a_bo"] = ca.to_out[0].bias.data
             d["a_wc"], d["a_wc_T"] = self._pack_matrix(blk.cond_adapter_connector.weight.data)
             d["a_bc"] = blk.cond_adapter_connector.bias.data
-            self._qscales.append((self._g(ca.to_q.weight), sc))
             for m in ("camera", "lidar"):
                 at = getattr(blk, "cross_modal_attn_" + m)
                 cn = getattr(blk, "cross_modal_connector_" + m)
@@ -279,7 +280,6 @@ class UNetTrainer:
                 d[m + "_bo"] = at.to_out[0].bias.data
                 d[m + "_wc"], d[m + "_wc_T"] = self._pack_matrix(cn.weight.data)
                 d[m + "_bc"] = cn.bias.data
-                self._qscales.append((self._g(at.to_q.weight), sc * LOG2E))
             tp[id(blk)] = d
         if self.bbox_embedder is not None:
             be = self.bbox_embedder
@@ -739,8 +739,9 @@ class UNetTrainer:
         if uncond and "bbox_uncond_vector" in self.flat.offsets:   # every row saw the same vector: sum over rows
             tops.colsum(self.d_context[:, 1].contiguous(), self.flat.grad("bbox_uncond_vector").reshape(1, -1))
         # gradients w.r.t. the scaled query projections -> w.r.t. to_q.weight
-        for gview, sc in self._qscales:
-            ops.scale_f32(gview, sc, out=gview)
+        ops.Stats.launches += 1
+        L.check(L.load().mobi_scale_segments(self.flat.grads.data_ptr(), self.flat.numel, self._seg_start.data_ptr(),
+                                             self._gseg_scale.data_ptr(), self._seg_start.numel(), L.stream()), "scale_segments")
         return self.loss_sum[0] / eps.numel()
 
     @torch.no_grad()
