@@ -103,6 +103,11 @@ typedef struct {
      * with batch > 1 and out_batch_stride = 0 the batch entries are K-slices of ONE product (split-K), e.g. a weight
      * gradient over 16,384 token rows whose 6 output tiles would otherwise occupy 6 of 148 SMs. */
     int32_t atomic_out;
+    /* Two-level batch: with batch_inner > 0 the batch index z splits into (z % batch_inner, z / batch_inner); the inner
+     * level uses the *_batch_stride fields, the outer level these (elements).  Heads inside batch rows: head h of batch row
+     * b of a token-major [B * T, H * D] matrix sits at b * T * ld + h * D, which no single stride expresses. */
+    int32_t batch_inner;
+    int64_t a_batch2_stride, b_batch2_stride, out_batch2_stride;
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);

@@ -31,6 +31,7 @@ class GemmArgs(C.Structure):
         ("KH", _i32), ("KW", _i32), ("pad_h", _i32), ("pad_w", _i32), ("tile_n", _i32), ("kernel", _i32),
         ("batch", _i32), ("a_batch_stride", _i64), ("b_batch_stride", _i64), ("out_batch_stride", _i64),
         ("pair", _i32), ("a_mn_major", _i32), ("b_mn_major", _i32), ("atomic_out", _i32),
+        ("batch_inner", _i32), ("a_batch2_stride", _i64), ("b_batch2_stride", _i64), ("out_batch2_stride", _i64),
     ]
 
 

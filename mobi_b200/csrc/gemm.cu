@@ -299,6 +299,28 @@ static int launch_gemm(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 
 using namespace mobi;
 
+// Operand tensor map for the (possibly batched, possibly two-level batched) GEMM: dim0 x dim1 matrix with row stride ld,
+// box0 x box1 tiles; batch entries `bs` elements apart, outer batch entries `bs2` elements apart.
+static int make_operand_map(CUtensorMap* tm, const void* base, uint64_t dim0, uint64_t dim1, uint64_t ld, uint32_t box0,
+                            uint32_t box1, int batch, int inner, int64_t bs, int64_t bs2) {
+    if (batch <= 1) {
+        uint64_t dims[2] = {dim0, dim1};
+        uint64_t strides[1] = {ld * 2};
+        uint32_t box[2] = {box0, box1};
+        return make_tensor_map_bf16(tm, base, 2, dims, strides, box);
+    }
+    if (inner <= 0) {
+        uint64_t dims[3] = {dim0, dim1, (uint64_t)batch};
+        uint64_t strides[2] = {ld * 2, (uint64_t)bs * 2};
+        uint32_t box[3] = {box0, box1, 1};
+        return make_tensor_map_bf16(tm, base, 3, dims, strides, box);
+    }
+    uint64_t dims[4] = {dim0, dim1, (uint64_t)inner, (uint64_t)(batch / inner)};
+    uint64_t strides[3] = {ld * 2, (uint64_t)bs * 2, (uint64_t)bs2 * 2};
+    uint32_t box[4] = {box0, box1, 1, 1};
+    return make_tensor_map_bf16(tm, base, 4, dims, strides, box);
+}
+
 extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
     MOBI_CHECK(a != nullptr, "mobi_gemm: null args");
@@ -333,6 +355,12 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     const bool batched = a->batch > 1;
     p.batch = batched ? a->batch : 1;
     p.out_batch_stride = batched ? a->out_batch_stride : 0;
+    p.batch_inner = (batched && a->batch_inner > 0) ? a->batch_inner : 0;
+    p.out_batch2_stride = p.batch_inner ? a->out_batch2_stride : 0;
+    if (p.batch_inner)
+        MOBI_CHECK(a->batch % a->batch_inner == 0 && a->a_batch2_stride % 8 == 0 && a->b_batch2_stride % 8 == 0 &&
+                       a->out_batch2_stride % 4 == 0 && a->kernel != 1,
+                   "mobi_gemm: batch_inner must divide batch; outer batch strides keep 16-byte alignment");
     if (batched) {
         MOBI_CHECK(p.mode == MOBI_EPI_PLAIN && !a->conv && a->out_seg == 0 && a->row_bias == nullptr,
                    "mobi_gemm: batch needs the PLAIN epilogue without conv / row segments / row_bias");
@@ -400,18 +428,16 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         MOBI_CHECK(a->lda % 8 == 0 && a->lda >= a->M, "mobi_gemm: MN-major A needs lda=%lld >= M and a multiple of 8",
                    (long long)a->lda);
         p.num_k_blocks = (int)((K + BK - 1) / BK);
-        uint64_t dims[3] = {(uint64_t)a->M, (uint64_t)K, (uint64_t)p.batch};
-        uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_batch_stride * 2};
-        uint32_t box[3] = {64, BK, 1};
-        if (make_tensor_map_bf16(&tmA, a->A, batched ? 3 : 2, dims, strides, box)) return 1;
+        if (make_operand_map(&tmA, a->A, (uint64_t)a->M, (uint64_t)K, (uint64_t)a->lda, 64, BK, p.batch, p.batch_inner,
+                             a->a_batch_stride, a->a_batch2_stride))
+            return 1;
     } else {
         MOBI_CHECK(a->K % 8 == 0 && a->lda % 8 == 0, "mobi_gemm: K=%lld and lda=%lld must be multiples of 8",
                    (long long)a->K, (long long)a->lda);
         p.num_k_blocks = (int)((K + BK - 1) / BK);
-        uint64_t dims[3] = {(uint64_t)K, (uint64_t)a->M, (uint64_t)p.batch};
-        uint64_t strides[2] = {(uint64_t)a->lda * 2, (uint64_t)a->a_batch_stride * 2};
-        uint32_t box[3] = {BK, BM, 1};
-        if (make_tensor_map_bf16(&tmA, a->A, batched ? 3 : 2, dims, strides, box)) return 1;
+        if (make_operand_map(&tmA, a->A, (uint64_t)K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM, p.batch, p.batch_inner,
+                             a->a_batch_stride, a->a_batch2_stride))
+            return 1;
     }
     p.atomic_out = a->atomic_out ? 1 : 0;
     if (p.atomic_out)
@@ -452,15 +478,14 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     p.pair = (a->kernel != 1 && gemm2_supported(p) && gemm2_pair_wanted(p, bn_tile, a->pair)) ? 1 : 0;
     MOBI_CHECK(a->pair != 1 || p.pair, "mobi_gemm: pair = 1 needs a problem the persistent kernel supports");
     if (p.b_mn) {
-        uint64_t dims[3] = {(uint64_t)a->N, (uint64_t)K, (uint64_t)p.batch};
-        uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)a->b_batch_stride * 2};
-        uint32_t box[3] = {64, BK, 1};
-        if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
+        if (make_operand_map(&tmB, a->B, (uint64_t)a->N, (uint64_t)K, (uint64_t)a->ldb, 64, BK, p.batch, p.batch_inner,
+                             a->b_batch_stride, a->b_batch2_stride))
+            return 1;
     } else {
-        uint64_t dims[3] = {(uint64_t)K, (uint64_t)a->N, (uint64_t)p.batch};
-        uint64_t strides[2] = {(uint64_t)a->ldb * 2, (uint64_t)a->b_batch_stride * 2};
-        uint32_t box[3] = {BK, (uint32_t)(p.pair ? bn_tile / 2 : bn_tile), 1};  // a CTA pair splits the B tile
-        if (make_tensor_map_bf16(&tmB, a->B, batched ? 3 : 2, dims, strides, box)) return 1;
+        // a CTA pair splits the B tile
+        if (make_operand_map(&tmB, a->B, (uint64_t)K, (uint64_t)a->N, (uint64_t)a->ldb, BK, (uint32_t)(p.pair ? bn_tile / 2 : bn_tile),
+                             p.batch, p.batch_inner, a->b_batch_stride, a->b_batch2_stride))
+            return 1;
     }
     MOBI_CHECK(!(p.a_mn || p.b_mn || p.atomic_out) || gemm2_supported(p),
                "mobi_gemm: MN-major operands / atomic_out are outside the persistent kernel's epilogue here");

@@ -317,6 +317,17 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
 // convolutions off the shared-memory read port.  The leader's warp 1 issues every MMA; TMA completions of both CTAs are
 // counted on the leader's `full` barriers, tcgen05.commit multicasts `empty` / `tfull` to both CTAs, and the epilogue
 // warps of both CTAs arrive on the leader's `tempty`.
+// Batched operand loads: one batch index z, or (z % inner, z / inner) over 4-D maps when the batch has two levels
+// (heads inside batch rows: head columns of token-major matrices have no single batch stride).
+__device__ __forceinline__ void tma_load_batched(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z, int inner) {
+    if (inner > 0) tma_load_4d(dst, tm, bar, x, y, z % inner, z / inner);
+    else tma_load_3d(dst, tm, bar, x, y, z);
+}
+__device__ __forceinline__ void tma_load_batched_pair(void* dst, const CUtensorMap* tm, uint64_t* bar, int x, int y, int z, int inner) {
+    if (inner > 0) tma_load_4d_pair(dst, tm, bar, x, y, z % inner, z / inner);
+    else tma_load_3d_pair(dst, tm, bar, x, y, z);
+}
+
 template <int BN, int MC, bool PAIR>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
@@ -407,8 +418,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             tma_load_4d_pair(dA, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w, y0 + kh - p.pad_h, n0);
                             tma_load_2d_pair(dB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0);
                         } else if (p.batch > 1) {
-                            tma_load_3d_pair(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
-                            tma_load_3d_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0, z);
+                            tma_load_batched_pair(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z, p.batch_inner);
+                            tma_load_batched_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0, z, p.batch_inner);
                         } else {
                             tma_load_2d_pair(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
                             tma_load_2d_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0);
@@ -421,21 +432,21 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         // the tile; K-major operands keep their single [rows][64 k] box
                         if (p.a_mn) {
                             for (int c = 0; c < BM / 64; ++c) {
-                                if (p.batch > 1) tma_load_3d(dA + c * 8192, &tmA, &full_bar[s], m_tile * BM + c * 64, kb * BK, z);
+                                if (p.batch > 1) tma_load_batched(dA + c * 8192, &tmA, &full_bar[s], m_tile * BM + c * 64, kb * BK, z, p.batch_inner);
                                 else tma_load_2d(dA + c * 8192, &tmA, &full_bar[s], m_tile * BM + c * 64, kb * BK);
                             }
                         } else if (p.batch > 1) {
-                            tma_load_3d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
+                            tma_load_batched(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z, p.batch_inner);
                         } else {
                             tma_load_2d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
                         }
                         if (p.b_mn) {
                             for (int c = 0; c < BN / 64; ++c) {
-                                if (p.batch > 1) tma_load_3d(dB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK, z);
+                                if (p.batch > 1) tma_load_batched(dB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK, z, p.batch_inner);
                                 else tma_load_2d(dB + c * 8192, &tmB, &full_bar[s], b_row0 + c * 64, kb * BK);
                             }
                         } else if (p.batch > 1) {
-                            tma_load_3d(dB, &tmB, &full_bar[s], kb * BK, b_row0, z);
+                            tma_load_batched(dB, &tmB, &full_bar[s], kb * BK, b_row0, z, p.batch_inner);
                         } else {
                             tma_load_2d(dB, &tmB, &full_bar[s], kb * BK, b_row0);
                         }
@@ -447,8 +458,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                         tma_load_4d(dA, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w, y0 + kh - p.pad_h, n0);
                         tma_load_2d(dB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0);
                     } else if (p.batch > 1) {
-                        tma_load_3d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z);
-                        tma_load_3d(dB, &tmB, &full_bar[s], kb * BK, b_row0, z);
+                        tma_load_batched(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM, z, p.batch_inner);
+                        tma_load_batched(dB, &tmB, &full_bar[s], kb * BK, b_row0, z, p.batch_inner);
                     } else {
                         tma_load_2d(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
                         tma_load_2d(dB, &tmB, &full_bar[s], kb * BK, b_row0);
@@ -507,7 +518,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
             gemm2_epilogue<BN, MC>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane,
-                               (long long)z * p.out_batch_stride);
+                               p.batch_inner > 0 ? (long long)(z % p.batch_inner) * p.out_batch_stride + (long long)(z / p.batch_inner) * p.out_batch2_stride
+                                                 : (long long)z * p.out_batch_stride);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {

@@ -30,6 +30,8 @@ struct GemmParams {
     int pair;                     // 1: run as 2-CTA clusters (cta_group::2, 256-row tiles, B box = BN / 2 rows)
     int batch;                    // > 1: batched problem, A/B through 3-D tensor maps
     long long out_batch_stride;   // elements
+    int batch_inner;              // > 0: two-level batch, z -> (z % batch_inner, z / batch_inner) over 4-D operand maps
+    long long out_batch2_stride;  // elements between outer batch entries of the output
     int atomic_out;               // f32 output accumulated with atomic adds (split-K over the batch index)
     int a_mn, b_mn;               // operand given MN-major ([K, M] / [K, N] row-major): 64 x 64 TMA boxes, UMMA major bits
 };

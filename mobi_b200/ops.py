@@ -85,7 +85,7 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
          tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
          kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0, a_mn=False, b_mn=False,
-         atomic_out=False):
+         atomic_out=False, batch_inner=0, a_batch2_stride=0, b_batch2_stride=0, out_batch2_stride=0):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
@@ -143,6 +143,8 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.pair = pair
     args.a_mn_major, args.b_mn_major = (1 if a_mn else 0), (1 if b_mn else 0)
     args.atomic_out = 1 if atomic_out else 0
+    args.batch_inner = batch_inner
+    args.a_batch2_stride, args.b_batch2_stride, args.out_batch2_stride = a_batch2_stride, b_batch2_stride, out_batch2_stride
     kind = "gemm"
     if _SHAPE_KINDS:   # MOBI_GEMM_SHAPES=1: per-shape accounting for tools/train_bench.py
         kind = "gemm M%d N%d K%d b%d%s%s%s" % (M, N, K, batch, " amn" if a_mn else "", " bmn" if b_mn else "",

@@ -340,6 +340,27 @@ class UNetTrainer:
             # reach HBM, only dS and P (bf16, both row-major) are written
             tops.attn_bwd_tiles(q, k, v, do, ws_all["stats"], ws_all["dS"], None, ws_all["Pt"], heads=H, tokens=T,
                                 head_dim=D, ld_do=C, dscale=tops.LN2, batch_rows=B)
+        if not fused and lse is None and B * H * TT * 14 <= (256 << 20):
+            # small levels (16 x 16, 8 x 8: head_dim 160): ALL batch rows and heads in one launch per product through the
+            # two-level batch of mobi_gemm (head h of batch row b of a token-major matrix = b * T * ld + h * D)
+            wsa = self._attn_ws(B * H, T, False)
+            two = dict(batch=B * H, batch_inner=H)
+            ldq, ldkv = dq_out.stride(0), dkv_out.stride(0)
+            ops.gemm(q, k, out=wsa["S"], out_dtype=f32, M=T, N=T, K=D, lda=D, ldb=D, ldo=T, batch=B * H, a_batch_stride=TD,
+                     b_batch_stride=TD, out_batch_stride=TT)
+            ops.gemm(do, v, out=wsa["dP"], out_dtype=f32, M=T, N=T, K=D, lda=C, ldb=D, ldo=T, a_batch_stride=D,
+                     a_batch2_stride=T * C, b_batch_stride=TD, b_batch2_stride=H * TD, out_batch_stride=TT,
+                     out_batch2_stride=H * TT, **two)
+            tops.attn_softmax_bwd(wsa["S"], wsa["dP"], wsa["dS"], wsa["dSt"], wsa["Pt"], wsa["stats"], T, T, tops.LN2,
+                                  batch=B * H)
+            for a_op, b_op, ldb_, bs1, bs2, out, ldo_ in (
+                    (wsa["dS"], k, D, TD, H * TD, dq_out[:, dq_col:dq_col + C], ldq),
+                    (wsa["dSt"], q, D, TD, H * TD, dkv_out[:, dk_col:dk_col + C], ldkv),
+                    (wsa["Pt"], do, C, D, T * C, dkv_out[:, dv_col:dv_col + C], ldkv)):
+                ops.gemm(a_op, b_op, out=out, M=T, N=D, K=T, lda=T, ldb=ldb_, ldo=ldo_, b_mn=True, a_batch_stride=TT,
+                         a_batch2_stride=H * TT, b_batch_stride=bs1, b_batch2_stride=bs2, out_batch_stride=D,
+                         out_batch2_stride=T * ldo_, **two)
+            return
         for b in range(B):
             rows = slice(b * T, (b + 1) * T)
             hs = slice(b * H, (b + 1) * H)
