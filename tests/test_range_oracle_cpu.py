@@ -82,3 +82,21 @@ def test_points_in_box_axis_aligned():
     corners = ro.box_corners((0, 0, 0), (2, 2, 2), 0.0)[None]
     pts = np.array([[0, 0, 0], [0.99, 0.99, 0.99], [1.0, 0, 0], [1.01, 0, 0], [0, -1.5, 0]], np.float32)
     assert ro.points_in_bbox_corners(pts, corners)[:, 0].tolist() == [True, True, False, False, False]
+
+
+def test_device_path_refuses_cpu_tensors():
+    """The product path has no CPU fallback: every entry of mobi_b200.lidar raises on host tensors before any launch."""
+    import torch
+    from mobi_b200 import lidar
+    x = torch.zeros(2, 1, 8, 8)
+    with pytest.raises(RuntimeError):
+        lidar.inverse_depth_normalization(x, 0.0, 0.5)
+    with pytest.raises(RuntimeError):
+        lidar.postprocess_range_depth(range_depth=x, range_depth_orig=torch.zeros(2, 4, 16), crop_left=torch.tensor([0, 0]),
+                                      width_crop=torch.tensor([8, 8]))
+    with pytest.raises(RuntimeError):
+        lidar.points_in_bbox_corners(torch.zeros(4, 3), torch.zeros(1, 8, 3))
+    with pytest.raises(RuntimeError):
+        lidar.postprocess_lidar_samples(torch.zeros(1, 3, 8, 8), {}, torch.zeros(1, 8, 3))
+    with pytest.raises(RuntimeError):
+        lidar.LidarConverter(H=4, W=16).range2pcd(torch.zeros(4, 16), torch.zeros(4, 16), torch.zeros(4, 16))
