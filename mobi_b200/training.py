@@ -316,9 +316,13 @@ class UNetTrainer:
     def _attn_bwd(self, q, k, v, do, B, H, D, T, dq_out, dq_col, dkv_out, dk_col, dv_col, o=None, lse=None):
         """Backward of softmax(q' k^T) v per (row, head) (CrossAttention.forward, attention.py:179-192).
         q, k, v: bf16 [B*H, T, D] (q' carries scale*log2e); do: bf16 [B*T, C] token-major.  Writes dq', dk, dv as
-        [T, D] blocks at the given column offsets of the token-major outputs.  Per batch row: five BATCHED (batch = heads)
-        tcgen05 GEMMs around one batched softmax-backward launch; the score tiles of one batch row (S, dP in f32; dS,
-        dS^T, P^T in bf16) live in a reused workspace."""
+        [T, D] blocks at the given column offsets of the token-major outputs.  Three routes:
+          * head_dim <= 128 and T % 128 == 0 (64^2 and 32^2 levels): exact statistics pass + the two flash-style kernels,
+            no T x T tile in HBM (attn_bwd_flash.cu);
+          * small levels (16^2, 8^2; head_dim 160): materialised f32 S / dP and bf16 dS / dS^T / P^T tiles, every product
+            ONE launch over all batch rows and heads through the two-level batch of mobi_gemm;
+          * otherwise (flash_backward=False, lse_backward=True, huge tiles): the same per batch row with a reused workspace,
+            the score tiles from the fused score-tile kernel when possible."""
         C = H * D
         TD, TT = T * D, T * T
         fused = D <= 128 and T % 128 == 0 and not (lse is not None and getattr(self, "lse_backward", False))
