@@ -139,3 +139,18 @@ def test_two_rank_gloo_gradient_allreduce_matches_full_batch():
             checked += 1
         off += sz
     assert checked == 81
+
+
+def test_wgrad_split_k_policy():
+    """Host logic of the split-K weight gradient: slices are a power of two that divides the token count, at least 512 rows
+    each, and only as many as it takes for tiles x slices to fill the SMs."""
+    from mobi_b200.train_ops import wgrad_splits
+    assert wgrad_splits(16384, 320, 320) == 32            # 6 output tiles on 148 SMs
+    assert wgrad_splits(8192, 320, 320) == 16             # slices never shorter than 512 rows
+    assert wgrad_splits(4096, 640, 640) == 8
+    assert wgrad_splits(1024, 1280, 1280) == 2
+    assert wgrad_splits(512, 1280, 1280) == 1
+    assert wgrad_splits(16384, 2560, 1280) == 1           # 160 tiles already fill the machine
+    for M in (520, 1000, 12288):
+        s = wgrad_splits(M, 320, 320)
+        assert M % s == 0 and (s == 1 or M // s >= 512)
