@@ -1,13 +1,17 @@
 #!/usr/bin/env python
 """bench.py — MObI joint camera+lidar inpainting throughput on B200 (contract: see the task brief).
 
-One "step" = one full 50-step DDIM sampling run with classifier-free guidance of a batch of joint samples at the
-mobi_nusc_512 shape (latent 64x64; 2 UNet rows per joint sample, 4 with CFG).  Work is sharded over GPUs by
-sample (no collective on the data path): every rank samples `--samples-per-gpu` joint samples, so the 8-GPU run
-is config[2] of BASELINE.json (batch 64 over 8 B200) and scaling is weak.
+Workload = BASELINE.json config 3 AS WRITTEN: mobi_nusc_512.yaml, 50-step DDIM joint camera+lidar inpainting with
+classifier-free guidance 5, batch 64 joint samples sharded over the N GPUs of one box (64 / N per GPU: 64 on one GPU,
+8 each on eight), i.e. STRONG scaling of a fixed job.  One "step" = one full 50-step DDIM sampling pass over the rank's
+shard (latent 64x64; 2 UNet rows per joint sample, 4 with CFG), run in micro-batches of --micro-batch joint samples
+(default 16 = 64 UNet rows per call).  No collective on the data path.  The weak-scaling figure of round 1 (8 joint
+samples per GPU whatever N) is kept as the secondary key `weak_8_per_gpu`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--samples-per-gpu 8] [--latent 64] [--ddim-steps 50]
-  python bench.py --impl reference ...     # the reference algorithm (oracle port) on the host CPU cores
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--total-samples 64] [--micro-batch 16] [--latent 64]
+  python bench.py --samples-per-gpu 8 ...  # fixed per-GPU shard instead of total / N (weak scaling)
+  python bench.py --impl reference ...     # the reference's own CPU path (unmodified reference modules where
+                                           # /root/reference exists, else the oracle port) on the host cores
 """
 import argparse
 import json
@@ -30,10 +34,16 @@ CFG_SCALE = 5.0
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
-    ap.add_argument("--samples-per-gpu", type=int, default=8)
+    ap.add_argument("--total-samples", type=int, default=64, help="joint samples of the whole job (config 3: 64)")
+    ap.add_argument("--samples-per-gpu", type=int, default=0,
+                    help="fixed per-GPU shard (weak scaling) instead of total-samples / gpus")
+    ap.add_argument("--micro-batch", type=int, default=16, help="joint samples per sampler call on one GPU")
+    ap.add_argument("--budget-s", type=float, default=760.0,
+                    help="wall-clock guard: the driver kills a run at 870 s; if W + K full steps would not fit, fewer "
+                         "timed steps are run and the line says so (steps_requested)")
     ap.add_argument("--latent", type=int, default=64)
     ap.add_argument("--ddim-steps", type=int, default=50)
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -88,58 +98,114 @@ class ClockSampler(threading.Thread):
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def workload_name(args):
+def job_shape(args, world):
+    """(joint samples per GPU, total joint samples, micro-batch, scaling) of this run."""
+    if args.samples_per_gpu > 0:
+        n, total, scaling = args.samples_per_gpu, args.samples_per_gpu * world, "weak"
+    else:
+        if args.total_samples % world:
+            raise SystemExit("bench.py: --total-samples %d is not divisible by %d GPUs" % (args.total_samples, world))
+        n, total, scaling = args.total_samples // world, args.total_samples, "strong"
+    mb = max(1, min(args.micro_batch, n))
+    while n % mb:
+        mb -= 1
+    return n, total, mb, scaling
+
+
+def workload_name(args, world=None):
+    world = world or args.gpus
+    n, total, mb, scaling = job_shape(args, world)
     if args.pbe:
-        return "pbe.yaml %d-step DDIM + CFG %.1f camera-only inpainting at latent %d, %d samples/GPU" % (
-            args.ddim_steps, CFG_SCALE, args.latent, args.samples_per_gpu)
+        return "pbe.yaml %d-step DDIM + CFG %.1f camera-only inpainting at latent %d, batch %d over %d GPU(s) = %d " \
+               "samples/GPU in micro-batches of %d" % (args.ddim_steps, CFG_SCALE, args.latent, total, world, n, mb)
     return ("mobi_nusc_512" if args.latent == 64 else "mobi_nusc_256") + \
-        " %d-step DDIM + CFG %.1f joint camera+lidar inpainting, %d joint samples/GPU" % (
-            args.ddim_steps, CFG_SCALE, args.samples_per_gpu)
+        " %d-step DDIM + CFG %.1f joint camera+lidar inpainting, batch %d joint samples over %d GPU(s) = %d/GPU in " \
+        "micro-batches of %d (%d UNet rows per call)" % (args.ddim_steps, CFG_SCALE, total, world, n, mb, 4 * mb)
 
 
 # ---------------------------------------------------------------------------------------------- reference arm
-def cpu_reference_step(latent, threads, n_joint=1, repeats=1):
-    """The reference algorithm (oracle port: oracle/unet_oracle.py + sampler_oracle.py) on the host CPU, fp32, all
-    cores: ONE DDIM step with CFG of `n_joint` joint samples (4 rows each).  Returns seconds per step."""
-    import torch
-    from oracle import sampler_oracle as so
-    from oracle import unet_oracle as uo
-    torch.set_num_threads(threads)
-    cfg = uo.default_unet_config(image_size=latent)
-    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
-    inp = uo.synth_inputs(n_joint, latent, seed=1)
-    sched = so.register_schedule()
-    apply_model = lambda x, t, c: uo.unet_forward(sd, cfg, x, t, c)
-    times = []
-    with torch.no_grad():
-        for _ in range(repeats):
-            t0 = time.perf_counter()
-            so.ddim_sample(apply_model, sched, 50, inp["x_T"], inp["cond"], inp["uc"], CFG_SCALE, inp["inpaint_image"],
-                           inp["inpaint_mask"], steps_to_run=1)
-            times.append(time.perf_counter() - t0)
-    return times
+class CpuReference:
+    """The reference's CPU implementation of the path, fp32, all host cores: ONE DDIM step with CFG (one p_sample_ddim
+    call, ddim.py:165-213 = the config-1 unit of BASELINE.json) of `n_joint` joint samples at the workload's latent size.
+
+    kind "reference": the UNMODIFIED reference modules (LatentDiffusion.apply_model + DDIMSampler.p_sample_ddim) imported
+    from MOBI_REFERENCE_ROOT through oracle/ref_shims.py, where that tree exists (the build container);
+    kind "port": oracle/unet_oracle.py + sampler_oracle.py (the GPU box has no reference tree).
+    A whole 50-step sample of one joint sample takes ~6 minutes of CPU time, so the bounded sample is one step and the
+    samples/s figure is that step x 50 ("extrapolated": true); `seconds` are the measured ones."""
+
+    def __init__(self, latent, threads, n_joint=1, state_dict=None):
+        import torch
+        from oracle import ref_shims
+        from oracle import sampler_oracle as so
+        from oracle import unet_oracle as uo
+        torch.set_num_threads(threads)
+        self.threads, self.latent, self.n_joint = threads, latent, n_joint
+        self.cfg = uo.default_unet_config(image_size=latent)
+        self.sd = state_dict if state_dict is not None else uo.synth_state_dict(uo.state_dict_shapes(self.cfg), seed=0)
+        self.inp = uo.synth_inputs(n_joint, latent, seed=1)
+        self.kind = "port"
+        self.so, self.uo = so, uo
+        self.sched = so.register_schedule()
+        if ref_shims.reference_available():
+            try:
+                ref_shims.install()
+                from oracle.make_golden import build_reference_ldm
+                from ldm.models.diffusion.ddim import DDIMSampler
+                model = build_reference_ldm(dict(self.cfg))
+                model.model.diffusion_model.load_state_dict(self.sd, strict=True)
+                self.sampler = DDIMSampler(model)
+                self.sampler.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+                self.kind = "reference"
+            except Exception as exc:   # an incomplete tree: fall back to the port and say why on stderr
+                print("bench.py: reference tree present but not usable (%s: %s); timing the oracle port"
+                      % (type(exc).__name__, str(exc)[:200]), file=sys.stderr)
+
+    def step(self):
+        """Returns (seconds, x_prev) of one DDIM + CFG step at index 49 (t = 981) from x_T."""
+        import torch
+        inp = self.inp
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            if self.kind == "reference":
+                ts = torch.full((inp["x_T"].shape[0],), 981, dtype=torch.long)
+                x_prev, _ = self.sampler.p_sample_ddim(
+                    inp["x_T"], inp["cond"], ts, index=49, unconditional_guidance_scale=CFG_SCALE,
+                    unconditional_conditioning=inp["uc"],
+                    test_model_kwargs=dict(inpaint_image=inp["inpaint_image"], inpaint_mask=inp["inpaint_mask"]))
+            else:
+                x_prev, _ = self.so.ddim_sample(lambda x, t, c: self.uo.unet_forward(self.sd, self.cfg, x, t, c),
+                                                self.sched, 50, inp["x_T"], inp["cond"], inp["uc"], CFG_SCALE,
+                                                inp["inpaint_image"], inp["inpaint_mask"], steps_to_run=1)
+        return time.perf_counter() - t0, x_prev
+
+    def describe(self, seconds, ddim_steps):
+        return {"value": 1.0 * self.n_joint / (ddim_steps * seconds), "unit": "samples/s", "cores": self.threads,
+                "kind": self.kind, "extrapolated": True, "measured_seconds": seconds,
+                "sample": "ONE DDIM step (one CFG UNet evaluation, %d rows) of %d joint sample(s) at latent %d, fp32, "
+                          "%.1f s measured; samples/s = 1 / (%d steps x that)"
+                          % (4 * self.n_joint, self.n_joint, self.latent, seconds, ddim_steps)}
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    import torch
     threads = os.cpu_count() or 1
-    # bounded sample: each bench "step" is ONE DDIM step (one CFG UNet evaluation) of ONE joint sample at the
-    # workload's latent size; samples/s = 1 / (ddim_steps * seconds per DDIM step)
-    times = cpu_reference_step(args.latent, threads, 1, repeats=args.warmup + args.steps)[args.warmup:]
+    ref = CpuReference(args.latent, threads, 1)
+    # bounded sample: each bench "step" is ONE DDIM step (one CFG UNet evaluation) of ONE joint sample at the workload's
+    # latent size; ms_per_step is what was measured, `value` extrapolates it to whole 50-step samples
+    times = [ref.step()[0] for _ in range(args.warmup + args.steps)][args.warmup:]
     sec = sum(times) / len(times)
-    value = 1.0 / (args.ddim_steps * sec)
-    sample = "1 DDIM step (CFG UNet call, 4 rows) of 1 joint sample at latent %d, fp32, x%d => /%d steps" % (
-        args.latent, args.ddim_steps, args.ddim_steps)
-    line = {"impl": "reference", "metric": "inpainted joint samples/sec (50-step DDIM + CFG)", "value": value,
+    base = ref.describe(sec, args.ddim_steps)
+    line = {"impl": "reference", "metric": "inpainted joint samples/sec (50-step DDIM + CFG)", "value": base["value"],
             "unit": "samples/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": sec * 1e3 * args.ddim_steps, "higher_is_better": True, "scaling": "weak",
+            "ms_per_step": sec * 1e3, "step_is": "one DDIM step of one joint sample (bounded sample of the workload)",
+            "higher_is_better": True, "scaling": "strong" if args.samples_per_gpu <= 0 else "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "inputs": "larger than L2 (4.2 GB fp32 weights)"},
-            "cpu_baseline": {"value": value, "unit": "samples/s", "cores": threads, "kind": "port", "sample": sample},
-            "e2e": {"value": value, "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "samples/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
@@ -235,6 +301,35 @@ def measure_range_post(dev, n, px, cpu_samples=2, iters=20):
             "matches_cpu_port_bit_exact": same}
 
 
+# ---------------------------------------------------------------------------------------------- VAE decode roofline
+VAE_DECODE_FLOPS = {64: (2.515e12, 2.685e12), 32: (0.622e12, 0.665e12)}   # per sample: camera, lidar
+
+
+def measure_vae_decode(ldm, dev, n, latent, peak_sustained, peak_burst, iters=3):
+    """decode_first_stage of `n` latents for both modalities, CUDA events on the launching stream; FLOPs = the reference's
+    own count per sample."""
+    import torch
+    z = torch.randn(n, 4, latent, latent, device=dev)
+    out = {}
+    for name, module_name, fl in (("camera", "first_stage_model", VAE_DECODE_FLOPS[latent][0]),
+                                  ("lidar", "lidar_stage_model", VAE_DECODE_FLOPS[latent][1])):
+        if getattr(ldm, module_name, None) is None:
+            continue
+        ldm.decode_first_stage(z, module_name=module_name)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(iters):
+            ldm.decode_first_stage(z, module_name=module_name)
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / iters
+        tf = n * fl / (ms / 1e3) / 1e12
+        out[name] = {"ms_per_%d_samples" % n: ms, "tflops": tf, "frac_of_sustained_peak": tf / peak_sustained,
+                     "frac_of_burst_peak": tf / peak_burst}
+    return out
+
+
 # ---------------------------------------------------------------------------------------------- native arm
 def run_native(args):
     import torch
@@ -242,6 +337,7 @@ def run_native(args):
     from mobi_b200 import ops, sharding, synth
     from mobi_b200.ddim import DDIMSampler
 
+    t_start = time.perf_counter()
     if not torch.cuda.is_available():
         raise RuntimeError("bench.py: no CUDA device; the native arm has no CPU fallback")
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -251,15 +347,15 @@ def run_native(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.samples_per_gpu
+    n, total, mb, scaling = job_shape(args, world)
     latent = args.latent
     rps = 1 if args.pbe else 2                 # UNet rows per sample: camera only, or (camera, lidar)
     ldm = synth.build_synthetic_ldm(latent=latent, use_lidar=not args.pbe, device=dev, seed=0, with_vae=True)
     sampler = DDIMSampler(ldm, use_cuda_graph=not args.no_graph)
-    # the job is n * world joint samples cut into per-rank shards between samples (mobi_b200/sharding.py); every
-    # sample's inputs and noise depend on its GLOBAL index only, so results do not depend on the number of GPUs
-    lo, hi = sharding.shard_bounds(n * world, world, rank)
-    full = synth.synthetic_inputs(n * world, latent, seed=1, rows_per_sample=rps, n_ctx=1 if args.pbe else 2)
+    # the job is `total` joint samples cut into per-rank shards between samples (mobi_b200/sharding.py); every sample's
+    # inputs and noise depend on its GLOBAL index only, so results do not depend on the number of GPUs
+    lo, hi = sharding.shard_bounds(total, world, rank)
+    full = synth.synthetic_inputs(total, latent, seed=1, rows_per_sample=rps, n_ctx=1 if args.pbe else 2)
     host = {k: sharding.shard_rows(v, world, rank, rows_per_sample=rps).contiguous() for k, v in full.items()}
     host["x_T"] = sharding.sample_noise((4, latent, latent), lo, hi, base_seed=1, rows_per_sample=rps)
     host = {k: v.pin_memory() for k, v in host.items()}
@@ -267,29 +363,38 @@ def run_native(args):
     px = 8 * latent
     host_img = torch.empty((n, 3, px, px), dtype=torch.float32).pin_memory()
     host_rng = torch.empty((n, 2, px, px), dtype=torch.float32).pin_memory()
+    chunks = [(i * mb * rps, (i + 1) * mb * rps) for i in range(n // mb)]   # micro-batches: row ranges of the shard
 
-    def sample_from(inp):
-        return sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=rps * n, shape=[4, latent, latent],
-                              verbose=False, unconditional_guidance_scale=CFG_SCALE,
-                              unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
-                              test_model_kwargs=dict(inpaint_image=inp["inpaint_image"],
-                                                     inpaint_mask=inp["inpaint_mask"]))[0]
+    def sample_rows(inp, a, b):
+        return sampler.sample(S=args.ddim_steps, conditioning=inp["cond"][a:b], batch_size=b - a,
+                              shape=[4, latent, latent], verbose=False, unconditional_guidance_scale=CFG_SCALE,
+                              unconditional_conditioning=inp["uc"][a:b], eta=0.0, x_T=inp["x_T"][a:b],
+                              test_model_kwargs=dict(inpaint_image=inp["inpaint_image"][a:b],
+                                                     inpaint_mask=inp["inpaint_mask"][a:b]))[0]
 
     def step_device():
-        return sample_from(devin)
+        return [sample_rows(devin, a, b) for a, b in chunks]
 
     def step_e2e():
         """What a user of the reference runs per batch (scripts/inference_test_bench.py:414-464): inputs from pinned host
         memory, sampler.sample, decode_sample, decode_first_stage for both modalities, decoded images back to the host."""
-        inp = {k: v.to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
-        out = sample_from(inp)
-        if args.pbe:
-            host_img.copy_(ldm.decode_first_stage(out), non_blocking=True)
-            return out
-        h_cam, h_lid = ldm.decode_sample(out, out[1::2])
-        host_img.copy_(ldm.decode_first_stage(h_cam), non_blocking=True)       # D2H of the results
-        host_rng.copy_(ldm.decode_first_stage(h_lid, module_name="lidar_stage_model"), non_blocking=True)
-        return out
+        outs = []
+        for a, b in chunks:
+            inp = {k: v[a:b].to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
+            out = sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=b - a, shape=[4, latent, latent],
+                                 verbose=False, unconditional_guidance_scale=CFG_SCALE,
+                                 unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
+                                 test_model_kwargs=dict(inpaint_image=inp["inpaint_image"],
+                                                        inpaint_mask=inp["inpaint_mask"]))[0]
+            s0, s1 = a // rps, b // rps
+            if args.pbe:
+                host_img[s0:s1].copy_(ldm.decode_first_stage(out), non_blocking=True)
+            else:
+                h_cam, h_lid = ldm.decode_sample(out, out[1::2])
+                host_img[s0:s1].copy_(ldm.decode_first_stage(h_cam), non_blocking=True)       # D2H of the results
+                host_rng[s0:s1].copy_(ldm.decode_first_stage(h_lid, module_name="lidar_stage_model"), non_blocking=True)
+            outs.append(out)
+        return outs
 
     def barrier():
         if world > 1:
@@ -309,40 +414,73 @@ def run_native(args):
             dist.all_reduce(ms, op=dist.ReduceOp.MAX)
         return ms.item()
 
-    for _ in range(args.warmup):
+    # ---- warm-up (first step also captures the CUDA graphs), then the wall-clock guard
+    steps, warmup = args.steps, max(args.warmup, 1)
+    tw0 = time.perf_counter()
+    step_device()
+    torch.cuda.synchronize()
+    t_first = time.perf_counter() - tw0
+    tw1 = time.perf_counter()
+    if warmup > 1:
+        step_device()
+        torch.cuda.synchronize()
+    t_step = (time.perf_counter() - tw1) if warmup > 1 else t_first
+    e2e_steps = min(steps, 3)
+    tail_s = 60.0 + (e2e_steps + 1) * t_step * 1.08          # e2e leg + roofline / train / CPU legs
+    projected = (time.perf_counter() - t_start) + (max(0, warmup - 2) + steps) * t_step + tail_s
+    steps_requested = steps
+    if projected > args.budget_s:
+        g = torch.tensor([max(3, int((args.budget_s - (time.perf_counter() - t_start) - tail_s) / t_step) -
+                              max(0, warmup - 2))], device=dev)
+        if world > 1:
+            dist.all_reduce(g, op=dist.ReduceOp.MIN)
+        steps = min(steps, int(g.item()))
+        print("bench.py: %d + %d steps of %.1f s would not fit the %.0f s wall-clock budget: timing %d steps"
+              % (warmup, steps_requested, t_step, args.budget_s, steps), file=sys.stderr)
+    for _ in range(max(0, warmup - 2)):
         step_device()
     clocks = ClockSampler(local)
     clocks.start()
     launches0, evals0 = ops.Stats.launches, sampler.launches
-    ms = timed(step_device, args.steps)
+    ms = timed(step_device, steps)
     gpu_launches = ops.Stats.launches - launches0
     unet_evals = sampler.launches - evals0
     clock_info = clocks.finish()
-    step_e2e()
-    ms_e2e = timed(step_e2e, args.steps)
+    first = step_e2e()[0]
+    ms_e2e = timed(step_e2e, e2e_steps)
 
-    total_samples = n * world * args.steps
-    value = total_samples / (ms / 1e3)
-    e2e_value = total_samples / (ms_e2e / 1e3)
+    value = n * world * steps / (ms / 1e3)
+    e2e_value = n * world * e2e_steps / (ms_e2e / 1e3)
     h2d = sum(v.numel() * v.element_size() for v in host.values())
     d2h = host_img.numel() * 4 + (0 if args.pbe else host_rng.numel() * 4)
 
+    # ---- weak-scaling figure of round 1: 8 joint samples per GPU whatever N (secondary)
+    weak = None
+    if not args.pbe and args.samples_per_gpu <= 0 and n >= 8:
+        w8 = lambda: sample_rows(devin, 0, 8 * rps)                                            # noqa: E731
+        w8()
+        ms_w = timed(w8, 3)
+        weak = {"joint_samples_per_gpu": 8, "value": 8 * world * 3 / (ms_w / 1e3), "unit": "samples/s",
+                "ms_per_step": ms_w / 3, "steps": 3, "unet_step_ms": ms_w / 3 / args.ddim_steps}
+
     # ---- roofline of the dominant kernel class (tcgen05 GEMM / implicit conv), timed live with CUDA events on
-    # the launching stream over one eager UNet evaluation of the same batch
+    # the launching stream over one eager UNet evaluation of one micro-batch
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     peak_tf = peaks.get("bf16_tflops_sustained", 1400.0)
-    peak_src = "of measured (MEASURED_PEAKS.json bf16_tflops_sustained)" if peaks else \
+    peak_burst = peaks.get("bf16_tflops", 1590.0)
+    peak_src = "of measured (MEASURED_PEAKS.json bf16_tflops_sustained; burst figure beside it)" if peaks else \
         "of fallback (1.4 PFLOP/s sustained under the power cap; B200_PROFILING.md; burst 1.59)"
-    roofline = None
+    roofline = vae = None
+    unet = ldm.model.diffusion_model
     if rank == 0:
-        x_in = torch.randn(2 * rps * n, 9, latent, latent, device=dev)
-        t_in = torch.full((2 * rps * n,), 481, device=dev, dtype=torch.long)
-        c_in = torch.cat([devin["uc"], devin["cond"]]).contiguous()
-        unet = ldm.model.diffusion_model
+        rows = 2 * rps * mb
+        x_in = torch.randn(rows, 9, latent, latent, device=dev)
+        t_in = torch.full((rows,), 481, device=dev, dtype=torch.long)
+        c_in = torch.cat([devin["uc"][:rps * mb], devin["cond"][:rps * mb]]).contiguous()
         unet(x_in, t_in, context=c_in)
         torch.cuda.synchronize()
         ops.Stats.begin_profile()
@@ -354,19 +492,24 @@ def run_native(args):
         all_ms = sum(v["ms"] for v in prof.values())
         achieved = tc_fl / (tc_ms / 1e3) / 1e12
         per_sample = UNET_FLOPS_PBE_ROW.get(latent, 0) if args.pbe else UNET_FLOPS_PER_JOINT.get(latent, 0)
-        step_flops = per_sample * 2 * n   # x2: CFG doubles the rows
-        ms_unet = ms / args.steps / max(1, unet_evals // args.steps)
-        # DRAM traffic of the dominant kernel from the committed `ncu --set full` capture (one representative launch: the
-        # level-0 conv3x3), next to the algorithmic bytes of that same launch
+        step_flops = per_sample * 2 * mb   # x2: CFG doubles the rows
+        ms_unet = ms / steps / max(1, unet_evals // steps)
+        step_tf = step_flops / (ms_unet / 1e3) / 1e12 if step_flops else None
+        # DRAM traffic of the dominant kernel: a STATIC figure from the committed `ncu --set full` capture of one
+        # representative launch (the level-0 conv3x3), not measured in this run
         traffic, traffic_note = None, None
-        try:
-            tj = json.load(open(os.path.join(ROOT, "profiles", "r01", "ncu_traffic.json")))
-            traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
-            traffic_note = {"launch": tj["kernel"], "algorithmic_bytes": tj["algorithmic_bytes"], "source": tj["source"]}
-        except Exception:
-            pass
+        for cand in ("r02", "r01"):
+            try:
+                tj = json.load(open(os.path.join(ROOT, "profiles", cand, "ncu_traffic.json")))
+                traffic = tj["dram_bytes_read"] + tj["dram_bytes_write"]
+                traffic_note = {"static": True, "launch": tj["kernel"], "algorithmic_bytes": tj["algorithmic_bytes"],
+                                "source": tj["source"]}
+                break
+            except Exception:
+                continue
         roofline = {"bound": "tensor", "kernel": "gemm2_kernel (persistent tcgen05 GEMM + implicit-GEMM conv3x3)",
                     "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s", "frac": achieved / peak_tf,
+                    "frac_of_burst_peak": achieved / peak_burst, "peak_burst": peak_burst,
                     "peak_source": peak_src, "traffic": traffic, "traffic_note": traffic_note,
                     "launches_per_unet_call": tc_n, "flops_per_launch_avg": tc_fl / max(1, tc_n),
                     "ms_per_launch_avg": tc_ms / max(1, tc_n),
@@ -374,9 +517,29 @@ def run_native(args):
                     "by_kernel_ms": {k: round(v["ms"], 3) for k, v in sorted(prof.items())},
                     "attention_tflops": (prof["attention"]["flops"] / (prof["attention"]["ms"] / 1e3) / 1e12)
                     if "attention" in prof else None,
-                    "unet_step_ms": ms_unet,
-                    "unet_step_algorithmic_tflops": step_flops / (ms_unet / 1e3) / 1e12 if step_flops else None,
-                    "unet_step_frac_of_peak": step_flops / (ms_unet / 1e3) / 1e12 / peak_tf if step_flops else None}
+                    "unet_rows_per_call": rows, "unet_step_ms": ms_unet,
+                    "unet_step_algorithmic_tflops": step_tf,
+                    "unet_step_frac_of_peak": step_tf / peak_tf if step_tf else None,
+                    "unet_step_frac_of_burst_peak": step_tf / peak_burst if step_tf else None}
+        try:
+            vae = measure_vae_decode(ldm, dev, min(mb, 8), latent, peak_tf, peak_burst)
+        except Exception as exc:
+            vae = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
+
+    # ---- parity check of this very model outside the timed region: one CFG DDIM step of joint sample 0 on the GPU
+    # path vs the CPU leg below (the reference / oracle port on the SAME weights and inputs)
+    check_in = None
+    if rank == 0 and not args.no_cpu_baseline and not args.pbe:
+        from oracle import unet_oracle as uo
+        ci = uo.synth_inputs(1, latent, seed=1)
+        smp1 = DDIMSampler(ldm, use_cuda_graph=False)
+        smp1.make_schedule(ddim_num_steps=50, ddim_eta=0.0, verbose=False)
+        cg = {k: v.to(dev) for k, v in ci.items()}
+        x_prev_gpu, _ = smp1.p_sample_ddim(cg["x_T"], cg["cond"], torch.full((2,), 981, device=dev, dtype=torch.long), 49,
+                                           unconditional_guidance_scale=CFG_SCALE, unconditional_conditioning=cg["uc"],
+                                           test_model_kwargs=dict(inpaint_image=cg["inpaint_image"],
+                                                                  inpaint_mask=cg["inpaint_mask"]))
+        check_in = (x_prev_gpu.float().cpu(), {k: v.detach().float().cpu() for k, v in unet.state_dict().items()})
 
     train = None
     if not args.no_train and not args.pbe:
@@ -393,30 +556,42 @@ def run_native(args):
     range_post = None
     if not args.pbe and not args.no_cpu_baseline:
         try:
-            range_post = measure_range_post(dev, n, px)
+            range_post = measure_range_post(dev, min(n, 32), px)
         except Exception as exc:
             range_post = {"error": "%s: %s" % (type(exc).__name__, str(exc)[:300])}
-    cpu_baseline = None
-    if not args.no_cpu_baseline and world == 1:
+    cpu_baseline = check = None
+    if not args.no_cpu_baseline:          # rank 0 at every N
         threads = os.cpu_count() or 1
-        t = cpu_reference_step(latent, threads, 1, repeats=1)[0]
-        cpu_baseline = {"value": 1.0 / (args.ddim_steps * t), "unit": "samples/s", "cores": threads, "kind": "port",
-                        "sample": "1 DDIM step (CFG UNet call, 4 rows) of 1 joint sample at latent %d, fp32 oracle "
-                                  "port, %.1f s, extrapolated x%d steps" % (latent, t, args.ddim_steps)}
+        ref = CpuReference(latent, threads, 1, state_dict=check_in[1] if check_in else None)
+        sec, x_prev_cpu = ref.step()
+        cpu_baseline = ref.describe(sec, args.ddim_steps)
+        if check_in is not None:
+            err = ((check_in[0].double() - x_prev_cpu.double()).abs().max() / x_prev_cpu.double().abs().max()).item()
+            check = {"what": "x_prev after one CFG-5 DDIM step (t=981) of joint sample 0: GPU path vs the CPU %s on the "
+                             "same weights and inputs, outside the timed region" % ref.kind,
+                     "max_abs_rel": err, "tolerance": 1e-2, "ok": bool(err < 1e-2)}
+            if not check["ok"]:
+                raise RuntimeError("bench.py: GPU result differs from the CPU %s: %r" % (ref.kind, check))
     line = {"metric": "inpainted joint samples/sec (50-step DDIM + CFG)", "value": value, "unit": "samples/s",
-            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms / steps,
+            "higher_is_better": True, "scaling": scaling, "vs_baseline": None,
             "dtype": "bf16 operands, fp32 accumulate/norms/residuals", "data": "synthetic",
-            "config": {"workload": workload_name(args), "latent": latent, "rows_per_unet_call": 2 * rps * n,
-                       "ddim_steps": args.ddim_steps, "cfg_scale": CFG_SCALE, "sharding": "samples/%d GPUs, no collective" % world,
+            "config": {"workload": workload_name(args, world), "latent": latent, "total_joint_samples": total,
+                       "joint_samples_per_gpu": n, "micro_batch": mb, "rows_per_unet_call": 2 * rps * mb,
+                       "ddim_steps": args.ddim_steps, "cfg_scale": CFG_SCALE,
+                       "sharding": "%d samples / %d GPUs, no collective" % (total, world),
                        "l2": "inputs larger than L2 (2.1 GB bf16 weights streamed per UNet call)",
                        "cuda_graph": not args.no_graph,
                        "e2e_includes": "pinned H2D of latents/conditioning, sampling, camera + range-view VAE decode "
-                                       "to %dx%d, D2H of decoded images" % (px, px)},
+                                       "to %dx%d, D2H of decoded images; %d timed steps" % (px, px, e2e_steps)},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": ms_e2e / args.steps},
+                    "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": gpu_launches, "unet_evals": unet_evals, "clocks": clock_info,
-            "roofline": roofline, "cpu_baseline": cpu_baseline, "train_step": train, "range_post": range_post}
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "check": check, "weak_8_per_gpu": weak,
+            "vae_decode": vae, "train_step": train, "range_post": range_post,
+            "first_step_s": t_first, "wall_s": time.perf_counter() - t_start}
+    if steps != steps_requested:
+        line["steps_requested"] = steps_requested
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -156,6 +156,13 @@ class BasicTransformerBlock(nn.Module):
             if hasattr(self, n):
                 ln = getattr(self, n)
                 p[n] = (_f32(ln.weight), _f32(ln.bias))
+        old = self._p
+        if old is not None and old.keys() == p.keys():
+            # refresh IN PLACE: captured CUDA graphs (samplers, UNetTrainer) hold the addresses of these tensors
+            for k, v in p.items():
+                for dst, src in zip(old[k] if isinstance(v, tuple) else (old[k],), v if isinstance(v, tuple) else (v,)):
+                    dst.copy_(src)
+            return
         self._p = p
 
     # ------------------------------------------------------------------ context tables (once per context)

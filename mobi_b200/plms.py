@@ -57,7 +57,10 @@ class PLMSSampler(SamplerBase):
         else:
             subset_end = int(min(timesteps / self.ddim_timesteps.shape[0], 1) * self.ddim_timesteps.shape[0]) - 1
             timesteps = self.ddim_timesteps[:subset_end]
-        intermediates = {"x_inter": [img], "pred_x0": [img]}
+        # with mask / x0 the step kernel blends the known latent into img IN PLACE (the reference builds a new tensor,
+        # ddim.py:148): logged intermediates are snapshots then, so a later step cannot rewrite them
+        keep = (lambda t: t.clone()) if mask is not None else (lambda t: t)
+        intermediates = {"x_inter": [keep(img)], "pred_x0": [keep(img)]}
         time_range = np.flip(timesteps)
         total_steps = timesteps.shape[0]
         rest_image, rest_mask = self._rest_from_kwargs(kwargs)
@@ -104,6 +107,6 @@ class PLMSSampler(SamplerBase):
             if img_callback:
                 img_callback(pred_x0, i)
             if index % log_every_t == 0 or index == total_steps - 1:
-                intermediates["x_inter"].append(img)
+                intermediates["x_inter"].append(keep(img))
                 intermediates["pred_x0"].append(pred_x0)
         return img, intermediates

@@ -123,10 +123,9 @@ class SamplerBase(object):
             self._c_in.copy_(c_new)
             if self._graph_ctx is not None:
                 self._graph_ctx.replay()
-                unet._ctx_tabs = self._ctx_tabs_static
-                unet._ctx_key = (self._c_in.data_ptr(), self._c_in._version, tuple(self._c_in.shape))
+                unet.pin_context(self._c_in, self._ctx_tabs_static)
             elif unet is not None:
-                unet.prepare_context(self._c_in)
+                unet.pin_context(self._c_in, unet.prepare_context(self._c_in))
             return
         self._static_key = None
         self._graph = self._graph_ctx = None
@@ -135,7 +134,7 @@ class SamplerBase(object):
         self._t_in = torch.empty((rows,), device=dev, dtype=torch.long)
         self._c_in = c_new.contiguous().clone()
         if unet is not None:
-            unet.prepare_context(self._c_in)
+            unet.pin_context(self._c_in, unet.prepare_context(self._c_in))
         if use_graph:
             self._t_in.fill_(1)
             self._x_in.zero_()
@@ -149,6 +148,7 @@ class SamplerBase(object):
             g_ctx = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g_ctx):
                 self._ctx_tabs_static = unet.prepare_context(self._c_in)
+            unet.pin_context(self._c_in, self._ctx_tabs_static)
             g = torch.cuda.CUDAGraph()
             before = ops.Stats.launches
             with torch.cuda.graph(g, pool=g_ctx.pool()):

@@ -43,7 +43,8 @@ class FlatParams:
     """Moves the selected parameters of `module` into one flat f32 buffer (views stay registered as the module's
     nn.Parameters, so state_dict()/load_state_dict() keep working) and allocates the matching gradient buffer."""
 
-    ALIGN = 4  # elements: every view starts on a 16-byte boundary (vector epilogues of the wgrad GEMM)
+    ALIGN = 8  # elements: every f32 view starts on a 32-byte boundary, so the bf16 mirror views at the same element
+    #            offsets (UNetTrainer._pack_matrix) start on 16 bytes: what TMA / tcgen05 operand bases need
 
     def __init__(self, module, select=is_trainable, device=None, extra=()):
         """extra: further (name, parameter) pairs appended after the selected parameters of `module` (the trainable
@@ -214,6 +215,7 @@ class UNetTrainer:
         view tagged for the dgrad GEMM dx = dy W, which reads it as an MN-major B operand (no transposed pack)."""
         off = (w.data_ptr() - self.flat.params.data_ptr()) // 4
         assert 0 <= off and off + w.numel() <= self.flat.numel and w.is_contiguous(), "not a view of the flat parameter buffer"
+        assert off % 8 == 0, "bf16 operand views must start on a 16-byte boundary (FlatParams.ALIGN)"
         self._segments.append((off, w.numel(), float(scale)))
         fwd = self._mirror[off:off + w.numel()].view(w.shape)
         return fwd, (_MnMajorB(fwd) if transposed else None)
@@ -238,7 +240,7 @@ class UNetTrainer:
         L.check(L.load().mobi_cast_bf16_segments(self.flat.params.data_ptr(), self._mirror.data_ptr(), self.flat.numel,
                                                    self._seg_start.data_ptr(), self._seg_scale.data_ptr(),
                                                    self._seg_start.numel(), L.stream()), "cast_bf16_segments")
-        self.unet._ctx_key = None
+        self.unet.mark_trainable_stale()
 
     def _build_packs(self):
         """Once: the pack views (self.tp) and the (start, scale) table of the segmented cast."""
@@ -287,7 +289,7 @@ class UNetTrainer:
             tp["bbox"] = [self._pack_matrix(m.weight.data) + (m.bias.data,) for m in lin]
         self.tp = tp
         # the inference packs fold these weights: they are stale now
-        self.unet._ctx_key = None
+        self.unet.mark_trainable_stale()
 
     # ------------------------------------------------------------------ attention helpers
     def _attn_fwd(self, q, k, v, B, H, D, T):
@@ -776,7 +778,9 @@ class UNetTrainer:
         self.steps += 1
         tops.adamw(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=self.lr if lr is None else lr,
                    beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self.steps)
-        self.repack_trainable()
+        self.repack_trainable()           # also marks the UNet's inference packs of these weights stale
+        if self.bbox_embedder is not None:
+            self.bbox_embedder.invalidate()
 
     def named_grads(self):
         return {n: self.flat.grad(n) for n in self.flat.names}

@@ -46,15 +46,22 @@ def test_ctypes_struct_sizes_match_the_header(tmp_path):
              ("mobi_groupnorm_bwd_args", L.GroupNormBwdArgs), ("mobi_attn_softmax_bwd_args", L.AttnSoftmaxBwdArgs),
              ("mobi_ctx_attn_qspace_args", L.CtxAttnQspaceArgs), ("mobi_latent_input_args", L.LatentInputArgs),
              ("mobi_attn_bwd_tiles_args", L.AttnBwdTilesArgs)]
-    prog = '#include <stdio.h>\n#include "%s"\nint main(void){' % HEADER
-    prog += "".join('printf("%%zu\\n", sizeof(%s));' % c for c, _ in pairs) + "return 0;}\n"
+    prog = '#include <stdio.h>\n#include <stddef.h>\n#include "%s"\nint main(void){' % HEADER
+    prog += "".join('printf("%%zu\\n", sizeof(%s));' % c for c, _ in pairs)
+    # every field by NAME: a reordering of same-size members between the header and the binding changes no sizeof
+    fields = [(c, ct, f[0]) for c, ct in pairs for f in ct._fields_]
+    prog += "".join('printf("%%zu\\n", offsetof(%s, %s));' % (c, f) for c, _, f in fields) + "return 0;}\n"
     src = tmp_path / "sizes.c"
     src.write_text(prog)
     exe = tmp_path / "sizes"
     subprocess.run(["gcc", "-o", str(exe), str(src)], check=True)
-    sizes = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    nums = [int(x) for x in subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout.split()]
+    sizes, offsets = nums[:len(pairs)], nums[len(pairs):]
     for (cname, ct), size in zip(pairs, sizes):
         assert C.sizeof(ct) == size, "%s: ctypes %d bytes, C %d bytes" % (cname, C.sizeof(ct), size)
+    assert len(offsets) == len(fields) > 200
+    for (cname, ct, f), off in zip(fields, offsets):
+        assert getattr(ct, f).offset == off, "%s.%s: ctypes offset %d, C offset %d" % (cname, f, getattr(ct, f).offset, off)
 
 
 def test_product_path_fails_loudly_without_cuda():

@@ -127,3 +127,31 @@ def test_cfg_shared_prefix_is_exact(setup):
         unet.cfg_shared_halves = False
     assert torch.equal(got, ref)
     assert not torch.equal(got[:4], got[4:])      # the halves do differ after the context enters
+
+
+def test_new_conditioning_at_a_recycled_address_is_not_served_from_a_cache(setup):
+    """forward() used to key its context tables on (data_ptr, _version, shape).  mobi_b200 ops write
+    through raw pointers (no version bump) and the caching allocator recycles addresses, so new conditioning could be
+    served the OLD tables.  Two different contexts through the SAME storage, written by an op kernel, must differ."""
+    from mobi_b200 import ops
+    ldm, cfg, apply_ref, sched, uo = setup
+    unet = ldm.model.diffusion_model
+    inp = uo.synth_inputs(2, 16, context_dim=cfg["context_dim"], seed=11, device="cuda")
+    x = torch.cat([inp["x_T"], inp["inpaint_image"], inp["inpaint_mask"]], 1)
+    t = torch.full((4,), 500, device="cuda", dtype=torch.long)
+    c = inp["cond"].clone()
+    version = c._version
+    e1 = unet(x, t, context=c).clone()
+    ops.scale_f32(inp["uc"].contiguous(), 1.0, out=c)          # new contents, same pointer, same version counter
+    assert c._version == version
+    e2 = unet(x, t, context=c)
+    with torch.no_grad():
+        r1, r2 = apply_ref(x, t, inp["cond"]), apply_ref(x, t, inp["uc"])
+    assert rel(e1, r1) < TOL and rel(e2, r2) < TOL and rel(e2, r1) > 4 * TOL
+    # del + realloc at the same address
+    ptr = c.data_ptr()
+    del c
+    c3 = inp["cond"].clone()
+    e3 = unet(x, t, context=c3)
+    print("recycled address: %s" % (c3.data_ptr() == ptr))
+    assert rel(e3, r1) < TOL

@@ -429,9 +429,12 @@ def test_adamw_step_tiny_vs_reference_golden():
     assert torch.isfinite(loss2).item()
 
 
-def test_training_step_fullwidth_vs_oracle():
-    """The real 1.04 B-parameter joint UNet (181.6 M trainable), 2 joint samples (config 5's batch_size) at latent
-    32 x 32, against torch.autograd over the fp32 oracle on the same device (TF32 off)."""
+@pytest.mark.parametrize("latent,n_joint", [(32, 2), (64, 1)])
+def test_training_step_fullwidth_vs_oracle(latent, n_joint):
+    """The real 1.04 B-parameter joint UNet (181.6 M trainable) against torch.autograd over the fp32 oracle on the same
+    device (TF32 off): 2 joint samples (config 5's batch_size) at latent 32 x 32, and config 5's own resolution, latent
+    64 x 64 (mobi_nusc_512; the flash attention backward at T = 4096 runs inside the step), with 1 joint sample (what the
+    oracle's eager autograd graph fits comfortably: every T x T score tensor is kept for the backward)."""
     from mobi_b200.ddpm import LatentDiffusion
     from mobi_b200.training import UNetTrainer
     from oracle import sampler_oracle as so
@@ -439,19 +442,19 @@ def test_training_step_fullwidth_vs_oracle():
     from oracle import unet_oracle as uo
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
-    cfg = uo.default_unet_config(image_size=32)
+    cfg = uo.default_unet_config(image_size=latent)
     sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
     with torch.device("meta"):
         ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg),
                               linear_start=0.00085, linear_end=0.0120, timesteps=1000, first_stage_key="inpaint",
-                              image_size=32, channels=4, conditioning_key="crossattn", use_camera=True, use_lidar=True)
+                              image_size=latent, channels=4, conditioning_key="crossattn", use_camera=True, use_lidar=True)
     ldm = ldm.to_empty(device="cuda")
     ldm.register_schedule(linear_start=0.00085, linear_end=0.0120, timesteps=1000)
     ldm = ldm.to("cuda").eval()
     ldm.model.diffusion_model.load_state_dict(sd, strict=True)
     tr = UNetTrainer(ldm)
     assert tr.flat.numel >= 180_394_240 and len(tr.flat.names) == 16 * 27   # tests/golden/shapes_512.json
-    inp = to.synth_train_inputs(2, 32, 768, seed=5, device="cuda")
+    inp = to.synth_train_inputs(n_joint, latent, 768, seed=5, device="cuda")
     loss = tr.forward_backward(inp["x_start"], inp["t"], inp["noise"], inp["cond"])
     torch.cuda.synchronize()
     sdc = {k: v.cuda() for k, v in sd.items()}
@@ -466,8 +469,8 @@ def test_training_step_fullwidth_vs_oracle():
         wcos = min(wcos, c)
     flat_ref = torch.cat([ref[n].reshape(-1) for n in tr.flat.names])
     flat_got = torch.cat([grads[n].reshape(-1) for n in tr.flat.names])
-    print("full-width training step: loss %.6f (oracle %.6f); worst per-tensor grad max-abs-rel %.3e (%s), min cosine "
-          "%.5f, whole-gradient cosine %.6f" % (loss.item(), ref_loss.item(), worst, wname, wcos, cos(flat_got, flat_ref)))
+    print("full-width training step at latent %d, %d joint sample(s): loss %.6f (oracle %.6f); worst per-tensor grad max-abs-rel %.3e (%s), min cosine "
+          "%.5f, whole-gradient cosine %.6f" % (latent, n_joint, loss.item(), ref_loss.item(), worst, wname, wcos, cos(flat_got, flat_ref)))
     assert abs(loss.item() - ref_loss.item()) <= 1e-2 * ref_loss.item()
     assert worst <= 5e-2 and wcos >= 0.999 and cos(flat_got, flat_ref) >= 0.9995
 
@@ -570,3 +573,30 @@ def test_conditioning_dropout_step_trains_bbox_uncond_vector():
     tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), uncond=True)
     tr.step()
     assert not torch.equal(ldm.bbox_uncond_vector.detach(), v0)          # AdamW moved it (it is a view of the flat buffer)
+
+
+def test_inference_after_training_steps_uses_the_updated_weights():
+    """UNetTrainer.step() refreshes the trainer's own bf16 mirror only; the inference packs that fold
+    the same weights (adapter tables, cross-modal q / kv / folded connector matrices) must follow, or sampling /
+    validation after training silently runs the PRE-training adapters.  A large learning rate makes the change visible."""
+    from oracle import unet_oracle as uo
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    tr, cfg, sd = _tiny_trainer()
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    unet = tr.unet
+    x, t, cond = cu("x_start"), cu("t"), cu("cond")
+    eps0 = unet(x, t, context=cond).clone()
+    for _ in range(3):
+        tr.forward_backward(x, t, cu("noise"), cond)
+        tr.step(lr=1e-2)
+    eps1 = unet(x, t, context=cond)
+    sd1 = {k: v.detach().float().cuda() for k, v in unet.state_dict().items()}
+    with torch.no_grad():
+        ref1 = uo.unet_forward(sd1, cfg, x, t, cond)
+        ref0 = uo.unet_forward({k: v.cuda() for k, v in sd.items()}, cfg, x, t, cond)
+    e_new, e_old = rel(eps1, ref1), rel(eps0, ref1)
+    print("inference after 3 AdamW steps (lr 1e-2): vs oracle on the updated weights %.3e; stale output would be %.3e off"
+          % (e_new, e_old))
+    assert rel(eps0, ref0) < 2.5e-2 and e_new < 2.5e-2 and e_old > 5e-2
+    # and the trainer keeps working on the refreshed (in place) packs
+    assert torch.isfinite(tr.forward_backward(x, t, cu("noise"), cond)).item()
