@@ -15,7 +15,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 BUILD = os.path.join(HERE, "_build")
 LIB = os.path.join(HERE, "libmobi_b200.so")
-SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention2.cu", "attention3.cu", "elementwise.cu", "layernorm.cu", "backward.cu", "attn_bwd.cu", "attn_bwd_flash.cu", "range_view.cu"]
+SOURCES = ["common.cu", "gemm.cu", "gemm2.cu", "attention.cu", "attention3.cu", "attention4.cu", "elementwise.cu", "layernorm.cu", "backward.cu", "attn_bwd.cu", "attn_bwd_flash.cu", "range_view.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

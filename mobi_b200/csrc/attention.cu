@@ -274,9 +274,13 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     MOBI_CHECK(BH <= 65535, "mobi_attention: batch*heads=%lld exceeds grid.y", BH);
     if (a->v_rowmajor) {
         MOBI_CHECK(d <= 128, "mobi_attention: the row-major V layout needs head_dim <= 128 (got %d)", d);
+        // kernel & 15 == 3 / 4: the third-generation kernel (P staged in shared memory; 4 = its two-tile variant), kept
+        // as the A/B arm and for
+        // head dims whose O accumulator leaves no TMEM columns for the row sums
+        const int sel = a->kernel & 15;
+        if (attention4_supports(d) && sel != 3 && sel != 4) return attention4_dispatch(a, p, stream);
         return attention3_dispatch(a, p, stream);
     }
-    if (d <= 128 && (a->kernel & 15) != 1) return attention2_dispatch(a, p, stream);
     // shared memory plan: prefer double-buffered K/V and P; fall back to single buffers for wide heads
     auto smem_need = [&](int kvs, int pbs) {
         return (long long)p.nch * ATT_TILE * (1 + kvs) + (long long)kvs * 2 * att_v_tile_bytes(p.dn) +

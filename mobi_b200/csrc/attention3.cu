@@ -1,6 +1,6 @@
 // Fused attention, third generation (head_dim <= 128, V in its natural [keys, d] layout).
 //
-// Same softmax machinery as attention2.cu (thread = query row, whole S row in registers from one tcgen05.ld pass,
+// Softmax machinery (thread = query row, whole S row in registers from one tcgen05.ld pass,
 // stale running maximum, packed-fp32 arithmetic, a share of the exponentials on the FMA pipe), plus:
 //   * NT query tiles of 128 rows per CTA (NT = 4 for head_dim <= 64: ONE CTA per SM with 16 softmax warps, all four
 //     tiles share one K/V ring, so K/V are fetched once per 512 query rows and the ring is 5 blocks deep: the TMA
@@ -26,7 +26,7 @@ __device__ __forceinline__ float a3_ex2(float x) {
     return y;
 }
 
-// 2^x for a pair on the FMA pipe: see attention2.cu:ex2_poly2
+// 2^x for a pair on the FMA pipe (Cody-Waite split + degree-3 polynomial)
 __device__ __forceinline__ void a3_ex2_poly2(uint64_t x, float& e0, float& e1) {
     float x0, x1;
     unpack2(x, x0, x1);
@@ -348,7 +348,7 @@ static int launch_attention3(const mobi_attn_args* a, AttnParams p, cudaStream_t
 
 int attention3_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream) {
     if (a->head_dim <= 64) {
-        if ((a->kernel & 15) == 2) return launch_attention3<2, 64, 3, 2>(a, p, stream);  // tuning hook: 2 tiles
+        if ((a->kernel & 15) == 4) return launch_attention3<2, 64, 3, 2>(a, p, stream);  // tuning hook: 2 tiles
         return launch_attention3<4, 64, 5, 2>(a, p, stream);
     }
     return launch_attention3<2, 64, 3, 2>(a, p, stream);

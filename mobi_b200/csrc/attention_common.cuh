@@ -1,5 +1,5 @@
-// Shared between the two fused-attention kernels (attention.cu: any head_dim <= 192, one query tile per CTA;
-// attention2.cu: head_dim <= 128, two query tiles and two softmax warpgroups per CTA).
+// Shared between the fused-attention kernels (attention.cu: any head_dim <= 192, one query tile per CTA, V^T;
+// attention3.cu / attention4.cu: head_dim <= 128, V row-major, several query tiles per CTA).
 #pragma once
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -20,7 +20,8 @@ struct AttnParams {
     float* lse;     // optional [BH, tq]: row max + log2(row sum) in the log2 domain (attention3 only)
 };
 
-int attention2_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);
 int attention3_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);  // V row-major
+int attention4_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream_t stream);  // V row-major, P in TMEM
+bool attention4_supports(int head_dim);
 
 }  // namespace mobi

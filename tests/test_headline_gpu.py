@@ -3,14 +3,19 @@ the real 1.04 B-parameter joint UNet (or the 0.92 B camera-only one) at latent 6
 through the drop-in classes and the C ABI, against the fp32 oracle on the same GPU (TF32 off) on the shared synthetic
 state dict.
 
-Tolerances (all max-abs error relative to the max-abs of the oracle tensor, the north star's "max-abs-rel"):
-  * one UNet evaluation (eps, before the CFG combine)                     <= 1e-2   (north star, bf16 operands)
-  * the same, teacher-forced at every one of the 50 DDIM / 51 PLMS steps  <= 1e-2   (per-step eps)
-  * final latents after the free-running 50-step CFG-5 run                <= 5e-2, cosine >= 0.999
-    (SURVEY.md §8c proposal: every step adds <= 1e-2 of eps error scaled by the step's DDIM coefficient; the guidance
-    combine e_u + 5 (e_c - e_u) amplifies the uncorrelated part of the two halves' errors; measured values are printed
-    and recorded in DESIGN.md §2)
-  * VAE decode at 512 px                                                  <= 1e-2
+Tolerances ("max-abs-rel" = max-abs error relative to the max-abs of the oracle tensor, the north star's measure;
+"rel-rms" = ||a - b|| / ||b||):
+  * one UNet evaluation (eps, before the CFG combine), also teacher-forced at every one of the 50 DDIM / 51 PLMS
+    steps: max-abs-rel <= 2e-2, rel-rms <= 1e-2, AND max-abs-rel <= 1.5 x the bf16-operand floor of the same call.
+    The north star's example figure (1e-2) is where this model's bf16-OPERAND FLOOR itself sits at latent 64: the fp32
+    oracle with nothing changed but the contraction operands rounded to bf16 (oracle/precision.py) is 0.9-1.4e-2 away
+    from the fp32 oracle, so no bf16-operand implementation can promise 1e-2 at every step; the floor is measured in
+    the test and printed beside the CUDA path's error (round-2 measurement: 32-row call 9.9e-3; per-step curve
+    7.1e-3 .. 1.4e-2, mean 9.5e-3; the numbers are recorded in DESIGN.md §2).
+  * final latents after the free-running 50-step CFG-5 run: max-abs-rel <= 2e-2, cosine >= 0.9995 (measured 6.8e-3 /
+    0.99998: per-step errors are largely independent between steps and DDIM averages them; SURVEY.md §8c had proposed
+    5e-2).
+  * VAE decode at 512 px: max-abs-rel <= 1e-2.
 """
 import numpy as np
 import pytest
@@ -18,14 +23,29 @@ import torch
 
 pytestmark = pytest.mark.gpu
 
-TOL_EPS = 1e-2
-TOL_FINAL = 5e-2
+TOL_EPS = 2e-2          # max-abs-rel of one UNet evaluation (cap; the binding bar is 1.5 x the bf16-operand floor)
+TOL_EPS_RMS = 1e-2      # rel-rms of one UNet evaluation
+TOL_FINAL = 2e-2        # final latents of a 50-step run
 TOL_VAE = 1e-2
 
 
 def relerr(a, b):
     a, b = a.double(), b.double()
     return ((a - b).abs().max() / b.abs().max()).item()
+
+
+def relrms(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm()).item()
+
+
+def check_eps(eps, ref, floor, what):
+    """The per-call bar: see the module docstring.  floor = (max-abs-rel, rel-rms) of the bf16-operand oracle."""
+    e, r = relerr(eps, ref), relrms(eps, ref)
+    print("%s: eps max-abs-rel %.3e rel-rms %.3e cosine %.6f | bf16-operand floor of the same call: %.3e / %.3e"
+          % (what, e, r, cosine(eps, ref), floor[0], floor[1]))
+    assert e < TOL_EPS and r < TOL_EPS_RMS and e < 1.5 * floor[0], (what, e, r, floor)
+    return e
 
 
 def cosine(a, b):
@@ -85,11 +105,10 @@ def test_unet_call_latent64_32rows_vs_oracle():
     x_in = torch.cat([x, x])
     t_in = torch.full((32,), 981, device="cuda", dtype=torch.long)
     c_in = torch.cat([inp["uc"], inp["cond"]]).contiguous()
+    from oracle.precision import bf16_operand_floor
     eps = net(x_in, t_in, context=c_in)
     ref = oracle_unet(sd, cfg)(x_in, t_in, c_in)
-    e = relerr(eps, ref)
-    print("UNet call, 32 rows at latent 64: eps max-abs-rel %.3e cosine %.6f" % (e, cosine(eps, ref)))
-    assert e < TOL_EPS
+    check_eps(eps, ref, bf16_operand_floor(sd, cfg, x_in, t_in, c_in, ref=ref), "UNet call, 32 rows at latent 64, t=981")
     # the CFG shared-prefix path (what the samplers run) gives the same bits
     net.cfg_shared_halves = True
     try:
@@ -135,7 +154,7 @@ def test_sampler_single_step_32rows_graph_on_and_off(graph):
                                 inp["inpaint_image"], inp["inpaint_mask"])
     e = relerr(got, ref)
     print("one CFG-5 DDIM step, 32 rows, graph=%s: x_prev max-abs-rel %.3e" % (graph, e))
-    assert e < TOL_EPS
+    assert e < 1e-2
 
 
 # ----------------------------------------------------------------------------------------------- (ii) full sampler runs
@@ -178,17 +197,26 @@ def _full_run(sampler_name, n_joint, use_lidar=True):
                             x_T=inp["x_T"], inpaint_image=inp["inpaint_image"], inpaint_mask=inp["inpaint_mask"])
         assert smp.launches == 51 and len(calls) == 51          # S + 1 UNet evaluations (plms.py:223-226)
     # per-step eps, teacher-forced: our UNet on the oracle's own inputs of every step (no drift in the comparison)
-    curve = []
+    from oracle.precision import bf16_operand_floor
+    curve, rms = [], []
     for x, t, c, out in calls:
         eps = ldm.apply_model(x, t, c)
         curve.append(relerr(eps, out))
+        rms.append(relrms(eps, out))
+    worst = int(np.argmax(curve))
+    floors = {i: bf16_operand_floor(sd, cfg, calls[i][0], calls[i][1], calls[i][2], ref=calls[i][3])
+              for i in sorted({0, worst, len(calls) - 1})}
     e_final, c_final = relerr(got, ref), cosine(got, ref)
-    print("%s 50 steps CFG 5 at latent 64 (%d rows x CFG, lidar=%s): per-step eps max-abs-rel max %.3e mean %.3e "
-          "(first %.3e last %.3e); final latents max-abs-rel %.3e cosine %.6f"
-          % (sampler_name, rows, use_lidar, max(curve), float(np.mean(curve)), curve[0], curve[-1], e_final, c_final))
+    print("%s 50 steps CFG 5 at latent 64 (%d rows x CFG, lidar=%s): per-step eps max-abs-rel max %.3e (step %d) mean "
+          "%.3e, rel-rms max %.3e; final latents max-abs-rel %.3e cosine %.6f"
+          % (sampler_name, rows, use_lidar, max(curve), worst, float(np.mean(curve)), max(rms), e_final, c_final))
+    print("  bf16-operand floor (max-abs-rel / rel-rms) at steps " +
+          ", ".join("%d: %.2e / %.2e" % (i, f[0], f[1]) for i, f in floors.items()))
     print("  eps error curve: " + " ".join("%.1e" % v for v in curve))
-    assert max(curve) < TOL_EPS
-    assert e_final < TOL_FINAL and c_final > 0.999
+    assert max(curve) < TOL_EPS and max(rms) < TOL_EPS_RMS
+    for i, f in floors.items():
+        assert curve[i] < 1.5 * f[0], (i, curve[i], f)
+    assert e_final < TOL_FINAL and c_final > 0.9995
     return ldm, got, ref
 
 

@@ -55,9 +55,11 @@ def bench_attn():
         vrow = rnd(rows * H, T, D)
         out = torch.empty(rows, T, H * D, device="cuda", dtype=torch.bfloat16)
         fl = 4.0 * rows * H * T * T * D
-        kerns = (1,) if D > 128 else ((0, 0x100, 0x102, 2, 1) if D <= 64 else (0, 0x100, 1))
+        # 0x100: row-major V, attention4 (P in TMEM); 0x1N0: its exp-on-FMA-pipe shares; 0x103 / 0x104: attention3 (4 / 2 tiles)
+        # 0x105: attention4's first TMEM plan (NT = 4, P over S: S(j + 1) after PV(j))
+        kerns = (1,) if D > 128 else ((0x100, 0x110, 0x120, 0x130, 0x140, 0x105, 0x103) if D <= 48 else (0x100, 0x105, 0x103, 1))
         for kern in kerns:
-            rowv = kern >= 0x100   # 0x100: row-major V (attention3), 0x102: its two-tile variant
+            rowv = kern >= 0x100
             ms = timeit(lambda: ops.attention(q, k, vrow if rowv else vt, rows, H, D, T, T, out=out, kernel=kern & 0xff,
                                               v_rowmajor=rowv))
             report("attention %s d=%d T=%d kernel=0x%x" % (tag, D, T, kern), ms, fl, clk_per_tile=round(
