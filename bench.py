@@ -350,7 +350,8 @@ def run_native(args):
     n, total, mb, scaling = job_shape(args, world)
     latent = args.latent
     rps = 1 if args.pbe else 2                 # UNet rows per sample: camera only, or (camera, lidar)
-    ldm = synth.build_synthetic_ldm(latent=latent, use_lidar=not args.pbe, device=dev, seed=0, with_vae=True)
+    ldm = synth.build_synthetic_ldm(latent=latent, use_lidar=not args.pbe, device=dev, seed=0, with_vae=True,
+                                    with_cond=not args.pbe)
     sampler = DDIMSampler(ldm, use_cuda_graph=not args.no_graph)
     # the job is `total` joint samples cut into per-rank shards between samples (mobi_b200/sharding.py); every sample's
     # inputs and noise depend on its GLOBAL index only, so results do not depend on the number of GPUs
@@ -375,25 +376,35 @@ def run_native(args):
     def step_device():
         return [sample_rows(devin, a, b) for a, b in chunks]
 
+    # the e2e leg of the joint model is the reference test bench's per-batch body (mobi_b200/pipeline.py): a batch with
+    # the DATASET's layout in pinned host memory (camera / range images, masks, conditioning, sweep tensors)
+    from mobi_b200 import pipeline
+    host_batch = None if args.pbe else synth.synthetic_dataset_batch(n, px=px, seed=100 + rank, pin=True)
+    host_out = {}
+
+    def to_host(name, t, s0, s1):
+        if name not in host_out:
+            host_out[name] = torch.empty((n,) + tuple(t.shape[1:]), dtype=t.dtype).pin_memory()
+        host_out[name][s0:s1].copy_(t, non_blocking=True)                                   # D2H of the results
+
     def step_e2e():
-        """What a user of the reference runs per batch (scripts/inference_test_bench.py:414-464): inputs from pinned host
-        memory, sampler.sample, decode_sample, decode_first_stage for both modalities, decoded images back to the host."""
+        """What a user of the reference runs per batch (scripts/inference_test_bench.py:414-464, 567-629): the batch from
+        pinned host memory, get_input (4 VAE encodes + latent assembly), conditioning tokens, sampler.sample, decode_sample,
+        decode_first_stage for both modalities, range-view post-processing, results back to the host."""
         outs = []
         for a, b in chunks:
-            inp = {k: v[a:b].to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
-            out = sampler.sample(S=args.ddim_steps, conditioning=inp["cond"], batch_size=b - a, shape=[4, latent, latent],
-                                 verbose=False, unconditional_guidance_scale=CFG_SCALE,
-                                 unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
-                                 test_model_kwargs=dict(inpaint_image=inp["inpaint_image"],
-                                                        inpaint_mask=inp["inpaint_mask"]))[0]
             s0, s1 = a // rps, b // rps
             if args.pbe:
+                inp = {k: v[a:b].to(dev, non_blocking=True) for k, v in host.items()}      # H2D from pinned memory
+                out = sample_rows(inp, 0, b - a)
                 host_img[s0:s1].copy_(ldm.decode_first_stage(out), non_blocking=True)
-            else:
-                h_cam, h_lid = ldm.decode_sample(out, out[1::2])
-                host_img[s0:s1].copy_(ldm.decode_first_stage(h_cam), non_blocking=True)       # D2H of the results
-                host_rng[s0:s1].copy_(ldm.decode_first_stage(h_lid, module_name="lidar_stage_model"), non_blocking=True)
-            outs.append(out)
+                outs.append(out)
+                continue
+            batch = pipeline.batch_to_device(pipeline.batch_slice(host_batch, s0, s1), dev)  # H2D from pinned memory
+            out = pipeline.inpaint_batch(ldm, sampler, batch, ddim_steps=args.ddim_steps, scale=CFG_SCALE)
+            for name in ("image_sample", "range_pred", "pred_instance_mask", "pred_points", "n_points"):
+                to_host(name, out[name], s0, s1)
+            outs.append(out["samples"])
         return outs
 
     def barrier():
@@ -451,8 +462,11 @@ def run_native(args):
 
     value = n * world * steps / (ms / 1e3)
     e2e_value = n * world * e2e_steps / (ms_e2e / 1e3)
-    h2d = sum(v.numel() * v.element_size() for v in host.values())
-    d2h = host_img.numel() * 4 + (0 if args.pbe else host_rng.numel() * 4)
+    if args.pbe:
+        h2d, d2h = sum(v.numel() * v.element_size() for v in host.values()), host_img.numel() * 4
+    else:
+        h2d = pipeline.batch_bytes(host_batch)
+        d2h = sum(v.numel() * v.element_size() for v in host_out.values())
 
     # ---- weak-scaling figure of round 1: 8 joint samples per GPU whatever N (secondary)
     weak = None
@@ -588,8 +602,14 @@ def run_native(args):
                        "sharding": "%d samples / %d GPUs, no collective" % (total, world),
                        "l2": "inputs larger than L2 (2.1 GB bf16 weights streamed per UNet call)",
                        "cuda_graph": not args.no_graph,
-                       "e2e_includes": "pinned H2D of latents/conditioning, sampling, camera + range-view VAE decode "
-                                       "to %dx%d, D2H of decoded images; %d timed steps" % (px, px, e2e_steps)},
+                       "e2e_includes": ("pinned H2D of latents/conditioning, sampling, camera VAE decode to %dx%d, D2H of "
+                                        "decoded images; %d timed steps" % (px, px, e2e_steps)) if args.pbe else
+                                       ("the reference test bench's per-batch body (mobi_b200.pipeline.inpaint_batch): "
+                                        "pinned H2D of the dataset-layout batch (%dx%d camera + range images, masks, "
+                                        "conditioning, sweeps), get_input = 4 VAE encodes + latent assembly, conditioning "
+                                        "tokens after the CLIP tower, sampling, decode_sample, camera + range-view VAE "
+                                        "decode, range-view post-processing, D2H of decoded image, edited sweep, instance "
+                                        "mask and point cloud; %d timed steps" % (px, px, e2e_steps))},
             "e2e": {"value": e2e_value, "unit": "samples/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps},
             "gpu_launches": gpu_launches, "unet_evals": unet_evals, "clocks": clock_info,

@@ -53,10 +53,32 @@ def load_config(source):
     return _resolve(raw, raw)
 
 
-def build_model(config, ckpt=None, device="cuda", strict=False, verbose=False):
+def build_model(config, ckpt=None, device="cuda", strict=False, verbose=False, clip_tower=None, meta_init=False):
     """config: a loaded reference config (or its `model` sub-dict).  Instantiates the drop-in LatentDiffusion (UNet, both
-    autoencoders, conditioning stage when configured) and optionally loads a reference checkpoint."""
+    autoencoders, conditioning stage when configured) and optionally loads a reference checkpoint.
+    clip_tower: the CLIP vision tower module to inject into the conditioning stage (out of scope of this package; without
+    it FrozenCLIPImageEmbedder loads `openai/clip-vit-large-patch14` from disk like the reference does).
+    meta_init: build on the meta device and materialise on `device` (skips the random init of 1.1 B parameters that a
+    checkpoint overwrites anyway); needs `ckpt`."""
     model_cfg = retarget(config["model"] if "model" in config else config)
+    if clip_tower is not None:
+        model_cfg["params"]["cond_stage_config"]["params"]["transformer"] = clip_tower
+    if meta_init:
+        assert ckpt is not None and device is not None, "meta_init materialises empty tensors: a checkpoint must fill them"
+        with torch.device("meta"):
+            model = instantiate_from_config(model_cfg)
+        model = model.to_empty(device=device)
+        p = model_cfg["params"]
+        model.register_schedule(linear_start=p.get("linear_start", 1e-4), linear_end=p.get("linear_end", 2e-2),
+                                timesteps=p.get("timesteps", 1000))
+        model = model.to(device)
+        missing, unexpected = load_checkpoint(model, ckpt, strict=strict, verbose=verbose)
+        params = {n for n, _ in model.named_parameters()}   # (schedule buffers were rebuilt by register_schedule above)
+        still = [k for k in missing if k in params and not k.startswith("cond_stage_model.transformer.")]
+        if still:
+            raise RuntimeError("build_model(meta_init=True): the checkpoint leaves %d tensors uninitialised, e.g. %s"
+                               % (len(still), still[:3]))
+        return model.eval()
     model = instantiate_from_config(model_cfg)
     if ckpt is not None:
         load_checkpoint(model, ckpt, strict=strict, verbose=verbose)

@@ -44,9 +44,12 @@ def vae_ddconfig(latent=64, lidar=False):
                 dropout=0.0, lidar_adapter=lidar)
 
 
-def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_cfg=None, with_vae=False):
+def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_cfg=None, with_vae=False, with_cond=False):
+    """with_cond: also the conditioning stage after the CLIP tower (mapper Transformer, final_ln, BBoxEmbedder, proj_out),
+    entered at the tower's pooler_output (PooledFeatureTower)."""
     from .ddpm import LatentDiffusion
     cfg = unet_cfg or mobi_unet_config(latent, use_lidar)
+    conditions = ["ref_image", "ref_bbox"]
     vae = lambda lidar: dict(target="mobi_b200.autoencoder.AutoencoderKL",
                              params=dict(ddconfig=vae_ddconfig(latent, lidar), embed_dim=4,
                                          lossconfig=dict(target="torch.nn.Identity")))
@@ -54,6 +57,10 @@ def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_c
         ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg),
                               first_stage_config=vae(False) if with_vae else None,
                               lidar_stage_config=vae(True) if (with_vae and use_lidar) else None,
+                              cond_stage_config=dict(target="mobi_b200.encoders.FrozenCLIPImageEmbedder",
+                                                     params=dict(conditions=conditions, transformer=PooledFeatureTower()))
+                              if with_cond else None,
+                              cond_stage_key=conditions if with_cond else "image",
                               linear_start=0.00085, linear_end=0.0120, timesteps=1000, first_stage_key="inpaint",
                               image_size=cfg["image_size"], channels=4, conditioning_key="crossattn",
                               scale_factor=0.18215, lidar_scale_factor=0.18215, use_camera=True, use_lidar=use_lidar)
@@ -65,6 +72,13 @@ def build_synthetic_ldm(latent=64, use_lidar=True, device="cuda", seed=0, unet_c
         init_synthetic_(ldm.first_stage_model, seed + 1)
         if ldm.lidar_stage_model is not None:
             init_synthetic_(ldm.lidar_stage_model, seed + 2)
+    g = torch.Generator(device=next(ldm.parameters()).device).manual_seed(seed + 3)
+    with torch.no_grad():   # to_empty() left these uninitialised: [learnable_vector, bbox_uncond_vector] ~ N(0, 1)
+        for p in (ldm.learnable_vector, ldm.bbox_uncond_vector):
+            p.copy_(torch.randn(p.shape, generator=g, device=p.device))
+    if with_cond:
+        init_synthetic_(ldm.cond_stage_model, seed + 4)
+        init_synthetic_(ldm.proj_out, seed + 5)
     return ldm.eval()
 
 
@@ -122,3 +136,38 @@ def synthetic_lidar_batch(n, px=512, H=32, W=1096, seed=3, device="cuda", obj_ra
                  range_yaw=yaw.contiguous(), range_instance_mask_orig=gt, range_shift_left=(col - wc // 2) % W + W,
                  width_crop=wc, min_depth_obj=torch.full((n,), d_obj - 0.03), max_depth_obj=torch.full((n,), d_obj + 0.03))
     return ({k: v.to(device) for k, v in batch.items()}, dec.to(device), bbox.to(device))
+
+
+class PooledFeatureTower(torch.nn.Module):
+    """Stand-in for the CLIP vision tower (out of scope: SURVEY.md §2; no checkpoint without a network): the "image" it
+    is given already IS the tower's pooler_output [B, 1024], so FrozenCLIPImageEmbedder.forward runs everything that
+    follows the tower (mapper Transformer, final_ln; then proj_out in get_learned_conditioning) unchanged."""
+
+    def forward(self, pixel_values=None):
+        from types import SimpleNamespace
+        return SimpleNamespace(pooler_output=pixel_values)
+
+
+def synthetic_dataset_batch(n, px=512, seed=7, pin=True):
+    """A batch with the layout of the reference dataset (ldm/data/nuscenes.py:452-489) filled with synthetic data, on the
+    HOST (pinned): camera / range images in [-1, 1], hole masks (1 = keep) with a centred ~20 % box, box corners in [0, 1]
+    image coordinates, CLIP pooler features [n, 1024] in place of the reference crop (see PooledFeatureTower), and the
+    sweep-side tensors of synthetic_lidar_batch for the post-processing."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    u = lambda *s: torch.rand(*s, generator=g) * 2 - 1                                      # noqa: E731
+    mask = torch.ones(n, 1, px, px)
+    side = int(round(px * 0.2 ** 0.5))
+    lo = (px - side) // 2
+    mask[:, :, lo:lo + side, lo:lo + side] = 0.0
+    sweep, _, bbox_3d = synthetic_lidar_batch(n, px=px, seed=seed + 1, device="cpu")
+    img_gt, rng_gt = u(n, 3, px, px), u(n, 2, px, px)
+    batch = dict(
+        image=dict(GT=img_gt, inpaint_image=img_gt * mask, inpaint_mask=mask.clone(),
+                   cond=dict(ref_image=torch.randn(n, 1024, generator=g), ref_bbox=torch.rand(n, 8, 3, generator=g))),
+        lidar=dict(range_data=rng_gt, range_data_inpaint=rng_gt * mask, range_mask=mask.clone(),
+                   cond=dict(ref_image=torch.randn(n, 1024, generator=g), ref_bbox=torch.rand(n, 8, 3, generator=g)), **sweep),
+        bbox_3d=bbox_3d)
+    if pin and torch.cuda.is_available():
+        pinned = lambda d: {k: (pinned(v) if isinstance(v, dict) else v.contiguous().pin_memory()) for k, v in d.items()}  # noqa: E731
+        batch = pinned(batch)
+    return batch

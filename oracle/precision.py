@@ -69,3 +69,31 @@ def bf16_operand_floor(sd, cfg, x, t, c, ref=None, chunk=8):
     out = torch.cat(outs).double()
     ref = (torch.cat(refs) if ref is None else ref).double()
     return ((out - ref).abs().max() / ref.abs().max()).item(), ((out - ref).norm() / ref.norm()).item()
+
+
+class _RoundingTorchBmm:
+    def __init__(self, dt):
+        self.dt = dt
+
+    def __getattr__(self, n):
+        return getattr(torch, n)
+
+    def bmm(self, a, b):
+        return torch.bmm(a.to(self.dt).float(), b.to(self.dt).float())
+
+
+def vae_decode_rounded(sd, cfg, z, dt=torch.bfloat16):
+    """oracle/vae_oracle.py:vae_decode with every conv / attention-product operand rounded to `dt` (fp32 accumulate)."""
+    from . import vae_oracle as vo
+    vo.F, vo.torch = _RoundingFunctional(conv=dt), _RoundingTorchBmm(dt)
+    try:
+        with torch.no_grad():
+            return vo.vae_decode(sd, cfg, z)
+    finally:
+        vo.F, vo.torch = RealF, torch
+
+
+def vae_bf16_operand_floor(sd, cfg, z, ref):
+    out = vae_decode_rounded(sd, cfg, z).double()
+    ref = ref.double()
+    return ((out - ref).abs().max() / ref.abs().max()).item(), ((out - ref).norm() / ref.norm()).item()

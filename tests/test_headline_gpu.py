@@ -15,7 +15,9 @@ Tolerances ("max-abs-rel" = max-abs error relative to the max-abs of the oracle 
   * final latents after the free-running 50-step CFG-5 run: max-abs-rel <= 2e-2, cosine >= 0.9995 (measured 6.8e-3 /
     0.99998: per-step errors are largely independent between steps and DDIM averages them; SURVEY.md §8c had proposed
     5e-2).
-  * VAE decode at 512 px: max-abs-rel <= 1e-2.
+  * VAE decode at 512 px: max-abs-rel <= 2e-2 and <= 1.5 x the bf16-operand floor of the same decode (the decoder is a
+    chain of ~30 convolutions at up to 512 x 512: its floor is measured in the test like the UNet's; round-2
+    measurement 1.07e-2 camera / 1.13e-2 lidar).
 """
 import numpy as np
 import pytest
@@ -26,7 +28,7 @@ pytestmark = pytest.mark.gpu
 TOL_EPS = 2e-2          # max-abs-rel of one UNet evaluation (cap; the binding bar is 1.5 x the bf16-operand floor)
 TOL_EPS_RMS = 1e-2      # rel-rms of one UNet evaluation
 TOL_FINAL = 2e-2        # final latents of a 50-step run
-TOL_VAE = 1e-2
+TOL_VAE = 2e-2          # cap; the binding bar is 1.5 x the bf16-operand floor of the same decode
 
 
 def relerr(a, b):
@@ -248,11 +250,13 @@ def test_pbe_50_steps_and_camera_decode_vs_oracle():
     with torch.no_grad():
         want_same_z = vo.vae_decode(vsd, dd, z)                  # decoder error alone
         want_e2e = vo.vae_decode(vsd, dd, ref / 0.18215)         # oracle sampler -> oracle decoder
+    from oracle.precision import vae_bf16_operand_floor
+    floor = vae_bf16_operand_floor(vsd, dd, z, want_same_z)
     e_dec, e_e2e = relerr(img, want_same_z), relerr(img, want_e2e)
-    print("pbe: 512-px decode of the sampled latents max-abs-rel %.3e; sampler+decode end to end %.3e cosine %.6f"
-          % (e_dec, e_e2e, cosine(img, want_e2e)))
+    print("pbe: 512-px decode of the sampled latents max-abs-rel %.3e (bf16-operand floor %.3e); sampler+decode end to "
+          "end %.3e cosine %.6f" % (e_dec, floor[0], e_e2e, cosine(img, want_e2e)))
     assert img.shape == (2, 3, 512, 512)
-    assert e_dec < TOL_VAE
+    assert e_dec < TOL_VAE and e_dec < 1.5 * floor[0]
     assert e_e2e < 2 * TOL_FINAL and cosine(img, want_e2e) > 0.995
 
 
@@ -275,7 +279,10 @@ def test_vae_decode_512px_vs_oracle(lidar):
     out = vae.decode(z)
     with torch.no_grad():
         ref = vo.vae_decode(sd, cfg, z)
+    from oracle.precision import vae_bf16_operand_floor
+    floor = vae_bf16_operand_floor(sd, cfg, z, ref)
     e = relerr(out, ref)
-    print("VAE decode at 512 px (lidar=%s): max-abs-rel %.3e cosine %.6f" % (lidar, e, cosine(out, ref)))
+    print("VAE decode at 512 px (lidar=%s): max-abs-rel %.3e rel-rms %.3e cosine %.6f | bf16-operand floor %.3e / %.3e"
+          % (lidar, e, relrms(out, ref), cosine(out, ref), floor[0], floor[1]))
     assert out.shape == (2, 2 if lidar else 3, 512, 512)
-    assert e < TOL_VAE
+    assert e < TOL_VAE and e < 1.5 * floor[0]

@@ -1,6 +1,8 @@
 """Parity of the CUDA first-stage / range autoencoder (AutoencoderKL.decode / encode through the drop-in classes and the
 C ABI) against (a) golden vectors produced by the unmodified reference (tests/golden/vae_tiny.npz) and (b) the fp32
-oracle on the GPU at the real model width.  Tolerance: max-abs-rel <= 1e-2 (bf16 operands, fp32 accumulation)."""
+oracle on the GPU at the real model width.  Tolerance: max-abs-rel <= 2e-2 (bf16 operands, fp32 accumulation) and, at
+full width, <= 1.5 x the bf16-operand floor of the same decode (oracle/precision.py: the fp32 oracle with only the conv /
+attention operands rounded to bf16 is itself ~1.2-1.5e-2 away from the fp32 oracle over the decoder's ~30 convolutions)."""
 import os
 
 import numpy as np
@@ -63,11 +65,13 @@ def test_vae_fullwidth_decode_vs_oracle(lidar):
     with torch.no_grad():
         ref = vo.vae_decode(sd, cfg, z)
     torch.cuda.synchronize()
+    from oracle.precision import vae_bf16_operand_floor
+    floor = vae_bf16_operand_floor(sd, cfg, z, ref)
     e = relerr(out, ref)
     cos = torch.nn.functional.cosine_similarity(out.flatten().double(), ref.flatten().double(), dim=0).item()
-    print("full-width vae decode (lidar=%s) max-abs-rel %.3e cosine %.6f" % (lidar, e, cos))
+    print("full-width vae decode (lidar=%s) max-abs-rel %.3e cosine %.6f | bf16-operand floor %.3e" % (lidar, e, cos, floor[0]))
     assert out.shape == (2, 2 if lidar else 3, 256, 256)
-    assert e < TOL
+    assert e < TOL and e < 1.5 * floor[0]
 
 
 def test_vae_fullwidth_encode_vs_oracle():
