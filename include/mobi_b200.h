@@ -519,6 +519,16 @@ int mobi_silu_bwd(const void* pre, int32_t pre_dtype, const void* dy, int32_t dy
 /* torch.optim.AdamW step over one flat f32 buffer (ddpm.py:1655): g is multiplied by grad_scale first. */
 int mobi_adamw(float* p, const float* g, float* m, float* v, int64_t n, float lr, float beta1, float beta2, float eps,
                float weight_decay, float bias_corr1, float bias_corr2, float grad_scale, void* stream);
+/* The same step with torch.optim.AdamW's handling of parameters whose gradient is None (ddpm.py:1655; Lightning's
+ * zero_grad sets unused gradients to None): the flat buffer is cut into up to three segments [0, bound1), [bound1, bound2),
+ * [bound2, n) (the UNet's adapters | the bbox_embedder | bbox_uncond_vector); a segment whose device flag
+ * flags[s] is <= 0 this step is skipped entirely (no weight decay, no moment decay, no step count), every other segment
+ * advances its OWN step counter steps[s] (device int32[3], in/out) and uses the bias corrections of that counter.
+ * The flags live on the device so that they can ride the gradient all-reduce (a segment is active when any rank gave
+ * it a gradient, as under DDP).  state: device scratch of 9 floats.  Two launches, no host synchronisation. */
+int mobi_adamw_segments(float* p, const float* g, float* m, float* v, int64_t n, int64_t bound1, int64_t bound2,
+                        const float* flags, int32_t* steps, float* state, float lr, float beta1, float beta2, float eps,
+                        float weight_decay, float grad_scale, void* stream);
 
 /* Input assembly before the loop / the training step: one modality of
  * LatentDiffusion.encode_all_stages (ldm/models/diffusion/ddpm.py:1010-1033) fused with the lidar alignment and the

@@ -242,6 +242,8 @@ SIGNATURES = {
     "mobi_bbox_renorm": (C.c_int, [_vp, _i64, _i32, _i32, _i32, _i32, _vp]),
     "mobi_silu_bwd": (C.c_int, [_vp, _i32, _vp, _i32, _vp, _i64, _vp]),
     "mobi_adamw": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _f32, _vp]),
+    "mobi_adamw_segments": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _i64, _vp, _vp, _vp, _f32, _f32, _f32, _f32, _f32, _f32,
+                                      _vp]),
     "mobi_attn_bwd_flash": (C.c_int, [C.POINTER(AttnBwdFlashArgs), _vp]),
     "mobi_range_map": (C.c_int, [C.POINTER(RangeMapArgs), _vp]),
     "mobi_range_undo_transforms": (C.c_int, [C.POINTER(RangeUndoArgs), _vp]),

@@ -119,23 +119,32 @@ __device__ __forceinline__ void a4_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
 
-template <int NT>
+// SPLIT (tuning arm, kernel & 15 == 6; NOT what runs): TWO softmax warps per 32-row TMEM lane group (8 per tile), each
+// turns ITS half of the 64 keys of a block into probabilities; the row maximum is agreed on by swapping partial maxima
+// through shared memory and a 64-thread named barrier per block.  The idea: warps issue in order, so with 3 of them per SM
+// sub-partition the MUFU pipe (61 % busy, ncu) and the FMA pipe wait on each other, and 6 should interleave better.
+// Measured at the level-0 shape (32 rows): 1.34-1.37 ms against 1.22 ms unsplit (1.51 ms when both warps re-read the
+// whole score row instead of exchanging the maximum); head_dim 80: 0.151 vs 0.153 ms.  More warps do not pay: the
+// per-block fixed costs (waits, TMEM round trips, the exchange) double while the exponentials per warp halve.
+template <int NT, int SPLIT = 0>
 struct A4Cfg {
     static constexpr int ROLE_WARPS = NT <= 3 ? 4 : 8;
-    static constexpr int WARPS = 4 * NT + ROLE_WARPS;
+    static constexpr int SW = SPLIT ? 8 : 4;             // softmax warps per query tile
+    static constexpr int WARPS = SW * NT + ROLE_WARPS;
     static constexpr int THREADS = WARPS * 32;
-    static constexpr int SOFTMAX_REGS = NT == 4 ? 96 : (NT == 3 ? 152 : 208);
+    static constexpr int SOFTMAX_REGS = SPLIT ? 0 : (NT == 4 ? 96 : (NT == 3 ? 152 : 208));  // 0: no setmaxnreg
     static constexpr int O_STRIDE = NT >= 3 ? 64 : 128;  // TMEM columns per O accumulator incl. the 16 row-sum columns
 };
 
 constexpr uint32_t A4_ROLE_SLEEP_NS = 64;
 
-template <int NT, int BKV, int KVS, int POLY, int DK16, int DEC>
-__global__ void __launch_bounds__(A4Cfg<NT>::THREADS, 1)
+template <int NT, int BKV, int KVS, int POLY, int DK16, int DEC, int SPLIT>
+__global__ void __launch_bounds__(A4Cfg<NT, SPLIT>::THREADS, 1)
 attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const AttnParams p) {
-    using Cfg = A4Cfg<NT>;
+    using Cfg = A4Cfg<NT, SPLIT>;
     static_assert(BKV == 64, "one 64-key block = 32 TMEM columns of packed probabilities");
+    static_assert(!SPLIT || DEC, "the split softmax is built on the decoupled TMEM plan");
     constexpr int DN = DK16 * 16;                      // head_dim rounded up to the MMA K / N granularity
     constexpr int NCH = (DN + 63) / 64;                // 64-wide chunks of the head dim
     constexpr int K_CHUNK = BKV * 128;                 // bytes of a BKV-row x 64-col bf16 chunk of K or V
@@ -146,7 +155,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     constexpr int P_BASE = DEC ? NT * BKV : 0;
     constexpr int P_STRIDE = DEC ? BKV / 2 : BKV;
     constexpr int O_BASE = ((NT * BKV + (DEC ? NT * BKV / 2 : 0)) + O_STRIDE - 1) / O_STRIDE * O_STRIDE;
-    constexpr int BASE = 4 * NT;                       // first role warp
+    constexpr int BASE = Cfg::SW * NT;                 // first role warp
     constexpr int ROLE_REGS = NT == 4 ? 40 : 56;
     static_assert(O_BASE + NT * O_STRIDE <= 512 && DN + 16 <= O_STRIDE, "TMEM budget");
     extern __shared__ uint8_t smem_raw[];
@@ -166,6 +175,7 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     uint64_t* kv_full = s_free + NT;
     uint64_t* kv_empty = kv_full + KVS;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(kv_empty + KVS);
+    float* sXch = reinterpret_cast<float*>(bars + 64);   // SPLIT: per (tile, lane group) 2 x 2 x 32 partial maxima
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -188,9 +198,9 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             }
             for (int i = 0; i < NT; ++i) {
                 mbar_init(&s_full[i], 1);
-                mbar_init(&p_full[i], 128);
+                mbar_init(&p_full[i], 32 * Cfg::SW);
                 mbar_init(&o_done[i], 1);
-                mbar_init(&s_free[i], 128);
+                mbar_init(&s_free[i], 32 * Cfg::SW);
             }
             fence_barrier_init();
         }
@@ -206,7 +216,8 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 
     if (warp >= BASE) {
         // donate registers to the softmax warpgroups
-        if constexpr (ROLE_REGS == 40) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if constexpr (SPLIT) {
+        } else if constexpr (ROLE_REGS == 40) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         else asm volatile("setmaxnreg.dec.sync.aligned.u32 56;");
         if (warp == BASE) {
             if (elect_one()) {
@@ -297,6 +308,132 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                     }
                     s = s1;
                     kv_par = kv_par1;
+                }
+            }
+        }
+    } else if constexpr (SPLIT) {
+        // ---------------- split softmax: warps [8t, 8t + 8) serve tile t; warp & 3 = TMEM lane group, (warp >> 2) & 1 =
+        // which 32 keys of the block this warp exponentiates
+        const int t = warp >> 3;
+        if (t < ntiles) {
+            const int lg = warp & 3, hf = (warp >> 2) & 1;
+            const int row = lg * 32 + lane;
+            const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+            const uint32_t tS = tmem_base + t * BKV + lane_addr;
+            const uint32_t tP = tmem_base + P_BASE + t * P_STRIDE + lane_addr + hf * 16;
+            float* xch = sXch + (t * 4 + lg) * 128;        // [parity][half][lane]: double-buffered over j
+            const int pair_bar = 1 + t * 4 + lg;           // named barrier of this (tile, lane group) pair (0 = __syncthreads)
+            const uint32_t tO = tmem_base + O_BASE + t * O_STRIDE + lane_addr;
+            const uint32_t b_s_full = smem_u32(&s_full[t]), b_p_full = smem_u32(&p_full[t]);
+            const uint32_t b_o_done = smem_u32(&o_done[t]), b_s_free = smem_u32(&s_free[t]);
+            float m_used = -INFINITY;
+            for (int j = 0; j < nblk; ++j) {
+                uint32_t sr[32];
+                a4_wait(b_s_full, j & 1);
+                tc_fence_after();
+                tmem_ld32(tS + hf * 32, sr);                 // this warp's 32 keys
+                tmem_ld_wait();
+                const int valid = p.tk - j * BKV;  // keys of this block that exist (>= BKV except in the last block)
+                tc_fence_before();
+                a4_arrive(b_s_free);  // the S columns may be overwritten by the next QK^T
+                if (valid < BKV) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i)
+                        if (hf * 32 + i >= valid) sr[i] = 0xff800000u;  // -inf
+                }
+                float mx4[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+#pragma unroll
+                for (int i = 0; i < 32; i += 8) {
+#pragma unroll
+                    for (int u = 0; u < 4; ++u)
+                        mx4[u] = fmaxf(mx4[u], fmaxf(__uint_as_float(sr[i + 2 * u]), __uint_as_float(sr[i + 2 * u + 1])));
+                }
+                const float mx_own = fmaxf(fmaxf(mx4[0], mx4[1]), fmaxf(mx4[2], mx4[3]));
+                // the row maximum of the whole block: swap partial maxima with the partner warp (same rows, other keys)
+                // through shared memory and a 64-thread named barrier; both warps then hold the identical value
+                xch[(j & 1) * 64 + hf * 32 + lane] = mx_own;
+                asm volatile("bar.sync %0, 64;" ::"r"(pair_bar) : "memory");
+                const float mx = fmaxf(mx_own, xch[(j & 1) * 64 + (hf ^ 1) * 32 + lane]);
+                if (j == 0) {
+                    m_used = mx;
+                } else {
+                    const bool need = mx > m_used + 8.0f;
+                    if (__any_sync(0xffffffffu, need)) {
+                        // both warps of the lane group take the same decision from the same scores; each rescales its
+                        // share of the O | l chunks once PV(j - 1) is complete
+                        a4_wait(b_o_done, (j & 1) ^ 1);
+                        tc_fence_after();
+                        const float m_new = fmaxf(m_used, mx);
+                        const float alpha = a4_ex2(m_used - m_new);
+                        m_used = m_new;
+#pragma unroll 1
+                        for (int c = hf * 16; c < DN + 16; c += 32) {
+                            uint32_t r[16];
+                            tmem_ld16(tO + c, r);
+                            tmem_ld_wait();
+#pragma unroll
+                            for (int i = 0; i < 16; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * alpha);
+                            tmem_st16(tO + c, r);
+                        }
+                    }
+                }
+                const uint64_t m2 = pack2(m_used, m_used);
+#pragma unroll
+                for (int c = 0; c < 32; c += 2) {
+                    const uint64_t x = sub2(pack2(__uint_as_float(sr[c]), __uint_as_float(sr[c + 1])), m2);
+                    float e0, e1;
+                    constexpr int kPolySlots[9] = {0x00, 0x08, 0x22, 0x2a, 0xaa, 0xab, 0xbb, 0xbf, 0xff};
+                    if ((kPolySlots[POLY] >> ((c >> 1) & 7)) & 1) {
+                        a4_ex2_poly2(x, e0, e1);
+                    } else {
+                        float x0, x1;
+                        unpack2(x, x0, x1);
+                        e0 = a4_ex2(x0);
+                        e1 = a4_ex2(x1);
+                    }
+                    sr[c >> 1] = pack_bf16x2(e0, e1);
+                }
+                if (j > 0) {  // P buffer free: PV(j - 1) has read it (almost always true by now)
+                    a4_wait(b_o_done, (j & 1) ^ 1);
+                    tc_fence_after();
+                }
+                tmem_st16(tP, reinterpret_cast<uint32_t(&)[16]>(sr[0]));
+                tmem_st_wait();
+                tc_fence_before();
+                a4_arrive(b_p_full);
+            }
+            // ---------------- epilogue: O / l -> out[b, t, h*d + :]; the two warps of a lane group take alternate 16-column chunks
+            a4_wait(b_o_done, (nblk - 1) & 1);
+            tc_fence_after();
+            float l;
+            {
+                uint32_t r[16];
+                tmem_ld16(tO + DN, r);
+                tmem_ld_wait();
+                l = __uint_as_float(r[0]);
+            }
+            const float inv_l = 1.0f / l;
+            const int tq_row = q0 + t * 128 + row;
+            if (hf == 0 && p.lse != nullptr && tq_row < p.tq) p.lse[(long long)bh * p.tq + tq_row] = m_used + log2f(l);
+            const int b = bh / p.heads, h = bh - b * p.heads;
+            __nv_bfloat16* orow = p.out + ((long long)b * p.tq + tq_row) * p.ld_out + h * p.head_dim;
+#pragma unroll 1
+            for (int c = hf * 16; c < DN; c += 32) {
+                uint32_t r[16];
+                tmem_ld16(tO + c, r);
+                tmem_ld_wait();
+                if (tq_row < p.tq) {
+#pragma unroll
+                    for (int u = 0; u < 2; ++u) {
+                        if (c + u * 8 + 8 <= p.head_dim) {
+                            uint4 pk;
+                            pk.x = pack_bf16x2(__uint_as_float(r[u * 8 + 0]) * inv_l, __uint_as_float(r[u * 8 + 1]) * inv_l);
+                            pk.y = pack_bf16x2(__uint_as_float(r[u * 8 + 2]) * inv_l, __uint_as_float(r[u * 8 + 3]) * inv_l);
+                            pk.z = pack_bf16x2(__uint_as_float(r[u * 8 + 4]) * inv_l, __uint_as_float(r[u * 8 + 5]) * inv_l);
+                            pk.w = pack_bf16x2(__uint_as_float(r[u * 8 + 6]) * inv_l, __uint_as_float(r[u * 8 + 7]) * inv_l);
+                            *reinterpret_cast<uint4*>(orow + c + u * 8) = pk;
+                        }
+                    }
                 }
             }
         }
@@ -438,11 +575,12 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     }
 }
 
-template <int NT, int BKV, int KVS, int POLY, int DK16, int DEC>
+template <int NT, int BKV, int KVS, int POLY, int DK16, int DEC, int SPLIT = 0>
 static int launch_attention4(const mobi_attn_args* a, AttnParams p, cudaStream_t stream) {
     const int d = a->head_dim;
     const long long BH = (long long)a->batch * a->heads;
-    const long long smem = (long long)NT * p.nch * A4_CHUNK + 2ll * KVS * p.nch * BKV * 128 + A4_ONES_BYTES + 512 + 1024;
+    const long long smem = (long long)NT * p.nch * A4_CHUNK + 2ll * KVS * p.nch * BKV * 128 + A4_ONES_BYTES + 512 +
+                           (SPLIT ? NT * 4 * 128 * 4 : 0) + 1024;
     const long long limit = 227 * 1024;
     MOBI_CHECK(smem <= limit, "mobi_attention: head_dim=%d needs %lld bytes of shared memory", d, smem);
     MOBI_CHECK(p.dk16 == DK16, "mobi_attention: head_dim=%d reached the kernel built for %d", d, DK16 * 16);
@@ -462,12 +600,12 @@ static int launch_attention4(const mobi_attn_args* a, AttnParams p, cudaStream_t
     }
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(attention4_kernel<NT, BKV, KVS, POLY, DK16, DEC>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MOBI_CUDA(cudaFuncSetAttribute(attention4_kernel<NT, BKV, KVS, POLY, DK16, DEC, SPLIT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        (int)limit));
         configured = true;
     }
     dim3 grid((a->tq + 128 * NT - 1) / (128 * NT), (unsigned)BH, 1);
-    attention4_kernel<NT, BKV, KVS, POLY, DK16, DEC><<<grid, A4Cfg<NT>::THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
+    attention4_kernel<NT, BKV, KVS, POLY, DK16, DEC, SPLIT><<<grid, A4Cfg<NT, SPLIT>::THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -484,6 +622,14 @@ int attention4_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream
         case 2: return launch_attention4<3, 64, 8, 2, 2, 1>(a, p, stream);
         case 3:  // head_dim 40: the level-0 attentions of the UNet
             if (coupled) return launch_attention4<4, 64, 6, 2, 3, 0>(a, p, stream);
+            if ((a->kernel & 15) == 6) {  // tuning hook: split softmax (two warps per lane group)
+                switch (poly) {
+                    case 1: return launch_attention4<3, 64, 8, 0, 3, 1, 1>(a, p, stream);
+                    case 2: return launch_attention4<3, 64, 8, 2, 3, 1, 1>(a, p, stream);
+                    case 4: return launch_attention4<3, 64, 8, 4, 3, 1, 1>(a, p, stream);
+                    default: return launch_attention4<3, 64, 8, 3, 3, 1, 1>(a, p, stream);
+                }
+            }
             switch (poly) {  // measured at the level-0 shape (32 rows): 1.41 / 1.39 / 1.25 / 1.22 / 1.27 ms
                 case 1: return launch_attention4<3, 64, 8, 0, 3, 1>(a, p, stream);
                 case 2: return launch_attention4<3, 64, 8, 1, 3, 1>(a, p, stream);
@@ -494,6 +640,7 @@ int attention4_dispatch(const mobi_attn_args* a, const AttnParams& p, cudaStream
         case 4: return launch_attention4<2, 64, 3, 2, 4, 1>(a, p, stream);
         case 5:  // head_dim 80: level 1
             if (coupled) return launch_attention4<2, 64, 3, 2, 5, 0>(a, p, stream);
+            if ((a->kernel & 15) == 6) return launch_attention4<2, 64, 3, 2, 5, 1, 1>(a, p, stream);
             return launch_attention4<2, 64, 3, 2, 5, 1>(a, p, stream);
         case 6: return launch_attention4<2, 64, 3, 2, 6, 1>(a, p, stream);
         default: return launch_attention4<2, 64, 3, 2, 7, 1>(a, p, stream);

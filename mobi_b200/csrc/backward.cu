@@ -995,6 +995,39 @@ __global__ void adamw_kernel(float* __restrict__ p, const float* __restrict__ g,
     p[i] = pv;
 }
 
+// Per-segment bookkeeping of mobi_adamw_segments: one thread per segment.
+__global__ void adamw_seg_prepare_kernel(const float* __restrict__ flags, int* __restrict__ steps, float* __restrict__ state,
+                                         float beta1, float beta2) {
+    const int s = threadIdx.x;
+    if (s >= 3) return;
+    const bool active = flags[s] > 0.f;
+    const int st = steps[s] + (active ? 1 : 0);
+    steps[s] = st;
+    state[3 * s + 0] = static_cast<float>(1.0 - pow(static_cast<double>(beta1), static_cast<double>(st)));
+    state[3 * s + 1] = static_cast<float>(1.0 - pow(static_cast<double>(beta2), static_cast<double>(st)));
+    state[3 * s + 2] = active ? 1.f : 0.f;
+}
+
+__global__ void adamw_seg_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m,
+                                 float* __restrict__ v, long long n, long long b1, long long b2,
+                                 const float* __restrict__ state, float lr, float beta1, float beta2, float eps,
+                                 float weight_decay, float grad_scale) {
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int s = (i >= b1) + (i >= b2);
+    if (state[3 * s + 2] == 0.f) return;  // gradient None this step: torch.optim.AdamW skips the parameter
+    const float bc1 = state[3 * s], bc2 = state[3 * s + 1];
+    const float gr = g[i] * grad_scale;
+    float pv = p[i] * (1.0f - lr * weight_decay);
+    const float mv = beta1 * m[i] + (1.0f - beta1) * gr;
+    const float vv = beta2 * v[i] + (1.0f - beta2) * gr * gr;
+    m[i] = mv;
+    v[i] = vv;
+    const float denom = sqrtf(vv) / sqrtf(bc2) + eps;
+    pv -= (lr / bc1) * mv / denom;
+    p[i] = pv;
+}
+
 // dst[segment-addressed row r, :] += src[r, :]  (src compact f32 or bf16): joins a gradient computed on the camera-only /
 // lidar-only rows (attention.py:246-261) back into the interleaved residual-stream gradient.
 __global__ void scatter_add_rows_kernel(const void* __restrict__ src, int is_f32, float* dst, long long rows, int C,
@@ -1347,6 +1380,20 @@ extern "C" int mobi_adamw(float* p, const float* g, float* m, float* v, int64_t 
     MOBI_CHECK(p && g && m && v && n > 0, "mobi_adamw: bad argument");
     adamw_kernel<<<bw_blocks(n, 256), 256, 0, stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, weight_decay, bias_corr1,
                                                         bias_corr2, grad_scale);
+    MOBI_CUDA(cudaGetLastError());
+    return 0;
+}
+
+extern "C" int mobi_adamw_segments(float* p, const float* g, float* m, float* v, int64_t n, int64_t bound1, int64_t bound2,
+                                   const float* flags, int32_t* steps, float* state, float lr, float beta1, float beta2,
+                                   float eps, float weight_decay, float grad_scale, void* stream_) {
+    MOBI_STREAM;
+    MOBI_CHECK(p && g && m && v && flags && steps && state && n > 0, "mobi_adamw_segments: bad argument");
+    MOBI_CHECK(0 <= bound1 && bound1 <= bound2 && bound2 <= n, "mobi_adamw_segments: segment bounds out of order");
+    adamw_seg_prepare_kernel<<<1, 32, 0, stream>>>(flags, steps, state, beta1, beta2);
+    MOBI_CUDA(cudaGetLastError());
+    adamw_seg_kernel<<<bw_blocks(n, 256), 256, 0, stream>>>(p, g, m, v, n, bound1, bound2, state, lr, beta1, beta2, eps,
+                                                           weight_decay, grad_scale);
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

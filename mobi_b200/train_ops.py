@@ -244,6 +244,21 @@ def adamw(p, g, m, v, *, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2
                                     weight_decay, bc1, bc2, grad_scale, L.stream()), "adamw")
 
 
+def adamw_segments(p, g, m, v, *, bounds, flags, steps, state, lr, beta1=0.9, beta2=0.999, eps=1e-8, weight_decay=1e-2,
+                   grad_scale=1.0):
+    """AdamW over a flat buffer cut at `bounds` = (bound1, bound2) into <= 3 segments; flags f32 [>= 3] (device): a
+    segment with flag <= 0 got no gradient this step and is skipped like torch.optim.AdamW skips grad-None parameters;
+    steps int32 [3] (device, in/out): per-segment step counts; state f32 [9] scratch.  See mobi_adamw_segments."""
+    _cuda(p, g, m, v, flags, steps, state)
+    assert flags.dtype == torch.float32 and steps.dtype == torch.int32 and state.dtype == torch.float32
+    assert flags.numel() >= 3 and steps.numel() >= 3 and state.numel() >= 9
+    with _timed("adamw", nbytes=p.numel() * 28, kernels=2):
+        L.check(L.load().mobi_adamw_segments(p.data_ptr(), g.data_ptr(), m.data_ptr(), v.data_ptr(), p.numel(),
+                                             int(bounds[0]), int(bounds[1]), flags.data_ptr(), steps.data_ptr(),
+                                             state.data_ptr(), lr, beta1, beta2, eps, weight_decay, grad_scale, L.stream()),
+                "adamw_segments")
+
+
 # ------------------------------------------------------------------------------------------------ composites
 def wgrad_splits(M, n_out, k_in, sms=148):
     """How many K-slices a weight gradient over M token rows is cut into: enough that tiles x slices fill the SMs, slices

@@ -62,7 +62,11 @@ class FlatParams:
             off += (p.numel() + self.ALIGN - 1) // self.ALIGN * self.ALIGN
         self.numel = off
         self.params = torch.zeros(off, device=device, dtype=torch.float32)
-        self.grads = torch.zeros(off, device=device, dtype=torch.float32)
+        # the gradient buffer carries 8 trailing floats: per-segment "received a gradient this step" flags that ride the
+        # gradient all-reduce (UNetTrainer.step: a segment is active when ANY rank gave it a gradient, as under DDP)
+        self.grads_full = torch.zeros(off + 8, device=device, dtype=torch.float32)
+        self.grads = self.grads_full[:off]
+        self.flags = self.grads_full[off:]
         with torch.no_grad():
             for n, p in named:
                 v = self.view(self.params, n)
@@ -151,6 +155,16 @@ class UNetTrainer:
         self.flat = FlatParams(unet, is_trainable, dev, extra=extra)
         self.exp_avg = torch.zeros_like(self.flat.params)
         self.exp_avg_sq = torch.zeros_like(self.flat.params)
+        # torch.optim.AdamW skips parameters whose gradient is None and counts steps per parameter: the flat buffer is
+        # [UNet adapters | bbox_embedder | bbox_uncond_vector]; the last two only receive gradients on some steps
+        # (bbox given / conditioning dropout, ddpm.py:1052-1056), so each segment has its own device-side step counter
+        b1 = min([self.flat.offsets[n] for n in self.flat.names if n.startswith(BBOX_PREFIX)], default=self.flat.numel)
+        b2 = self.flat.offsets.get("bbox_uncond_vector", self.flat.numel)
+        self._adam_bounds = (b1, b2)
+        self._adam_steps = torch.zeros(4, device=dev, dtype=torch.int32)
+        self._adam_state = torch.zeros(12, device=dev, dtype=torch.float32)
+        self._flag_rows = torch.tensor([[1, 0, 0, 0, 0, 0, 0, 0], [1, 1, 0, 0, 0, 0, 0, 0], [1, 0, 1, 0, 0, 0, 0, 0],
+                                        [1, 1, 1, 0, 0, 0, 0, 0]], device=dev, dtype=torch.float32)
         self.lr, self.betas, self.eps, self.weight_decay = lr, betas, eps, weight_decay
         self.group = group
         self.steps = 0
@@ -716,6 +730,9 @@ class UNetTrainer:
         p = u._p
         R = x_start.shape[0]
         self.flat.grads.zero_()
+        # which segments receive a gradient this step: the adapters always, the bbox_embedder when its token is computed
+        # here, bbox_uncond_vector on conditioning-dropout steps (everything else is a None gradient for the optimizer)
+        self.flat.flags.copy_(self._flag_rows[(1 if bbox is not None else 0) + (2 if uncond else 0)])
         self.loss_sum.zero_()
         t = t.to(torch.int64).contiguous()
         x_noisy = tops.q_sample(x_start.float().contiguous(), noise.float().contiguous(), ldm.sqrt_alphas_cumprod,
@@ -774,10 +791,12 @@ class UNetTrainer:
     @torch.no_grad()
     def step(self, lr=None):
         """DDP gradient all-reduce (mean) + AdamW over the flat buffers + repack of the bf16 operand copies."""
-        allreduce_mean_(self.flat.grads, self.group)
+        allreduce_mean_(self.flat.grads_full, self.group)      # gradients + the per-segment activity flags behind them
         self.steps += 1
-        tops.adamw(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, lr=self.lr if lr is None else lr,
-                   beta1=self.betas[0], beta2=self.betas[1], eps=self.eps, weight_decay=self.weight_decay, step=self.steps)
+        tops.adamw_segments(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, bounds=self._adam_bounds,
+                            flags=self.flat.flags, steps=self._adam_steps, state=self._adam_state,
+                            lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
+                            weight_decay=self.weight_decay)
         self.repack_trainable()           # also marks the UNet's inference packs of these weights stale
         if self.bbox_embedder is not None:
             self.bbox_embedder.invalidate()

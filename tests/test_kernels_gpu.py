@@ -201,12 +201,12 @@ def test_conv_im2col(N, H, W, C, Cout, k, stride, pads):
     (1, 8, 40, 4096, 4096), (1, 4, 80, 384, 200), (2, 3, 40, 300, 136), (1, 2, 128, 512, 320), (1, 2, 64, 256, 1024),
     (40, 8, 40, 1024, 1024), (1, 2, 48, 700, 100),
 ])
-@pytest.mark.parametrize("kernel", [1, 3, 4, 5, 6, 7])
+@pytest.mark.parametrize("kernel", [1, 3, 4, 5, 6, 7, 8])
 def test_attention(B, H, D, Tq, Tk, kernel):
     """kernel 1 = the one-tile kernel (takes V^T; what head_dim 160 runs); 3.. take V row-major (MN-major tcgen05
     operand): 3 = attention4 (P in TMEM, row sums on the tensor core: what the UNet runs for head_dim <= 112),
     4 = attention3 (P staged in shared memory; head_dim 113..128 and the A/B arm), 5 = its two-tile variant,
-    6 = attention4 with a larger share of the exponentials on the FMA pipe, 7 = attention4's first TMEM plan (P over S)."""
+    6 = attention4 with a larger share of the exponentials on the FMA pipe, 7 = attention4's first TMEM plan (P over S), 8 = attention4 with the split softmax (two warps per lane group)."""
     rowv = kernel >= 3
     if rowv and D > 128:
         pytest.skip("row-major V needs head_dim <= 128")
@@ -225,7 +225,7 @@ def test_attention(B, H, D, Tq, Tk, kernel):
     ref = torch.einsum("bij,bjd->bid", s.softmax(-1), vb.float())
     ref = ref.reshape(B, H, Tq, D).permute(0, 2, 1, 3).reshape(B, Tq, H * D)
     vt = vb.contiguous() if rowv else vb.transpose(1, 2).contiguous()
-    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk, kernel={3: 0, 4: 3, 5: 4, 6: 0x40, 7: 5}.get(kernel, kernel), v_rowmajor=rowv)
+    out = ops.attention(qs, kb, vt, B, H, D, Tq, Tk, kernel={3: 0, 4: 3, 5: 4, 6: 0x40, 7: 5, 8: 6}.get(kernel, kernel), v_rowmajor=rowv)
     torch.cuda.synchronize()
     assert relerr(out, ref) < 1e-2, describe(out, ref)
 

@@ -212,6 +212,69 @@ def test_adamw_matches_torch():
     assert (p - ref.detach()).abs().max().item() < 3e-6
 
 
+def test_adamw_segments_skip_gradient_none_parameters_like_torch():
+    """torch.optim.AdamW skips parameters whose gradient is None (no decay, no moment update, no
+    step count): bbox_uncond_vector off the conditioning-dropout steps, the whole bbox_embedder on them.  A cond / uncond /
+    cond / cond sequence over three segments against three torch Parameters whose .grad is None on their inactive steps."""
+    from mobi_b200 import train_ops as tops
+    n, b1, b2 = 3008, 1000, 2000
+    p = rnd(n, seed=1)
+    refs = [torch.nn.Parameter(p[a:b].clone()) for a, b in ((0, b1), (b1, b2), (b2, n))]
+    opt = torch.optim.AdamW(refs, lr=1e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    steps = torch.zeros(4, device="cuda", dtype=torch.int32)
+    state = torch.zeros(12, device="cuda")
+    for it, active in enumerate([(1, 1, 0), (1, 0, 1), (1, 1, 0), (1, 1, 0), (1, 0, 1)]):
+        g = rnd(n, seed=20 + it, scale=1e-2)
+        for r, (a, b), on in zip(refs, ((0, b1), (b1, b2), (b2, n)), active):
+            r.grad = g[a:b].clone() if on else None
+        opt.step()
+        flags = torch.tensor(list(active) + [0] * 5, device="cuda", dtype=torch.float32)
+        tops.adamw_segments(p, g, m, v, bounds=(b1, b2), flags=flags, steps=steps, state=state, lr=1e-3)
+    want = torch.cat([r.detach() for r in refs])
+    assert steps[:3].tolist() == [5, 3, 2]
+    assert (p - want).abs().max().item() < 2e-6, (p - want).abs().max().item()
+    # a plain adamw() over the same sequence (decay + stale momentum on the inactive steps) is visibly different
+    assert (p[b2:] - rnd(n, seed=1)[b2:]).abs().max().item() > 1e-3
+
+
+def test_trainer_optimizer_skips_segments_without_gradient():
+    """UNetTrainer.step(): on a non-dropout step without a bbox, bbox_uncond_vector and the bbox_embedder stay bit-identical
+    (no weight decay, no momentum); a dropout step then moves bbox_uncond_vector with bias corrections of ITS first step."""
+    from mobi_b200 import encoders
+    from mobi_b200.ddpm import LatentDiffusion
+    from mobi_b200.training import UNetTrainer
+    from oracle import unet_oracle as uo
+    g = np.load(os.path.join(GOLDEN, "train_tiny.npz"))
+    cfg = uo.tiny_unet_config()
+    sd = uo.synth_state_dict(uo.state_dict_shapes(cfg), seed=0)
+    ldm = LatentDiffusion(unet_config=dict(target="mobi_b200.openaimodel.UNetModel", params=cfg), linear_start=0.00085,
+                          linear_end=0.0120, timesteps=1000, first_stage_key="inpaint", image_size=16, channels=4,
+                          conditioning_key="crossattn", use_camera=True, use_lidar=True)
+    ldm.learnable_vector = torch.nn.Parameter(rnd(1, 1, 32, seed=60).cpu(), requires_grad=False)
+    ldm.bbox_uncond_vector = torch.nn.Parameter(rnd(1, 1, 32, seed=61).cpu())
+    ldm = ldm.cuda().eval()
+    ldm.model.diffusion_model.load_state_dict(sd, strict=True)
+    be = encoders.BBoxEmbedder(proj_dims=(48, 40, 40, 32)).cuda()
+    tr = UNetTrainer(ldm, bbox_embedder=be, lr=1e-3)
+    cu = lambda k: torch.from_numpy(g[k]).cuda()
+    v0 = ldm.bbox_uncond_vector.detach().clone()
+    w0 = be.bbox_proj.weight.detach().clone()
+    for _ in range(2):                                   # two plain steps: context given, no bbox -> segments 1, 2 idle
+        tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), cu("cond"))
+        tr.step()
+    assert torch.equal(ldm.bbox_uncond_vector.detach(), v0) and torch.equal(be.bbox_proj.weight.detach(), w0)
+    assert tr._adam_steps[:3].tolist() == [2, 0, 0]
+    tr.forward_backward(cu("x_start"), cu("t"), cu("noise"), uncond=True)
+    gvec = tr.flat.grad("bbox_uncond_vector").reshape(-1).clone()
+    tr.step()
+    assert tr._adam_steps[:3].tolist() == [3, 0, 1] and torch.equal(be.bbox_proj.weight.detach(), w0)
+    # first Adam step of that parameter: update = lr * sign(g) (+ decay), whatever the global step count is
+    upd = (ldm.bbox_uncond_vector.detach().reshape(-1) - v0.reshape(-1) * (1 - 1e-3 * 1e-2))
+    big = gvec.abs() > 1e-6
+    assert big.any() and rel(upd[big], -1e-3 * torch.sign(gvec[big])) < 1e-2
+
+
 @pytest.mark.parametrize("cin,cout,hw,stride", [(64, 128, 16, 1), (128, 64, 8, 1), (64, 4, 16, 1), (64, 64, 16, 2)])
 def test_conv_dgrad(cin, cout, hw, stride):
     """dX of conv3x3 as a conv of dY (zero-inserted for stride 2) with the flipped, transposed filter."""

@@ -57,7 +57,8 @@ def bench_attn():
         fl = 4.0 * rows * H * T * T * D
         # 0x100: row-major V, attention4 (P in TMEM); 0x1N0: its exp-on-FMA-pipe shares; 0x103 / 0x104: attention3 (4 / 2 tiles)
         # 0x105: attention4's first TMEM plan (NT = 4, P over S: S(j + 1) after PV(j))
-        kerns = (1,) if D > 128 else ((0x100, 0x110, 0x120, 0x130, 0x140, 0x105, 0x103) if D <= 48 else (0x100, 0x105, 0x103, 1))
+        # 0x106 / 0x1N6: attention4 with the split softmax (two warps per TMEM lane group)
+        kerns = (1,) if D > 128 else ((0x100, 0x106, 0x116, 0x126, 0x146, 0x105, 0x103) if D <= 48 else (0x100, 0x106, 0x103, 1))
         for kern in kerns:
             rowv = kern >= 0x100
             ms = timeit(lambda: ops.attention(q, k, vrow if rowv else vt, rows, H, D, T, T, out=out, kernel=kern & 0xff,
