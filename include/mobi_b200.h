@@ -108,6 +108,14 @@ typedef struct {
      * b of a token-major [B * T, H * D] matrix sits at b * T * ld + h * D, which no single stride expresses. */
     int32_t batch_inner;
     int64_t a_batch2_stride, b_batch2_stride, out_batch2_stride;
+    /* Optional (PLAIN epilogue, f32 output, persistent kernel, no batch / row segments): per-column sums and sums of
+     * squares of the FINAL output values (after bias, row bias, activation and residual) over every group of 32
+     * consecutive output rows, as f32 [2][ceil(M / 32)][N] (plane 0 = sums, plane 1 = sums of squares).  They are the
+     * statistics the GroupNorm that consumes this output needs (openaimodel.py:255-275, attention.py:302-313), computed
+     * while the tile is still in registers: mobi_groupnorm then reads its input once instead of twice.  Per-COLUMN sums
+     * are consumer-agnostic: the same tensor feeds GroupNorms with different group widths (as h, and later as a skip
+     * connection inside a wider concatenation, openaimodel.py:892). */
+    float* colstats;
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);
@@ -160,6 +168,11 @@ typedef struct {
     int32_t out_dtype; /* dtype of `out`: MOBI_DTYPE_BF16 (default, a GEMM/conv operand) or MOBI_DTYPE_F32 */
     int32_t force_two_pass; /* 1: always run the statistics + apply kernel pair (default 0: single-pass cluster kernel
                                whenever one cluster's slab set fits L2) */
+    /* Optional: the per-column statistics mobi_gemm left for x1 / x2 (mobi_gemm_args.colstats; f32 [2][n_img * hw / 32][c];
+     * hw must be a multiple of 32).  When given for every input, no statistics pass runs: a small kernel folds the column
+     * sums into the (image, group) sums and the apply kernel streams the input once (4 B read + 2 B written per element). */
+    const float* colstats1;
+    const float* colstats2;
 } mobi_groupnorm_args;
 
 int64_t mobi_groupnorm_scratch_bytes(int32_t n_img, int32_t hw, int32_t c, int32_t groups);

@@ -32,6 +32,7 @@ class GemmArgs(C.Structure):
         ("batch", _i32), ("a_batch_stride", _i64), ("b_batch_stride", _i64), ("out_batch_stride", _i64),
         ("pair", _i32), ("a_mn_major", _i32), ("b_mn_major", _i32), ("atomic_out", _i32),
         ("batch_inner", _i32), ("a_batch2_stride", _i64), ("b_batch2_stride", _i64), ("out_batch2_stride", _i64),
+        ("colstats", _vp),
     ]
 
 
@@ -49,6 +50,7 @@ class GroupNormArgs(C.Structure):
         ("partials", _vp),
         ("n_img", _i32), ("hw", _i32), ("c1", _i32), ("c2", _i32), ("groups", _i32),
         ("in_dtype", _i32), ("silu", _i32), ("eps", _f32), ("out_dtype", _i32), ("force_two_pass", _i32),
+        ("colstats1", _vp), ("colstats2", _vp),
     ]
 
 

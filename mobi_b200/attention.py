@@ -41,10 +41,18 @@ def _f32(t):
 
 
 def repeat_rows2(t):
-    """cat([t, t]) along the batch dimension as two device-to-device copies (data movement only)."""
+    """cat([t, t]) along the batch dimension as two device-to-device copies (data movement only); the producer-side
+    GroupNorm statistics of `t` (ops.carry_colstats: [2][row groups][C]) are repeated the same way."""
     out = torch.empty((2 * t.shape[0],) + tuple(t.shape[1:]), device=t.device, dtype=t.dtype)
     out[:t.shape[0]].copy_(t)
     out[t.shape[0]:].copy_(t)
+    st = getattr(t, "_colstats", None)
+    if st is not None:
+        half = st.view(2, -1)
+        st2 = torch.empty((2, 2 * half.shape[1]), device=st.device, dtype=st.dtype)
+        st2[:, :half.shape[1]].copy_(half)
+        st2[:, half.shape[1]:].copy_(half)
+        out._colstats = st2.view(-1)
     return out
 
 
@@ -354,8 +362,8 @@ class SpatialTransformer(nn.Module):
             R, attn1_done = 2 * R, True
         for i, blk in enumerate(self.transformer_blocks):
             x = blk.run(x, R, T, tabs[i], out_bf16=(i == n - 1), attn1_done=(attn1_done and i == 0))
-        out = ops.gemm(x, p["w_out"], bias=p["b_out"], residual=h.reshape(R * T, C), out_dtype=torch.float32)
-        return out.reshape(R, Hh, Ww, C)
+        out = ops.gemm(x, p["w_out"], bias=p["b_out"], residual=h.reshape(R * T, C), out_dtype=torch.float32, colstats=True)
+        return ops.carry_colstats(out.reshape(R, Hh, Ww, C), out)
 
     def forward(self, x, context=None):
         """Reference signature: x NCHW f32 -> NCHW f32."""

@@ -214,6 +214,132 @@ gn_apply_kernel(const void* x1, const void* x2, const float* __restrict__ gamma,
 }
 
 
+// Producer-side statistics (mobi_gemm_args.colstats): the GEMM / conv that wrote x1 (and x2) left per-column sums and sums
+// of squares for every group of 32 output rows, f32 [2][rows / 32][c].  grid (groups, n_img): one CTA folds the
+// (row group, channel) cells of one (image, group) into the sums gn_apply_kernel finalises ([n_img][1][groups][2]), so no
+// statistics pass reads the image.  Cells are read with the channel index fastest: consecutive threads, consecutive floats.
+__global__ void __launch_bounds__(GN_THREADS)
+gn_colstats_fold_kernel(const float* __restrict__ st1, const float* __restrict__ st2, float* __restrict__ partials,
+                        int n_img, int hw, int c1, int c2, int groups) {
+    __shared__ double red[2][GN_WARPS];
+    const int C = c1 + c2;
+    const int cpg = C / groups;
+    const int slabs = hw >> 5;
+    const int g = blockIdx.x, n = blockIdx.y;
+    const long long plane1 = (long long)n_img * slabs * c1, plane2 = (long long)n_img * slabs * c2;
+    double s = 0.0, q = 0.0;
+    const int cells = slabs * cpg;
+    for (int i = threadIdx.x; i < cells; i += GN_THREADS) {
+        const int slab = i / cpg;
+        const int c = g * cpg + (i - slab * cpg);
+        const bool first = c < c1;
+        const float* src = first ? st1 : st2;
+        const long long idx = ((long long)n * slabs + slab) * (first ? c1 : c2) + (first ? c : c - c1);
+        s += (double)src[idx];
+        q += (double)src[(first ? plane1 : plane2) + idx];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        q += __shfl_xor_sync(0xffffffffu, q, o);
+    }
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) {
+        red[0][warp] = s;
+        red[1][warp] = q;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double ss = 0.0, qq = 0.0;
+#pragma unroll
+        for (int w = 0; w < GN_WARPS; ++w) {
+            ss += red[0][w];
+            qq += red[1][w];
+        }
+        partials[((long long)n * groups + g) * 2 + 0] = (float)ss;
+        partials[((long long)n * groups + g) * 2 + 1] = (float)qq;
+    }
+}
+
+// Streaming normalise pass for the producer-statistics path: grid (slabs, n_img, sources).  One source (x1 or x2 of the
+// concatenation) is read as a flat stream of 16-byte vectors, four independent loads in flight per thread; the per-channel
+// scale / shift of this source's channels sit in shared memory.  4 B read + 2 B written per element, nothing else.
+constexpr int GNS_UN = 4;
+
+template <bool OUT_F32>
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stream_kernel(const float* __restrict__ x1, const float* __restrict__ x2, const float* __restrict__ gamma,
+                 const float* __restrict__ beta, void* __restrict__ out_, __nv_bfloat16* __restrict__ out_concat,
+                 const float* __restrict__ partials, int hw, int c1, int c2, int groups, float eps, int silu,
+                 long long vec_per_cta) {
+    extern __shared__ float gn_smem[];  // scale[c_src], shift[c_src]
+    __shared__ float s_mean[32], s_rstd[32];
+    const int C = c1 + c2;
+    const int cpg = C / groups;
+    const int n = blockIdx.y;
+    const bool second = blockIdx.z != 0;
+    const float* x = second ? x2 : x1;
+    const int c_src = second ? c2 : c1, c_off = second ? c1 : 0;
+    const int nvs = c_src >> 2;
+    if (threadIdx.x < groups) {
+        const double cnt = (double)hw * cpg;
+        const double sm = (double)partials[((long long)n * groups + threadIdx.x) * 2 + 0];
+        const double sq = (double)partials[((long long)n * groups + threadIdx.x) * 2 + 1];
+        const double mean = sm / cnt;
+        double var = sq / cnt - mean * mean;
+        if (var < 0.0) var = 0.0;
+        s_mean[threadIdx.x] = (float)mean;
+        s_rstd[threadIdx.x] = (float)(1.0 / sqrt(var + (double)eps));
+    }
+    __syncthreads();
+    float* s_scale = gn_smem;
+    float* s_shift = gn_smem + c_src;
+    for (int c = threadIdx.x; c < c_src; c += GN_THREADS) {
+        const int g = (c_off + c) / cpg;
+        const float a = gamma[c_off + c] * s_rstd[g];
+        s_scale[c] = a;
+        s_shift[c] = beta[c_off + c] - s_mean[g] * a;
+    }
+    __syncthreads();
+    const long long total = (long long)hw * nvs;  // vectors of this source in this image
+    const long long v0 = (long long)blockIdx.x * vec_per_cta;
+    const long long v1 = min(total, v0 + vec_per_cta);
+    const float4* src = reinterpret_cast<const float4*>(x) + (long long)n * total;
+    for (long long base = v0 + threadIdx.x; base < v1; base += (long long)GN_THREADS * GNS_UN) {
+        float4 f[GNS_UN];
+#pragma unroll
+        for (int k = 0; k < GNS_UN; ++k) {
+            const long long idx = base + (long long)k * GN_THREADS;
+            if (idx < v1) f[k] = __ldcs(src + idx);   // streamed once: do not keep it in L2 in front of the weights
+        }
+#pragma unroll
+        for (int k = 0; k < GNS_UN; ++k) {
+            const long long idx = base + (long long)k * GN_THREADS;
+            if (idx >= v1) break;
+            const unsigned pixel = (unsigned)(idx / (unsigned)nvs);
+            const int v = (int)(idx - (long long)pixel * nvs);
+            const float4 sc = *reinterpret_cast<const float4*>(s_scale + 4 * v);
+            const float4 sh = *reinterpret_cast<const float4*>(s_shift + 4 * v);
+            const float4 g = f[k];
+            float y0 = g.x * sc.x + sh.x, y1 = g.y * sc.y + sh.y, y2 = g.z * sc.z + sh.z, y3 = g.w * sc.w + sh.w;
+            if (silu) {
+                y0 = silu_f(y0);
+                y1 = silu_f(y1);
+                y2 = silu_f(y2);
+                y3 = silu_f(y3);
+            }
+            const long long o = ((long long)n * hw + pixel) * C + c_off + 4 * v;
+            if (OUT_F32)
+                *reinterpret_cast<float4*>(reinterpret_cast<float*>(out_) + o) = make_float4(y0, y1, y2, y3);
+            else
+                *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(out_) + o) =
+                    make_uint2(pack_bf16x2(y0, y1), pack_bf16x2(y2, y3));
+            if (out_concat)
+                *reinterpret_cast<uint2*>(out_concat + o) = make_uint2(pack_bf16x2(g.x, g.y), pack_bf16x2(g.z, g.w));
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // Single-pass GroupNorm: one 8-CTA thread-block cluster per (image, chunk of `gpc` groups).  Each CTA owns a pixel slab:
 // it accumulates the statistics of its slab, the cluster combines them through distributed shared memory, and the CTA
@@ -762,6 +888,56 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
         MOBI_CUDA(cudaFuncSetAttribute(gn_stats_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024));
         configured = true;
     }
+    // apply pass: finer slabs so small images still fill the machine
+    long long pix2 = (128 * 1024) / ((long long)C * 4);
+    if (pix2 < GN_WARPS) pix2 = GN_WARPS;
+    const int slabs2 = (int)((a->hw + pix2 - 1) / pix2);
+    const int pix_per_slab2 = (a->hw + slabs2 - 1) / slabs2;
+    const dim3 grid2(slabs2, a->n_img);
+    const size_t smem2 = (size_t)2 * C * sizeof(float);
+#define GN_APPLY(INF, OUTF, NSLABS)                                                                                    \
+    gn_apply_kernel<INF, OUTF><<<grid2, GN_THREADS, smem2, stream>>>(                                                  \
+        a->x1, a->x2, a->gamma, a->beta, a->out, reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, NSLABS, \
+        a->hw, a->c1, a->c2, a->groups, a->eps, a->silu, pix_per_slab2)
+#define GN_APPLY_ANY(NSLABS)                       \
+    do {                                           \
+        if (f32 && of32) GN_APPLY(true, true, NSLABS);     \
+        else if (f32) GN_APPLY(true, false, NSLABS);       \
+        else if (of32) GN_APPLY(false, true, NSLABS);      \
+        else GN_APPLY(false, false, NSLABS);               \
+    } while (0)
+    if (a->colstats1 != nullptr) {
+        // statistics came with the producer's epilogue: fold the column sums, then ONE streaming pass over the image
+        MOBI_CHECK(a->hw % 32 == 0 && (a->c2 == 0 || a->colstats2 != nullptr),
+                   "mobi_groupnorm: colstats need hw %% 32 == 0 and statistics for both inputs");
+        gn_colstats_fold_kernel<<<dim3(a->groups, a->n_img), GN_THREADS, 0, stream>>>(
+            a->colstats1, a->colstats2, a->partials, a->n_img, a->hw, a->c1, a->c2, a->groups);
+        MOBI_CUDA(cudaGetLastError());
+        if (f32) {
+            const int cmax = a->c1 > a->c2 ? a->c1 : a->c2;
+            const long long vec_img = (long long)a->hw * (cmax >> 2);
+            // >= 4 rounds of GN_THREADS x GNS_UN vectors per CTA, at most ~16 CTAs per SM over the grid
+            long long per = (long long)GN_THREADS * GNS_UN * 4;
+            const long long want = (148ll * 16 + a->n_img - 1) / a->n_img;
+            if ((vec_img + per - 1) / per > want) per = ((vec_img + want - 1) / want + GN_THREADS * GNS_UN - 1) / (GN_THREADS * GNS_UN) * (GN_THREADS * GNS_UN);
+            const dim3 grid((unsigned)((vec_img + per - 1) / per), a->n_img, a->c2 > 0 ? 2 : 1);
+            const size_t smem = (size_t)2 * cmax * sizeof(float);
+            if (of32)
+                gn_stream_kernel<true><<<grid, GN_THREADS, smem, stream>>>(
+                    reinterpret_cast<const float*>(a->x1), reinterpret_cast<const float*>(a->x2), a->gamma, a->beta, a->out,
+                    reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, a->hw, a->c1, a->c2, a->groups, a->eps,
+                    a->silu, per);
+            else
+                gn_stream_kernel<false><<<grid, GN_THREADS, smem, stream>>>(
+                    reinterpret_cast<const float*>(a->x1), reinterpret_cast<const float*>(a->x2), a->gamma, a->beta, a->out,
+                    reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, a->hw, a->c1, a->c2, a->groups, a->eps,
+                    a->silu, per);
+        } else {
+            GN_APPLY_ANY(1);
+        }
+        MOBI_CUDA(cudaGetLastError());
+        return 0;
+    }
     const int gpc = a->force_two_pass ? 0 : gn_fused_gpc(a->hw, C, a->groups, f32 ? 4 : 2);
     if (gpc > 0) {
         dim3 grid(GNF_CLUSTER * (a->groups / gpc), a->n_img);
@@ -783,7 +959,6 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
     const int slabs = gn_slabs(a->hw, C);
     const int pix_per_slab = (a->hw + slabs - 1) / slabs;
     const size_t smem1 = (size_t)GN_WARPS * C * 2 * sizeof(float);
-    const size_t smem2 = (size_t)2 * C * sizeof(float);
     MOBI_CHECK(smem1 <= 160 * 1024, "mobi_groupnorm: C=%d too large", C);
     dim3 grid1(slabs, a->n_img);
     if (f32)
@@ -793,20 +968,8 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
         gn_stats_kernel<false><<<grid1, GN_THREADS, smem1, stream>>>(a->x1, a->x2, a->partials, a->hw, a->c1, a->c2,
                                                                      a->groups, pix_per_slab);
     MOBI_CUDA(cudaGetLastError());
-    // apply: finer slabs so small images still fill the machine
-    long long pix2 = (128 * 1024) / ((long long)C * 4);
-    if (pix2 < GN_WARPS) pix2 = GN_WARPS;
-    int slabs2 = (int)((a->hw + pix2 - 1) / pix2);
-    const int pix_per_slab2 = (a->hw + slabs2 - 1) / slabs2;
-    dim3 grid2(slabs2, a->n_img);
-#define GN_APPLY(INF, OUTF)                                                                                            \
-    gn_apply_kernel<INF, OUTF><<<grid2, GN_THREADS, smem2, stream>>>(                                                  \
-        a->x1, a->x2, a->gamma, a->beta, a->out, reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, slabs, \
-        a->hw, a->c1, a->c2, a->groups, a->eps, a->silu, pix_per_slab2)
-    if (f32 && of32) GN_APPLY(true, true);
-    else if (f32) GN_APPLY(true, false);
-    else if (of32) GN_APPLY(false, true);
-    else GN_APPLY(false, false);
+    GN_APPLY_ANY(slabs);
+#undef GN_APPLY_ANY
 #undef GN_APPLY
     MOBI_CUDA(cudaGetLastError());
     return 0;

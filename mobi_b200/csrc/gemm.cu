@@ -440,6 +440,12 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
             return 1;
     }
     p.atomic_out = a->atomic_out ? 1 : 0;
+    p.colstats = a->colstats;
+    if (p.colstats)
+        MOBI_CHECK(p.mode == MOBI_EPI_PLAIN && p.out_f32 && !batched && a->out_seg == 0 && !a->atomic_out && a->kernel != 1 &&
+                       a->N % 4 == 0,
+                   "mobi_gemm: colstats needs the PLAIN epilogue with f32 output on the persistent kernel (no batch, row "
+                   "segments or atomic accumulation)");
     if (p.atomic_out)
         MOBI_CHECK(p.out_f32 && p.mode == MOBI_EPI_PLAIN && !a->bias && !a->row_bias && !a->residual && a->act == 0 &&
                        a->kernel != 1 && a->out_seg == 0,
@@ -490,6 +496,7 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     MOBI_CHECK(!(p.a_mn || p.b_mn || p.atomic_out) || gemm2_supported(p),
                "mobi_gemm: MN-major operands / atomic_out are outside the persistent kernel's epilogue here");
     if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);
+    MOBI_CHECK(p.colstats == nullptr, "mobi_gemm: colstats requested but this problem falls back to the one-tile kernel");
     MOBI_CHECK(!batched, "mobi_gemm: this batched problem is outside the persistent kernel's epilogue (N %% 4, "
                          "16-byte aligned out / residual / bias)");
     switch (bn_tile) {

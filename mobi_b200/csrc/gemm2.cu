@@ -243,6 +243,8 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 coloff = (long long)h * p.tokens * p.head_dim + dd;
                 hbase = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
             }
+            // column statistics of the final values for the GroupNorm that consumes this output (mobi_gemm_args.colstats)
+            uint64_t cs01 = 0, cs23 = 0, cq01 = 0, cq23 = 0;  // packed (0.f, 0.f)
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int rr = it * 4 + rsub;
@@ -272,6 +274,13 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 if (p.residual) {
                     v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w;
                 }
+                if (MC <= 1 && p.colstats) {
+                    const uint64_t v01 = pack2(v.x, v.y), v23 = pack2(v.z, v.w);
+                    cs01 = add2(cs01, v01);
+                    cs23 = add2(cs23, v23);
+                    cq01 = fma2(v01, v01, cq01);
+                    cq23 = fma2(v23, v23, cq23);
+                }
                 if (p.out_f32) {
                     float* dst = reinterpret_cast<float*>(p.out) + er.off[it] + n;
                     if (p.atomic_out) {
@@ -287,6 +296,25 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                     pk.x = pack_bf16x2(v.x, v.y);
                     pk.y = pack_bf16x2(v.z, v.w);
                     *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + er.off[it] + n) = pk;
+                }
+            }
+            if (MC <= 1 && p.colstats) {
+                // the 4 lanes that share this 4-column unit (rsub = 0..3) hold the 32 rows of the warp's lane group
+                float c[8];
+                unpack2(cs01, c[0], c[1]);
+                unpack2(cs23, c[2], c[3]);
+                unpack2(cq01, c[4], c[5]);
+                unpack2(cq23, c[6], c[7]);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    c[i] += __shfl_xor_sync(0xffffffffu, c[i], 8);
+                    c[i] += __shfl_xor_sync(0xffffffffu, c[i], 16);
+                }
+                if (rsub == 0 && col_ok && m_base < p.M) {
+                    const long long groups32 = (p.M + 31) / 32;
+                    float* dst = p.colstats + (long long)(m_base >> 5) * p.N + n;
+                    *reinterpret_cast<float4*>(dst) = make_float4(c[0], c[1], c[2], c[3]);
+                    *reinterpret_cast<float4*>(dst + groups32 * p.N) = make_float4(c[4], c[5], c[6], c[7]);
                 }
             }
         } else {

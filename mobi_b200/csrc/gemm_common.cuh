@@ -34,6 +34,7 @@ struct GemmParams {
     long long out_batch2_stride;  // elements between outer batch entries of the output
     int atomic_out;               // f32 output accumulated with atomic adds (split-K over the batch index)
     int a_mn, b_mn;               // operand given MN-major ([K, M] / [K, N] row-major): 64 x 64 TMA boxes, UMMA major bits
+    float* colstats;              // optional f32 [2][ceil(M / 32)][N]: column sums / sums of squares per 32-row group
 };
 
 constexpr int BM = 128;

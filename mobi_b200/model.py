@@ -43,7 +43,7 @@ class Upsample(nn.Module):
     def run(self, h):
         if not self.with_conv:
             return ops.upsample_nearest2x(h)
-        return Conv3x3.run(self._p, ops.upsample_nearest2x(h, torch.bfloat16))
+        return Conv3x3.run(self._p, ops.upsample_nearest2x(h, torch.bfloat16), colstats=True)
 
 
 class Downsample(nn.Module):
@@ -61,7 +61,7 @@ class Downsample(nn.Module):
         self._p = Conv3x3.pack(self.conv)
 
     def run(self, h):
-        return Conv3x3.run(self._p, h, pad_override=(0, 0, 1, 1))
+        return Conv3x3.run(self._p, h, pad_override=(0, 0, 1, 1), colstats=True)
 
 
 class ResnetBlock(nn.Module):
@@ -101,14 +101,14 @@ class ResnetBlock(nn.Module):
         need_raw = "w_skip" in p
         g = ops.groupnorm(h, p["gn1"][0], p["gn1"][1], 1e-6, silu=True, want_concat=need_raw)
         hn, raw = g if need_raw else (g, None)
-        h1 = Conv3x3.run(p["conv1"], hn)
+        h1 = Conv3x3.run(p["conv1"], hn, colstats=True)
         hn2 = ops.groupnorm(h1, p["gn2"][0], p["gn2"][1], 1e-6, silu=True)
         if need_raw:
             res = ops.gemm(raw.reshape(n * hh * ww, -1), p["w_skip"], bias=p["b_skip"], out_dtype=torch.float32)
             res = res.reshape(n, hh, ww, self.out_channels)
         else:
             res = h
-        return Conv3x3.run(p["conv2"], hn2, residual=res)
+        return Conv3x3.run(p["conv2"], hn2, residual=res, colstats=True)
 
 
 class AttnBlock(nn.Module):
@@ -150,8 +150,8 @@ class AttnBlock(nn.Module):
             ops.gemm(qi[:, :c], qi[:, c:], out=s, out_dtype=torch.float32)              # S = Q K^T  (log2 units)
             ops.softmax_rows(s, out=pr)
             ops.gemm(pr, vt[i], out=o[i * t:(i + 1) * t], out_dtype=torch.bfloat16)     # O = P V
-        out = ops.gemm(o, p["w_o"], bias=p["b_o"], residual=h.reshape(n * t, c), out_dtype=torch.float32)
-        return out.reshape(n, hh, ww, c)
+        out = ops.gemm(o, p["w_o"], bias=p["b_o"], residual=h.reshape(n * t, c), out_dtype=torch.float32, colstats=True)
+        return ops.carry_colstats(out.reshape(n, hh, ww, c), out)
 
 
 def make_attn(in_channels, attn_type="vanilla"):
@@ -226,7 +226,7 @@ class Encoder(nn.Module):
     def run(self, h):
         """h: NHWC f32 image -> NHWC f32 [N, h/8, w/8, 2*z]."""
         p = self._p
-        h = Conv3x3.run(p["conv_in"], h)
+        h = Conv3x3.run(p["conv_in"], h, colstats=True)
         if self.lidar_adapter:
             h = self.res_block_lidar1.run(h)
             h = self.res_block_lidar2.run(h)
@@ -322,7 +322,7 @@ class Decoder(nn.Module):
         """z: NHWC f32 latent [N, h, w, z_channels] -> NHWC f32 image [N, 8h, 8w, out_ch]."""
         p = self._p
         self.last_z_shape = z.shape
-        h = Conv3x3.run(p["conv_in"], z)
+        h = Conv3x3.run(p["conv_in"], z, colstats=True)
         h = self.mid.block_1.run(h)
         h = self.mid.attn_1.run(h)
         h = self.mid.block_2.run(h)

@@ -36,15 +36,16 @@ class Conv3x3(nn.Module):
                     cout=o, stride=conv.stride[0], pad=(conv.padding[0], conv.padding[1]))
 
     @staticmethod
-    def run(p, x, *, row_bias=None, residual=None, out_dtype=torch.float32, pad_override=None):
-        """x: NHWC (bf16 for the implicit path; f32 or bf16 for the im2col path)."""
+    def run(p, x, *, row_bias=None, residual=None, out_dtype=torch.float32, pad_override=None, colstats=False):
+        """x: NHWC (bf16 for the implicit path; f32 or bf16 for the im2col path).
+        colstats: the output feeds a GroupNorm: have the epilogue leave its column statistics (ops.carry_colstats)."""
         n, h, w, c = x.shape
         kh, kw, stride = p["kh"], p["kw"], p["stride"]
         ph, pw = p["pad"]
         if stride == 1 and pad_override is None and x.dtype == torch.bfloat16 and ops.conv_implicit_ok(h, w, c) \
                 and p["w"].shape[1] == kh * kw * c:
             return ops.conv_implicit(x, p["w"], kh, kw, ph, pw, bias=p["b"], row_bias=row_bias, residual=residual,
-                                     out_dtype=out_dtype)
+                                     out_dtype=out_dtype, colstats=colstats)
         if pad_override is not None:  # VAE Downsample: pad (0,1,0,1) then a valid stride-2 conv (model.py:72-76)
             pt, pl, pb, pr = pad_override
         else:
@@ -55,8 +56,8 @@ class Conv3x3(nn.Module):
         cols = ops.im2col(x, kh, kw, stride, pt, pl, ho, wo)
         out = ops.gemm(cols, p["w"], bias=p["b"], row_bias=row_bias, rows_per_group=ho * wo,
                        residual=None if residual is None else residual.reshape(n * ho * wo, p["cout"]),
-                       out_dtype=out_dtype)
-        return out.reshape(n, ho, wo, p["cout"])
+                       out_dtype=out_dtype, colstats=colstats)
+        return ops.carry_colstats(out.reshape(n, ho, wo, p["cout"]), out)
 
 
 class Upsample(nn.Module):
@@ -81,7 +82,7 @@ class Upsample(nn.Module):
         if not self.use_conv:
             return ops.upsample_nearest2x(h)
         up = ops.upsample_nearest2x(h, torch.bfloat16)
-        return Conv3x3.run(self._p, up)
+        return Conv3x3.run(self._p, up, colstats=True)
 
     def forward(self, x):
         if self._p is None:
@@ -109,7 +110,7 @@ class Downsample(nn.Module):
 
     def run(self, h):
         assert h.shape[-1] == self.channels
-        return Conv3x3.run(self._p, h)
+        return Conv3x3.run(self._p, h, colstats=True)
 
     def forward(self, x):
         if self._p is None:
@@ -157,7 +158,7 @@ class ResBlock(TimestepBlock):
         need_raw = "w_skip" in p
         g = ops.groupnorm(h, p["gn1"][0], p["gn1"][1], 1e-5, x2=skip, silu=True, want_concat=need_raw)
         hn, raw = g if need_raw else (g, None)
-        h1 = Conv3x3.run(p["conv1"], hn, row_bias=emb_out)                       # conv + bias + emb (255-272)
+        h1 = Conv3x3.run(p["conv1"], hn, row_bias=emb_out, colstats=True)        # conv + bias + emb (255-272)
         hn2 = ops.groupnorm(h1, p["gn2"][0], p["gn2"][1], 1e-5, silu=True)
         if need_raw:
             res = ops.gemm(raw.reshape(R * Hh * Ww, -1), p["w_skip"], bias=p["b_skip"], out_dtype=torch.float32)
@@ -165,7 +166,7 @@ class ResBlock(TimestepBlock):
         else:
             assert skip is None
             res = h
-        return Conv3x3.run(p["conv2"], hn2, residual=res)                        # skip_connection(x) + h (275)
+        return Conv3x3.run(p["conv2"], hn2, residual=res, colstats=True)         # skip_connection(x) + h (275)
 
     def forward(self, x, emb):
         """Reference signature: x NCHW, emb [N, emb_channels] -> NCHW."""
@@ -402,7 +403,7 @@ class UNetModel(nn.Module):
             # Everything before the first context injection is computed once for the identical halves: conv_in, the first
             # ResBlock, the first SpatialTransformer's GroupNorm / proj_in and its first self-attention.
             Rh = R // 2
-            h0 = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x[:Rh].detach().float().contiguous()))
+            h0 = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x[:Rh].detach().float().contiguous()), colstats=True)
             hs.append(repeat_rows2(h0))
             off = p["emb_offs"][id(first[0])]
             hr = first[0].run(h0, emb_all[:Rh, off:off + first[0].out_channels])
@@ -410,7 +411,7 @@ class UNetModel(nn.Module):
             hs.append(h)
             blocks = blocks[1:]
         else:
-            h = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x.detach().float().contiguous()))
+            h = Conv3x3.run(p["conv_in"], ops.nchw_to_nhwc(x.detach().float().contiguous()), colstats=True)
             hs.append(h)
         for seq in blocks:
             h = self._run_block(seq, h, None, emb_all)

@@ -66,6 +66,23 @@ def _cuda(*ts):
             raise RuntimeError("mobi_b200 ops need contiguous tensors, got strides %s" % (t.stride(),))
 
 
+# Producer-side GroupNorm statistics (mobi_gemm_args.colstats).  A GEMM / conv launched with colstats=True leaves the column
+# sums of its output in a side buffer, kept as the attribute `_colstats` of the tensor it returns; groupnorm() picks it up
+# from its inputs and then streams them once.  Views lose Python attributes: carry_colstats() hands the buffer on.
+COLSTATS = os.environ.get("MOBI_GN_COLSTATS", "1") == "1"
+
+
+def _colstats_buffer(M, N, device):
+    return torch.empty(2 * ((M + 31) // 32) * N, device=device, dtype=torch.float32)
+
+
+def carry_colstats(dst, src):
+    st = getattr(src, "_colstats", None)
+    if st is not None:
+        dst._colstats = st
+    return dst
+
+
 def _rows_view(t, what):
     """Checks that `t` is a CUDA matrix view (unit inner stride, uniform row stride) and returns its row stride."""
     if not t.is_cuda:
@@ -85,8 +102,9 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
          out_dtype=torch.bfloat16, epilogue=L.EPI_PLAIN, act=0, heads=0, head_dim=0, tokens=0, out2=None, out3=None,
          tile_n=0, M=None, K=None, lda=None, ldb=None, ldo=None, out_seg=0, out_seg_stride=0, out_seg_offset=0,
          kernel=0, N=None, batch=1, a_batch_stride=0, b_batch_stride=0, out_batch_stride=0, pair=0, a_mn=False, b_mn=False,
-         atomic_out=False, batch_inner=0, a_batch2_stride=0, b_batch2_stride=0, out_batch2_stride=0):
+         atomic_out=False, batch_inner=0, a_batch2_stride=0, b_batch2_stride=0, out_batch2_stride=0, colstats=False):
     """out[M,N] = a[M,K] @ w[N,K]^T (+bias +row_bias +residual), bf16 operands, fp32 accumulate.
+    colstats: also leave the per-column statistics of the output for the GroupNorm that consumes it (out._colstats).
 
     Mirrors torch.nn.functional.linear(a, w, bias); see include/mobi_b200.h for the epilogues.  a, w and out
     may be column slices of wider matrices (row strides are taken from the views or given explicitly).
@@ -145,17 +163,23 @@ def gemm(a, w, *, bias=None, row_bias=None, rows_per_group=1, ld_row_bias=0, res
     args.atomic_out = 1 if atomic_out else 0
     args.batch_inner = batch_inner
     args.a_batch2_stride, args.b_batch2_stride, args.out_batch2_stride = a_batch2_stride, b_batch2_stride, out_batch2_stride
+    st = None
+    if colstats and COLSTATS and epilogue == L.EPI_PLAIN and out.dtype == torch.float32 and N % 4 == 0 and kernel == 0:
+        st = _colstats_buffer(M, N, a.device)
+        args.colstats = st.data_ptr()
     kind = "gemm"
     if _SHAPE_KINDS:   # MOBI_GEMM_SHAPES=1: per-shape accounting for tools/train_bench.py
         kind = "gemm M%d N%d K%d b%d%s%s%s" % (M, N, K, batch, " amn" if a_mn else "", " bmn" if b_mn else "",
                                                 " atomic" if atomic_out else "")
     with _timed(kind, 2.0 * M * N * K * max(1, batch)):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm")
+    if st is not None:
+        out._colstats = st
     return out
 
 
 def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_row_bias=0, residual=None, out=None,
-                  out_dtype=torch.float32, tile_n=0, kernel=0, pair=0):
+                  out_dtype=torch.float32, tile_n=0, kernel=0, pair=0, colstats=False):
     """Stride-1 'same' convolution of an NHWC bf16 image by implicit GEMM.
 
     x: [N, H, W, C] bf16; w: [Cout, kh*kw*C] bf16 with K ordered (kh, kw, c). Returns [N, H, W, Cout].
@@ -186,8 +210,14 @@ def conv_implicit(x, w, kh, kw, pad_h, pad_w, *, bias=None, row_bias=None, ld_ro
     args.tile_n = tile_n
     args.kernel = kernel
     args.pair = pair
+    st = None
+    if colstats and COLSTATS and out.dtype == torch.float32 and cout % 4 == 0 and kernel == 0:
+        st = _colstats_buffer(n * h * wd, cout, x.device)
+        args.colstats = st.data_ptr()
     with _timed("conv", 2.0 * n * h * wd * cout * kh * kw * c):
         L.check(L.load().mobi_gemm(C.byref(args), L.stream()), "gemm(conv)")
+    if st is not None:
+        out._colstats = st
     return out
 
 
@@ -261,9 +291,18 @@ def groupnorm(x1, gamma, beta, eps, *, x2=None, silu=True, groups=32, want_conca
     a.n_img, a.hw, a.c1, a.c2, a.groups = n, hw, c1, c2, groups
     a.in_dtype, a.silu, a.eps, a.out_dtype = L.dt(x1), int(silu), eps, L.dt(out)
     a.force_two_pass = int(two_pass)
-    with _timed("groupnorm", 0.0, x1.numel() * x1.element_size() * 2 + (x2.numel() * x2.element_size() * 2 if x2 is not None else 0)
-                + out.numel() * 2 * (2 if want_concat else 1),
-                kernels=lib.mobi_groupnorm_launches(hw, c, groups, a.in_dtype, a.force_two_pass)):
+    # statistics left by the producers of x1 / x2 (see carry_colstats): one streaming pass instead of two reads
+    st1 = getattr(x1, "_colstats", None)
+    st2 = getattr(x2, "_colstats", None) if x2 is not None else None
+    fused_stats = (st1 is not None and (x2 is None or st2 is not None) and hw % 32 == 0 and hw >= 256 and not two_pass
+                   and st1.numel() == 2 * (n * hw // 32) * c1 and (st2 is None or st2.numel() == 2 * (n * hw // 32) * c2))
+    if fused_stats:
+        a.colstats1, a.colstats2 = st1.data_ptr(), L.ptr(st2)
+        kernels, nbytes = 2, x1.numel() * x1.element_size() + (x2.numel() * x2.element_size() if x2 is not None else 0)
+    else:
+        kernels = lib.mobi_groupnorm_launches(hw, c, groups, a.in_dtype, a.force_two_pass)
+        nbytes = x1.numel() * x1.element_size() * 2 + (x2.numel() * x2.element_size() * 2 if x2 is not None else 0)
+    with _timed("groupnorm", 0.0, nbytes + out.numel() * 2 * (2 if want_concat else 1), kernels=kernels):
         L.check(lib.mobi_groupnorm(C.byref(a), L.stream()), "groupnorm")
     return (out, cat) if want_concat else out
 

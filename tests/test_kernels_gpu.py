@@ -411,3 +411,64 @@ def test_sampler_kernels():
     xr = (0.8 * x0 + 0.6 * nz) * bm + (1 - bm) * x
     assert torch.allclose(xb, xr, atol=1e-6)
     assert torch.allclose(x_in[:B], torch.cat([xr, img, mask], 1), atol=1e-6)
+
+
+# ----------------------------------------------------------------------------------------------- producer-side GroupNorm statistics
+@pytest.mark.parametrize("M,N,K,res", [(4096, 320, 320, True), (2100, 640, 128, False), (8192, 1280, 64, True)])
+def test_gemm_colstats(M, N, K, res):
+    """mobi_gemm_args.colstats: per-column sums / sums of squares of the FINAL output over every 32-row group."""
+    ops = _ops()
+    a = rnd(M, K, seed=1, dtype=torch.float32).to(torch.bfloat16)
+    w = rnd(N, K, seed=2, dtype=torch.float32, scale=K ** -0.5).to(torch.bfloat16)
+    b = rnd(N, seed=3, dtype=torch.float32)
+    r = rnd(M, N, seed=4, dtype=torch.float32) if res else None
+    out = ops.gemm(a, w, bias=b, residual=r, out_dtype=torch.float32, colstats=True)
+    st = out._colstats.view(2, (M + 31) // 32, N)
+    torch.cuda.synchronize()
+    pad = (-M) % 32
+    o = torch.nn.functional.pad(out, (0, 0, 0, pad)).view(-1, 32, N)
+    assert relerr(st[0], o.sum(1)) < 1e-5 and relerr(st[1], (o * o).sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("N,HW,C1,C2,silu", [(2, 4096, 320, 0, True), (3, 1024, 1280, 640, True), (2, 64, 1280, 1280, False),
+                                             (2, 256, 640, 320, True)])
+def test_groupnorm_with_producer_statistics(N, HW, C1, C2, silu):
+    """GroupNorm fed by the column statistics its producers left (ops.carry_colstats): same result as the statistics pass,
+    incl. a concatenation whose groups straddle the two inputs (1280 + 640 channels -> groups of 60)."""
+    ops = _ops()
+    side = int(HW ** 0.5)
+
+    def produced(C, seed):   # a conv-like producer: 1x1 GEMM over [N*HW, C] with colstats
+        a = rnd(N * HW, 64, seed=seed, dtype=torch.float32).to(torch.bfloat16)
+        w = rnd(C, 64, seed=seed + 1, dtype=torch.float32, scale=0.125).to(torch.bfloat16)
+        bias = rnd(C, seed=seed + 2, dtype=torch.float32) * 2      # a mean well away from zero
+        out = ops.gemm(a, w, bias=bias, out_dtype=torch.float32, colstats=True)
+        return ops.carry_colstats(out.reshape(N, side, side, C), out)
+
+    x1 = produced(C1, 10)
+    x2 = produced(C2, 20) if C2 else None
+    C = C1 + C2
+    g, b = 1 + 0.1 * rnd(C, seed=5, dtype=torch.float32), 0.1 * rnd(C, seed=6, dtype=torch.float32)
+    got = ops.groupnorm(x1, g, b, 1e-5, x2=x2, silu=silu)
+    plain1 = x1.clone()
+    plain2 = x2.clone() if x2 is not None else None                  # clones carry no statistics: the two-read path
+    want = ops.groupnorm(plain1, g, b, 1e-5, x2=plain2, silu=silu)
+    xx = x1 if x2 is None else torch.cat([x1, x2], -1)
+    ref = torch.nn.functional.group_norm(xx.permute(0, 3, 1, 2), 32, g, b, 1e-5)
+    ref = (torch.nn.functional.silu(ref) if silu else ref).permute(0, 2, 3, 1)
+    torch.cuda.synchronize()
+    assert relerr(got, ref) < 1e-2 and relerr(got.float(), want.float()) < 1e-2
+    assert (got.float() - want.float()).abs().max().item() <= 2 * 2 ** -7 * ref.abs().max().item()   # <= a bf16 ulp apart
+
+
+def test_conv_colstats_and_cfg_duplicate():
+    ops = _ops()
+    from mobi_b200.attention import repeat_rows2
+    x = rnd(2, 32, 32, 64, seed=1, dtype=torch.float32).to(torch.bfloat16)
+    w = rnd(128, 9 * 64, seed=2, dtype=torch.float32, scale=(9 * 64) ** -0.5).to(torch.bfloat16)
+    out = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=rnd(128, seed=3, dtype=torch.float32), colstats=True)
+    st = out._colstats.view(2, -1, 128)
+    o = out.reshape(-1, 32, 128)
+    assert relerr(st[0], o.sum(1)) < 1e-5 and relerr(st[1], (o * o).sum(1)) < 1e-5
+    dup = repeat_rows2(out)
+    assert dup._colstats.numel() == 2 * st.numel() and torch.equal(dup._colstats.view(2, -1, 128)[:, st.shape[1]:], st)

@@ -147,6 +147,13 @@ def bench_gn():
         report("groupnorm+silu C=%d+%d @%d" % (C1, C2, S), timeit(lambda: ops.groupnorm(x1, g, b, 1e-5, x2=x2)), 0, E * 10)
         report("groupnorm+silu C=%d+%d @%d two-pass" % (C1, C2, S),
                timeit(lambda: ops.groupnorm(x1, g, b, 1e-5, x2=x2, two_pass=True)), 0, E * 10)
+        # producer-side statistics (timing only: the statistics buffers hold noise)
+        x1._colstats = torch.rand(2 * (R * S * S // 32) * C1, device="cuda")
+        if x2 is not None:
+            x2._colstats = torch.rand(2 * (R * S * S // 32) * C2, device="cuda")
+        report("groupnorm+silu C=%d+%d @%d producer statistics" % (C1, C2, S),
+               timeit(lambda: ops.groupnorm(x1, g, b, 1e-5, x2=x2)), 0, E * 6)
+        del x1._colstats
 
 
 if __name__ == "__main__":
