@@ -135,7 +135,7 @@ class UNetTrainer:
     """forward_backward(x_start, t, noise, context) -> loss; step() -> all-reduce + AdamW + repack."""
 
     def __init__(self, ldm, lr=8e-5, betas=(0.9, 0.999), eps=1e-8, weight_decay=1e-2, group=None, use_cuda_graph=True,
-                 lse_backward=False, bbox_embedder=None, flash_backward=True):
+                 lse_backward=False, bbox_embedder=None, flash_backward=True, overlap_allreduce=True):
         self.ldm = ldm
         self.unet = ldm.model.diffusion_model if hasattr(ldm, "model") else ldm
         unet = self.unet
@@ -184,6 +184,10 @@ class UNetTrainer:
         # three batched GEMMs (kept as the A/B reference and for other shapes)
         self.flash_backward = flash_backward
         self._fb_graphs, self._seg_start = {}, None
+        # overlap_allreduce: under torch.distributed the gradient buckets are all-reduced on a side stream while the next
+        # phase of the backward runs (what DDP's bucketed reducer does for the reference, main.py:509-510)
+        self.overlap_allreduce = overlap_allreduce
+        self._comm_stream, self._pending = None, []
         unet.invalidate()
         unet.pack()
         self._pack_frozen_backward()
@@ -272,6 +276,23 @@ class UNetTrainer:
         # the same table for the gradients: the flat gradient buffer shares the parameter offsets, and only the to_q
         # segments carry a scale (every other pack is cast with scale 1)
         self._gseg_scale = self._seg_scale.clone()
+        # gradient buckets in the order the backward completes them (flat offsets follow module order: input_blocks,
+        # middle_block, output_blocks, then the extras): A = middle + output blocks, B = input blocks of the two coarser
+        # levels, C = the level-0 input blocks, D = bbox_embedder / bbox_uncond_vector + the activity flags
+        names = [n for n in self.flat.names if not (n.startswith(BBOX_PREFIX) or n == "bbox_uncond_vector")]
+        first = lambda pred: min([self.flat.offsets[n] for n in names if pred(n)], default=None)           # noqa: E731
+        unet_end = self._adam_bounds[0]
+        a_lo = first(lambda n: n.startswith("middle_block") or n.startswith("output_blocks"))
+        b_lo = first(lambda n: n.startswith("input_blocks.") and int(n.split(".")[1]) >= 4)
+        a_lo = unet_end if a_lo is None else a_lo
+        b_lo = a_lo if b_lo is None else b_lo
+        self._buckets = [(a_lo, unet_end), (b_lo, a_lo), (0, b_lo), (unet_end, self.flat.numel + 8)]
+        self._bucket_scale = []
+        for lo, hi in self._buckets[:3]:   # the q-gradient rescale of scale_segments, cut at the bucket bounds
+            st = [lo] + [b for b in starts if lo < b < hi]
+            sc = [bounds[max(b2 for b2 in starts if b2 <= b)] for b in st]
+            self._bucket_scale.append((torch.tensor([b - lo for b in st], device=self.device, dtype=torch.int64),
+                                       torch.tensor(sc, device=self.device, dtype=torch.float32)))
 
     def _repack_trainable(self):
         tp = {}
@@ -668,11 +689,21 @@ class UNetTrainer:
                 self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"], uncond)
             torch.cuda.current_stream().wait_stream(side)
             torch.cuda.synchronize()
-            g = torch.cuda.CUDAGraph()
+            # one CUDA graph per phase of the backward (shared memory pool): between two replays the gradients of the
+            # finished bucket go to the all-reduce on the communication stream
+            gen = self._fb_phases(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"], uncond)
+            graphs, pool, loss = [], None, None
             before = ops.Stats.launches
-            with torch.cuda.graph(g):
-                loss = self._forward_backward(st["x"], st["t"], st["noise"], st["ctx"], st["bbox"], uncond)
-            entry = dict(graph=g, static=st, loss=loss, d_context=self.d_context, kernels=ops.Stats.launches - before)
+            while loss is None:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g, pool=pool):
+                    try:
+                        next(gen)
+                    except StopIteration as done:
+                        loss = done.value
+                pool = g.pool()
+                graphs.append(g)
+            entry = dict(graphs=graphs, static=st, loss=loss, d_context=self.d_context, kernels=ops.Stats.launches - before)
             self._fb_graphs[key] = entry
         st = entry["static"]
         st["x"].copy_(x_start)
@@ -681,10 +712,38 @@ class UNetTrainer:
         st["ctx"].copy_(context)
         if bbox is not None:
             st["bbox"].copy_(bbox)
-        entry["graph"].replay()
+        overlap = self._overlap_world() > 1
+        self._pending = []
+        for i, g in enumerate(entry["graphs"]):
+            g.replay()
+            if overlap:
+                self._start_allreduce([i] if i < len(entry["graphs"]) - 1 else [i, 3])
         ops.Stats.launches += entry["kernels"]
         self.d_context = entry["d_context"]
         return entry["loss"]
+
+    # ------------------------------------------------------------------ gradient exchange overlapped with the backward
+    def _overlap_world(self):
+        import torch.distributed as dist
+        if not self.overlap_allreduce or not (dist.is_available() and dist.is_initialized()):
+            return 1
+        return dist.get_world_size(self.group)
+
+    def _start_allreduce(self, buckets):
+        """SUM all-reduce of the given gradient buckets on the communication stream, ordered after everything the compute
+        stream has issued so far; step() waits for them and folds the 1 / world of the mean into AdamW's gradient scale."""
+        import torch.distributed as dist
+        if self._comm_stream is None:
+            self._comm_stream = torch.cuda.Stream()
+        ev = torch.cuda.Event()
+        ev.record()
+        with torch.cuda.stream(self._comm_stream):
+            self._comm_stream.wait_event(ev)
+            for b in buckets:
+                lo, hi = self._buckets[b]
+                if hi > lo:
+                    self._pending.append(dist.all_reduce(self.flat.grads_full[lo:hi], op=dist.ReduceOp.SUM,
+                                                         group=self.group, async_op=True))
 
     def _uncond_context(self, R):
         """[learnable_vector, bbox_uncond_vector] repeated for every row (ddpm.py:1053-1056)."""
@@ -726,6 +785,31 @@ class UNetTrainer:
             d = tops.silu_bwd(pre[i], dx) if pre[i] is not None else dx
 
     def _forward_backward(self, x_start, t, noise, context, bbox=None, uncond=False):
+        """All phases back to back (eager mode / warm-up)."""
+        gen = self._fb_phases(x_start, t, noise, context, bbox, uncond)
+        while True:
+            try:
+                next(gen)
+            except StopIteration as done:
+                return done.value
+
+    def _scale_bucket(self, i):
+        """The q-gradient rescale (to_q packs carry the attention scale) of gradient bucket i, in place."""
+        lo, hi = self._buckets[i]
+        if hi <= lo:
+            return
+        st, sc = self._bucket_scale[i]
+        ops.Stats.launches += 1
+        L.check(L.load().mobi_scale_segments(self.flat.grads[lo:hi].data_ptr(), hi - lo, st.data_ptr(), sc.data_ptr(),
+                                             st.numel(), L.stream()), "scale_segments")
+
+    def _fb_phases(self, x_start, t, noise, context, bbox=None, uncond=False):
+        """Generator over the three phases of one forward + backward; after phase i the gradients of bucket i
+        (self._buckets) are final, so their all-reduce can run while the next phase computes:
+          phase 0: forward, loss, backward of the output blocks and the middle block   -> bucket 0
+          phase 1: backward of the input blocks of the coarser levels                  -> bucket 1
+          phase 2: backward of the level-0 input blocks, bbox_embedder, uncond vector  -> buckets 2, 3
+        Returns the loss (StopIteration.value)."""
         u, ldm = self.unet, self.ldm
         p = u._p
         R = x_start.shape[0]
@@ -774,29 +858,44 @@ class UNetTrainer:
             dh, dskip = self._seq_backward(seq, tp_, dh, ctx_f32)
             d_hs.append(dskip)                                     # gradients of hs[0], hs[1], ... in order
         dh, _ = self._seq_backward(u.middle_block, tape_mid, dh, ctx_f32)
+        # gradients w.r.t. the scaled query projections -> w.r.t. to_q.weight, bucket by bucket
+        self._scale_bucket(0)
+        yield 0
         inputs = list(u.input_blocks)
+        cut = False
         for i in range(len(inputs) - 1, 0, -1):
+            if i == 3:            # what is left are the level-0 blocks (input_blocks 1, 2): bucket 1 is final
+                self._scale_bucket(1)
+                cut = True
+                yield 1
             dh = ops.add_f32(dh, d_hs[i])
             dh, _ = self._seq_backward(inputs[i], tapes_in[i - 1], dh, ctx_f32, first=(i == 1))
+        if not cut:               # shallow (test) models with fewer than four input blocks
+            self._scale_bucket(1)
+            yield 1
         if bbox_tape is not None:
             self._bbox_backward(bbox_tape, self.d_context[:, 1])
         if uncond and "bbox_uncond_vector" in self.flat.offsets:   # every row saw the same vector: sum over rows
             tops.colsum(self.d_context[:, 1].contiguous(), self.flat.grad("bbox_uncond_vector").reshape(1, -1))
-        # gradients w.r.t. the scaled query projections -> w.r.t. to_q.weight
-        ops.Stats.launches += 1
-        L.check(L.load().mobi_scale_segments(self.flat.grads.data_ptr(), self.flat.numel, self._seg_start.data_ptr(),
-                                             self._gseg_scale.data_ptr(), self._seg_start.numel(), L.stream()), "scale_segments")
+        self._scale_bucket(2)
         return self.loss_sum[0] / eps.numel()
 
     @torch.no_grad()
     def step(self, lr=None):
         """DDP gradient all-reduce (mean) + AdamW over the flat buffers + repack of the bf16 operand copies."""
-        allreduce_mean_(self.flat.grads_full, self.group)      # gradients + the per-segment activity flags behind them
+        grad_scale = 1.0
+        if self._pending:       # bucket all-reduces (SUM) started by forward_backward: wait, average inside AdamW
+            for work in self._pending:
+                work.wait()
+            self._pending = []
+            grad_scale = 1.0 / self._overlap_world()
+        else:                   # gradients + the per-segment activity flags behind them
+            allreduce_mean_(self.flat.grads_full, self.group)
         self.steps += 1
         tops.adamw_segments(self.flat.params, self.flat.grads, self.exp_avg, self.exp_avg_sq, bounds=self._adam_bounds,
                             flags=self.flat.flags, steps=self._adam_steps, state=self._adam_state,
                             lr=self.lr if lr is None else lr, beta1=self.betas[0], beta2=self.betas[1], eps=self.eps,
-                            weight_decay=self.weight_decay)
+                            weight_decay=self.weight_decay, grad_scale=grad_scale)
         self.repack_trainable()           # also marks the UNet's inference packs of these weights stale
         if self.bbox_embedder is not None:
             self.bbox_embedder.invalidate()

@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-overlap", action="store_true", help="one blocking all-reduce after the backward (round-1 behaviour)")
     args = ap.parse_args()
     import torch.distributed as dist
     from mobi_b200 import ops, synth
@@ -35,7 +36,7 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     n = args.samples_per_gpu
     ldm = synth.build_synthetic_ldm(latent=args.latent, device=dev, seed=0)
-    tr = UNetTrainer(ldm, use_cuda_graph=not args.no_graph)
+    tr = UNetTrainer(ldm, use_cuda_graph=not args.no_graph, overlap_allreduce=not args.no_overlap)
     g = torch.Generator(device=dev).manual_seed(100 + rank)
     R, h = 2 * n, args.latent
     x_start = torch.randn(R, 9, h, h, device=dev, generator=g)
@@ -61,6 +62,7 @@ def main():
     e1.record()
     torch.cuda.synchronize()
     launches = (ops.Stats.launches - l0) // args.steps
+    p_l2, p_sum = tr.flat.params.double().norm().item(), tr.flat.params.double().sum().item()   # same on every rank after DDP steps
     ms = torch.tensor([e0.elapsed_time(e1) / args.steps], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -81,7 +83,8 @@ def main():
         tc_ms, tc_fl = sum(v["ms"] for v in tc.values()), sum(v["flops"] for v in tc.values())
         line = {"metric": "training step (UNet fwd+bwd, adapter grads, all-reduce, AdamW)", "ms_per_step": ms.item(),
                 "samples_per_s": n * world / (ms.item() / 1e3), "n_gpus": world, "joint_samples_per_gpu": n,
-                "latent": args.latent, "cuda_graph": not args.no_graph, "loss": loss.item(), "trainable_params": tr.flat.numel,
+                "latent": args.latent, "cuda_graph": not args.no_graph, "overlap_allreduce": not args.no_overlap,
+                "loss": loss.item(), "trainable_params": tr.flat.numel, "params_l2_after": p_l2, "params_sum_after": p_sum,
                 "kernel_launches_per_step": launches,
                 "nominal_tflops_3x_forward": 3 * fwd / (ms.item() / 1e3) / 1e12,
                 "tensor_core_launch_tflops": tc_fl / (tc_ms / 1e3) / 1e12 if tc_ms else None, "peak_tflops": peak,
