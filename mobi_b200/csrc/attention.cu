@@ -71,6 +71,8 @@ attention_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant_
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();
+    pdl_trigger();
     const uint32_t tmem_base = *tmem_slot;
     const uint32_t tmem_S0 = tmem_base;          // columns [0,128) and [128,256)
     const uint32_t tmem_O = tmem_base + 256;     // columns [256, 256+dn)
@@ -326,7 +328,6 @@ extern "C" int mobi_attention(const mobi_attn_args* a, void* stream_) {
     }
     dim3 grid((a->tq + ATT_BM - 1) / ATT_BM, (unsigned)BH, 1);
     MOBI_CHECK(BH <= 65535, "mobi_attention: batch*heads=%lld exceeds grid.y", BH);
-    attention_kernel<<<grid, 192, smem, stream>>>(tmQ, tmK, tmV, p);
-    MOBI_CUDA(cudaGetLastError());
+    MOBI_CUDA(launch_pdl(attention_kernel, grid, dim3(192), (size_t)smem, stream, tmQ, tmK, tmV, p));
     return 0;
 }

@@ -212,6 +212,8 @@ attention4_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
+    pdl_wait();  // barriers, TMEM and the ones tile were set up under the tail of the previous kernel (q / k / v producer)
+    pdl_trigger();
     const uint32_t tmem_base = *tmem_slot;
 
     if (warp >= BASE) {
@@ -605,8 +607,8 @@ static int launch_attention4(const mobi_attn_args* a, AttnParams p, cudaStream_t
         configured = true;
     }
     dim3 grid((a->tq + 128 * NT - 1) / (128 * NT), (unsigned)BH, 1);
-    attention4_kernel<NT, BKV, KVS, POLY, DK16, DEC, SPLIT><<<grid, A4Cfg<NT, SPLIT>::THREADS, smem, stream>>>(tmQ, tmK, tmV, p);
-    MOBI_CUDA(cudaGetLastError());
+    MOBI_CUDA(launch_pdl(attention4_kernel<NT, BKV, KVS, POLY, DK16, DEC, SPLIT>, grid, dim3(A4Cfg<NT, SPLIT>::THREADS), smem,
+                         stream, tmQ, tmK, tmV, p));
     return 0;
 }
 

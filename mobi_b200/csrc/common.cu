@@ -1,3 +1,4 @@
+#include <stdlib.h>
 #include "common.cuh"
 
 #include <cudaTypedefs.h>
@@ -64,6 +65,15 @@ int sm_count() {
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) n = 148;
     return n;
+}
+
+bool pdl_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char* e = getenv("MOBI_PDL");
+        on = (e && e[0] == '1') ? 1 : 0;   // opt-in: measured 1 % slower inside the captured UNet graph (profiles/r02/)
+    }
+    return on != 0;
 }
 
 }  // namespace mobi

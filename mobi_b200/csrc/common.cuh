@@ -34,4 +34,28 @@ int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uin
 
 int sm_count();
 
+// Programmatic dependent launch (griddepcontrol): kernels that execute pdl_wait() before their first global access are
+// launched with cudaLaunchAttributeProgrammaticStreamSerialization, so their CTAs are scheduled and run their prologue
+// (barrier initialisation, TMEM allocation, descriptor prefetch) while the previous kernel of the stream drains; inside a
+// captured CUDA graph the edge becomes a programmatic dependency.  OPT-IN (MOBI_PDL=1): the A/B of round 2 on the 444-node
+// UNet graph (profiles/r02/pdl_ab.md) found it 1 % SLOWER than plain graph edges (95.96 vs 94.80 ms per 64-row step,
+// 49.51 vs 49.06 ms at 32 rows) although the eager per-kernel sum improved (91.2 vs 92.9 ms): graph kernel-to-kernel edges
+// already cost ~1 us, and early-scheduled dependents hold SM slots next to the persistent GEMM CTAs.
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 }  // namespace mobi

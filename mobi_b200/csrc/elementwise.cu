@@ -222,6 +222,8 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_colstats_fold_kernel(const float* __restrict__ st1, const float* __restrict__ st2, float* __restrict__ partials,
                         int n_img, int hw, int c1, int c2, int groups) {
     __shared__ double red[2][GN_WARPS];
+    pdl_wait();
+    pdl_trigger();
     const int C = c1 + c2;
     const int cpg = C / groups;
     const int slabs = hw >> 5;
@@ -274,6 +276,8 @@ gn_stream_kernel(const float* __restrict__ x1, const float* __restrict__ x2, con
                  long long vec_per_cta) {
     extern __shared__ float gn_smem[];  // scale[c_src], shift[c_src]
     __shared__ float s_mean[32], s_rstd[32];
+    pdl_wait();
+    pdl_trigger();
     const int C = c1 + c2;
     const int cpg = C / groups;
     const int n = blockIdx.y;
@@ -910,9 +914,8 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
         // statistics came with the producer's epilogue: fold the column sums, then ONE streaming pass over the image
         MOBI_CHECK(a->hw % 32 == 0 && (a->c2 == 0 || a->colstats2 != nullptr),
                    "mobi_groupnorm: colstats need hw %% 32 == 0 and statistics for both inputs");
-        gn_colstats_fold_kernel<<<dim3(a->groups, a->n_img), GN_THREADS, 0, stream>>>(
-            a->colstats1, a->colstats2, a->partials, a->n_img, a->hw, a->c1, a->c2, a->groups);
-        MOBI_CUDA(cudaGetLastError());
+        MOBI_CUDA(launch_pdl(gn_colstats_fold_kernel, dim3(a->groups, a->n_img), dim3(GN_THREADS), (size_t)0, stream,
+                             a->colstats1, a->colstats2, a->partials, a->n_img, a->hw, a->c1, a->c2, a->groups));
         if (f32) {
             const int cmax = a->c1 > a->c2 ? a->c1 : a->c2;
             const long long vec_img = (long long)a->hw * (cmax >> 2);
@@ -923,15 +926,15 @@ extern "C" int mobi_groupnorm(const mobi_groupnorm_args* a, void* stream_) {
             const dim3 grid((unsigned)((vec_img + per - 1) / per), a->n_img, a->c2 > 0 ? 2 : 1);
             const size_t smem = (size_t)2 * cmax * sizeof(float);
             if (of32)
-                gn_stream_kernel<true><<<grid, GN_THREADS, smem, stream>>>(
-                    reinterpret_cast<const float*>(a->x1), reinterpret_cast<const float*>(a->x2), a->gamma, a->beta, a->out,
-                    reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, a->hw, a->c1, a->c2, a->groups, a->eps,
-                    a->silu, per);
+                MOBI_CUDA(launch_pdl(gn_stream_kernel<true>, grid, dim3(GN_THREADS), smem, stream,
+                                     reinterpret_cast<const float*>(a->x1), reinterpret_cast<const float*>(a->x2), a->gamma,
+                                     a->beta, a->out, reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, a->hw,
+                                     a->c1, a->c2, a->groups, a->eps, a->silu, per));
             else
-                gn_stream_kernel<false><<<grid, GN_THREADS, smem, stream>>>(
-                    reinterpret_cast<const float*>(a->x1), reinterpret_cast<const float*>(a->x2), a->gamma, a->beta, a->out,
-                    reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, a->hw, a->c1, a->c2, a->groups, a->eps,
-                    a->silu, per);
+                MOBI_CUDA(launch_pdl(gn_stream_kernel<false>, grid, dim3(GN_THREADS), smem, stream,
+                                     reinterpret_cast<const float*>(a->x1), reinterpret_cast<const float*>(a->x2), a->gamma,
+                                     a->beta, a->out, reinterpret_cast<__nv_bfloat16*>(a->out_concat), a->partials, a->hw,
+                                     a->c1, a->c2, a->groups, a->eps, a->silu, per));
         } else {
             GN_APPLY_ANY(1);
         }

@@ -407,6 +407,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     if (PAIR) cluster_sync_all();  // barriers of BOTH CTAs initialised before any remote arrive / TMA signal
     else __syncthreads();
     tc_fence_after();
+    pdl_wait();     // everything above overlapped the tail of the previous kernel; its results are needed from here on
+    pdl_trigger();
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = p.num_k_blocks;
     // tiles are 128 x BN (or 256 x BN per pair: m_tiles then counts 256-row tiles)
@@ -584,13 +586,15 @@ static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     cfg.blockDim = dim3(G2_THREADS, 1, 1);
     cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeClusterDimension;
     attr[0].val.clusterDim.x = 2;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = 2;
     MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, true>, tmA, tmB, p, m_tiles2, n_tiles));
     return 0;
 }
@@ -609,8 +613,8 @@ static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     const long long total = (long long)m_tiles * n_tiles * (p.batch > 1 ? p.batch : 1);
     MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    gemm2_kernel<BN, MC, false><<<grid, G2_THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p, m_tiles, n_tiles);
-    MOBI_CUDA(cudaGetLastError());
+    MOBI_CUDA(launch_pdl(gemm2_kernel<BN, MC, false>, dim3(grid), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p,
+                         m_tiles, n_tiles));
     return 0;
 }
 

@@ -83,6 +83,8 @@ __global__ void __launch_bounds__(256)
 layernorm_kernel(float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ beta,
                  __nv_bfloat16* __restrict__ out, const float* __restrict__ add_vec, int rows, int C, int seg,
                  int seg_stride, int seg_offset, int add_rows_per_vec, float eps) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -132,6 +134,8 @@ __device__ __forceinline__ void dual_emit(const DualParams& d, const float4 (&v)
 template <int MAXV>
 __global__ void __launch_bounds__(256)
 ln_dual_kernel(const float* __restrict__ x, DualParams d, int rows, int C, int T, float eps) {
+    pdl_wait();
+    pdl_trigger();
     const int lane = threadIdx.x & 31;
     const int row = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     if (row >= rows) return;
@@ -205,6 +209,8 @@ template <int MAXV>
 __global__ void __launch_bounds__(AD_WARPS * 32)
 ln_adapter_kernel(AdapterParams p, DualParams d) {
     extern __shared__ float ad_smem[];
+    pdl_wait();   // (the tables read below were written once per sampling run, but x comes from the previous kernel)
+    pdl_trigger();
     const int C = p.C, T = p.T;
     const int nv = C >> 2;
     const int b = blockIdx.y;
@@ -359,10 +365,11 @@ extern "C" int mobi_layernorm(const mobi_layernorm_args* a, void* stream_) {
     const int seg_stride = a->seg > 0 ? (int)a->seg_stride : (int)a->rows;
     const int rpv = a->add_rows_per_vec > 0 ? (int)a->add_rows_per_vec : 1;
     const int warps = 8;
-#define LN_LAUNCH(MV)                                                                                             \
-    layernorm_kernel<MV><<<(unsigned)((a->rows + warps - 1) / warps), warps * 32, 0, stream>>>(                   \
-        reinterpret_cast<float*>(a->x), a->gamma, a->beta, reinterpret_cast<__nv_bfloat16*>(a->out), a->add_vec, \
-        (int)a->rows, a->C, seg, seg_stride, (int)a->seg_offset, rpv, a->eps)
+#define LN_LAUNCH(MV)                                                                                                  \
+    MOBI_CUDA(launch_pdl(layernorm_kernel<MV>, dim3((unsigned)((a->rows + warps - 1) / warps)), dim3(warps * 32), (size_t)0, \
+                         stream, reinterpret_cast<float*>(a->x), a->gamma, a->beta,                                    \
+                         reinterpret_cast<__nv_bfloat16*>(a->out), a->add_vec, (int)a->rows, a->C, seg, seg_stride,      \
+                         (int)a->seg_offset, rpv, a->eps))
     if (a->C <= 384) LN_LAUNCH(3);
     else if (a->C <= 768) LN_LAUNCH(6);
     else LN_LAUNCH(12);
@@ -384,9 +391,9 @@ extern "C" int mobi_ln_dual(const float* x, const mobi_ln_dual_spec* spec, int32
     MOBI_CHECK(rows < (1ll << 31), "mobi_ln_dual: too many rows");
     const int warps = 8;
     const unsigned blocks = (unsigned)((rows + warps - 1) / warps);
-    if (C <= 384) ln_dual_kernel<3><<<blocks, warps * 32, 0, stream>>>(x, d, (int)rows, C, tokens, eps);
-    else if (C <= 768) ln_dual_kernel<6><<<blocks, warps * 32, 0, stream>>>(x, d, (int)rows, C, tokens, eps);
-    else ln_dual_kernel<12><<<blocks, warps * 32, 0, stream>>>(x, d, (int)rows, C, tokens, eps);
+    if (C <= 384) MOBI_CUDA(launch_pdl(ln_dual_kernel<3>, dim3(blocks), dim3(warps * 32), (size_t)(0), stream, x, d, (int)rows, C, tokens, eps));
+    else if (C <= 768) MOBI_CUDA(launch_pdl(ln_dual_kernel<6>, dim3(blocks), dim3(warps * 32), (size_t)(0), stream, x, d, (int)rows, C, tokens, eps));
+    else MOBI_CUDA(launch_pdl(ln_dual_kernel<12>, dim3(blocks), dim3(warps * 32), (size_t)(0), stream, x, d, (int)rows, C, tokens, eps));
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
@@ -426,9 +433,9 @@ extern "C" int mobi_ln_adapter(const mobi_ln_adapter_args* a, void* stream_) {
     }
     MOBI_CHECK(smem <= 200 * 1024, "mobi_ln_adapter: C=%d needs %zu bytes of shared memory", a->C, smem);
     dim3 grid((a->tokens + rpc - 1) / rpc, a->batch);
-    if (a->C <= 384) ln_adapter_kernel<3><<<grid, AD_WARPS * 32, smem, stream>>>(p, d);
-    else if (a->C <= 768) ln_adapter_kernel<6><<<grid, AD_WARPS * 32, smem, stream>>>(p, d);
-    else ln_adapter_kernel<12><<<grid, AD_WARPS * 32, smem, stream>>>(p, d);
+    if (a->C <= 384) MOBI_CUDA(launch_pdl(ln_adapter_kernel<3>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
+    else if (a->C <= 768) MOBI_CUDA(launch_pdl(ln_adapter_kernel<6>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
+    else MOBI_CUDA(launch_pdl(ln_adapter_kernel<12>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }

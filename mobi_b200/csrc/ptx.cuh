@@ -24,6 +24,12 @@ __device__ __forceinline__ bool elect_one() {
     return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// wait: blocks until every grid this one depends on has completed and its memory is visible (no-op when the kernel was not
+// launched with programmatic stream serialisation); trigger: dependents of this grid may start launching.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");

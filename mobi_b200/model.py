@@ -143,13 +143,19 @@ class AttnBlock(nn.Module):
         vt = torch.empty((n, c, t), device=h.device, dtype=torch.bfloat16)             # V^T per image
         ops.gemm(hn, p["w_v"], bias=p["b_v"], epilogue=L.EPI_HEADS_T, heads=1, head_dim=c, tokens=t, out=vt)
         o = torch.empty((n * t, c), device=h.device, dtype=torch.bfloat16)
-        s = torch.empty((t, t), device=h.device, dtype=torch.float32)
-        pr = torch.empty((t, t), device=h.device, dtype=torch.bfloat16)
-        for i in range(n):
-            qi = qk[i * t:(i + 1) * t]
-            ops.gemm(qi[:, :c], qi[:, c:], out=s, out_dtype=torch.float32)              # S = Q K^T  (log2 units)
-            ops.softmax_rows(s, out=pr)
-            ops.gemm(pr, vt[i], out=o[i * t:(i + 1) * t], out_dtype=torch.bfloat16)     # O = P V
+        # all images in three launches (batched tcgen05 GEMMs around one row softmax); images are processed in groups whose
+        # fp32 score matrices (t x t each) stay below ~1 GB
+        grp = max(1, min(n, (1 << 30) // (4 * t * t)))
+        s = torch.empty((grp, t, t), device=h.device, dtype=torch.float32)
+        pr = torch.empty((grp, t, t), device=h.device, dtype=torch.bfloat16)
+        for i0 in range(0, n, grp):
+            g = min(grp, n - i0)
+            qi = qk[i0 * t:(i0 + g) * t]
+            ops.gemm(qi[:, :c], qi[:, c:], out=s[:g], out_dtype=torch.float32, M=t, N=t, K=c, lda=2 * c, ldb=2 * c, ldo=t,
+                     batch=g, a_batch_stride=t * 2 * c, b_batch_stride=t * 2 * c, out_batch_stride=t * t)   # S = Q K^T (log2 units)
+            ops.softmax_rows(s[:g].reshape(g * t, t), out=pr[:g].reshape(g * t, t))
+            ops.gemm(pr[:g], vt[i0:i0 + g], out=o[i0 * t:(i0 + g) * t], out_dtype=torch.bfloat16, M=t, N=c, K=t, lda=t,
+                     ldb=t, ldo=c, batch=g, a_batch_stride=t * t, b_batch_stride=c * t, out_batch_stride=t * c)   # O = P V
         out = ops.gemm(o, p["w_o"], bias=p["b_o"], residual=h.reshape(n * t, c), out_dtype=torch.float32, colstats=True)
         return ops.carry_colstats(out.reshape(n, hh, ww, c), out)
 
