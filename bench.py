@@ -5,10 +5,10 @@ Workload = BASELINE.json config 3 AS WRITTEN: mobi_nusc_512.yaml, 50-step DDIM j
 classifier-free guidance 5, batch 64 joint samples sharded over the N GPUs of one box (64 / N per GPU: 64 on one GPU,
 8 each on eight), i.e. STRONG scaling of a fixed job.  One "step" = one full 50-step DDIM sampling pass over the rank's
 shard (latent 64x64; 2 UNet rows per joint sample, 4 with CFG), run in micro-batches of --micro-batch joint samples
-(default 16 = 64 UNet rows per call).  No collective on the data path.  The weak-scaling figure of round 1 (8 joint
+(default 32 = 128 UNet rows per call).  No collective on the data path.  The weak-scaling figure of round 1 (8 joint
 samples per GPU whatever N) is kept as the secondary key `weak_8_per_gpu`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--total-samples 64] [--micro-batch 16] [--latent 64]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--total-samples 64] [--micro-batch 32] [--latent 64]
   python bench.py --samples-per-gpu 8 ...  # fixed per-GPU shard instead of total / N (weak scaling)
   python bench.py --impl reference ...     # the reference's own CPU path (unmodified reference modules where
                                            # /root/reference exists, else the oracle port) on the host cores
@@ -40,7 +40,7 @@ def parse():
     ap.add_argument("--total-samples", type=int, default=64, help="joint samples of the whole job (config 3: 64)")
     ap.add_argument("--samples-per-gpu", type=int, default=0,
                     help="fixed per-GPU shard (weak scaling) instead of total-samples / gpus")
-    ap.add_argument("--micro-batch", type=int, default=16, help="joint samples per sampler call on one GPU")
+    ap.add_argument("--micro-batch", type=int, default=32, help="joint samples per sampler call on one GPU")
     ap.add_argument("--budget-s", type=float, default=760.0,
                     help="wall-clock guard: the driver kills a run at 870 s; if W + K full steps would not fit, fewer "
                          "timed steps are run and the line says so (steps_requested)")
