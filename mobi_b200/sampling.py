@@ -9,31 +9,35 @@ from . import ops
 
 
 def make_ddim_timesteps(ddim_discr_method, num_ddim_timesteps, num_ddpm_timesteps, verbose=True):
-    """ldm/modules/diffusionmodules/util.py:46-60."""
+    """The DDPM timesteps a DDIM run visits (same values as ldm/modules/diffusionmodules/util.py:46-60): "uniform" takes
+    every (T // S)-th step, "quad" spaces them quadratically over the first 80 % of the schedule; both are shifted by one so
+    that the final alpha of a run is the first alpha of the DDPM schedule."""
     if ddim_discr_method == "uniform":
-        c = num_ddpm_timesteps // num_ddim_timesteps
-        ddim_timesteps = np.asarray(list(range(0, num_ddpm_timesteps, c)))
+        stride = num_ddpm_timesteps // num_ddim_timesteps
+        steps = np.arange(0, num_ddpm_timesteps, stride)
     elif ddim_discr_method == "quad":
-        ddim_timesteps = ((np.linspace(0, np.sqrt(num_ddpm_timesteps * .8), num_ddim_timesteps)) ** 2).astype(int)
+        steps = np.square(np.linspace(0, np.sqrt(num_ddpm_timesteps * .8), num_ddim_timesteps)).astype(int)
     else:
         raise NotImplementedError(f'There is no ddim discretization method called "{ddim_discr_method}"')
-    steps_out = ddim_timesteps + 1
+    steps = np.asarray(steps) + 1
     if verbose:
-        print(f"Selected timesteps for ddim sampler: {steps_out}")
-    return steps_out
+        print("DDIM timesteps: %s" % (steps,))
+    return steps
 
 
 def make_ddim_sampling_parameters(alphacums, ddim_timesteps, eta, verbose=True):
-    """util.py:63-74.  alphacums: float32 numpy array; returns float32 (alphas) / float64 (alphas_prev, sigmas)
-    arrays exactly like the reference's mixed torch/numpy arithmetic."""
+    """(sigmas, alphas, alphas_prev) of a DDIM run, with the reference's dtypes (util.py:63-74): alphas is the float32
+    gather of the cumulative products, alphas_prev and sigmas come out of float64 numpy arithmetic; the alpha before the
+    first visited step is alphacums[0], not 1."""
     alphacums = np.asarray(alphacums, dtype=np.float32)
     alphas = alphacums[ddim_timesteps]
-    alphas_prev = np.asarray([alphacums[0]] + alphacums[ddim_timesteps[:-1]].tolist())
+    earlier = alphacums[ddim_timesteps[:-1]]
+    # the reference builds this array from a Python list of floats, i.e. float64 - except for a one-step run, where the
+    # list holds a single float32 scalar and numpy keeps that dtype
+    alphas_prev = np.concatenate([alphacums[:1], earlier]).astype(np.float64 if earlier.size else np.float32)
     sigmas = eta * np.sqrt((1 - alphas_prev) / (1 - alphas) * (1 - alphas / alphas_prev))
     if verbose:
-        print(f"Selected alphas for ddim sampler: a_t: {alphas}; a_(t-1): {alphas_prev}")
-        print(f"For the chosen value of eta, which is {eta}, "
-              f"this results in the following sigma_t schedule for ddim sampler {sigmas}")
+        print("DDIM schedule: eta %s, a_t %s, a_(t-1) %s, sigma_t %s" % (eta, alphas, alphas_prev, sigmas))
     return sigmas, alphas, alphas_prev
 
 

@@ -9,27 +9,36 @@ import importlib
 import torch
 
 
+_SENTINELS = ("__is_first_stage__", "__is_unconditional__")   # config values the reference treats as "no module"
+
+
 def get_obj_from_str(string, reload=False):
-    module, cls = string.rsplit(".", 1)
+    """Resolves a dotted "package.module.Name" path to the object it names (same contract as ldm/util.py:86-91)."""
+    module_name, _, attr = string.rpartition(".")
+    module = importlib.import_module(module_name)
     if reload:
-        importlib.reload(importlib.import_module(module))
-    return getattr(importlib.import_module(module, package=None), cls)
+        module = importlib.reload(module)
+    return getattr(module, attr)
 
 
 def instantiate_from_config(config):
-    if "target" not in config:
-        if config in ("__is_first_stage__", "__is_unconditional__"):
+    """{target: dotted path, params: kwargs} -> instance (the reference's plug-in mechanism, ldm/util.py:76-83)."""
+    target = config.get("target") if hasattr(config, "get") else None
+    if target is None:
+        if config in _SENTINELS:
             return None
         raise KeyError("Expected key `target` to instantiate.")
-    return get_obj_from_str(config["target"])(**config.get("params", dict()))
+    kwargs = config.get("params") or {}
+    return get_obj_from_str(target)(**kwargs)
 
 
 def cat_interleave(tensors):
-    """ldm/util.py:213-221: [cam0, lid0, cam1, lid1, ...] along the batch dimension."""
-    if len(tensors) == 0:
+    """ldm/util.py:213-221: [cam0, lid0, cam1, lid1, ...] along the batch dimension (stack on a new axis 1, fold it
+    into the batch)."""
+    if not tensors:
         return tensors
-    t = torch.cat([u.unsqueeze(1) for u in tensors], dim=1)
-    return t.reshape(-1, *t.shape[2:])
+    stacked = torch.stack(list(tensors), dim=1)
+    return stacked.flatten(0, 1)
 
 
 # Reference class paths -> drop-in class paths (what INTEGRATION.md asks a maintainer to change in the YAML).
