@@ -72,33 +72,31 @@ class SamplerBase(object):
         setattr(self, name, attr)
 
     def make_schedule(self, ddim_num_steps, ddim_discretize="uniform", ddim_eta=0., verbose=True):
-        """ddim.py:25-54 / plms.py:24-55."""
-        self.ddim_timesteps = make_ddim_timesteps(ddim_discr_method=ddim_discretize, num_ddim_timesteps=ddim_num_steps,
-                                                  num_ddpm_timesteps=self.ddpm_num_timesteps, verbose=verbose)
-        alphas_cumprod = self.model.alphas_cumprod
-        assert alphas_cumprod.shape[0] == self.ddpm_num_timesteps, "alphas have to be defined for each timestep"
-        to_torch = lambda x: x.clone().detach().to(torch.float32).to(self.model.device)
-        ac = alphas_cumprod.detach().cpu()
-        self.register_buffer("betas", to_torch(self.model.betas))
-        self.register_buffer("alphas_cumprod", to_torch(alphas_cumprod))
-        self.register_buffer("alphas_cumprod_prev", to_torch(self.model.alphas_cumprod_prev))
-        self.register_buffer("sqrt_alphas_cumprod", to_torch(np.sqrt(ac)))
-        self.register_buffer("sqrt_one_minus_alphas_cumprod", to_torch(np.sqrt(1. - ac)))
-        self.register_buffer("log_one_minus_alphas_cumprod", to_torch(np.log(1. - ac)))
-        self.register_buffer("sqrt_recip_alphas_cumprod", to_torch(np.sqrt(1. / ac)))
-        self.register_buffer("sqrt_recipm1_alphas_cumprod", to_torch(np.sqrt(1. / ac - 1)))
-        ddim_sigmas, ddim_alphas, ddim_alphas_prev = make_ddim_sampling_parameters(
+        """Builds every schedule attribute the reference samplers expose (ddim.py:25-54 / plms.py:24-55) under the same
+        names.  Device buffers are only what callers of the reference read back; the step kernels take host scalars, so
+        the DDIM arrays stay numpy and nothing is indexed on the device during the loop."""
+        model = self.model
+        if model.alphas_cumprod.shape[0] != self.ddpm_num_timesteps:
+            raise AssertionError("alphas have to be defined for each timestep")
+        self.ddim_timesteps = make_ddim_timesteps(ddim_discretize, ddim_num_steps, self.ddpm_num_timesteps, verbose=verbose)
+        ac = model.alphas_cumprod.detach().cpu()
+        acp = model.alphas_cumprod_prev.detach().cpu()
+        on_device = lambda t: torch.as_tensor(t).clone().detach().to(dtype=torch.float32, device=model.device)   # noqa: E731
+        derived = {
+            "betas": model.betas, "alphas_cumprod": model.alphas_cumprod, "alphas_cumprod_prev": model.alphas_cumprod_prev,
+            "sqrt_alphas_cumprod": np.sqrt(ac), "sqrt_one_minus_alphas_cumprod": np.sqrt(1. - ac),
+            "log_one_minus_alphas_cumprod": np.log(1. - ac), "sqrt_recip_alphas_cumprod": np.sqrt(1. / ac),
+            "sqrt_recipm1_alphas_cumprod": np.sqrt(1. / ac - 1),
+        }
+        for name, value in derived.items():
+            self.register_buffer(name, on_device(value))
+        self.ddim_sigmas, self.ddim_alphas, self.ddim_alphas_prev = make_ddim_sampling_parameters(
             alphacums=ac.numpy(), ddim_timesteps=self.ddim_timesteps, eta=ddim_eta, verbose=verbose)
-        # host-side copies (numpy): the step kernels take scalars, nothing is indexed on the device
-        self.ddim_sigmas = ddim_sigmas
-        self.ddim_alphas = ddim_alphas
-        self.ddim_alphas_prev = ddim_alphas_prev
-        self.ddim_sqrt_one_minus_alphas = np.sqrt(np.float32(1.) - ddim_alphas)
+        self.ddim_sqrt_one_minus_alphas = np.sqrt(np.float32(1.) - self.ddim_alphas)
         self._sqrt_ac_host = np.sqrt(ac.numpy())
         self._sqrt_1mac_host = np.sqrt(np.float32(1.) - ac.numpy())
-        acp = self.model.alphas_cumprod_prev.detach().cpu()
-        self.register_buffer("ddim_sigmas_for_original_num_steps", ddim_eta * torch.sqrt(
-            (1 - acp) / (1 - ac) * (1 - ac / acp)).to(self.model.device))
+        sigmas_full = ddim_eta * torch.sqrt((1 - acp) / (1 - ac) * (1 - ac / acp))
+        self.register_buffer("ddim_sigmas_for_original_num_steps", sigmas_full.to(model.device))
 
     # ------------------------------------------------------------------ model evaluation
     def _native_unet(self):
