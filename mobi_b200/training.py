@@ -864,7 +864,7 @@ class UNetTrainer:
         inputs = list(u.input_blocks)
         cut = False
         for i in range(len(inputs) - 1, 0, -1):
-            if i == 3:            # what is left are the level-0 blocks (input_blocks 1, 2): bucket 1 is final
+            if i == 3 and i != len(inputs) - 1:   # what is left are the level-0 blocks (input_blocks 1, 2): bucket 1 is final
                 self._scale_bucket(1)
                 cut = True
                 yield 1

@@ -6,7 +6,7 @@ state dict.
 Tolerances ("max-abs-rel" = max-abs error relative to the max-abs of the oracle tensor, the north star's measure;
 "rel-rms" = ||a - b|| / ||b||):
   * one UNet evaluation (eps, before the CFG combine), also teacher-forced at every one of the 50 DDIM / 51 PLMS
-    steps: max-abs-rel <= 2e-2, rel-rms <= 1e-2, AND max-abs-rel <= 1.5 x the bf16-operand floor of the same call.
+    steps: max-abs-rel <= 2e-2, rel-rms <= 1.5e-2, AND both <= 1.5 x the bf16-operand floor of the same call.
     The north star's example figure (1e-2) is where this model's bf16-OPERAND FLOOR itself sits at latent 64: the fp32
     oracle with nothing changed but the contraction operands rounded to bf16 (oracle/precision.py) is 0.9-1.4e-2 away
     from the fp32 oracle, so no bf16-operand implementation can promise 1e-2 at every step; the floor is measured in
@@ -26,7 +26,7 @@ import torch
 pytestmark = pytest.mark.gpu
 
 TOL_EPS = 2e-2          # max-abs-rel of one UNet evaluation (cap; the binding bar is 1.5 x the bf16-operand floor)
-TOL_EPS_RMS = 1e-2      # rel-rms of one UNet evaluation
+TOL_EPS_RMS = 1.5e-2    # rel-rms of one UNet evaluation (cap; the bf16-operand floor's own rel-rms is 0.7-1.06e-2)
 TOL_FINAL = 2e-2        # final latents of a 50-step run
 TOL_VAE = 2e-2          # cap; the binding bar is 1.5 x the bf16-operand floor of the same decode
 
@@ -46,7 +46,7 @@ def check_eps(eps, ref, floor, what):
     e, r = relerr(eps, ref), relrms(eps, ref)
     print("%s: eps max-abs-rel %.3e rel-rms %.3e cosine %.6f | bf16-operand floor of the same call: %.3e / %.3e"
           % (what, e, r, cosine(eps, ref), floor[0], floor[1]))
-    assert e < TOL_EPS and r < TOL_EPS_RMS and e < 1.5 * floor[0], (what, e, r, floor)
+    assert e < TOL_EPS and r < TOL_EPS_RMS and e < 1.5 * floor[0] and r < 1.5 * floor[1], (what, e, r, floor)
     return e
 
 
@@ -217,7 +217,7 @@ def _full_run(sampler_name, n_joint, use_lidar=True):
     print("  eps error curve: " + " ".join("%.1e" % v for v in curve))
     assert max(curve) < TOL_EPS and max(rms) < TOL_EPS_RMS
     for i, f in floors.items():
-        assert curve[i] < 1.5 * f[0], (i, curve[i], f)
+        assert curve[i] < 1.5 * f[0] and rms[i] < 1.5 * f[1], (i, curve[i], rms[i], f)
     assert e_final < TOL_FINAL and c_final > 0.9995
     return ldm, got, ref
 
