@@ -155,3 +155,23 @@ def test_new_conditioning_at_a_recycled_address_is_not_served_from_a_cache(setup
     e3 = unet(x, t, context=c3)
     print("recycled address: %s" % (c3.data_ptr() == ptr))
     assert rel(e3, r1) < TOL
+
+
+def test_logged_intermediates_are_snapshots_on_the_blend_path(setup):
+    """with mask / x0 the step kernel blends the known latent into the running sample in place; the tensors
+    already appended to intermediates['x_inter'] must not change afterwards (the reference builds a new tensor per step)."""
+    from mobi_b200.ddim import DDIMSampler
+    ldm, cfg, apply_ref, sched, uo = setup
+    inp = uo.synth_inputs(2, 16, context_dim=cfg["context_dim"], seed=21, device="cuda")
+    mask = (torch.rand(4, 1, 16, 16, device="cuda") > 0.5).float()
+    x0 = torch.randn(4, 4, 16, 16, device="cuda")
+    seen = []
+    smp = DDIMSampler(ldm)
+    _, inter = smp.sample(S=4, conditioning=inp["cond"], batch_size=4, shape=[4, 16, 16], verbose=False,
+                          unconditional_guidance_scale=3.0, unconditional_conditioning=inp["uc"], eta=0.0, x_T=inp["x_T"],
+                          mask=mask, x0=x0, log_every_t=1,
+                          img_callback=lambda p, i: seen.append(None),
+                          test_model_kwargs=dict(inpaint_image=inp["inpaint_image"], inpaint_mask=inp["inpaint_mask"]))
+    assert len(inter["x_inter"]) == 5 and len(seen) == 4
+    assert torch.equal(inter["x_inter"][0], inp["x_T"])                       # the start noise was not blended over
+    assert all(not torch.equal(a, b) for a, b in zip(inter["x_inter"][:-1], inter["x_inter"][1:]))
