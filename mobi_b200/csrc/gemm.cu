@@ -391,13 +391,13 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
 
     CUtensorMap tmA, tmB;
     int64_t K = a->K;
+    int bw = 0, bh = 0, bn = 0;   // conv: the 128 pixels of an A tile as a (w, h, image) box
     if (a->conv) {
         MOBI_CHECK(a->C % 8 == 0, "mobi_gemm(conv): C=%d must be a multiple of 8", a->C);
         MOBI_CHECK(a->KH >= 1 && a->KW >= 1 && (long long)a->n_img * a->H * a->W == a->M,
                    "mobi_gemm(conv): M != n_img*H*W");
         K = (int64_t)a->KH * a->KW * a->C;
         MOBI_CHECK(a->K == K, "mobi_gemm(conv): K=%lld != KH*KW*C=%lld", (long long)a->K, (long long)K);
-        int bw, bh, bn;
         if (a->W >= BM) {
             MOBI_CHECK(a->W % BM == 0, "mobi_gemm(conv): W=%d must be a multiple of 128 (or <= 128 power of 2)", a->W);
             bw = BM;
@@ -481,8 +481,41 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
             }
         }
     }
-    p.pair = (a->kernel != 1 && gemm2_supported(p) && gemm2_pair_wanted(p, bn_tile, a->pair)) ? 1 : 0;
-    MOBI_CHECK(a->pair != 1 || p.pair, "mobi_gemm: pair = 1 needs a problem the persistent kernel supports");
+    int pair_request = a->pair;
+    if (a->tile_n == 0 && a->pair == 0 && a->kernel != 1 && !a->conv && p.mode != MOBI_EPI_PLAIN && !p.a_mn && !p.b_mn &&
+        gemm2_supported(p)) {
+        // bf16-output epilogues (head-split QKV, GEGLU): with K = 320..1280 these are bound by the L2 -> shared-memory
+        // traffic of the operand tiles and by the epilogue, not by the MMAs.  A CTA pair on a 256 x 256 tile moves 32 KB
+        // per 128 x 256 x 64 MMA block instead of 36 KB per 128 x 160 x 64 (0.55x the bytes per FLOP); measured on the
+        // UNet's shapes it is 4-16 % faster wherever N fills the wide tiles (profiles/r02/kbench_gemm_tiles.log).
+        const long long nt = (a->N + 255) / 256, m2 = (a->M + 2 * BM - 1) / (2 * BM);
+        if (nt * 256 * 10 <= (long long)a->N * 11 && m2 * nt * p.batch >= sm_count() / 2) {
+            bn_tile = 256;
+            pair_request = 1;
+        }
+    }
+    p.pair = (a->kernel != 1 && gemm2_supported(p) && gemm2_pair_wanted(p, bn_tile, pair_request)) ? 1 : 0;
+    MOBI_CHECK(a->pair < 1 || p.pair, "mobi_gemm: pair = 1 / 2 needs a problem the persistent kernel supports");
+    if (a->pair == 2) {
+        MOBI_CHECK(gemm2_quad_ok(p, bn_tile), "mobi_gemm: pair = 2 (4-CTA clusters) needs the PLAIN epilogue, tile_n >= 128, an "
+                                              "even number of n-tiles, K-major operands and no batch");
+        p.pair = 2;
+    }
+    if (p.pair == 2) {
+        // the A box shrinks to the 64 rows each CTA fetches (and multicasts to its counterpart)
+        if (a->conv) {
+            uint32_t hw = (uint32_t)bw, hh = (uint32_t)bh, hn = (uint32_t)bn;
+            if (hn >= 2) hn /= 2;
+            else if (hh >= 2) hh /= 2;
+            else hw /= 2;
+            uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
+            uint64_t strides[3] = {(uint64_t)a->C * 2, (uint64_t)a->W * a->C * 2, (uint64_t)a->H * a->W * a->C * 2};
+            uint32_t box[4] = {BK, hw, hh, hn};
+            if (make_tensor_map_bf16(&tmA, a->A, 4, dims, strides, box)) return 1;
+        } else {
+            if (make_operand_map(&tmA, a->A, (uint64_t)K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM / 2, 1, 0, 0, 0)) return 1;
+        }
+    }
     if (p.b_mn) {
         if (make_operand_map(&tmB, a->B, (uint64_t)a->N, (uint64_t)K, (uint64_t)a->ldb, 64, BK, p.batch, p.batch_inner,
                              a->b_batch_stride, a->b_batch2_stride))

@@ -84,7 +84,7 @@ struct EpiRow {          // per-lane view of the 8 rows this lane serves in the 
 // 3 = head-split layouts without a transposed part (HEADS, QKV_ROW, KV_ROW).
 template <int BN, int MC>
 __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc_tmem, float* stg, int m_tile,
-                                               int n_tile, int lg, int half, int lane, long long batch_off) {
+                                               int n_tile, int lg, int half, int lane, long long batch_off, int flip) {
     using Cfg = Gemm2Cfg<BN>;
     const int mode = MC == 1 ? MOBI_EPI_PLAIN : (MC == 2 ? MOBI_EPI_GEGLU2 : p.mode);
     const int u = lane & 7;        // 4-column unit inside a 32-column chunk
@@ -131,12 +131,24 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
     const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
     uint8_t* srow = reinterpret_cast<uint8_t*>(stg) + lane * 128;  // row-domain staging row of this thread
 
-    const int c_begin = half * ((Cfg::CHUNKS + 1) / 2);
-    const int c_end = half == 0 ? (Cfg::CHUNKS + 1) / 2 : Cfg::CHUNKS;
+    // With an odd chunk count (BN = 160: 5) the extra chunk alternates between the two column halves from tile to tile
+    // (`flip`), so both warps of a lane group do 5 chunks per two tiles instead of one doing 6 and the other waiting.
+    const int split = (Cfg::CHUNKS + 1 - flip) / 2;
+    const int c_begin = half == 0 ? 0 : split;
+    const int c_end = half == 0 ? split : Cfg::CHUNKS;
+    // The accumulator chunk of iteration c + 1 is requested as soon as the registers of chunk c have been staged, so the
+    // TMEM read runs under the transposed-domain work (shared-memory reads, activation, global stores) of chunk c.
+    // Only for the bf16-output classes (GEGLU2, head-split): the fp32 / residual class needs the 32 registers for its
+    // residual prefetch and spills with both (measured 3-8 % slower).
+    constexpr bool TMEM_AHEAD = MC >= 2;
+    uint32_t r[32];
+    if (TMEM_AHEAD && c_begin < c_end && n_tile * BN + c_begin * 32 < p.N)
+        tmem_ld32(acc_tmem + lane_addr + c_begin * 32, r);
 #pragma unroll 1
     for (int c = c_begin; c < c_end; ++c) {
         const int n0 = n_tile * BN + c * 32;
         if (n0 >= p.N) break;
+        const bool more = c + 1 < c_end && n0 + 32 < p.N;
         const int n = n0 + 4 * u;             // first of this lane's 4 columns (transposed domain)
         const bool col_ok = n < p.N;          // N % 4 == 0: the unit is entirely inside or outside
         // bias of this lane's 4 columns: issued before the accumulator load so its latency hides under it
@@ -161,10 +173,9 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 }
             }
         }
-        // ---- accumulator chunk -> registers (thread = row)
-        uint32_t r[32];
-        tmem_ld32(acc_tmem + lane_addr + c * 32, r);
-        tmem_ld_wait();
+        // ---- accumulator chunk -> registers (thread = row): requested one iteration ago
+        if (!TMEM_AHEAD) tmem_ld32(acc_tmem + lane_addr + c * 32, r);
+        tmem_ld_wait32(r);
         int out_units = 8;  // 16-byte units per staged row
         if (mode == MOBI_EPI_GEGLU) {
             // [8 value | 8 gate] groups: activation in the row domain, 16 outputs per chunk
@@ -214,6 +225,7 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                     make_uint4(r[4 * unit], r[4 * unit + 1], r[4 * unit + 2], r[4 * unit + 3]);
         }
         __syncwarp();
+        if (TMEM_AHEAD && more) tmem_ld32(acc_tmem + lane_addr + (c + 1) * 32, r);
         // ---- transposed domain
         if (mode == MOBI_EPI_GEGLU2) {
             // (value, gate) column pairs: two outputs per lane, no cross-lane traffic.  Branch-free math over the 8
@@ -243,59 +255,69 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                 coloff = (long long)h * p.tokens * p.head_dim + dd;
                 hbase = reinterpret_cast<__nv_bfloat16*>(which == 0 ? p.out : (which == 1 ? p.out2 : p.out3));
             }
-            // column statistics of the final values for the GroupNorm that consumes this output (mobi_gemm_args.colstats)
-            uint64_t cs01 = 0, cs23 = 0, cq01 = 0, cq23 = 0;  // packed (0.f, 0.f)
+            // all 8 rows of this lane leave the staging buffer before any of them is used (one shared-memory latency per
+            // chunk instead of one per row; the per-row predicates only guard the global accesses)
+            float4 v[8];
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
                 const int rr = it * 4 + rsub;
-                float4 v = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + rr * 128 +
-                                                            ((u ^ (rr & 7)) << 4));
-                if (!col_ok || !((er.ok >> it) & 1)) continue;
-                if (head_mode) {
-                    if (is_vt) continue;
-                    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                    uint2 pk;
-                    pk.x = pack_bf16x2(v.x, v.y);
-                    pk.y = pack_bf16x2(v.z, v.w);
-                    *reinterpret_cast<uint2*>(hbase + er.off[it] + coloff) = pk;
-                    continue;
-                }
-                v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
-                if (p.row_bias) {
-                    const float4 rb = __ldg(reinterpret_cast<const float4*>(p.row_bias + er.rb[it] + n));
-                    v.x += rb.x; v.y += rb.y; v.z += rb.z; v.w += rb.w;
-                }
-                if (p.act == 1) {
-                    v.x = silu_fast(v.x); v.y = silu_fast(v.y); v.z = silu_fast(v.z); v.w = silu_fast(v.w);
-                } else if (p.act == 2) {
-                    v.x = gelu_fast(v.x); v.y = gelu_fast(v.y); v.z = gelu_fast(v.z); v.w = gelu_fast(v.w);
-                }
-
-                if (p.residual) {
-                    v.x += res[it].x; v.y += res[it].y; v.z += res[it].z; v.w += res[it].w;
-                }
-                if (MC <= 1 && p.colstats) {
-                    const uint64_t v01 = pack2(v.x, v.y), v23 = pack2(v.z, v.w);
-                    cs01 = add2(cs01, v01);
-                    cs23 = add2(cs23, v23);
-                    cq01 = fma2(v01, v01, cq01);
-                    cq23 = fma2(v23, v23, cq23);
-                }
-                if (p.out_f32) {
-                    float* dst = reinterpret_cast<float*>(p.out) + er.off[it] + n;
-                    if (p.atomic_out) {
-                        atomicAdd(dst, v.x);
-                        atomicAdd(dst + 1, v.y);
-                        atomicAdd(dst + 2, v.z);
-                        atomicAdd(dst + 3, v.w);
-                    } else {
-                        *reinterpret_cast<float4*>(dst) = v;
+                v[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + rr * 128 +
+                                                         ((u ^ (rr & 7)) << 4));
+            }
+            // column statistics of the final values for the GroupNorm that consumes this output (mobi_gemm_args.colstats)
+            uint64_t cs01 = 0, cs23 = 0, cq01 = 0, cq23 = 0;  // packed (0.f, 0.f)
+            if (head_mode) {
+                if (col_ok && !is_vt) {
+#pragma unroll
+                    for (int it = 0; it < 8; ++it) {
+                        uint2 pk;
+                        pk.x = pack_bf16x2(v[it].x + b4.x, v[it].y + b4.y);
+                        pk.y = pack_bf16x2(v[it].z + b4.z, v[it].w + b4.w);
+                        if ((er.ok >> it) & 1) *reinterpret_cast<uint2*>(hbase + er.off[it] + coloff) = pk;
                     }
-                } else {
-                    uint2 pk;
-                    pk.x = pack_bf16x2(v.x, v.y);
-                    pk.y = pack_bf16x2(v.z, v.w);
-                    *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + er.off[it] + n) = pk;
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < 8; ++it) {
+                    const bool live = col_ok && ((er.ok >> it) & 1);
+                    float4 w = v[it];
+                    w.x += b4.x; w.y += b4.y; w.z += b4.z; w.w += b4.w;
+                    if (p.row_bias && live) {
+                        const float4 rb = __ldg(reinterpret_cast<const float4*>(p.row_bias + er.rb[it] + n));
+                        w.x += rb.x; w.y += rb.y; w.z += rb.z; w.w += rb.w;
+                    }
+                    if (p.act == 1) {
+                        w.x = silu_fast(w.x); w.y = silu_fast(w.y); w.z = silu_fast(w.z); w.w = silu_fast(w.w);
+                    } else if (p.act == 2) {
+                        w.x = gelu_fast(w.x); w.y = gelu_fast(w.y); w.z = gelu_fast(w.z); w.w = gelu_fast(w.w);
+                    }
+                    if (p.residual) {
+                        w.x += res[it].x; w.y += res[it].y; w.z += res[it].z; w.w += res[it].w;
+                    }
+                    if (!live) continue;
+                    if (MC <= 1 && p.colstats) {
+                        const uint64_t v01 = pack2(w.x, w.y), v23 = pack2(w.z, w.w);
+                        cs01 = add2(cs01, v01);
+                        cs23 = add2(cs23, v23);
+                        cq01 = fma2(v01, v01, cq01);
+                        cq23 = fma2(v23, v23, cq23);
+                    }
+                    if (p.out_f32) {
+                        float* dst = reinterpret_cast<float*>(p.out) + er.off[it] + n;
+                        if (p.atomic_out) {
+                            atomicAdd(dst, w.x);
+                            atomicAdd(dst + 1, w.y);
+                            atomicAdd(dst + 2, w.z);
+                            atomicAdd(dst + 3, w.w);
+                        } else {
+                            *reinterpret_cast<float4*>(dst) = w;
+                        }
+                    } else {
+                        uint2 pk;
+                        pk.x = pack_bf16x2(w.x, w.y);
+                        pk.y = pack_bf16x2(w.z, w.w);
+                        *reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(p.out) + er.off[it] + n) = pk;
+                    }
                 }
             }
             if (MC <= 1 && p.colstats) {
@@ -356,10 +378,20 @@ __device__ __forceinline__ void tma_load_batched_pair(void* dst, const CUtensorM
     else tma_load_3d_pair(dst, tm, bar, x, y, z);
 }
 
-template <int BN, int MC, bool PAIR>
+//
+// QUAD (PM = 2): clusters of FOUR CTAs = two pairs on the same 256 rows and on neighbouring n-tiles (2j, 2j + 1).  Both pairs
+// need the same A tiles, so each CTA loads only HALF of its 128 x 64 A tile (64 rows, 8 KB) and multicasts it to its
+// counterpart in the other pair (rank ^ 2): per k-block a CTA pulls 8 KB of A + BN / 2 rows of B through L2 instead of
+// 16 KB + BN / 2 rows.  These kernels sit at ~80 % of the L2 -> SM throughput cap with the tensor pipe half idle
+// (profiles/r02/ncu_gemm_l2_bound.md); A is 60 % of that traffic at BN = 160.  The ring of the two pairs moves in
+// lock-step: every `empty` barrier counts the commits of BOTH leaders (a stage is refilled by two CTAs), everything else
+// (full / tfull / tempty, TMEM) stays per pair.
+template <int BN, int MC, int PM>
 __global__ void __launch_bounds__(G2_THREADS, 1)
 gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
              const int m_tiles, const int n_tiles) {
+    constexpr bool PAIR = PM >= 1;
+    constexpr bool QUAD = PM == 2;
     using Cfg = Gemm2Cfg<BN, PAIR>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
@@ -376,9 +408,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
-    const int cta_rank = PAIR ? (int)cluster_ctarank() : 0;
-    const int worker = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;       // persistent worker = CTA or CTA pair
-    const int n_workers = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+    const int cl_rank = PAIR ? (int)cluster_ctarank() : 0;   // rank in the cluster (0..1, or 0..3 for a quad)
+    const int cta_rank = cl_rank & 1;                          // rank in the pair: 0 = leader
+    const int quad_pair = QUAD ? cl_rank >> 1 : 0;             // which pair of the quad = which of its two n-tiles
+    const int worker = QUAD ? (int)(blockIdx.x >> 2) : (PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x);  // CTA / pair / quad
+    const int n_workers = QUAD ? (int)(gridDim.x >> 2) : (PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x);
+    const int n_cols = QUAD ? n_tiles >> 1 : n_tiles;          // tile columns a worker walks (a quad takes two n-tiles)
 
     if (warp == 0) {
         if (elect_one()) {
@@ -386,7 +421,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             tma_prefetch_desc(&tmB);
             for (int s = 0; s < STAGES; ++s) {
                 mbar_init(&full_bar[s], 1);
-                mbar_init(&empty_bar[s], 1);
+                mbar_init(&empty_bar[s], QUAD ? 2 : 1);
             }
             for (int s = 0; s < 2; ++s) {
                 mbar_init(&tfull_bar[s], 1);
@@ -412,7 +447,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     const uint32_t tmem_base = *tmem_slot;
     const int nkb = p.num_k_blocks;
     // tiles are 128 x BN (or 256 x BN per pair: m_tiles then counts 256-row tiles)
-    const int per_batch = m_tiles * n_tiles;
+    const int per_batch = m_tiles * n_cols;
     const int total = per_batch * (p.batch > 1 ? p.batch : 1);
 
     if (warp == 0) {
@@ -421,12 +456,14 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             uint32_t it = 0;
             for (int tile = worker; tile < total; tile += n_workers) {
                 const int z = tile / per_batch, rem = tile - z * per_batch;
-                const int m_tile = PAIR ? (rem / n_tiles) * 2 + cta_rank : rem / n_tiles;   // this CTA's 128-row tile
-                const int n_tile = rem % n_tiles;
+                const int m_tile = PAIR ? (rem / n_cols) * 2 + cta_rank : rem / n_cols;   // this CTA's 128-row tile
+                const int n_tile = QUAD ? (rem % n_cols) * 2 + quad_pair : rem % n_cols;
                 const int b_row0 = n_tile * BN + (PAIR ? cta_rank * (BN / 2) : 0);           // this CTA's rows of B
+                const int a_half = QUAD ? quad_pair * (BM / 2) : 0;   // quad: the 64 rows of the A tile this CTA fetches
+                const uint16_t a_mask = (uint16_t)((1u << cl_rank) | (1u << (cl_rank ^ 2)));
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
-                    const long long pix = (long long)m_tile * BM;
+                    const long long pix = (long long)m_tile * BM + a_half;
                     x0 = (int)(pix % p.W);
                     y0 = (int)((pix / p.W) % p.H);
                     n0 = (int)(pix / ((long long)p.W * p.H));
@@ -440,7 +477,22 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (PAIR) {
                         // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_TILE_BYTES + Cfg::B_TILE_BYTES));
-                        if (p.conv) {
+                        if (QUAD) {
+                            // half of the A tile (the A map's box is 64 rows), written into this CTA and its counterpart
+                            uint8_t* dAh = dA + a_half * 128;
+                            if (p.conv) {
+                                const int tap = kb / p.cblocks;
+                                const int cb = kb - tap * p.cblocks;
+                                const int kh = tap / p.KW;
+                                const int kw = tap - kh * p.KW;
+                                tma_load_4d_pair_mc(dAh, &tmA, &full_bar[s], a_mask, cb * BK, x0 + kw - p.pad_w,
+                                                    y0 + kh - p.pad_h, n0);
+                                tma_load_2d_pair(dB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0);
+                            } else {
+                                tma_load_2d_pair_mc(dAh, &tmA, &full_bar[s], a_mask, kb * BK, m_tile * BM + a_half);
+                                tma_load_2d_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0);
+                            }
+                        } else if (p.conv) {
                             const int tap = kb / p.cblocks;
                             const int cb = kb - tap * p.cblocks;
                             const int kh = tap / p.KW;
@@ -527,10 +579,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                             umma_bf16_ss(d_tmem, ad, bd, idesc, (kb | k) != 0 ? 1u : 0u);
                         }
                     }
-                    if (PAIR) umma_commit_pair(&empty_bar[s]);
+                    if (QUAD) umma_commit_mask(&empty_bar[s], 0xF);   // the stage is refilled by CTAs of both pairs
+                    else if (PAIR) umma_commit_pair(&empty_bar[s]);
                     else umma_commit(&empty_bar[s]);
                 }
-                if (PAIR) umma_commit_pair(&tfull_bar[as]);
+                if (QUAD) umma_commit_mask(&tfull_bar[as], (uint16_t)(3u << (2 * quad_pair)));
+                else if (PAIR) umma_commit_pair(&tfull_bar[as]);
                 else umma_commit(&tfull_bar[as]);
             }
         }
@@ -542,14 +596,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
         uint32_t lt = 0;
         for (int tile = worker; tile < total; tile += n_workers, ++lt) {
             const int z = tile / per_batch, rem = tile - z * per_batch;
-            const int m_tile = PAIR ? (rem / n_tiles) * 2 + cta_rank : rem / n_tiles;
-            const int n_tile = rem % n_tiles;
+            const int m_tile = PAIR ? (rem / n_cols) * 2 + cta_rank : rem / n_cols;
+            const int n_tile = QUAD ? (rem % n_cols) * 2 + quad_pair : rem % n_cols;
             const uint32_t as = lt & 1;
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
             gemm2_epilogue<BN, MC>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane,
                                p.batch_inner > 0 ? (long long)(z % p.batch_inner) * p.out_batch_stride + (long long)(z / p.batch_inner) * p.out_batch2_stride
-                                                 : (long long)z * p.out_batch_stride);
+                                                 : (long long)z * p.out_batch_stride,
+                               (Cfg::CHUNKS & 1) ? (int)(lt & 1) : 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -568,12 +623,51 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     }
 }
 
+// Clusters of 4 that fit on the device at once (GPCs whose SM count is not a multiple of 4 leave SMs idle: 136 of 148
+// SMs on this part), asked from the occupancy calculator once per kernel.
+template <int BN, int MC>
+static int launch_gemm2_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN, true>;
+    static int max_quads = 0;
+    cudaLaunchConfig_t cfg = {};
+    cfg.blockDim = dim3(G2_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 4;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if (max_quads == 0) {
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        cfg.gridDim = dim3(4 * (sm_count() / 4), 1, 1);
+        int n = 0;
+        MOBI_CUDA(cudaOccupancyMaxActiveClusters(&n, gemm2_kernel<BN, MC, 2>, &cfg));
+        MOBI_CHECK(n > 0, "mobi_gemm: no 4-CTA cluster of the persistent kernel fits on this device");
+        max_quads = n;
+    }
+    const int m_tiles2 = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + BN - 1) / BN;
+    MOBI_CHECK(n_tiles % 2 == 0, "mobi_gemm: 4-CTA clusters need an even number of n-tiles");
+    const long long total = (long long)m_tiles2 * (n_tiles / 2) * (p.batch > 1 ? p.batch : 1);
+    MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
+    const int quads = (int)(total < max_quads ? total : max_quads);
+    cfg.gridDim = dim3(4 * quads, 1, 1);
+    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 2>, tmA, tmB, p, m_tiles2, n_tiles));
+    return 0;
+}
+
 template <int BN, int MC>
 static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+    if (p.pair == 2) {
+        if constexpr (MC == 1 && BN != 64) return launch_gemm2_quad<BN, MC>(tmA, tmB, p, stream);
+        MOBI_CHECK(false, "mobi_gemm: 4-CTA clusters are built for the PLAIN epilogue with tile_n >= 128");
+    }
     using Cfg = Gemm2Cfg<BN, true>;
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
         configured = true;
     }
@@ -595,7 +689,7 @@ static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, true>, tmA, tmB, p, m_tiles2, n_tiles));
+    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 1>, tmA, tmB, p, m_tiles2, n_tiles));
     return 0;
 }
 
@@ -605,7 +699,7 @@ static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     using Cfg = Gemm2Cfg<BN>;
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
         configured = true;
     }
@@ -613,7 +707,7 @@ static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     const long long total = (long long)m_tiles * n_tiles * (p.batch > 1 ? p.batch : 1);
     MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    MOBI_CUDA(launch_pdl(gemm2_kernel<BN, MC, false>, dim3(grid), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p,
+    MOBI_CUDA(launch_pdl(gemm2_kernel<BN, MC, 0>, dim3(grid), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p,
                          m_tiles, n_tiles));
     return 0;
 }
@@ -651,6 +745,12 @@ bool gemm2_supported(const GemmParams& p) {
             return false;
     }
     return true;
+}
+
+// pair_request 2 = clusters of two pairs that share their A tiles by multicast (the caller checks `gemm2_quad_ok`).
+bool gemm2_quad_ok(const GemmParams& p, int bn_tile) {
+    const int n_tiles = (p.N + bn_tile - 1) / bn_tile;
+    return p.mode == MOBI_EPI_PLAIN && bn_tile != 64 && n_tiles % 2 == 0 && p.batch <= 1 && !p.a_mn && !p.b_mn;
 }
 
 bool gemm2_pair_wanted(const GemmParams& p, int bn_tile, int pair_request) {

@@ -27,7 +27,8 @@ struct GemmParams {
     int act;
     int heads, head_dim, tokens;
     long long out_seg, out_seg_stride, out_seg_offset;
-    int pair;                     // 1: run as 2-CTA clusters (cta_group::2, 256-row tiles, B box = BN / 2 rows)
+    int pair;                     // 1: run as 2-CTA clusters (cta_group::2, 256-row tiles, B box = BN / 2 rows); 2: two such pairs
+                                  // per cluster on neighbouring n-tiles, A tiles multicast between them (A box = 64 rows)
     int batch;                    // > 1: batched problem, A/B through 3-D tensor maps
     long long out_batch_stride;   // elements
     int batch_inner;              // > 0: two-level batch, z -> (z % batch_inner, z / batch_inner) over 4-D operand maps
@@ -46,5 +47,6 @@ bool gemm2_supported(const GemmParams& p);
 int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn_tile, cudaStream_t stream);
 // true when the 2-CTA (cta_group::2) variant should run this problem with tile width bn_tile
 bool gemm2_pair_wanted(const GemmParams& p, int bn_tile, int pair_request);
+bool gemm2_quad_ok(const GemmParams& p, int bn_tile);
 
 }  // namespace mobi

@@ -213,6 +213,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
         : "r"(taddr)
         : "memory");
 }
+// tcgen05.wait::ld that also "rewrites" the 32 destination registers of an earlier tcgen05.ld: with the load issued long
+// before its wait (software pipelining over epilogue chunks) the compiler must not read, copy or spill-and-reuse those
+// registers between the two; the in/out constraints make every later use depend on this statement.
+__device__ __forceinline__ void tmem_ld_wait32(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]),
+                   "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+                 :
+                 : "memory");
+}
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16]) {
     asm volatile(
         "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
@@ -262,6 +274,26 @@ __device__ __forceinline__ void tma_load_4d_pair(void* smem, const CUtensorMap* 
         "r"(c2), "r"(c3)
         : "memory");
 }
+// Multicast flavours for a cluster of two pairs ("quad"): the box is written at the same offset in every CTA of `mask`
+// and each destination's bytes are signalled on the barrier of ITS pair's leader.
+__device__ __forceinline__ void tma_load_2d_pair_mc(void* smem, const CUtensorMap* m, uint64_t* bar, uint16_t mask, int c0,
+                                                    int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5}], [%2], %3;"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "h"(mask), "r"(c0),
+        "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void tma_load_4d_pair_mc(void* smem, const CUtensorMap* m, uint64_t* bar, uint16_t mask, int c0,
+                                                    int c1, int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+        "[%0], [%1, {%4, %5, %6, %7}], [%2], %3;"
+        ::"r"(smem_u32(smem)), "l"(reinterpret_cast<uint64_t>(m)), "r"(smem_u32(bar) & PEER_BIT_MASK), "h"(mask), "r"(c0),
+        "r"(c1), "r"(c2), "r"(c3)
+        : "memory");
+}
 __device__ __forceinline__ void tmem_alloc_pair(uint32_t* dst_smem, uint32_t ncols) {
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)),
                  "r"(ncols)
@@ -291,6 +323,14 @@ __device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
         "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
             smem_u32(bar)),
         "h"(static_cast<uint16_t>(3))
+        : "memory");
+}
+// Same, on the barrier at this offset in every CTA of `mask` (cluster ranks).
+__device__ __forceinline__ void umma_commit_mask(uint64_t* bar, uint16_t mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+            smem_u32(bar)),
+        "h"(mask)
         : "memory");
 }
 // Arrive on the LEADER's copy of a barrier (from either CTA of the pair).

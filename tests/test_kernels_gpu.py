@@ -173,6 +173,49 @@ def test_conv_implicit(N, H, W, C, Cout, kh, kw, kernel):
     assert relerr(out, ref) < 2e-3, describe(out.reshape(-1, Cout), ref.reshape(-1, Cout))
 
 
+@pytest.mark.parametrize("N,H,W,C,Cout,tile_n", [
+    (2, 64, 64, 320, 320, 160), (4, 32, 32, 640, 640, 160), (4, 16, 16, 1280, 1280, 160), (4, 8, 8, 2560, 1280, 160),
+    (3, 8, 8, 1280, 1280, 128), (1, 128, 128, 128, 256, 128), (2, 64, 64, 960, 320, 160), (8, 4, 4, 1280, 512, 256),
+    (5, 64, 64, 64, 320, 160),
+])
+def test_conv_implicit_quad_clusters(N, H, W, C, Cout, tile_n):
+    """pair = 2: clusters of two CTA pairs on neighbouring n-tiles, each CTA fetching half of its A tile and multicasting it
+    to its counterpart.  Same result as the pair kernel bit for bit (same MMAs, same order), and the PyTorch reference."""
+    ops = _ops()
+    x = rnd(N, H, W, C, seed=1)
+    w = rnd(Cout, 9 * C, seed=2, scale=(9 * C) ** -0.5)
+    b = rnd(Cout, seed=3, dtype=torch.float32)
+    emb = rnd(N, Cout, seed=4, dtype=torch.float32)
+    res = rnd(N, H, W, Cout, seed=5, dtype=torch.float32)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().reshape(Cout, 3, 3, C).permute(0, 3, 1, 2), b,
+                                     padding=1).permute(0, 2, 3, 1) + emb[:, None, None, :] + res
+    pair = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=b, row_bias=emb, residual=res, tile_n=tile_n, pair=1)
+    quad = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=b, row_bias=emb, residual=res, tile_n=tile_n, pair=2, colstats=True)
+    torch.cuda.synchronize()
+    assert relerr(quad, ref) < 2e-3, describe(quad.reshape(-1, Cout), ref.reshape(-1, Cout))
+    assert torch.equal(quad, pair)
+    if hasattr(quad, "_colstats") and (N * H * W) % 32 == 0:
+        g = N * H * W // 32
+        want = quad.reshape(g, 32, Cout).sum(1)
+        assert relerr(quad._colstats[:g * Cout].reshape(g, Cout), want) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K,tile_n", [(4096, 320, 320, 160), (1000, 640, 1280, 160), (8192, 1280, 5120, 160),
+                                          (300, 512, 64, 128), (2048, 1024, 2560, 256)])
+def test_gemm_quad_clusters(M, N, K, tile_n):
+    ops = _ops()
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    res = rnd(M, N, seed=4, dtype=torch.float32)
+    ref = a.float() @ w.float().t() + bias + res
+    pair = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, tile_n=tile_n, pair=1)
+    quad = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, tile_n=tile_n, pair=2)
+    torch.cuda.synchronize()
+    assert relerr(quad, ref) < 2e-3, describe(quad, ref)
+    assert torch.equal(quad, pair)
+
+
 @pytest.mark.parametrize("N,H,W,C,Cout,k,stride,pads", [
     (2, 64, 64, 320, 320, 3, 2, (1, 1)), (2, 32, 32, 9, 320, 3, 1, (1, 1)), (1, 64, 64, 128, 128, 3, 2, (0, 0)),
 ])

@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2: `ncu --set full` of the five level-0 transformer GEMMs (K = 320: qkv, to_out + residual, ff1 GEGLU, ff2 + residual,
+# proj_in) -- one launch per shape (KB_WARMUP=0 KB_REPS=1), so the first five gemm2 launches are those shapes in order.
+mkdir -p gpurun_out
+python -c "from mobi_b200 import build; build.build()" || exit 1
+KB_WARMUP=0 KB_REPS=1 timeout 600 ncu --set full --import-source on --clock-control none -f -k regex:gemm2_kernel -c 5 \
+    -o gpurun_out/ncu_r02_gemm_l0 python tools/kbench.py gemm > gpurun_out/ncu_r02_gemm_l0.log 2>&1
+echo "ncu rc=$?"; tail -5 gpurun_out/ncu_r02_gemm_l0.log
+python tools/kbench.py gemm 2>&1 | tail -16
+ls -la gpurun_out | grep ncu_r02_gemm

@@ -18,12 +18,14 @@ from mobi_b200 import ops  # noqa: E402
 
 R = int(os.environ.get("KB_ROWS", "32"))
 GK = int(os.environ.get("KB_GEMM_KERNEL", "0"))  # 1 = force the one-tile GEMM kernel
+GT = int(os.environ.get("KB_GEMM_TILE", "0"))    # 0 = the library's choice, else tile_n (64 / 128 / 160 / 256)
+GP = int(os.environ.get("KB_GEMM_PAIR", "0"))    # 0 = the library's choice, 1 = CTA pairs, -1 = never
 OUT = os.path.join(ROOT, "gpurun_out", "kbench.jsonl")
 os.makedirs(os.path.dirname(OUT), exist_ok=True)
 
 
-def timeit(fn, reps=10):
-    for _ in range(3):
+def timeit(fn, reps=int(os.environ.get("KB_REPS", "10"))):
+    for _ in range(int(os.environ.get("KB_WARMUP", "3"))):     # KB_WARMUP=0 KB_REPS=1: one launch per shape (ncu captures)
         fn()
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -87,22 +89,22 @@ def bench_gemm():
             vr = torch.empty_like(q)
             ep = L.EPI_QKV_ROW if D <= 128 else L.EPI_QKV
             fn = lambda: ops.gemm(a, w, epilogue=ep, heads=H, head_dim=D, tokens=T, out=q, out2=k,
-                                  out3=vr if D <= 128 else vt, kernel=GK)
+                                  out3=vr if D <= 128 else vt, kernel=GK, tile_n=GT, pair=GP if GP != 2 else 0)
             nb = M * K * 2 + M * N * 2
         elif kind == "res":
             x = rnd(M, N, dtype=torch.float32)
-            fn = lambda: ops.gemm(a, w, bias=bias, residual=x, out=x, kernel=GK)
+            fn = lambda: ops.gemm(a, w, bias=bias, residual=x, out=x, kernel=GK, tile_n=GT, pair=GP)
             nb = M * K * 2 + M * N * 8
         elif kind == "geglu":
             from mobi_b200.packing import interleave_geglu_pairs
             w2, b2 = interleave_geglu_pairs(w.float(), bias)
             w2 = w2.to(torch.bfloat16)
             o = torch.empty(M, N // 2, device="cuda", dtype=torch.bfloat16)
-            fn = lambda: ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU2, out=o, kernel=GK)
+            fn = lambda: ops.gemm(a, w2, bias=b2, epilogue=L.EPI_GEGLU2, out=o, kernel=GK, tile_n=GT, pair=GP if GP != 2 else 0)
             nb = M * K * 2 + M * N
         else:
             o = torch.empty(M, N, device="cuda", dtype=torch.float32)
-            fn = lambda: ops.gemm(a, w, bias=bias, out=o, kernel=GK)
+            fn = lambda: ops.gemm(a, w, bias=bias, out=o, kernel=GK, tile_n=GT, pair=GP)
             nb = M * K * 2 + M * N * 4
         report("gemm %s M=%d N=%d K=%d" % (name, M, N, K), timeit(fn), fl, nb)
 
@@ -115,7 +117,7 @@ def bench_conv():
         res = rnd(R, S, S, Co, dtype=torch.float32)
         out = torch.empty(R, S, S, Co, device="cuda", dtype=torch.float32)
         fl = 2.0 * R * S * S * Co * 9 * C
-        ms = timeit(lambda: ops.conv_implicit(x, w, 3, 3, 1, 1, bias=bias, residual=res, out=out, kernel=GK))
+        ms = timeit(lambda: ops.conv_implicit(x, w, 3, 3, 1, 1, bias=bias, residual=res, out=out, kernel=GK, tile_n=GT, pair=GP))
         report("conv3x3 %d->%d @%d" % (C, Co, S), ms, fl, x.numel() * 2 + out.numel() * 8)
 
 
