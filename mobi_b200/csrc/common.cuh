@@ -29,6 +29,8 @@ void set_error(const char* fmt, ...);
 
 // Encodes a bf16 tiled tensor map with the 128-byte swizzle. dims/box are innermost-first; strides are in
 // bytes for dims 1..rank-1. Returns 0 on success.
+int make_tensor_map_2d_plain(CUtensorMap* map, const void* base, int elem_bytes, uint64_t cols, uint64_t rows,
+                             uint64_t row_stride_bytes, uint32_t box_cols, uint32_t box_rows);
 int make_tensor_map_bf16(CUtensorMap* map, const void* base, int rank, const uint64_t* dims,
                          const uint64_t* strides_bytes, const uint32_t* box);
 
@@ -42,6 +44,7 @@ int sm_count();
 // 49.51 vs 49.06 ms at 32 rows) although the eager per-kernel sum improved (91.2 vs 92.9 ms): graph kernel-to-kernel edges
 // already cost ~1 us, and early-scheduled dependents hold SM slots next to the persistent GEMM CTAs.
 bool pdl_enabled();
+bool res_prefetch_enabled();   // L2 prefetch of the GEMM epilogue's residual boxes (MOBI_RES_PREFETCH=0 turns it off)
 
 template <typename... KArgs, typename... Args>
 cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args) {

@@ -528,7 +528,21 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
     }
     MOBI_CHECK(!(p.a_mn || p.b_mn || p.atomic_out) || gemm2_supported(p),
                "mobi_gemm: MN-major operands / atomic_out are outside the persistent kernel's epilogue here");
-    if (a->kernel != 1 && gemm2_supported(p)) return launch_gemm2(tmA, tmB, p, bn_tile, stream);
+    if (a->kernel != 1 && gemm2_supported(p)) {
+        // residual boxes go to L2 ahead of the epilogue (one TMA prefetch per tile by the producer thread)
+        CUtensorMap tmR = tmA;
+        const int rb = p.res_f32 ? 4 : 2;
+        const uint32_t box_cols = (uint32_t)(bn_tile < p.N ? bn_tile : p.N);
+        if (p.residual && p.mode == MOBI_EPI_PLAIN && p.out_seg == 0 && p.batch <= 1 && !p.atomic_out &&
+            ((long long)p.ldo * rb) % 16 == 0 && (box_cols * rb) % 16 == 0 && p.num_k_blocks <= 10 && res_prefetch_enabled()) {
+            // short K only (measured: to_out + residual, K = 320 / 640: 4 % faster; with K >= 1280 the operand stream
+            // already fills HBM and the extra early traffic costs 3-5 %)
+            if (make_tensor_map_2d_plain(&tmR, p.residual, rb, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * rb, box_cols, BM))
+                return 1;
+            p.res_prefetch = 1;
+        }
+        return launch_gemm2(tmA, tmB, tmR, p, bn_tile, stream);
+    }
     MOBI_CHECK(p.colstats == nullptr, "mobi_gemm: colstats requested but this problem falls back to the one-tile kernel");
     MOBI_CHECK(!batched, "mobi_gemm: this batched problem is outside the persistent kernel's epilogue (N %% 4, "
                          "16-byte aligned out / residual / bias)");

@@ -79,6 +79,99 @@ struct EpiRow {          // per-lane view of the 8 rows this lane serves in the 
     unsigned ok;         // bit i: row i exists (m < M)
 };
 
+// The PLAIN epilogue of the hot f32 paths (attention / feed-forward output projections with their residual, proj_in /
+// proj_out, every convolution): whole tiles (M % 128 == 0, N % 32 == 0), f32 output, optional f32 residual, bias, one
+// row-bias row per 32-row group, optional column statistics; no activation, no atomics, no row segments.  Everything the
+// general version decides per row is decided once per tile here, so the 8-row loop is straight-line code: the general
+// version spent a third of its samples on branch resolution, reconvergence and instruction fetch
+// (profiles/r02/ncu_gemm_l2_bound.md).
+template <int BN>
+__device__ __forceinline__ void gemm2_epilogue_plain_fast(const GemmParams& p, uint32_t acc_tmem, float* stg, int m_tile,
+                                                          int n_tile, int lg, int half, int lane, long long batch_off,
+                                                          int flip) {
+    using Cfg = Gemm2Cfg<BN>;
+    const int u = lane & 7, rsub = lane >> 3;
+    const int m_base = m_tile * BM + lg * 32;
+    const long long row0 = (long long)(m_base + rsub) * p.ldo + batch_off + 4 * u;   // row `it` of this lane: + it * step
+    const long long step = 4ll * p.ldo;
+    float* outp = reinterpret_cast<float*>(p.out) + row0;
+    const float* resp = p.residual ? reinterpret_cast<const float*>(p.residual) + row0 : nullptr;
+    const float* rbp = p.row_bias ? p.row_bias + (long long)(m_base / p.rows_per_group) * p.ld_row_bias + 4 * u : nullptr;
+    const float* biasp = p.bias ? p.bias + 4 * u : nullptr;
+    const uint32_t lane_addr = static_cast<uint32_t>(lg * 32) << 16;
+    uint8_t* srow = reinterpret_cast<uint8_t*>(stg) + lane * 128;
+    const int split = (Cfg::CHUNKS + 1 - flip) / 2;
+    const int c_begin = half == 0 ? 0 : split;
+    const int c_end = half == 0 ? split : Cfg::CHUNKS;
+#pragma unroll 1
+    for (int c = c_begin; c < c_end; ++c) {
+        const int n0 = n_tile * BN + c * 32;
+        if (n0 >= p.N) break;
+        float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (biasp) b4 = __ldg(reinterpret_cast<const float4*>(biasp + n0));
+        if (rbp) {
+            const float4 rb = __ldg(reinterpret_cast<const float4*>(rbp + n0));
+            b4.x += rb.x; b4.y += rb.y; b4.z += rb.z; b4.w += rb.w;
+        }
+        float4 res[8];
+        if (resp) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) res[it] = *reinterpret_cast<const float4*>(resp + n0 + it * step);
+        } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) res[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+        uint32_t r[32];
+        tmem_ld32(acc_tmem + lane_addr + c * 32, r);
+        tmem_ld_wait32(r);
+#pragma unroll
+        for (int unit = 0; unit < 8; ++unit)
+            *reinterpret_cast<uint4*>(srow + ((unit ^ (lane & 7)) << 4)) =
+                make_uint4(r[4 * unit], r[4 * unit + 1], r[4 * unit + 2], r[4 * unit + 3]);
+        __syncwarp();
+        float4 v[8];
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;
+            v[it] = *reinterpret_cast<const float4*>(reinterpret_cast<const uint8_t*>(stg) + rr * 128 + ((u ^ (rr & 7)) << 4));
+        }
+        uint64_t cs01 = 0, cs23 = 0, cq01 = 0, cq23 = 0;
+        const uint64_t b01 = pack2(b4.x, b4.y), b23 = pack2(b4.z, b4.w);
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+            const uint64_t w01 = add2(add2(pack2(v[it].x, v[it].y), b01), pack2(res[it].x, res[it].y));
+            const uint64_t w23 = add2(add2(pack2(v[it].z, v[it].w), b23), pack2(res[it].z, res[it].w));
+            cs01 = add2(cs01, w01);
+            cs23 = add2(cs23, w23);
+            cq01 = fma2(w01, w01, cq01);
+            cq23 = fma2(w23, w23, cq23);
+            float4 w;
+            unpack2(w01, w.x, w.y);
+            unpack2(w23, w.z, w.w);
+            *reinterpret_cast<float4*>(outp + n0 + it * step) = w;
+        }
+        if (p.colstats) {
+            float cst[8];
+            unpack2(cs01, cst[0], cst[1]);
+            unpack2(cs23, cst[2], cst[3]);
+            unpack2(cq01, cst[4], cst[5]);
+            unpack2(cq23, cst[6], cst[7]);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                cst[i] += __shfl_xor_sync(0xffffffffu, cst[i], 8);
+                cst[i] += __shfl_xor_sync(0xffffffffu, cst[i], 16);
+            }
+            if (rsub == 0) {
+                const long long groups32 = (p.M + 31) / 32;
+                float* dst = p.colstats + (long long)(m_base >> 5) * p.N + n0 + 4 * u;
+                *reinterpret_cast<float4*>(dst) = make_float4(cst[0], cst[1], cst[2], cst[3]);
+                *reinterpret_cast<float4*>(dst + groups32 * p.N) = make_float4(cst[4], cst[5], cst[6], cst[7]);
+            }
+        }
+        __syncwarp();
+    }
+}
+
 // MC = epilogue class fixed at compile time (the runtime `p.mode` branches, the integer divisions of the head-split
 // layouts and their registers disappear from the other classes): 0 = any mode (runtime), 1 = PLAIN, 2 = GEGLU2,
 // 3 = head-split layouts without a transposed part (HEADS, QKV_ROW, KV_ROW).
@@ -86,6 +179,14 @@ template <int BN, int MC>
 __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc_tmem, float* stg, int m_tile,
                                                int n_tile, int lg, int half, int lane, long long batch_off, int flip) {
     using Cfg = Gemm2Cfg<BN>;
+    if constexpr (MC == 1) {
+        const bool fast = p.out_f32 && !p.atomic_out && p.act == 0 && p.out_seg == 0 && (p.M % BM) == 0 && (p.N % 32) == 0 &&
+                          (p.residual == nullptr || p.res_f32) && (p.row_bias == nullptr || (p.rows_per_group % 32) == 0);
+        if (fast) {
+            gemm2_epilogue_plain_fast<BN>(p, acc_tmem, stg, m_tile, n_tile, lg, half, lane, batch_off, flip);
+            return;
+        }
+    }
     const int mode = MC == 1 ? MOBI_EPI_PLAIN : (MC == 2 ? MOBI_EPI_GEGLU2 : p.mode);
     const int u = lane & 7;        // 4-column unit inside a 32-column chunk
     const int rsub = lane >> 3;    // row inside a group of 4
@@ -388,8 +489,8 @@ __device__ __forceinline__ void tma_load_batched_pair(void* dst, const CUtensorM
 // (full / tfull / tempty, TMEM) stays per pair.
 template <int BN, int MC, int PM>
 __global__ void __launch_bounds__(G2_THREADS, 1)
-gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const GemmParams p,
-             const int m_tiles, const int n_tiles) {
+gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+             const __grid_constant__ CUtensorMap tmR, const GemmParams p, const int m_tiles, const int n_tiles) {
     constexpr bool PAIR = PM >= 1;
     constexpr bool QUAD = PM == 2;
     using Cfg = Gemm2Cfg<BN, PAIR>;
@@ -461,6 +562,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int b_row0 = n_tile * BN + (PAIR ? cta_rank * (BN / 2) : 0);           // this CTA's rows of B
                 const int a_half = QUAD ? quad_pair * (BM / 2) : 0;   // quad: the 64 rows of the A tile this CTA fetches
                 const uint16_t a_mask = (uint16_t)((1u << cl_rank) | (1u << (cl_rank ^ 2)));
+                // The residual of this CTA's 128 x BN output box starts its way from HBM to L2 now, one to two tile periods
+                // before the epilogue warps read it: their loads then wait for an L2 hit instead of a DRAM access (the
+                // narrow f32 GEMMs were bound by exactly that latency, profiles/r02/ncu_gemm_l2_bound.md).
+                if (p.res_prefetch) tma_prefetch_l2_2d(&tmR, n_tile * BN, m_tile * BM);
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
                     const long long pix = (long long)m_tile * BM + a_half;
@@ -626,7 +731,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 // Clusters of 4 that fit on the device at once (GPCs whose SM count is not a multiple of 4 leave SMs idle: 136 of 148
 // SMs on this part), asked from the occupancy calculator once per kernel.
 template <int BN, int MC>
-static int launch_gemm2_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm2_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
+                             cudaStream_t stream) {
     using Cfg = Gemm2Cfg<BN, true>;
     static int max_quads = 0;
     cudaLaunchConfig_t cfg = {};
@@ -654,15 +760,19 @@ static int launch_gemm2_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int quads = (int)(total < max_quads ? total : max_quads);
     cfg.gridDim = dim3(4 * quads, 1, 1);
-    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 2>, tmA, tmB, p, m_tiles2, n_tiles));
+    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 2>, tmA, tmB, tmR, p, m_tiles2, n_tiles));
     return 0;
 }
 
 template <int BN, int MC>
-static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
+static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
+                             cudaStream_t stream) {
     if (p.pair == 2) {
-        if constexpr (MC == 1 && BN != 64) return launch_gemm2_quad<BN, MC>(tmA, tmB, p, stream);
-        MOBI_CHECK(false, "mobi_gemm: 4-CTA clusters are built for the PLAIN epilogue with tile_n >= 128");
+        if constexpr (MC == 1 && BN != 64) {
+            return launch_gemm2_quad<BN, MC>(tmA, tmB, tmR, p, stream);
+        } else {
+            MOBI_CHECK(false, "mobi_gemm: 4-CTA clusters are built for the PLAIN epilogue with tile_n >= 128");
+        }
     }
     using Cfg = Gemm2Cfg<BN, true>;
     static bool configured = false;
@@ -689,13 +799,14 @@ static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
     cfg.attrs = attr;
     cfg.numAttrs = 2;
-    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 1>, tmA, tmB, p, m_tiles2, n_tiles));
+    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 1>, tmA, tmB, tmR, p, m_tiles2, n_tiles));
     return 0;
 }
 
 template <int BN, int MC>
-static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    if (p.pair) return launch_gemm2_pair<BN, MC>(tmA, tmB, p, stream);
+static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
+                           cudaStream_t stream) {
+    if (p.pair) return launch_gemm2_pair<BN, MC>(tmA, tmB, tmR, p, stream);
     using Cfg = Gemm2Cfg<BN>;
     static bool configured = false;
     if (!configured) {
@@ -707,18 +818,19 @@ static int launch_gemm2_tm(const CUtensorMap& tmA, const CUtensorMap& tmB, const
     const long long total = (long long)m_tiles * n_tiles * (p.batch > 1 ? p.batch : 1);
     MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
     const int grid = (int)(total < sm_count() ? total : sm_count());
-    MOBI_CUDA(launch_pdl(gemm2_kernel<BN, MC, 0>, dim3(grid), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p,
-                         m_tiles, n_tiles));
+    MOBI_CUDA(launch_pdl(gemm2_kernel<BN, MC, 0>, dim3(grid), dim3(G2_THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, tmR,
+                         p, m_tiles, n_tiles));
     return 0;
 }
 
 template <int BN>
-static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, cudaStream_t stream) {
-    if (p.mode == MOBI_EPI_PLAIN) return launch_gemm2_tm<BN, 1>(tmA, tmB, p, stream);
-    if (p.mode == MOBI_EPI_GEGLU2) return launch_gemm2_tm<BN, 2>(tmA, tmB, p, stream);
+static int launch_gemm2_t(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
+                          cudaStream_t stream) {
+    if (p.mode == MOBI_EPI_PLAIN) return launch_gemm2_tm<BN, 1>(tmA, tmB, tmR, p, stream);
+    if (p.mode == MOBI_EPI_GEGLU2) return launch_gemm2_tm<BN, 2>(tmA, tmB, tmR, p, stream);
     if (p.mode == MOBI_EPI_HEADS || p.mode == MOBI_EPI_QKV_ROW || p.mode == MOBI_EPI_KV_ROW)
-        return launch_gemm2_tm<BN, 3>(tmA, tmB, p, stream);
-    return launch_gemm2_tm<BN, 0>(tmA, tmB, p, stream);
+        return launch_gemm2_tm<BN, 3>(tmA, tmB, tmR, p, stream);
+    return launch_gemm2_tm<BN, 0>(tmA, tmB, tmR, p, stream);
 }
 
 bool gemm2_supported(const GemmParams& p) {
@@ -762,12 +874,13 @@ bool gemm2_pair_wanted(const GemmParams& p, int bn_tile, int pair_request) {
     return p.num_k_blocks >= 16 && tiles >= sm_count() / 2;
 }
 
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn_tile, cudaStream_t stream) {
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p, int bn_tile,
+                 cudaStream_t stream) {
     switch (bn_tile) {
-        case 64: return launch_gemm2_t<64>(tmA, tmB, p, stream);
-        case 128: return launch_gemm2_t<128>(tmA, tmB, p, stream);
-        case 160: return launch_gemm2_t<160>(tmA, tmB, p, stream);
-        case 256: return launch_gemm2_t<256>(tmA, tmB, p, stream);
+        case 64: return launch_gemm2_t<64>(tmA, tmB, tmR, p, stream);
+        case 128: return launch_gemm2_t<128>(tmA, tmB, tmR, p, stream);
+        case 160: return launch_gemm2_t<160>(tmA, tmB, tmR, p, stream);
+        case 256: return launch_gemm2_t<256>(tmA, tmB, tmR, p, stream);
         default: MOBI_CHECK(false, "mobi_gemm: unsupported tile_n %d", bn_tile);
     }
     return 0;

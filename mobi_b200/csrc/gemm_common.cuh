@@ -27,6 +27,7 @@ struct GemmParams {
     int act;
     int heads, head_dim, tokens;
     long long out_seg, out_seg_stride, out_seg_offset;
+    int res_prefetch;             // 1: the producer pulls each tile's residual box into L2 ahead of the epilogue (tmR is valid)
     int pair;                     // 1: run as 2-CTA clusters (cta_group::2, 256-row tiles, B box = BN / 2 rows); 2: two such pairs
                                   // per cluster on neighbouring n-tiles, A tiles multicast between them (A box = 64 rows)
     int batch;                    // > 1: batched problem, A/B through 3-D tensor maps
@@ -44,7 +45,8 @@ constexpr int A_TILE_BYTES = BM * BK * 2;
 
 // true when the persistent kernel's vectorised epilogue can take this problem
 bool gemm2_supported(const GemmParams& p);
-int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p, int bn_tile, cudaStream_t stream);
+int launch_gemm2(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p, int bn_tile,
+                 cudaStream_t stream);
 // true when the 2-CTA (cta_group::2) variant should run this problem with tile width bn_tile
 bool gemm2_pair_wanted(const GemmParams& p, int bn_tile, int pair_request);
 bool gemm2_quad_ok(const GemmParams& p, int bn_tile);
