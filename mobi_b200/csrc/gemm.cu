@@ -533,11 +533,15 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         CUtensorMap tmR = tmA;
         const int rb = p.res_f32 ? 4 : 2;
         const uint32_t box_cols = (uint32_t)(bn_tile < p.N ? bn_tile : p.N);
-        if (p.residual && p.mode == MOBI_EPI_PLAIN && p.out_seg == 0 && p.batch <= 1 && !p.atomic_out &&
+        // rows of the output / residual buffer the mapped tiles can touch (row segments spread them out)
+        const long long out_rows = p.out_seg > 0 ? ((long long)(p.M + p.out_seg - 1) / p.out_seg - 1) * p.out_seg_stride +
+                                                       p.out_seg_offset + p.out_seg
+                                                 : (long long)p.M;
+        if (p.residual && p.mode == MOBI_EPI_PLAIN && (p.out_seg % BM) == 0 && out_rows < (1ll << 31) && p.batch <= 1 && !p.atomic_out &&
             ((long long)p.ldo * rb) % 16 == 0 && (box_cols * rb) % 16 == 0 && p.num_k_blocks <= 10 && res_prefetch_enabled()) {
             // short K only (measured: to_out + residual, K = 320 / 640: 4 % faster; with K >= 1280 the operand stream
             // already fills HBM and the extra early traffic costs 3-5 %)
-            if (make_tensor_map_2d_plain(&tmR, p.residual, rb, (uint64_t)p.N, (uint64_t)p.M, (uint64_t)p.ldo * rb, box_cols, BM))
+            if (make_tensor_map_2d_plain(&tmR, p.residual, rb, (uint64_t)p.N, (uint64_t)out_rows, (uint64_t)p.ldo * rb, box_cols, BM))
                 return 1;
             p.res_prefetch = 1;
         }

@@ -90,9 +90,16 @@ __device__ __forceinline__ void gemm2_epilogue_plain_fast(const GemmParams& p, u
                                                           int n_tile, int lg, int half, int lane, long long batch_off,
                                                           int flip) {
     using Cfg = Gemm2Cfg<BN>;
+    if (m_tile * BM >= p.M) return;   // the second CTA of a pair on an odd number of 128-row tiles
     const int u = lane & 7, rsub = lane >> 3;
     const int m_base = m_tile * BM + lg * 32;
-    const long long row0 = (long long)(m_base + rsub) * p.ldo + batch_off + 4 * u;   // row `it` of this lane: + it * step
+    // row segments (out_seg % 128 == 0 here): the 128 rows of a tile stay consecutive in the output
+    long long mo = m_base + rsub;
+    if (p.out_seg > 0) {
+        const int sg = (m_tile * BM) / (int)p.out_seg;
+        mo += (long long)sg * (p.out_seg_stride - p.out_seg) + p.out_seg_offset;
+    }
+    const long long row0 = mo * p.ldo + batch_off + 4 * u;   // row `it` of this lane: + it * step
     const long long step = 4ll * p.ldo;
     float* outp = reinterpret_cast<float*>(p.out) + row0;
     const float* resp = p.residual ? reinterpret_cast<const float*>(p.residual) + row0 : nullptr;
@@ -180,7 +187,8 @@ __device__ __forceinline__ void gemm2_epilogue(const GemmParams& p, uint32_t acc
                                                int n_tile, int lg, int half, int lane, long long batch_off, int flip) {
     using Cfg = Gemm2Cfg<BN>;
     if constexpr (MC == 1) {
-        const bool fast = p.out_f32 && !p.atomic_out && p.act == 0 && p.out_seg == 0 && (p.M % BM) == 0 && (p.N % 32) == 0 &&
+        const bool fast = p.out_f32 && !p.atomic_out && p.act == 0 && (p.out_seg % BM) == 0 && (p.M % BM) == 0 && (p.N % 32) == 0 &&
+                          (p.out_seg == 0 || p.colstats == nullptr) &&
                           (p.residual == nullptr || p.res_f32) && (p.row_bias == nullptr || (p.rows_per_group % 32) == 0);
         if (fast) {
             gemm2_epilogue_plain_fast<BN>(p, acc_tmem, stg, m_tile, n_tile, lg, half, lane, batch_off, flip);
@@ -565,7 +573,11 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 // The residual of this CTA's 128 x BN output box starts its way from HBM to L2 now, one to two tile periods
                 // before the epilogue warps read it: their loads then wait for an L2 hit instead of a DRAM access (the
                 // narrow f32 GEMMs were bound by exactly that latency, profiles/r02/ncu_gemm_l2_bound.md).
-                if (p.res_prefetch) tma_prefetch_l2_2d(&tmR, n_tile * BN, m_tile * BM);
+                if (p.res_prefetch) {
+                    long long mo = (long long)m_tile * BM;
+                    if (p.out_seg > 0) mo += (mo / p.out_seg) * (p.out_seg_stride - p.out_seg) + p.out_seg_offset;
+                    tma_prefetch_l2_2d(&tmR, n_tile * BN, (int)mo);
+                }
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
                     const long long pix = (long long)m_tile * BM + a_half;

@@ -45,6 +45,7 @@ def rnd(*shape, seed=0, dtype=torch.bfloat16, scale=1.0):
     (128, 64, 64, 64), (128, 128, 64, 128), (256, 256, 128, 256), (128, 160, 64, 160),
     (512, 320, 320, 0), (1000, 320, 320, 64), (4096, 640, 640, 0), (300, 1280, 1280, 256),
     (4, 1280, 320, 0), (260, 4, 2880, 64), (128, 128, 88, 128), (1024, 2560, 320, 0),
+    (128, 23680, 1280, 0), (384, 12800, 1280, 160),      # CTA pairs on an odd number of 128-row tiles (the embedding GEMM)
 ])
 @pytest.mark.parametrize("kernel", [0, 1])
 def test_gemm_plain(M, N, K, tile_n, kernel):
@@ -59,6 +60,25 @@ def test_gemm_plain(M, N, K, tile_n, kernel):
     assert relerr(out, ref) < 2e-3, describe(out, ref)
     out16 = ops.gemm(a, w, bias=bias, out_dtype=torch.bfloat16, tile_n=tile_n, kernel=kernel)
     assert relerr(out16, ref) < 1e-2, describe(out16, ref)
+
+
+@pytest.mark.parametrize("Rh,T,C,K", [(2, 256, 320, 320), (3, 1024, 640, 640), (2, 64, 1280, 1280), (4, 128, 320, 1280)])
+@pytest.mark.parametrize("off", [0, 1])
+def test_gemm_row_segments_in_place(Rh, T, C, K, off):
+    """The cross-modal output projection (attention.py:255-262): rows of one modality, T at a time, land in every other
+    T-row segment of the interleaved residual stream, which is also the residual (in place).  T % 128 == 0 takes the
+    straight-line epilogue (+ the L2 prefetch of the residual boxes), T = 64 the general one."""
+    ops = _ops()
+    a = rnd(Rh * T, K, seed=1)
+    w = rnd(C, K, seed=2, scale=K ** -0.5)
+    bias = rnd(C, seed=3, dtype=torch.float32)
+    x = rnd(2 * Rh * T, C, seed=4, dtype=torch.float32)
+    ref = x.clone().reshape(Rh, 2, T, C)
+    ref[:, off] += (a.float() @ w.float().t() + bias).reshape(Rh, T, C)
+    ops.gemm(a, w, bias=bias, residual=x, out=x, ldo=C, out_seg=T, out_seg_stride=2 * T, out_seg_offset=off * T)
+    torch.cuda.synchronize()
+    assert relerr(x, ref.reshape(2 * Rh * T, C)) < 2e-3, describe(x, ref.reshape(2 * Rh * T, C))
+    assert torch.equal(x.reshape(Rh, 2, T, C)[:, 1 - off], ref[:, 1 - off])       # the other modality's rows are untouched
 
 
 def test_gemm_residual_rowbias_act():
