@@ -92,7 +92,9 @@ typedef struct {
     int64_t a_batch_stride, b_batch_stride, out_batch_stride;
     /* CTA pairs (tcgen05 cta_group::2, 256-row tiles): 0 = choose, 1 = force on (persistent kernel only), -1 = off,
      * 2 = clusters of two pairs on neighbouring n-tiles that fetch their common A tiles in halves and multicast them
-     * (PLAIN epilogue, tile_n >= 128, even number of n-tiles, no batch; a tuning arm: never chosen automatically). */
+     * (PLAIN epilogue, tile_n >= 128, even number of n-tiles, no batch; a tuning arm: never chosen automatically),
+     * 3 = pairs on 256 x 320 tiles (tile_n = 160, two N = 160 MMAs per k-step on one A tile, three rotating TMEM
+     * accumulator slots; no batch): chosen automatically for convolutions with N % 320 == 0 and a full wave of tiles. */
     int32_t pair;
     /* MN-major ("transposed") operands, persistent kernel only, no conv / CTA pairs: with a_mn_major, A is given as the
      * row-major [K, M] matrix (lda = its row stride >= M) and read as A^T by the tensor core (tcgen05 instruction-descriptor

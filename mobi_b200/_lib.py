@@ -8,7 +8,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libmobi_b200.so")
+# MOBI_B200_LIB: an alternative build of the SAME library (kernel experiments compiled with other -D flags); never a fallback
+LIB_PATH = os.environ.get("MOBI_B200_LIB") or os.path.join(_HERE, "libmobi_b200.so")
 
 DT_BF16, DT_F32 = 0, 1
 EPI_PLAIN, EPI_GEGLU, EPI_HEADS, EPI_HEADS_T, EPI_QKV, EPI_KV, EPI_GEGLU2 = 0, 1, 2, 3, 4, 5, 6

@@ -494,12 +494,29 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
             pair_request = 1;
         }
     }
+    if (a->tile_n == 0 && a->pair == 0 && a->kernel != 1 && a->conv && a->N % 320 == 0 && p.num_k_blocks >= 16 &&
+        p.batch <= 1 && gemm2_supported(p)) {
+        // 3x3 convolutions whose width is a multiple of 320 (every ResBlock of the UNet): a CTA pair takes 256 x 320 tiles as
+        // two N = 160 MMAs per k-step on ONE A tile, which cuts the operand bytes delivered to an SM per FLOP by 31 % --
+        // what bounds these kernels (profiles/r02/ncu_gemm_l2_bound.md).  1.15-1.5x on the UNet's shapes once there is a
+        // full wave of such tiles (profiles/r02/kbench_gemm_tiles.log).
+        const long long m2 = (a->M + 2 * BM - 1) / (2 * BM);
+        if (m2 * (a->N / 320) >= sm_count() / 2) {
+            bn_tile = 160;
+            pair_request = 3;
+        }
+    }
     p.pair = (a->kernel != 1 && gemm2_supported(p) && gemm2_pair_wanted(p, bn_tile, pair_request)) ? 1 : 0;
-    MOBI_CHECK(a->pair < 1 || p.pair, "mobi_gemm: pair = 1 / 2 needs a problem the persistent kernel supports");
+    MOBI_CHECK(a->pair < 1 || p.pair, "mobi_gemm: pair = 1 / 2 / 3 needs a problem the persistent kernel supports");
     if (a->pair == 2) {
         MOBI_CHECK(gemm2_quad_ok(p, bn_tile), "mobi_gemm: pair = 2 (4-CTA clusters) needs the PLAIN epilogue, tile_n >= 128, an "
                                               "even number of n-tiles, K-major operands and no batch");
         p.pair = 2;
+    }
+    if (a->pair == 3 || pair_request == 3) {
+        MOBI_CHECK(p.pair && bn_tile == 160 && p.batch <= 1 && !p.a_mn && !p.b_mn,
+                   "mobi_gemm: pair = 3 (320-column tiles on CTA pairs) needs tile_n = 160, K-major operands and no batch");
+        p.pair = 3;
     }
     if (p.pair == 2) {
         // the A box shrinks to the 64 rows each CTA fetches (and multicasts to its counterpart)

@@ -24,13 +24,23 @@ namespace mobi {
 constexpr int G2_THREADS = 320;
 constexpr int G2_STAGING_BYTES = 8 * 4096;  // 8 epilogue warps x (32 rows x 128 B)
 
-template <int BN, bool PAIR = false>
+// PM: 0 = one CTA per tile, 1 = CTA pair (256 x BN), 2 = two pairs per cluster with multicast A, 3 = WIDE pair: a
+// 256 x 2BN tile per pair as two N = BN MMAs per k-step that share the A tile (see the kernel).
+template <int BN, int PM = 0>
 struct Gemm2Cfg {
-    static constexpr int B_ROWS = PAIR ? BN / 2 : BN;  // rows of B this CTA stages per k-block
+    static constexpr bool WIDE = PM == 3;
+    static constexpr int B_ROWS = WIDE ? BN : (PM >= 1 ? BN / 2 : BN);  // rows of B this CTA stages per k-block
     static constexpr int B_TILE_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_TILE_BYTES + B_TILE_BYTES;
-    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : 256);
-    static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
+#ifdef G2_ACC160
+    static constexpr int ACC_STRIDE = BN <= 64 ? 64 : (BN <= 128 ? 128 : (BN == 160 ? 160 : 256));   // experiment: 160-aligned D
+    static constexpr int TMEM_COLS = BN == 160 ? 512 : 2 * ACC_STRIDE;
+#else
+    // WIDE: three BN-column slots that the tiles take two at a time, round robin (BN = 160: columns 0 / 160 / 320; a
+    // 160-column accumulator may start at any multiple of 32 columns, tools/gpu_r02_acc160.sh)
+    static constexpr int ACC_STRIDE = WIDE ? BN : (BN <= 64 ? 64 : (BN <= 128 ? 128 : 256));
+    static constexpr int TMEM_COLS = WIDE ? 512 : 2 * ACC_STRIDE;
+#endif
     static constexpr int BUDGET = 227 * 1024 - 1024 - G2_STAGING_BYTES - 512;
     static constexpr int STAGES = (BUDGET / STAGE_BYTES) > 8 ? 8 : (BUDGET / STAGE_BYTES);
     static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + G2_STAGING_BYTES + 512 + 1024;
@@ -501,7 +511,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
              const __grid_constant__ CUtensorMap tmR, const GemmParams p, const int m_tiles, const int n_tiles) {
     constexpr bool PAIR = PM >= 1;
     constexpr bool QUAD = PM == 2;
-    using Cfg = Gemm2Cfg<BN, PAIR>;
+    constexpr bool WIDE = PM == 3;
+    using Cfg = Gemm2Cfg<BN, PM>;
     constexpr int STAGES = Cfg::STAGES;
     extern __shared__ uint8_t smem_raw[];
     // align by OFFSET so the pointer keeps its shared address space (LDS/STS instead of generic LD/ST in the epilogue)
@@ -511,9 +522,9 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
     float* staging = reinterpret_cast<float*>(sB + STAGES * Cfg::B_TILE_BYTES);
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(staging) + G2_STAGING_BYTES);
     uint64_t* empty_bar = full_bar + STAGES;
-    uint64_t* tfull_bar = empty_bar + STAGES;   // 2
-    uint64_t* tempty_bar = tfull_bar + 2;       // 2
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+    uint64_t* tfull_bar = empty_bar + STAGES;   // 2 (3 accumulator slots for WIDE)
+    uint64_t* tempty_bar = tfull_bar + 3;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 3);
 
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     const int lane = threadIdx.x & 31;
@@ -532,9 +543,10 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 mbar_init(&full_bar[s], 1);
                 mbar_init(&empty_bar[s], QUAD ? 2 : 1);
             }
-            for (int s = 0; s < 2; ++s) {
+            for (int s = 0; s < 3; ++s) {
                 mbar_init(&tfull_bar[s], 1);
-                mbar_init(&tempty_bar[s], PAIR ? 16 : 8);  // one elected arrive per epilogue warp (of both CTAs)
+                // one elected arrive per epilogue warp (of both CTAs)
+                mbar_init(&tempty_bar[s], PAIR ? 16 : 8);
             }
             fence_barrier_init();
         }
@@ -567,7 +579,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const int z = tile / per_batch, rem = tile - z * per_batch;
                 const int m_tile = PAIR ? (rem / n_cols) * 2 + cta_rank : rem / n_cols;   // this CTA's 128-row tile
                 const int n_tile = QUAD ? (rem % n_cols) * 2 + quad_pair : rem % n_cols;
-                const int b_row0 = n_tile * BN + (PAIR ? cta_rank * (BN / 2) : 0);           // this CTA's rows of B
+                // this CTA's rows of B (WIDE: its BN / 2 rows of the tile's first N-half; the second half is BN further)
+                const int b_row0 = n_tile * (WIDE ? 2 * BN : BN) + (PAIR ? cta_rank * (BN / 2) : 0);
                 const int a_half = QUAD ? quad_pair * (BM / 2) : 0;   // quad: the 64 rows of the A tile this CTA fetches
                 const uint16_t a_mask = (uint16_t)((1u << cl_rank) | (1u << (cl_rank ^ 2)));
                 // The residual of this CTA's 128 x BN output box starts its way from HBM to L2 now, one to two tile periods
@@ -576,7 +589,8 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (p.res_prefetch) {
                     long long mo = (long long)m_tile * BM;
                     if (p.out_seg > 0) mo += (mo / p.out_seg) * (p.out_seg_stride - p.out_seg) + p.out_seg_offset;
-                    tma_prefetch_l2_2d(&tmR, n_tile * BN, (int)mo);
+                    tma_prefetch_l2_2d(&tmR, n_tile * (WIDE ? 2 * BN : BN), (int)mo);
+                    if (WIDE) tma_prefetch_l2_2d(&tmR, n_tile * 2 * BN + BN, (int)mo);
                 }
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
@@ -594,7 +608,23 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     if (PAIR) {
                         // both CTAs' bytes are counted on the leader's barrier; only the leader arms it
                         if (cta_rank == 0) mbar_arrive_expect_tx(&full_bar[s], 2 * (A_TILE_BYTES + Cfg::B_TILE_BYTES));
-                        if (QUAD) {
+                        if (WIDE) {
+                            // the A tile once, the CTA's B rows of both N-halves (two boxes of BN / 2 rows)
+                            constexpr int HB = (BN / 2) * BK * 2;
+                            if (p.conv) {
+                                const int tap = kb / p.cblocks;
+                                const int cb = kb - tap * p.cblocks;
+                                const int kh = tap / p.KW;
+                                const int kw = tap - kh * p.KW;
+                                tma_load_4d_pair(dA, &tmA, &full_bar[s], cb * BK, x0 + kw - p.pad_w, y0 + kh - p.pad_h, n0);
+                                tma_load_2d_pair(dB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0);
+                                tma_load_2d_pair(dB + HB, &tmB, &full_bar[s], tap * p.C + cb * BK, b_row0 + BN);
+                            } else {
+                                tma_load_2d_pair(dA, &tmA, &full_bar[s], kb * BK, m_tile * BM);
+                                tma_load_2d_pair(dB, &tmB, &full_bar[s], kb * BK, b_row0);
+                                tma_load_2d_pair(dB + HB, &tmB, &full_bar[s], kb * BK, b_row0 + BN);
+                            }
+                        } else if (QUAD) {
                             // half of the A tile (the A map's box is 64 rows), written into this CTA and its counterpart
                             uint8_t* dAh = dA + a_half * 128;
                             if (p.conv) {
@@ -672,10 +702,15 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, BN) | (p.a_mn ? 1u << 15 : 0u) | (p.b_mn ? 1u << 16 : 0u);
             uint32_t it = 0, lt = 0;
             for (int tile = worker; tile < total; tile += n_workers, ++lt) {
-                const uint32_t as = lt & 1;
-                mbar_wait(&tempty_bar[as], ((lt >> 1) & 1) ^ 1);  // epilogue has drained this accumulator stage
+                // WIDE: accumulator uses are numbered u = 2 lt + half and take slot u % 3; the (u / 3)-th use of a slot
+                const uint32_t u0 = 2 * lt, u1 = 2 * lt + 1;
+                const uint32_t as = WIDE ? u0 % 3 : (lt & 1);
+                const uint32_t as1 = u1 % 3;
+                mbar_wait(&tempty_bar[as], WIDE ? (((u0 / 3) & 1) ^ 1) : (((lt >> 1) & 1) ^ 1));  // the epilogue has drained it
+                if (WIDE) mbar_wait(&tempty_bar[as1], ((u1 / 3) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
+                const uint32_t d_tmem1 = tmem_base + as1 * Cfg::ACC_STRIDE;
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -685,7 +720,12 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        if (PAIR) {
+                        if (WIDE) {
+                            // both N-halves against the same A slice: second B block (BN / 2 rows) 1024-aligned behind the first
+                            constexpr uint64_t HB16 = ((BN / 2) * BK * 2) >> 4;
+                            umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                            umma_bf16_ss_pair(d_tmem1, adesc + 2 * k, bdesc + HB16 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        } else if (PAIR) {
                             umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         } else {
                             // MN-major: 16 k-rows = 2048 B into every 64-element chunk, chunks 8192 B apart (LBO)
@@ -703,6 +743,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (QUAD) umma_commit_mask(&tfull_bar[as], (uint16_t)(3u << (2 * quad_pair)));
                 else if (PAIR) umma_commit_pair(&tfull_bar[as]);
                 else umma_commit(&tfull_bar[as]);
+                if (WIDE) umma_commit_pair(&tfull_bar[as1]);
             }
         }
     } else {
@@ -715,13 +756,32 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const int z = tile / per_batch, rem = tile - z * per_batch;
             const int m_tile = PAIR ? (rem / n_cols) * 2 + cta_rank : rem / n_cols;
             const int n_tile = QUAD ? (rem % n_cols) * 2 + quad_pair : rem % n_cols;
+            const long long boff = p.batch_inner > 0 ? (long long)(z % p.batch_inner) * p.out_batch_stride +
+                                                           (long long)(z / p.batch_inner) * p.out_batch2_stride
+                                                     : (long long)z * p.out_batch_stride;
+            if (WIDE) {
+                // Both accumulators of the tile, the first N-half first and by ALL warps: the next tile's second half
+                // reuses exactly that slot, so the MMA issuer gets it back after half an epilogue.  The odd chunk of
+                // each half goes to the other warp of the lane group (3 + 2 chunks per warp and tile).
+#pragma unroll 1
+                for (int part = 0; part < 2; ++part) {
+                    const uint32_t u = 2 * lt + part;                 // u-th accumulator use: slot u % 3, its (u / 3)-th use
+                    const uint32_t as = u % 3;
+                    mbar_wait(&tfull_bar[as], (u / 3) & 1);
+                    tc_fence_after();
+                    gemm2_epilogue<BN, MC>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, 2 * n_tile + part, lg, half, lane, boff,
+                                           (int)((lt + part) & 1));
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
+                }
+                continue;
+            }
             const uint32_t as = lt & 1;
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
-            gemm2_epilogue<BN, MC>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane,
-                               p.batch_inner > 0 ? (long long)(z % p.batch_inner) * p.out_batch_stride + (long long)(z / p.batch_inner) * p.out_batch2_stride
-                                                 : (long long)z * p.out_batch_stride,
-                               (Cfg::CHUNKS & 1) ? (int)(lt & 1) : 0);
+            gemm2_epilogue<BN, MC>(p, tmem_base + as * Cfg::ACC_STRIDE, stg, m_tile, n_tile, lg, half, lane, boff,
+                                   (Cfg::CHUNKS & 1) ? (int)(lt & 1) : 0);
             tc_fence_before();
             __syncwarp();
             if (lane == 0) {
@@ -745,7 +805,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
 template <int BN, int MC>
 static int launch_gemm2_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
                              cudaStream_t stream) {
-    using Cfg = Gemm2Cfg<BN, true>;
+    using Cfg = Gemm2Cfg<BN, 1>;
     static int max_quads = 0;
     cudaLaunchConfig_t cfg = {};
     cfg.blockDim = dim3(G2_THREADS, 1, 1);
@@ -776,9 +836,48 @@ static int launch_gemm2_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, con
     return 0;
 }
 
+// WIDE pairs: n_tiles counts 2 BN-wide tiles.
+template <int BN, int MC>
+static int launch_gemm2_wide(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
+                             cudaStream_t stream) {
+    using Cfg = Gemm2Cfg<BN, 3>;
+    static bool configured = false;
+    if (!configured) {
+        MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES));
+        configured = true;
+    }
+    const int m_tiles2 = (p.M + 2 * BM - 1) / (2 * BM), n_tiles = (p.N + 2 * BN - 1) / (2 * BN);
+    const long long total = (long long)m_tiles2 * n_tiles * (p.batch > 1 ? p.batch : 1);
+    MOBI_CHECK(total < (1ll << 31), "mobi_gemm: too many tiles");
+    const int pairs = (int)(total < sm_count() / 2 ? total : sm_count() / 2);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(2 * pairs, 1, 1);
+    cfg.blockDim = dim3(G2_THREADS, 1, 1);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = 2;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = pdl_enabled() ? 1 : 0;
+    cfg.attrs = attr;
+    cfg.numAttrs = 2;
+    MOBI_CUDA(cudaLaunchKernelEx(&cfg, gemm2_kernel<BN, MC, 3>, tmA, tmB, tmR, p, m_tiles2, n_tiles));
+    return 0;
+}
+
 template <int BN, int MC>
 static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmR, const GemmParams& p,
                              cudaStream_t stream) {
+    if (p.pair == 3) {
+        if constexpr (BN == 160) {
+            return launch_gemm2_wide<BN, MC>(tmA, tmB, tmR, p, stream);
+        } else {
+            MOBI_CHECK(false, "mobi_gemm: wide pairs are built for tile_n = 160 (320-column tiles)");
+        }
+    }
     if (p.pair == 2) {
         if constexpr (MC == 1 && BN != 64) {
             return launch_gemm2_quad<BN, MC>(tmA, tmB, tmR, p, stream);
@@ -786,7 +885,7 @@ static int launch_gemm2_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, con
             MOBI_CHECK(false, "mobi_gemm: 4-CTA clusters are built for the PLAIN epilogue with tile_n >= 128");
         }
     }
-    using Cfg = Gemm2Cfg<BN, true>;
+    using Cfg = Gemm2Cfg<BN, 1>;
     static bool configured = false;
     if (!configured) {
         MOBI_CUDA(cudaFuncSetAttribute(gemm2_kernel<BN, MC, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -220,6 +220,59 @@ def test_conv_implicit_quad_clusters(N, H, W, C, Cout, tile_n):
         assert relerr(quad._colstats[:g * Cout].reshape(g, Cout), want) < 1e-5
 
 
+@pytest.mark.parametrize("N,H,W,C,Cout", [
+    (2, 64, 64, 320, 320), (4, 32, 32, 640, 640), (4, 16, 16, 1280, 1280), (4, 8, 8, 2560, 1280), (3, 8, 8, 1280, 640),
+    (2, 64, 64, 960, 320), (6, 64, 64, 64, 320), (2, 32, 32, 320, 480), (1, 16, 16, 128, 4),
+])
+def test_conv_implicit_wide_pairs(N, H, W, C, Cout):
+    """pair = 3: a CTA pair owns a 256 x 320 tile as two N = 160 MMAs per k-step on the same A tile (three rotating TMEM
+    slots).  Bit-identical to the pair kernel with 160-wide tiles (same MMAs on the same operands)."""
+    ops = _ops()
+    x = rnd(N, H, W, C, seed=1)
+    w = rnd(Cout, 9 * C, seed=2, scale=(9 * C) ** -0.5)
+    b = rnd(Cout, seed=3, dtype=torch.float32)
+    emb = rnd(N, Cout, seed=4, dtype=torch.float32)
+    res = rnd(N, H, W, Cout, seed=5, dtype=torch.float32)
+    ref = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float().reshape(Cout, 3, 3, C).permute(0, 3, 1, 2), b,
+                                     padding=1).permute(0, 2, 3, 1) + emb[:, None, None, :] + res
+    pair = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=b, row_bias=emb, residual=res, tile_n=160, pair=1)
+    wide = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=b, row_bias=emb, residual=res, tile_n=160, pair=3, colstats=True)
+    torch.cuda.synchronize()
+    assert relerr(wide, ref) < 2e-3, describe(wide.reshape(-1, Cout), ref.reshape(-1, Cout))
+    assert torch.equal(wide, pair)
+    if hasattr(wide, "_colstats") and (N * H * W) % 32 == 0:
+        g = N * H * W // 32
+        want = wide.reshape(g, 32, Cout).sum(1)
+        assert relerr(wide._colstats[:g * Cout].reshape(g, Cout), want) < 1e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(4096, 320, 320), (1000, 640, 1280), (8192, 1280, 5120), (300, 960, 64), (128, 23680, 1280),
+                                   (256, 200, 640)])
+def test_gemm_wide_pairs(M, N, K):
+    ops = _ops()
+    a = rnd(M, K, seed=1)
+    w = rnd(N, K, seed=2, scale=K ** -0.5)
+    bias = rnd(N, seed=3, dtype=torch.float32)
+    res = rnd(M, N, seed=4, dtype=torch.float32)
+    ref = a.float() @ w.float().t() + bias + res
+    pair = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, tile_n=160, pair=1)
+    wide = ops.gemm(a, w, bias=bias, residual=res, out_dtype=torch.float32, tile_n=160, pair=3)
+    torch.cuda.synchronize()
+    assert relerr(wide, ref) < 2e-3, describe(wide, ref)
+    assert torch.equal(wide, pair)
+    # the bf16 head-split and GEGLU epilogues on wide tiles
+    if N == 960:
+        H, D, T = 8, 40, 100
+        outs = []
+        for pr in (1, 3):
+            q = torch.zeros(3 * H, T, D, device="cuda", dtype=torch.bfloat16)
+            k, v = torch.zeros_like(q), torch.zeros_like(q)
+            ops.gemm(a, w, epilogue=_L().EPI_QKV_ROW, heads=H, head_dim=D, tokens=T, out=q, out2=k, out3=v, tile_n=160, pair=pr)
+            outs.append((q, k, v))
+        torch.cuda.synchronize()
+        assert all(torch.equal(x, y) for x, y in zip(*outs))
+
+
 @pytest.mark.parametrize("M,N,K,tile_n", [(4096, 320, 320, 160), (1000, 640, 1280, 160), (8192, 1280, 5120, 160),
                                           (300, 512, 64, 128), (2048, 1024, 2560, 256)])
 def test_gemm_quad_clusters(M, N, K, tile_n):
