@@ -707,10 +707,53 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 const uint32_t as = WIDE ? u0 % 3 : (lt & 1);
                 const uint32_t as1 = u1 % 3;
                 mbar_wait(&tempty_bar[as], WIDE ? (((u0 / 3) & 1) ^ 1) : (((lt >> 1) & 1) ^ 1));  // the epilogue has drained it
-                if (WIDE) mbar_wait(&tempty_bar[as1], ((u1 / 3) & 1) ^ 1);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
                 const uint32_t d_tmem1 = tmem_base + as1 * Cfg::ACC_STRIDE;
+                if (WIDE) {
+                    // The slot of the SECOND N-half is the one the previous tile's first half is still being drained
+                    // from; the first half's slot has been free for a whole tile.  So the first-half MMAs start at once
+                    // and run up to STAGES - 1 k-blocks ahead (their stages stay held) while the epilogue finishes; the
+                    // second half catches up as soon as its slot is released.  Stages are committed after both halves.
+                    constexpr uint64_t HB16 = ((BN / 2) * BK * 2) >> 4;
+                    const uint32_t par1 = ((u1 / 3) & 1) ^ 1;
+                    const uint32_t it0 = it;
+                    bool ready1 = false;
+                    int done1 = 0;
+                    for (int kb = 0; kb < nkb; ++kb, ++it) {
+                        const int s = it % STAGES;
+                        mbar_wait(&full_bar[s], (it / STAGES) & 1);
+                        tc_fence_after();
+                        const uint64_t adesc = make_kmajor_sw128_desc(smem_u32(sA + s * A_TILE_BYTES));
+                        const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES));
+#pragma unroll
+                        for (int k = 0; k < BK / 16; ++k)
+                            umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
+                        if (!ready1) {
+                            if (kb - done1 >= STAGES - 2 || kb == nkb - 1) {
+                                mbar_wait(&tempty_bar[as1], par1);
+                                ready1 = true;
+                            } else {
+                                ready1 = mbar_try_wait(&tempty_bar[as1], par1);
+                            }
+                            if (ready1) tc_fence_after();
+                        }
+                        if (ready1) {
+                            for (; done1 <= kb; ++done1) {
+                                const int s1 = (it0 + done1) % STAGES;
+                                const uint64_t ad1 = make_kmajor_sw128_desc(smem_u32(sA + s1 * A_TILE_BYTES));
+                                const uint64_t bd1 = make_kmajor_sw128_desc(smem_u32(sB + s1 * Cfg::B_TILE_BYTES)) + HB16;
+#pragma unroll
+                                for (int k = 0; k < BK / 16; ++k)
+                                    umma_bf16_ss_pair(d_tmem1, ad1 + 2 * k, bd1 + 2 * k, idesc, (done1 | k) != 0 ? 1u : 0u);
+                                umma_commit_pair(&empty_bar[s1]);
+                            }
+                        }
+                    }
+                    umma_commit_pair(&tfull_bar[as]);
+                    umma_commit_pair(&tfull_bar[as1]);
+                    continue;
+                }
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -720,12 +763,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     const uint64_t bdesc = make_kmajor_sw128_desc(smem_u32(sB + s * Cfg::B_TILE_BYTES));
 #pragma unroll
                     for (int k = 0; k < BK / 16; ++k) {
-                        if (WIDE) {
-                            // both N-halves against the same A slice: second B block (BN / 2 rows) 1024-aligned behind the first
-                            constexpr uint64_t HB16 = ((BN / 2) * BK * 2) >> 4;
-                            umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                            umma_bf16_ss_pair(d_tmem1, adesc + 2 * k, bdesc + HB16 + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
-                        } else if (PAIR) {
+                        if (PAIR) {
                             umma_bf16_ss_pair(d_tmem, adesc + 2 * k, bdesc + 2 * k, idesc, (kb | k) != 0 ? 1u : 0u);
                         } else {
                             // MN-major: 16 k-rows = 2048 B into every 64-element chunk, chunks 8192 B apart (LBO)
@@ -743,7 +781,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 if (QUAD) umma_commit_mask(&tfull_bar[as], (uint16_t)(3u << (2 * quad_pair)));
                 else if (PAIR) umma_commit_pair(&tfull_bar[as]);
                 else umma_commit(&tfull_bar[as]);
-                if (WIDE) umma_commit_pair(&tfull_bar[as1]);
+                (void)d_tmem1;
             }
         }
     } else {
