@@ -710,7 +710,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + as * Cfg::ACC_STRIDE;
                 const uint32_t d_tmem1 = tmem_base + as1 * Cfg::ACC_STRIDE;
-                if (WIDE) {
+                if constexpr (WIDE) {
                     // The slot of the SECOND N-half is the one the previous tile's first half is still being drained
                     // from; the first half's slot has been free for a whole tile.  So the first-half MMAs start at once
                     // and run up to STAGES - 1 k-blocks ahead (their stages stay held) while the epilogue finishes; the
@@ -752,8 +752,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     }
                     umma_commit_pair(&tfull_bar[as]);
                     umma_commit_pair(&tfull_bar[as1]);
-                    continue;
-                }
+                } else {
                 for (int kb = 0; kb < nkb; ++kb, ++it) {
                     const int s = it % STAGES;
                     const uint32_t ph = (it / STAGES) & 1;
@@ -782,6 +781,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                 else if (PAIR) umma_commit_pair(&tfull_bar[as]);
                 else umma_commit(&tfull_bar[as]);
                 (void)d_tmem1;
+                }
             }
         }
     } else {
@@ -797,7 +797,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             const long long boff = p.batch_inner > 0 ? (long long)(z % p.batch_inner) * p.out_batch_stride +
                                                            (long long)(z / p.batch_inner) * p.out_batch2_stride
                                                      : (long long)z * p.out_batch_stride;
-            if (WIDE) {
+            if constexpr (WIDE) {
                 // Both accumulators of the tile, the first N-half first and by ALL warps: the next tile's second half
                 // reuses exactly that slot, so the MMA issuer gets it back after half an epilogue.  The odd chunk of
                 // each half goes to the other warp of the lane group (3 + 2 chunks per warp and tile).
@@ -813,8 +813,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     __syncwarp();
                     if (lane == 0) mbar_arrive_leader(&tempty_bar[as]);
                 }
-                continue;
-            }
+            } else {
             const uint32_t as = lt & 1;
             mbar_wait(&tfull_bar[as], (lt >> 1) & 1);
             tc_fence_after();
@@ -825,6 +824,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
             if (lane == 0) {
                 if (PAIR) mbar_arrive_leader(&tempty_bar[as]);
                 else mbar_arrive(&tempty_bar[as]);
+            }
             }
         }
     }
