@@ -10,7 +10,12 @@
 //                           s_j = rstd * <d * gamma, U_j> + <beta, U_j> (U = W_q^T k * scale, 2 keys x 8 heads = 16 rows)
 //                           p   = 2-way softmax per head ;  x += sum_j p_j Z_j + zb     (Z = W_conn W_out v)
 //                         followed by the same dual action as ln_dual_kernel on the updated row.
-//                         U*gamma and Z live in shared memory as fp32, two token rows per warp share every load.
+//                         The softmax is over TWO keys per head, so only score differences matter:
+//                           p_h = sigmoid(<d, U_h0 - U_h1> * rstd + (sb_h0 - sb_h1)),
+//                           x  += (zb + sum_h Z_h1) + sum_h p_h (Z_h0 - Z_h1):
+//                         8 difference rows per table instead of 16 rows (built while the tables are staged in shared
+//                         memory as fp32), which halves the shared-memory reads, the FMAs and the accumulators and lets
+//                         four token rows per warp share every table load.
 #include "../../include/mobi_b200.h"
 #include "common.cuh"
 #include "ptx.cuh"
@@ -148,9 +153,27 @@ ln_dual_kernel(const float* __restrict__ x, DualParams d, int rows, int C, int T
 }
 
 // ------------------------------------------------------------------------------------------------ adapter
-constexpr int AD_HK = 16;      // 2 keys x 8 head slots (heads < 8 are zero padded by the host)
+constexpr int AD_HK = 16;      // table rows of the ABI: 2 keys x 8 head slots (heads < 8 are zero padded by the host)
+constexpr int AD_H = 8;        // difference rows kept in shared memory (key 0 minus key 1 of every head slot)
 constexpr int AD_WARPS = 8;
-constexpr int AD_ROWS = 2;     // token rows per warp per iteration (share the table loads)
+#ifndef AD_B3
+#define AD_B3 3   // CTAs per SM the register allocation must allow, by channel-count class (measured: tools/gpu_r02_lnad.sh)
+#endif
+#ifndef AD_B6
+#define AD_B6 2
+#endif
+#ifndef AD_B12
+#define AD_B12 2
+#endif
+#ifndef AD_R3
+#define AD_R3 2   // token rows per warp per iteration (share the table loads), by channel-count class
+#endif
+#ifndef AD_R6
+#define AD_R6 2
+#endif
+#ifndef AD_R12
+#define AD_R12 1
+#endif
 
 struct AdapterParams {
     float* x;
@@ -165,48 +188,40 @@ struct AdapterParams {
     float eps;
 };
 
-// Sums 16 per-lane values over the 32 lanes with 16 shuffles; on return lane l holds the total of slot
-// j(l) = 8*bit4(l) + 4*bit3(l) + 2*bit2(l) + bit1(l)   (lanes l and l^1 hold the same slot).
-__device__ __forceinline__ float reduce16(float (&a)[AD_HK], int lane) {
-    float b8[8], b4[4], b2[2];
+// Sums 8 per-lane values over the 32 lanes with 9 shuffles; on return lane l holds the total of slot
+// h(l) = 4*bit4(l) + 2*bit3(l) + bit2(l)   (the four lanes that share bits 4..2 hold the same slot).
+__device__ __forceinline__ float reduce8(float (&a)[AD_H], int lane) {
+    float b4[4], b2[2];
     {
         const bool hi = lane & 16;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const float keep = hi ? a[i + 8] : a[i];
-            const float send = hi ? a[i] : a[i + 8];
-            b8[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        for (int i = 0; i < 4; ++i) {
+            const float keep = hi ? a[i + 4] : a[i];
+            const float send = hi ? a[i] : a[i + 4];
+            b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
         }
     }
     {
         const bool hi = lane & 8;
 #pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            const float keep = hi ? b8[i + 4] : b8[i];
-            const float send = hi ? b8[i] : b8[i + 4];
-            b4[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-        }
-    }
-    {
-        const bool hi = lane & 4;
-#pragma unroll
         for (int i = 0; i < 2; ++i) {
             const float keep = hi ? b4[i + 2] : b4[i];
             const float send = hi ? b4[i] : b4[i + 2];
-            b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            b2[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
         }
     }
-    const bool hi = lane & 2;
+    const bool hi = lane & 4;
     const float keep = hi ? b2[1] : b2[0];
     const float send = hi ? b2[0] : b2[1];
-    float r = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+    float r = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+    r += __shfl_xor_sync(0xffffffffu, r, 2);
     r += __shfl_xor_sync(0xffffffffu, r, 1);
     return r;
 }
 
-// grid (ceil(T / rows_per_cta), R); 256 threads.  dynamic smem: Ug[16][C] | Z[16][C] fp32
-template <int MAXV>
-__global__ void __launch_bounds__(AD_WARPS * 32)
+// grid (ceil(T / rows_per_cta), R); 256 threads.  dynamic smem: dU[8][C] | dZ[8][C] | zc[C] fp32
+template <int MAXV, int AD_ROWS, int MINB>
+__global__ void __launch_bounds__(AD_WARPS * 32, MINB)
 ln_adapter_kernel(AdapterParams p, DualParams d) {
     extern __shared__ float ad_smem[];
     pdl_wait();   // (the tables read below were written once per sampling run, but x comes from the previous kernel)
@@ -215,23 +230,35 @@ ln_adapter_kernel(AdapterParams p, DualParams d) {
     const int nv = C >> 2;
     const int b = blockIdx.y;
     float4* sU = reinterpret_cast<float4*>(ad_smem);
-    float4* sZ = sU + AD_HK * nv;
+    float4* sZ = sU + AD_H * nv;
+    float4* sZc = sZ + AD_H * nv;
     {
         const float4* gU = reinterpret_cast<const float4*>(p.Ug + (long long)b * AD_HK * C);
         const float4* gZ = reinterpret_cast<const float4*>(p.Z + (long long)b * AD_HK * C);
-        for (int i = threadIdx.x; i < AD_HK * nv; i += blockDim.x) {
-            sU[i] = __ldg(gU + i);
-            sZ[i] = __ldg(gZ + i);
+        const float4* zb4 = reinterpret_cast<const float4*>(p.zb);
+        for (int i = threadIdx.x; i < AD_H * nv; i += blockDim.x) {
+            const float4 u0 = __ldg(gU + i), u1 = __ldg(gU + AD_H * nv + i);       // key 0 / key 1 of the same head slot
+            const float4 z0 = __ldg(gZ + i), z1 = __ldg(gZ + AD_H * nv + i);
+            sU[i] = make_float4(u0.x - u1.x, u0.y - u1.y, u0.z - u1.z, u0.w - u1.w);
+            sZ[i] = make_float4(z0.x - z1.x, z0.y - z1.y, z0.z - z1.z, z0.w - z1.w);
+        }
+        for (int i = threadIdx.x; i < nv; i += blockDim.x) {
+            float4 acc = __ldg(zb4 + i);
+#pragma unroll
+            for (int h = 0; h < AD_H; ++h) {
+                const float4 z1 = __ldg(gZ + (AD_H + h) * nv + i);
+                acc.x += z1.x; acc.y += z1.y; acc.z += z1.z; acc.w += z1.w;
+            }
+            sZc[i] = acc;
         }
     }
     __syncthreads();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const int slot = 8 * ((lane >> 4) & 1) + 4 * ((lane >> 3) & 1) + 2 * ((lane >> 2) & 1) + ((lane >> 1) & 1);
-    const float my_sb = __ldg(p.sb + b * AD_HK + slot);
+    const int slot = 4 * ((lane >> 4) & 1) + 2 * ((lane >> 3) & 1) + ((lane >> 2) & 1);
+    const float my_dsb = __ldg(p.sb + b * AD_HK + slot) - __ldg(p.sb + b * AD_HK + AD_H + slot);
     const int t_begin = blockIdx.x * p.rows_per_cta;
     const int t_end = min(T, t_begin + p.rows_per_cta);
     const float4* av = p.add_vec ? reinterpret_cast<const float4*>(p.add_vec + (long long)b * C) : nullptr;
-    const float4* zb4 = reinterpret_cast<const float4*>(p.zb);
 
     for (int t0 = t_begin + warp * AD_ROWS; t0 < t_end; t0 += AD_WARPS * AD_ROWS) {
         float4 v[AD_ROWS][MAXV];
@@ -261,12 +288,12 @@ ln_adapter_kernel(AdapterParams p, DualParams d) {
         float mean[AD_ROWS], rstd[AD_ROWS];
 #pragma unroll
         for (int r = 0; r < AD_ROWS; ++r) ln_stats(v[r], nv, lane, C, p.eps, mean[r], rstd[r]);
-        // scores against the 16 table rows (centred values, so no cancellation against the mean)
-        float acc[AD_ROWS][AD_HK];
+        // score differences against the 8 table rows (centred values, so no cancellation against the mean)
+        float acc[AD_ROWS][AD_H];
 #pragma unroll
         for (int r = 0; r < AD_ROWS; ++r)
 #pragma unroll
-            for (int j = 0; j < AD_HK; ++j) acc[r][j] = 0.f;
+            for (int j = 0; j < AD_H; ++j) acc[r][j] = 0.f;
 #pragma unroll
         for (int k = 0; k < MAXV; ++k) {
             const int i = lane + 32 * k;
@@ -276,7 +303,7 @@ ln_adapter_kernel(AdapterParams p, DualParams d) {
                 for (int r = 0; r < AD_ROWS; ++r)
                     dv[r] = make_float4(v[r][k].x - mean[r], v[r][k].y - mean[r], v[r][k].z - mean[r], v[r][k].w - mean[r]);
 #pragma unroll
-                for (int j = 0; j < AD_HK; ++j) {
+                for (int j = 0; j < AD_H; ++j) {
                     const float4 u = sU[j * nv + i];
 #pragma unroll
                     for (int r = 0; r < AD_ROWS; ++r)
@@ -284,16 +311,15 @@ ln_adapter_kernel(AdapterParams p, DualParams d) {
                 }
             }
         }
-        float pj[AD_ROWS][AD_HK];
+        float pj[AD_ROWS][AD_H];
 #pragma unroll
         for (int r = 0; r < AD_ROWS; ++r) {
-            const float s = reduce16(acc[r], lane) * rstd[r] + my_sb;  // this lane's slot
-            const float other = __shfl_xor_sync(0xffffffffu, s, 16);   // same head, other key
-            const float pr = 1.0f / (1.0f + __expf(other - s));        // 2-way softmax
+            const float ds = reduce8(acc[r], lane) * rstd[r] + my_dsb;   // this lane's head slot: s(key 0) - s(key 1)
+            const float pr = 1.0f / (1.0f + __expf(-ds));                // 2-way softmax: weight of key 0
 #pragma unroll
-            for (int j = 0; j < AD_HK; ++j) {
-                // a lane that holds slot j: bits 4..1 of the lane id spell j
-                const int src = ((j >> 3) & 1) * 16 + ((j >> 2) & 1) * 8 + ((j >> 1) & 1) * 4 + (j & 1) * 2;
+            for (int j = 0; j < AD_H; ++j) {
+                // a lane that holds slot j: bits 4..2 of the lane id spell j
+                const int src = ((j >> 2) & 1) * 16 + ((j >> 1) & 1) * 8 + (j & 1) * 4;
                 pj[r][j] = __shfl_sync(0xffffffffu, pr, src);
             }
         }
@@ -301,12 +327,12 @@ ln_adapter_kernel(AdapterParams p, DualParams d) {
         for (int k = 0; k < MAXV; ++k) {
             const int i = lane + 32 * k;
             if (i < nv) {
-                const float4 zb = __ldg(zb4 + i);
+                const float4 zc = sZc[i];
                 float4 o[AD_ROWS];
 #pragma unroll
-                for (int r = 0; r < AD_ROWS; ++r) o[r] = zb;
+                for (int r = 0; r < AD_ROWS; ++r) o[r] = zc;
 #pragma unroll
-                for (int j = 0; j < AD_HK; ++j) {
+                for (int j = 0; j < AD_H; ++j) {
                     const float4 z = sZ[j * nv + i];
 #pragma unroll
                     for (int r = 0; r < AD_ROWS; ++r) {
@@ -423,19 +449,19 @@ extern "C" int mobi_ln_adapter(const mobi_ln_adapter_args* a, void* stream_) {
     int rpc = 128;
     while (rpc > 16 && (long long)a->batch * ((a->tokens + rpc - 1) / rpc) < 2 * sm_count()) rpc >>= 1;
     p.rows_per_cta = rpc;
-    const size_t smem = (size_t)2 * AD_HK * a->C * sizeof(float);
+    const size_t smem = (size_t)(2 * AD_H + 1) * a->C * sizeof(float);
     static bool configured = false;
     if (!configured) {
-        MOBI_CUDA(cudaFuncSetAttribute(ln_adapter_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MOBI_CUDA(cudaFuncSetAttribute(ln_adapter_kernel<6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-        MOBI_CUDA(cudaFuncSetAttribute(ln_adapter_kernel<12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOBI_CUDA(cudaFuncSetAttribute(ln_adapter_kernel<3, AD_R3, AD_B3>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOBI_CUDA(cudaFuncSetAttribute(ln_adapter_kernel<6, AD_R6, AD_B6>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+        MOBI_CUDA(cudaFuncSetAttribute(ln_adapter_kernel<12, AD_R12, AD_B12>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
         configured = true;
     }
     MOBI_CHECK(smem <= 200 * 1024, "mobi_ln_adapter: C=%d needs %zu bytes of shared memory", a->C, smem);
     dim3 grid((a->tokens + rpc - 1) / rpc, a->batch);
-    if (a->C <= 384) MOBI_CUDA(launch_pdl(ln_adapter_kernel<3>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
-    else if (a->C <= 768) MOBI_CUDA(launch_pdl(ln_adapter_kernel<6>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
-    else MOBI_CUDA(launch_pdl(ln_adapter_kernel<12>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
+    if (a->C <= 384) MOBI_CUDA(launch_pdl(ln_adapter_kernel<3, AD_R3, AD_B3>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
+    else if (a->C <= 768) MOBI_CUDA(launch_pdl(ln_adapter_kernel<6, AD_R6, AD_B6>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
+    else MOBI_CUDA(launch_pdl(ln_adapter_kernel<12, AD_R12, AD_B12>, dim3(grid), dim3(AD_WARPS * 32), (size_t)(smem), stream, p, d));
     MOBI_CUDA(cudaGetLastError());
     return 0;
 }
