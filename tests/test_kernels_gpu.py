@@ -289,6 +289,75 @@ def test_gemm_quad_clusters(M, N, K, tile_n):
     assert torch.equal(quad, pair)
 
 
+def _fuzz_cases(n, seed):
+    import random
+    rng = random.Random(seed)
+    cases = []
+    for i in range(n):
+        M = rng.choice([4, 64, 128, 256, 384, 1000, 2048, 4096, 8192, 20000, 128 * rng.randint(1, 80)])
+        N = rng.choice([4, 32, 64, 160, 320, 640, 960, 1280, 2560, 4 * rng.randint(1, 500), 32 * rng.randint(1, 60)])
+        K = rng.choice([64, 320, 640, 1280, 2880, 8 * rng.randint(1, 400)])
+        cases.append((i, M, N, K, rng.random() < 0.5, rng.random() < 0.6, rng.random() < 0.4, rng.choice([0, 0, 1, 2]),
+                      rng.random() < 0.3))
+    return cases
+
+
+@pytest.mark.parametrize("case", _fuzz_cases(36, 2024), ids=lambda c: "M%d-N%d-K%d-%d" % (c[1], c[2], c[3], c[0]))
+def test_gemm_policy_fuzz(case):
+    """Whatever tile shape / CTA grouping / epilogue class the library picks for a problem (160- and 256-wide tiles, pairs,
+    the straight-line f32 epilogue, the residual prefetch, ...) gives the result of the plainest configuration (64-wide
+    tiles, one CTA per tile) on the same operands -- the accumulation order per output element is the same -- and both
+    match PyTorch.  Seeded random shapes incl. tails in M, N and K, odd tile counts and every PLAIN epilogue option."""
+    i, M, N, K, out_f32, use_res, use_rb, act, stats = case
+    ops = _ops()
+    a = rnd(M, K, seed=10 + i)
+    w = rnd(N, K, seed=50 + i, scale=K ** -0.5)
+    bias = rnd(N, seed=90 + i, dtype=torch.float32)
+    res = rnd(M, N, seed=130 + i, dtype=torch.float32) if use_res else None
+    rpg = 32 if M % 32 == 0 else 1
+    rb = rnd((M + rpg - 1) // rpg, N, seed=170 + i, dtype=torch.float32) if use_rb else None
+    kw = dict(bias=bias, residual=res, row_bias=rb, rows_per_group=rpg, act=act,
+              out_dtype=torch.float32 if out_f32 else torch.bfloat16)
+    ref = a.float() @ w.float().t() + bias
+    if rb is not None:
+        ref = ref + rb.repeat_interleave(rpg, 0)[:M]
+    if act == 1:
+        ref = torch.nn.functional.silu(ref)
+    elif act == 2:
+        ref = torch.nn.functional.gelu(ref)
+    if res is not None:
+        ref = ref + res
+    plain = ops.gemm(a, w, tile_n=64, pair=-1, **kw)
+    auto = ops.gemm(a, w, colstats=stats and out_f32 and act == 0, **kw)
+    torch.cuda.synchronize()
+    tol = 2e-3 if out_f32 else 1e-2
+    assert relerr(auto, ref) < tol, describe(auto, ref)
+    assert relerr(auto, plain) < 1e-6 if out_f32 else torch.equal(auto, plain), describe(auto, plain)
+    st = getattr(auto, "_colstats", None)
+    if st is not None and M % 32 == 0:
+        g = M // 32
+        assert relerr(st[:g * N].reshape(g, N), auto.reshape(g, 32, N).sum(1)) < 1e-5
+
+
+@pytest.mark.parametrize("case", [(2, 64, 64, 320, 320), (1, 32, 32, 640, 1280), (7, 16, 16, 1280, 640), (3, 8, 8, 1280, 1280),
+                                  (5, 64, 64, 64, 320), (1, 64, 64, 320, 4), (9, 32, 32, 128, 960), (16, 16, 16, 320, 320)],
+                         ids=lambda c: "n%d-%dx%d-%d-%d" % c)
+def test_conv_policy_vs_plainest_tiles(case):
+    """The same for the implicit-GEMM convolution: the automatic choice (wide pair tiles where N % 320 == 0 and the tiles
+    fill the machine) against 64-wide tiles on single CTAs."""
+    N, H, W, C, Cout = case
+    ops = _ops()
+    x = rnd(N, H, W, C, seed=1)
+    w = rnd(Cout, 9 * C, seed=2, scale=(9 * C) ** -0.5)
+    b = rnd(Cout, seed=3, dtype=torch.float32)
+    emb = rnd(N, Cout, seed=4, dtype=torch.float32)
+    res = rnd(N, H, W, Cout, seed=5, dtype=torch.float32)
+    plain = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=b, row_bias=emb, residual=res, tile_n=64, pair=-1)
+    auto = ops.conv_implicit(x, w, 3, 3, 1, 1, bias=b, row_bias=emb, residual=res, colstats=True)
+    torch.cuda.synchronize()
+    assert relerr(auto, plain) < 1e-6, describe(auto.reshape(-1, Cout), plain.reshape(-1, Cout))
+
+
 @pytest.mark.parametrize("N,H,W,C,Cout,k,stride,pads", [
     (2, 64, 64, 320, 320, 3, 2, (1, 1)), (2, 32, 32, 9, 320, 3, 1, (1, 1)), (1, 64, 64, 128, 128, 3, 2, (0, 0)),
 ])
