@@ -123,6 +123,10 @@ typedef struct {
 } mobi_gemm_args;
 
 int mobi_gemm(const mobi_gemm_args* args, void* stream);
+/* What mobi_gemm would do with these arguments, without touching the device: the tile width it picks (64 / 128 / 160 / 256),
+ * the CTA grouping (the values of `pair` above; 0 = one CTA per tile) and whether the persistent kernel takes the problem.
+ * Same validation and error behaviour as mobi_gemm; pointers are only checked for null / alignment, never dereferenced. */
+int mobi_gemm_plan(const mobi_gemm_args* args, int32_t* tile_n, int32_t* pair, int32_t* persistent);
 
 /*
  * Flash-style fused attention: O = softmax(Q K^T) V per (batch*head), scores never leave the SM.

@@ -201,6 +201,7 @@ SIGNATURES = {
     "mobi_last_error": (C.c_char_p, []),
     "mobi_version": (C.c_int, []),
     "mobi_gemm": (C.c_int, [C.POINTER(GemmArgs), _vp]),
+    "mobi_gemm_plan": (C.c_int, [C.POINTER(GemmArgs), C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32)]),
     "mobi_attention": (C.c_int, [C.POINTER(AttnArgs), _vp]),
     "mobi_groupnorm_scratch_bytes": (_i64, [_i32, _i32, _i32, _i32]),
     "mobi_groupnorm_launches": (_i32, [_i32, _i32, _i32, _i32, _i32]),

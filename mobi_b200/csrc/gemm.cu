@@ -321,8 +321,10 @@ static int make_operand_map(CUtensorMap* tm, const void* base, uint64_t dim0, ui
     return make_tensor_map_bf16(tm, base, 4, dims, strides, box);
 }
 
-extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
-    cudaStream_t stream = reinterpret_cast<cudaStream_t>(stream_);
+// `plan` != nullptr: validate the problem and decide tile shape / CTA grouping exactly as a launch would, but build no
+// tensor maps and launch nothing (no device needed): plan[0] = tile_n, plan[1] = pair mode (0 / 1 / 2 / 3), plan[2] = 1 when
+// the persistent kernel takes the problem (0: the one-tile kernel).
+static int gemm_impl(const mobi_gemm_args* a, cudaStream_t stream, int32_t* plan) {
     MOBI_CHECK(a != nullptr, "mobi_gemm: null args");
     MOBI_CHECK(a->M > 0 && a->N > 0 && a->K > 0, "mobi_gemm: empty problem M=%lld N=%lld K=%lld", (long long)a->M,
                (long long)a->N, (long long)a->K);
@@ -423,20 +425,20 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         uint64_t dims[4] = {(uint64_t)a->C, (uint64_t)a->W, (uint64_t)a->H, (uint64_t)a->n_img};
         uint64_t strides[3] = {(uint64_t)a->C * 2, (uint64_t)a->W * a->C * 2, (uint64_t)a->H * a->W * a->C * 2};
         uint32_t box[4] = {BK, (uint32_t)bw, (uint32_t)bh, (uint32_t)bn};
-        if (make_tensor_map_bf16(&tmA, a->A, 4, dims, strides, box)) return 1;
+        if (!plan && make_tensor_map_bf16(&tmA, a->A, 4, dims, strides, box)) return 1;
     } else if (a->a_mn_major) {
         MOBI_CHECK(a->lda % 8 == 0 && a->lda >= a->M, "mobi_gemm: MN-major A needs lda=%lld >= M and a multiple of 8",
                    (long long)a->lda);
         p.num_k_blocks = (int)((K + BK - 1) / BK);
-        if (make_operand_map(&tmA, a->A, (uint64_t)a->M, (uint64_t)K, (uint64_t)a->lda, 64, BK, p.batch, p.batch_inner,
-                             a->a_batch_stride, a->a_batch2_stride))
+        if (!plan && make_operand_map(&tmA, a->A, (uint64_t)a->M, (uint64_t)K, (uint64_t)a->lda, 64, BK, p.batch, p.batch_inner,
+                                      a->a_batch_stride, a->a_batch2_stride))
             return 1;
     } else {
         MOBI_CHECK(a->K % 8 == 0 && a->lda % 8 == 0, "mobi_gemm: K=%lld and lda=%lld must be multiples of 8",
                    (long long)a->K, (long long)a->lda);
         p.num_k_blocks = (int)((K + BK - 1) / BK);
-        if (make_operand_map(&tmA, a->A, (uint64_t)K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM, p.batch, p.batch_inner,
-                             a->a_batch_stride, a->a_batch2_stride))
+        if (!plan && make_operand_map(&tmA, a->A, (uint64_t)K, (uint64_t)a->M, (uint64_t)a->lda, BK, BM, p.batch, p.batch_inner,
+                                      a->a_batch_stride, a->a_batch2_stride))
             return 1;
     }
     p.atomic_out = a->atomic_out ? 1 : 0;
@@ -518,6 +520,12 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
                    "mobi_gemm: pair = 3 (320-column tiles on CTA pairs) needs tile_n = 160, K-major operands and no batch");
         p.pair = 3;
     }
+    if (plan) {
+        plan[0] = bn_tile;
+        plan[1] = p.pair;
+        plan[2] = (a->kernel != 1 && gemm2_supported(p)) ? 1 : 0;
+        return 0;
+    }
     if (p.pair == 2) {
         // the A box shrinks to the 64 rows each CTA fetches (and multicasts to its counterpart)
         if (a->conv) {
@@ -574,5 +582,18 @@ extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
         case 256: return launch_gemm<256>(tmA, tmB, p, stream);
         default: MOBI_CHECK(false, "mobi_gemm: unsupported tile_n %d", bn_tile);
     }
+    return 0;
+}
+
+extern "C" int mobi_gemm(const mobi_gemm_args* a, void* stream_) {
+    return gemm_impl(a, reinterpret_cast<cudaStream_t>(stream_), nullptr);
+}
+
+extern "C" int mobi_gemm_plan(const mobi_gemm_args* a, int32_t* tile_n, int32_t* pair, int32_t* persistent) {
+    int32_t plan[3] = {0, 0, 0};
+    if (gemm_impl(a, nullptr, plan)) return 1;
+    if (tile_n) *tile_n = plan[0];
+    if (pair) *pair = plan[1];
+    if (persistent) *persistent = plan[2];
     return 0;
 }
