@@ -585,7 +585,7 @@ gemm2_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CU
                     long long mo = (long long)m_tile * BM;
                     if (p.out_seg > 0) mo += (mo / p.out_seg) * (p.out_seg_stride - p.out_seg) + p.out_seg_offset;
                     tma_prefetch_l2_2d(&tmR, n_tile * (WIDE ? 2 * BN : BN), (int)mo);
-                    if (WIDE) tma_prefetch_l2_2d(&tmR, n_tile * 2 * BN + BN, (int)mo);
+                    if (WIDE && n_tile * 2 * BN + BN < p.N) tma_prefetch_l2_2d(&tmR, n_tile * 2 * BN + BN, (int)mo);
                 }
                 int x0 = 0, y0 = 0, n0 = 0;
                 if (p.conv) {
